@@ -1,0 +1,319 @@
+/*
+ * topay_b200.h — C ABI of the B200-native hot path of the TopAY planner.
+ *
+ * Two opaque objects cross this boundary:
+ *
+ *   topay_field   replaces the distance-field half of the reference:
+ *                 GridMap            (src/map/include/map/grid_map.h:77-219,
+ *                                     src/map/src/grid_map.cpp:6-87,125-521,716-809)
+ *   topay_solver  replaces the NLP-solve half of the reference:
+ *                 MomaTrajOpt        (src/planner/include/planner/moma_traj_opt.h:613-675,
+ *                                     src/planner/src/moma_traj_opt.cpp:142-498,817-1829)
+ *
+ * The reference has no FFI layer of its own: these entry points
+ * are what a maintainer binds from `Planner` (src/planner/src/planner.cpp:873-885)
+ * through the C++ shims in shim/ (same class names and members).
+ *
+ * Conventions: plain pointers and sizes, caller-owned HOST buffers unless the
+ * name ends in `_dev`, row-major, fp64 unless stated, int32 status return
+ * (TOPAY_OK == 0; negative = error, see topay_strerror), no exceptions cross the
+ * boundary, one host thread per handle. There is no CPU fallback: every compute
+ * entry point fails with TOPAY_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef TOPAY_B200_H
+#define TOPAY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+enum {
+    TOPAY_OK = 0,
+    TOPAY_ERR_INVALID_ARG = -1,
+    TOPAY_ERR_NO_DEVICE = -2,   /* no usable CUDA device: the product path refuses to run */
+    TOPAY_ERR_CUDA = -3,        /* a CUDA runtime call failed; see topay_last_error() */
+    TOPAY_ERR_ALLOC = -4,
+    TOPAY_ERR_TOO_LARGE = -5,   /* n_cand / piece_num / int_K above the solver's capacity */
+    TOPAY_ERR_NOT_READY = -6    /* field queried/solved before topay_field_rebuild */
+};
+const char* topay_strerror(int code);
+const char* topay_last_error(void);   /* thread-local detail of the last failure */
+const char* topay_version(void);
+
+/* L-BFGS return codes, numerically identical to the reference's enum
+ * (src/planner/include/utils/lbfgs.hpp:135-184). */
+enum {
+    TOPAY_LBFGS_CONVERGENCE = 0,
+    TOPAY_LBFGS_STOP = 1,
+    TOPAY_LBFGS_CANCELED = 2,
+    TOPAY_LBFGSERR_UNKNOWNERROR = -1024,
+    TOPAY_LBFGSERR_INVALID_N = -1023,
+    TOPAY_LBFGSERR_INVALID_MEMSIZE = -1022,
+    TOPAY_LBFGSERR_INVALID_GEPSILON = -1021,
+    TOPAY_LBFGSERR_INVALID_TESTPERIOD = -1020,
+    TOPAY_LBFGSERR_INVALID_DELTA = -1019,
+    TOPAY_LBFGSERR_INVALID_MINSTEP = -1018,
+    TOPAY_LBFGSERR_INVALID_MAXSTEP = -1017,
+    TOPAY_LBFGSERR_INVALID_FDECCOEFF = -1016,
+    TOPAY_LBFGSERR_INVALID_SCURVCOEFF = -1015,
+    TOPAY_LBFGSERR_INVALID_MACHINEPREC = -1014,
+    TOPAY_LBFGSERR_INVALID_MAXLINESEARCH = -1013,
+    TOPAY_LBFGSERR_INVALID_FUNCVAL = -1012,
+    TOPAY_LBFGSERR_MINIMUMSTEP = -1011,
+    TOPAY_LBFGSERR_MAXIMUMSTEP = -1010,
+    TOPAY_LBFGSERR_MAXIMUMLINESEARCH = -1009,
+    TOPAY_LBFGSERR_MAXIMUMITERATION = -1008,
+    TOPAY_LBFGSERR_WIDTHTOOSMALL = -1007,
+    TOPAY_LBFGSERR_INVALIDPARAMETERS = -1006,
+    TOPAY_LBFGSERR_INCREASEGRADIENT = -1005
+};
+
+/* ------------------------------------------------------------------ params */
+
+#define TOPAY_DOF 7          /* arm joints, MomaParam::dof_num (moma_param.h:53) */
+#define TOPAY_DIM 9          /* spline dimensions: theta, arc, q1..q7 */
+#define TOPAY_NSPHERE 12     /* arm collision spheres (moma_param.h:94-109) */
+#define TOPAY_NTERMS 13      /* cost breakdown, order of moma_traj_opt.h:926-938 */
+
+/* Order of the 13 per-evaluation term costs (DebugManager names,
+ * src/planner/include/planner/moma_traj_opt.h:926-938). */
+enum {
+    TOPAY_TERM_JERK = 0, TOPAY_TERM_TIME, TOPAY_TERM_CHASSIS_COLLI, TOPAY_TERM_MOMENT,
+    TOPAY_TERM_ACC, TOPAY_TERM_DOMEGA, TOPAY_TERM_MANI_COLLI, TOPAY_TERM_SELF_COLLI,
+    TOPAY_TERM_MANI_POS, TOPAY_TERM_MANI_VEL, TOPAY_TERM_MANI_ACC, TOPAY_TERM_MEAN_TIME,
+    TOPAY_TERM_ENDP   /* stage 2: ALM end-point term; stage 1: path-point tracking term */
+};
+
+/* Robot constants — mirrors struct MomaParam
+ * (src/simulator/fake_moma/include/fake_moma/moma_param.h:33-144). */
+typedef struct topay_robot_params {
+    double chassis_height;            /* 0.155 */
+    double chassis_colli_radius;      /* 0.4   */
+    double max_v, max_a, max_w, max_dw;
+    double colli_length[TOPAY_DOF + 1];
+    double colli_points[2 * (TOPAY_DOF + 1)];        /* 0.0 entries are skipped */
+    double colli_point_radius[2 * (TOPAY_DOF + 1)];
+    double joint_pos_limit_max[TOPAY_DOF];           /* symmetric limits */
+    double joint_vel_limit[TOPAY_DOF];
+    double joint_acc_limit[TOPAY_DOF];
+    double relative_R[9];                            /* row-major */
+    double relative_t[3];
+    int32_t collision_matrix[TOPAY_NSPHERE * TOPAY_NSPHERE]; /* -1 => pair is checked */
+} topay_robot_params;
+
+/* Fills the defaults exactly as MomaParam::MomaParam() does (moma_param.h:72-144),
+ * including the zero-pose derivation of collision_matrix. Pure host code. */
+void topay_robot_params_default(topay_robot_params* out);
+
+/* lbfgs::lbfgs_parameter_t (src/planner/include/utils/lbfgs.hpp:13-129). */
+typedef struct topay_lbfgs_params {
+    int32_t mem_size;
+    double  g_epsilon;
+    int32_t past;
+    double  delta;
+    int32_t max_iterations;
+    int32_t max_linesearch;
+    double  min_step, max_step;
+    double  f_dec_coeff, s_curv_coeff, cautious_factor, machine_prec;
+} topay_lbfgs_params;
+
+/* MomaTrajOptParam (moma_traj_opt.h:432-564) with the values of
+ * src/planner/params/optimizer.yaml as defaults. */
+typedef struct topay_opt_params {
+    int32_t int_K;
+    int32_t min_piece_num;
+    double  relu_mu;
+    double  sample_interval;
+    double  energy_weights[TOPAY_DIM];
+    /* first stage */
+    double  s1_time_weight, s1_moment_weight, s1_acc_weight, s1_domega_weight;
+    double  s1_mean_time_weight, s1_path_pos_weight;
+    int32_t s1_lbfgs_normal_past, s1_lbfgs_shot_path_past;
+    double  s1_shot_path_horizon;
+    topay_lbfgs_params s1_lbfgs;
+    /* second stage */
+    double  s2_time_weight, s2_moment_weight, s2_acc_weight, s2_domega_weight;
+    double  s2_collision_weight, s2_mani_colli_weight, s2_self_colli_weight;
+    double  s2_mani_pos_weight, s2_mani_vel_weight, s2_mani_acc_weight, s2_mean_time_weight;
+    topay_lbfgs_params s2_lbfgs;
+    double  alm_init_lambda[2], alm_init_rho[2], alm_rho_max[2], alm_gamma[2];
+    double  alm_tolerance;
+    /* The reference bounds the ALM loop by 1.0 s of wall clock
+     * (moma_traj_opt.cpp:403). A deterministic cap replaces it on both the
+     * device path and the oracle: at most this many inner solves. */
+    int32_t alm_max_rounds;
+} topay_opt_params;
+
+void topay_opt_params_default(topay_opt_params* out);
+
+/* Dense GridMap geometry — the rosparams of src/planner/params/grid_map.yaml;
+ * everything else is derived exactly as GridMap::init does (grid_map.cpp:33-54). */
+typedef struct topay_grid_desc {
+    double map_size[3];
+    double resolution;
+    double chassis_colli_radius;   /* threshold of the inflated 2-D maps (grid_map.cpp:288,360) */
+    double chassis_height;         /* rasterisation threshold of occ_2d (grid_map.cpp:740) */
+} topay_grid_desc;
+
+typedef struct topay_field  topay_field;
+typedef struct topay_solver topay_solver;
+
+/* which 2-D map a query reads (GridMap::getDisWithGradI2d flags, grid_map.h:364-429) */
+enum { TOPAY_MAP2D_FLAT = 0, TOPAY_MAP2D_INFLATE = 1, TOPAY_MAP2D_CRITICAL = 2, TOPAY_MAP3D = 3 };
+
+/* ------------------------------------------------------------------- field */
+
+/* GridMap::init (grid_map.cpp:6-65): allocates occupancy + ESDF buffers in HBM. */
+int topay_field_create(const topay_grid_desc* desc, int device, topay_field** out);
+void topay_field_destroy(topay_field* f);
+/* voxel_num as GridMap::getVoxelNum (grid_map.h:179). */
+int topay_field_dims(const topay_field* f, int32_t dims[3]);
+
+/* GridMap::loadMap (grid_map.cpp:800-809) semantics when occ2d_critical == NULL:
+ * occ_2d and occ_3d are replaced, the critical occupancy is left as it is.
+ * A NULL occ3d / occ2d leaves that buffer unchanged. Values are 0/1, layout
+ * x*Ny*Nz + y*Nz + z (grid_map.h:808-816) and x*Ny + y (grid_map.h:798-806). */
+int topay_field_set_occupancy(topay_field* f, const int8_t* occ3d, const int8_t* occ2d,
+                              const int8_t* occ2d_critical);
+/* The reset GridMap::regenerateMap / regenerateDesk perform before rasterising
+ * (grid_map.cpp:719-722): occ_2d and occ_3d are zeroed; occ_2d_critical is
+ * kept unless clear_critical != 0 (reference quirk). */
+int topay_field_clear(topay_field* f, int clear_critical);
+/* Point-cloud ingest of regenerateMap / cloudCallback (grid_map.cpp:733-747,
+ * 554-568): float32 xyz triples, promoted to double before indexing. */
+int topay_field_rasterize_points(topay_field* f, const float* xyz, int64_t n_points);
+/* GridMap::updateESDF (grid_map.cpp:125-521): four signed 2-D maps + the signed 3-D map. */
+int topay_field_rebuild(topay_field* f);
+
+/* GridMap::getDisWithGradI3d (grid_map.h:443-509); grad may be NULL. pos is n x 3. */
+int topay_field_query3d(topay_field* f, const double* pos, int64_t n, double* dist, double* grad);
+/* GridMap::getDisWithGradI2d (grid_map.h:364-441); pos is n x 2, grad n x 2 or NULL. */
+int topay_field_query2d(topay_field* f, const double* pos, int64_t n, int which, double* dist,
+                        double* grad);
+/* GridMap::getDistance3d / getDistance2d (grid_map.h:256-362): value only, 1e10 outside. */
+int topay_field_distance3d(topay_field* f, const double* pos, int64_t n, double* dist);
+int topay_field_distance2d(topay_field* f, const double* pos, int64_t n, double* dist);
+/* GridMap::isWholeBodyCollision (grid_map.h:613-650); states are n x 10; out 0/1. */
+int topay_field_whole_body_collision(topay_field* f, const topay_robot_params* robot,
+                                     const double* states, int64_t n, int8_t* out);
+/* Same queries with DEVICE pointers (inputs and outputs already in HBM), asynchronous
+ * on the field's stream; used by the resident benchmark and by the solver. */
+int topay_field_query3d_dev(topay_field* f, const double* pos_dev, int64_t n, double* dist_dev,
+                            double* grad_dev);
+int topay_field_sync(topay_field* f);
+
+/* getESDFBuffer2d/3d (grid_map.h:216-217) and the other two 2-D maps; `which` as above. */
+int topay_field_download(topay_field* f, int which, double* esdf_out);
+/* The integer squared distances (in cells^2) behind a map: pos_sq to the nearest
+ * occupied cell, neg_sq to the nearest free cell; INT32_MAX where the reference
+ * carries DBL_MAX (no source cell on the whole grid). Either pointer may be NULL. */
+int topay_field_download_sqdist(topay_field* f, int which, int32_t* pos_sq, int32_t* neg_sq);
+int topay_field_download_occupancy(topay_field* f, int which, int8_t* occ_out);
+/* Device time of the last topay_field_rebuild, measured with CUDA events on the
+ * field's stream; ms_3d is the 3-D part alone. */
+int topay_field_last_rebuild_ms(topay_field* f, float* ms_total, float* ms_3d);
+
+/* ------------------------------------------------------------------ solver */
+
+/* One solver = the device-side state for up to max_cand candidates of up to
+ * max_pieces pieces each (what the reference keeps in <= 8 MomaTrajOpt
+ * instances, planner.cpp:59-66). The field is borrowed, read-only. */
+int topay_solver_create(const topay_opt_params* opt, const topay_robot_params* robot,
+                        topay_field* field, int max_cand, int max_pieces, topay_solver** out);
+void topay_solver_destroy(topay_solver* s);
+
+/* The fixed data of each candidate's NLP, i.e. what optimizeTraj derives before it
+ * packs x (moma_traj_opt.cpp:281-304). Host pointers. */
+typedef struct topay_problem_batch {
+    int32_t        n_cand;
+    const int32_t* piece_num;      /* [n_cand] */
+    const double*  head_pva;       /* [n_cand][9][3]  minco_start_state */
+    const double*  tail_pva;       /* [n_cand][9][3]  minco_end_state; [1][0] is overwritten by x */
+    const double*  start_xy;       /* [n_cand][2]     start_state.head(2) */
+    const double*  end_xy;         /* [n_cand][2]     end_state.head(2) */
+    const double*  init_inner_xy;  /* [n_cand][max_pieces][2] stage-1 targets, first piece_num rows used */
+    const double*  alm_lambda;     /* [n_cand][2]  stage 2 only (may be NULL for stage 1) */
+    const double*  alm_rho;        /* [n_cand][2] */
+} topay_problem_batch;
+
+/* One cost+gradient evaluation per candidate: firstStageCostCallback (stage == 1,
+ * moma_traj_opt.cpp:817-883) or secondStageCostCallback (stage == 2, :885-955).
+ * x and grad are [n_cand][x_stride] with the layout of moma_traj_opt.cpp:324-344
+ * (tau(N) | theta(N-1) | arc(N) | vq(7 x (N-1), column-major)); cost is [n_cand];
+ * term_costs is [n_cand][TOPAY_NTERMS] or NULL; coeff_out is
+ * [n_cand][6*max_pieces][9] or NULL; final_xy_out [n_cand][2] or NULL. */
+int topay_solver_eval(topay_solver* s, int stage, const topay_problem_batch* prob,
+                      const double* x, int x_stride, double* cost, double* grad,
+                      double* term_costs, double* coeff_out, double* final_xy_out);
+
+/* Number of optimisation variables of an N-piece candidate: 9(N-1)+N+1. */
+static inline int topay_num_vars(int piece_num) { return 10 * piece_num - 8; }
+
+/* MomaTrajOpt::optimizeTraj pre-processing (moma_traj_opt.cpp:146-344): waypoints ->
+ * problem data + initial x. Host-side helper of solve_batch, exported for parity
+ * tests. init_path is path_len x 10 (x,y,yaw,q1..q7); bvel/bacc are 10 x 2
+ * row-major (planner.cpp:873-875). Outputs sized for max_pieces; returns the
+ * piece count in *piece_num or TOPAY_ERR_TOO_LARGE. */
+int topay_prepare_candidate(const topay_opt_params* opt, const topay_robot_params* robot,
+                            const double* init_path, int path_len, const double* bvel,
+                            const double* bacc, int max_pieces, int32_t* piece_num,
+                            double* head_pva /*27*/, double* tail_pva /*27*/,
+                            double* start_xy /*2*/, double* end_xy /*2*/,
+                            double* init_inner_xy /*max_pieces x 2*/, double* x0 /*10*max_pieces-8*/,
+                            int32_t* s1_past);
+
+/* Results of a batched solve; host pointers, any may be NULL except status. */
+typedef struct topay_result_batch {
+    int32_t* status;        /* [n] 1 = optimizeTraj returned true, 0 = false */
+    int32_t* lbfgs_code;    /* [n] return code of the last lbfgs_optimize call */
+    int32_t* piece_num;     /* [n] */
+    int32_t* iters;         /* [n] L-BFGS iterations, both stages */
+    int32_t* evals;         /* [n] cost/gradient evaluations, both stages */
+    int32_t* alm_rounds;    /* [n] */
+    double*  cost;          /* [n] traj_cost (moma_traj_opt.cpp:495) */
+    double*  duration;      /* [n] sum of piece durations of the returned trajectory */
+    double*  T;             /* [n][max_pieces] */
+    double*  coeff;         /* [n][6*max_pieces][9] minco coefficients of the last evaluation */
+    double*  final_xy_err;  /* [n][2] */
+    double*  x;             /* [n][10*max_pieces-8] final variables */
+} topay_result_batch;
+
+/* The batched replacement of n_cand concurrent MomaTrajOpt::optimizeTraj calls
+ * (planner.cpp:878): pre-processing on the host, then stage 1, then the stage-2
+ * ALM loop entirely on the device. init_paths holds the candidates' waypoint
+ * lists back to back (sum(path_len) x 10). best_by_duration follows the
+ * reference's selection rule (planner.cpp:999-1010), best_by_cost is the
+ * north-star's argmin over successful candidates; -1 when none succeeded. */
+int topay_solver_solve_batch(topay_solver* s, int n_cand, const int32_t* path_len,
+                             const double* init_paths, const double* bvel, const double* bacc,
+                             topay_result_batch* out, int32_t* best_by_duration,
+                             int32_t* best_by_cost);
+
+/* Split form for resident benchmarking: upload + pre-process once, then run the
+ * device solve any number of times from the same initial state. */
+int topay_solver_upload(topay_solver* s, int n_cand, const int32_t* path_len,
+                        const double* init_paths, const double* bvel, const double* bacc);
+int topay_solver_run(topay_solver* s);          /* device solve of the uploaded batch, blocking */
+int topay_solver_download(topay_solver* s, topay_result_batch* out, int32_t* best_by_duration,
+                          int32_t* best_by_cost);
+
+/* Device-side counters of the last run: kernel launches issued, lock-step ticks,
+ * device ms spent in the evaluation kernels and in the whole solve (CUDA events). */
+typedef struct topay_solver_stats {
+    int64_t kernel_launches;
+    int64_t ticks;
+    int64_t evals_total;       /* sum over candidates */
+    float   ms_total;
+    float   ms_eval;           /* penalty-node kernel only */
+    int64_t eval_launches;     /* launches of the penalty-node kernel */
+    int64_t eval_nodes;        /* penalty nodes processed by them (active candidates only) */
+} topay_solver_stats;
+int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPAY_B200_H */

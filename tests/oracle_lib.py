@@ -1,0 +1,253 @@
+"""ctypes binding of oracle/liboracle.so — the CPU restatement of the reference hot path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
+--impl reference legs of bench.py. The product package (topay_b200/) never imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from topay_b200._structs import (GridDesc, LbfgsParams, OptParams, RobotParams, NTERMS, num_vars)
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "liboracle.so")
+
+
+def build(force=False):
+    srcs = [os.path.join(_ROOT, "oracle", f) for f in
+            ("oracle_capi.cpp", "oracle_field.hpp", "oracle_robot.hpp", "oracle_solve.hpp")]
+    srcs.append(os.path.join(_ROOT, "include", "topay_b200.h"))
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "liboracle.so"])
+    return _SO
+
+
+class SolveOut(C.Structure):
+    _fields_ = [("status", C.c_int32), ("lbfgs_code", C.c_int32), ("piece_num", C.c_int32),
+                ("iters", C.c_int32), ("evals", C.c_int32), ("alm_rounds", C.c_int32),
+                ("cost", C.c_double), ("duration", C.c_double), ("final_xy_err", C.c_double * 2)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.oracle_field_create.restype = C.c_void_p
+    return _lib
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def robot_defaults():
+    rp = RobotParams()
+    lib().oracle_robot_params_default(C.byref(rp))
+    return rp
+
+
+def opt_defaults():
+    o = OptParams()
+    lib().oracle_opt_params_default(C.byref(o))
+    return o
+
+
+class Field:
+    def __init__(self, desc: GridDesc):
+        self.h = C.c_void_p(lib().oracle_field_create(C.byref(desc)))
+        d = (C.c_int32 * 3)()
+        lib().oracle_field_dims(self.h, d)
+        self.dims = tuple(d)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_field_destroy(self.h)
+            self.h = None
+
+    def set_occupancy(self, occ3d=None, occ2d=None, occ2d_critical=None):
+        a = [None if o is None else np.ascontiguousarray(o, dtype=np.int8) for o in (occ3d, occ2d, occ2d_critical)]
+        lib().oracle_field_set_occupancy(self.h, *[_p(x, C.c_int8) for x in a])
+
+    def clear(self, clear_critical=False):
+        lib().oracle_field_clear(self.h, int(clear_critical))
+
+    def rasterize(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        lib().oracle_field_rasterize(self.h, _p(xyz, C.c_float), C.c_int64(xyz.shape[0]))
+
+    def rebuild(self):
+        lib().oracle_field_rebuild(self.h)
+
+    def query3d(self, pos):
+        pos = _f64(pos)
+        n = pos.shape[0]
+        d, g = np.empty(n), np.empty((n, 3))
+        lib().oracle_field_query3d(self.h, _p(pos), C.c_int64(n), _p(d), _p(g))
+        return d, g
+
+    def query2d(self, pos, which=0):
+        pos = _f64(pos)
+        n = pos.shape[0]
+        d, g = np.empty(n), np.empty((n, 2))
+        lib().oracle_field_query2d(self.h, _p(pos), C.c_int64(n), which, _p(d), _p(g))
+        return d, g
+
+    def distance3d(self, pos):
+        pos = _f64(pos)
+        d = np.empty(pos.shape[0])
+        lib().oracle_field_distance3d(self.h, _p(pos), C.c_int64(pos.shape[0]), _p(d))
+        return d
+
+    def distance2d(self, pos):
+        pos = _f64(pos)
+        d = np.empty(pos.shape[0])
+        lib().oracle_field_distance2d(self.h, _p(pos), C.c_int64(pos.shape[0]), _p(d))
+        return d
+
+    def whole_body_collision(self, rp, states):
+        states = _f64(states)
+        out = np.empty(states.shape[0], dtype=np.int8)
+        lib().oracle_field_whole_body_collision(self.h, C.byref(rp), _p(states), C.c_int64(states.shape[0]),
+                                                _p(out, C.c_int8))
+        return out
+
+    def _shape(self, which):
+        return self.dims if which == 3 else self.dims[:2]
+
+    def download(self, which):
+        out = np.empty(self._shape(which))
+        lib().oracle_field_download(self.h, which, _p(out))
+        return out
+
+    def download_sqdist(self, which):
+        a = np.empty(self._shape(which), dtype=np.int32)
+        b = np.empty(self._shape(which), dtype=np.int32)
+        lib().oracle_field_download_sqdist(self.h, which, _p(a, C.c_int32), _p(b, C.c_int32))
+        return a, b
+
+    def download_occupancy(self, which):
+        a = np.empty(self._shape(which), dtype=np.int8)
+        lib().oracle_field_download_occupancy(self.h, which, _p(a, C.c_int8))
+        return a
+
+
+def colli_pts(rp, pos10):
+    pos10 = _f64(pos10)
+    out = np.zeros((12, 4))
+    n = lib().oracle_colli_pts(C.byref(rp), _p(pos10), _p(out))
+    return out[:n]
+
+
+def colli_grads(rp, pos10, grads):
+    pos10, grads = _f64(pos10), _f64(grads)
+    out = np.zeros(10)
+    lib().oracle_colli_grads(C.byref(rp), _p(pos10), _p(grads), _p(out))
+    return out
+
+
+def minco_generate(N, ew, head, tail, inner, T):
+    """inner: (N-1, 9) array (row i = inner point i). Returns coeff (6N,9), jerk, gdC, gdT."""
+    ew, head, tail, inner, T = map(_f64, (ew, head, tail, inner, T))
+    coeff = np.zeros((6 * N, 9))
+    jerk = C.c_double()
+    gdC, gdT = np.zeros((6 * N, 9)), np.zeros(N)
+    lib().oracle_minco_generate(N, _p(ew), _p(head), _p(tail), _p(inner), _p(T), _p(coeff), C.byref(jerk),
+                                _p(gdC), _p(gdT))
+    return coeff, jerk.value, gdC, gdT
+
+
+def minco_backprop(N, ew, head, tail, inner, T, gdC, gdT):
+    ew, head, tail, inner, T, gdC = map(_f64, (ew, head, tail, inner, T, gdC))
+    gdT = _f64(gdT).copy()
+    gdP, gdTail = np.zeros((max(N - 1, 0), 9)), np.zeros((9, 3))
+    lib().oracle_minco_backprop(N, _p(ew), _p(head), _p(tail), _p(inner), _p(T), _p(gdC), _p(gdT), _p(gdP),
+                                _p(gdTail))
+    return gdP, gdTail, gdT
+
+
+def banded_solve(dense, p, q, B, adjoint=False):
+    dense = _f64(dense)
+    B = _f64(B).copy()
+    n, m = B.shape
+    lib().oracle_banded_solve(n, p, q, _p(dense), m, _p(B), int(adjoint))
+    return B
+
+
+def lbfgs_test_problem(a, c, b, params: LbfgsParams, x0):
+    a, c = _f64(a), _f64(c)
+    x = _f64(x0).copy()
+    f, it, ev = C.c_double(), C.c_int(), C.c_int()
+    r = lib().oracle_lbfgs_test_problem(len(x), _p(a), _p(c), C.c_double(b), C.byref(params), _p(x), C.byref(f),
+                                        C.byref(it), C.byref(ev))
+    return r, x, f.value, it.value, ev.value
+
+
+def prepare_candidate(opt, rp, init_path, bvel, bacc, max_pieces):
+    init_path, bvel, bacc = _f64(init_path), _f64(bvel), _f64(bacc)
+    N = C.c_int32()
+    past = C.c_int32()
+    head, tail = np.zeros((9, 3)), np.zeros((9, 3))
+    sxy, exy = np.zeros(2), np.zeros(2)
+    inner_xy = np.zeros((max_pieces, 2))
+    x0 = np.zeros(num_vars(max_pieces))
+    rc = lib().oracle_prepare_candidate(C.byref(opt), C.byref(rp), _p(init_path), init_path.shape[0], _p(bvel),
+                                        _p(bacc), max_pieces, C.byref(N), _p(head), _p(tail), _p(sxy), _p(exy),
+                                        _p(inner_xy), _p(x0), C.byref(past))
+    return dict(rc=rc, piece_num=N.value, head_pva=head, tail_pva=tail, start_xy=sxy, end_xy=exy,
+                init_inner_xy=inner_xy, x0=x0[:num_vars(N.value)] if rc == 0 else x0, s1_past=past.value)
+
+
+def eval_one(opt, rp, field: Field, stage, N, head, tail, sxy, exy, inner_xy, lam, rho, x):
+    head, tail, sxy, exy, inner_xy, x = map(_f64, (head, tail, sxy, exy, inner_xy, x))
+    lam = _f64(lam) if lam is not None else np.zeros(2)
+    rho = _f64(rho) if rho is not None else np.ones(2)
+    n = num_vars(N)
+    cost = C.c_double()
+    grad, terms = np.zeros(n), np.zeros(NTERMS)
+    coeff, fxy = np.zeros((6 * N, 9)), np.zeros(2)
+    lib().oracle_eval(C.byref(opt), C.byref(rp), field.h, stage, N, _p(head), _p(tail), _p(sxy), _p(exy),
+                      _p(inner_xy), _p(lam), _p(rho), _p(x), C.byref(cost), _p(grad), _p(terms), _p(coeff), _p(fxy))
+    return cost.value, grad, terms, coeff, fxy
+
+
+def solve_one(opt, rp, field: Field, init_path, bvel, bacc, max_pieces=64, wall_cap_s=0.0, trace=False):
+    init_path, bvel, bacc = _f64(init_path), _f64(bvel), _f64(bacc)
+    out = SolveOut()
+    T = np.zeros(max_pieces)
+    coeff = np.zeros((6 * max_pieces, 9))
+    x = np.zeros(num_vars(max_pieces))
+    cap = 4 * 200000
+    tr = np.zeros(cap) if trace else None
+    tl = C.c_int(0)
+    lib().oracle_solve(C.byref(opt), C.byref(rp), field.h, _p(init_path), init_path.shape[0], _p(bvel), _p(bacc),
+                       C.c_double(wall_cap_s), C.byref(out), _p(T), _p(coeff), _p(x), _p(tr), cap, C.byref(tl))
+    N = out.piece_num
+    res = dict(status=out.status, lbfgs_code=out.lbfgs_code, piece_num=N, iters=out.iters, evals=out.evals,
+               alm_rounds=out.alm_rounds, cost=out.cost, duration=out.duration,
+               final_xy_err=np.array(out.final_xy_err[:]), T=T[:N].copy(), coeff=coeff[:6 * N].copy(),
+               x=x[:num_vars(N)].copy())
+    if trace:
+        res["trace"] = tr[:tl.value].reshape(-1, 4).copy()
+    return res
+
+
+def solve_batch(opt, rp, field: Field, paths, bvel, bacc, n_threads, wall_cap_s=0.0):
+    """paths: list of (len_i, 10) arrays; bvel/bacc: (n, 10, 2). Thread-per-candidate like planner.cpp:921."""
+    n = len(paths)
+    plen = np.array([p.shape[0] for p in paths], dtype=np.int32)
+    flat = _f64(np.concatenate(paths, axis=0))
+    bvel, bacc = _f64(bvel), _f64(bacc)
+    outs = (SolveOut * n)()
+    lib().oracle_solve_batch(C.byref(opt), C.byref(rp), field.h, n, _p(plen, C.c_int32), _p(flat), _p(bvel),
+                             _p(bacc), C.c_double(wall_cap_s), n_threads, outs)
+    return [dict(status=o.status, lbfgs_code=o.lbfgs_code, piece_num=o.piece_num, iters=o.iters, evals=o.evals,
+                 alm_rounds=o.alm_rounds, cost=o.cost, duration=o.duration) for o in outs]

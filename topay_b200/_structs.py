@@ -1,0 +1,96 @@
+"""ctypes mirrors of the C structs in include/topay_b200.h (field order must match)."""
+import ctypes as C
+
+DOF, DIM, NSPHERE, NTERMS = 7, 9, 12, 13
+TERM_NAMES = ["jerk", "time", "chassis_colli", "moment", "acc", "domega", "mani_colli",
+              "self_colli", "mani_pos", "mani_vel", "mani_acc", "mean_time", "endp"]
+MAP2D_FLAT, MAP2D_INFLATE, MAP2D_CRITICAL, MAP3D = 0, 1, 2, 3
+
+
+class RobotParams(C.Structure):
+    _fields_ = [
+        ("chassis_height", C.c_double), ("chassis_colli_radius", C.c_double),
+        ("max_v", C.c_double), ("max_a", C.c_double), ("max_w", C.c_double), ("max_dw", C.c_double),
+        ("colli_length", C.c_double * (DOF + 1)),
+        ("colli_points", C.c_double * (2 * (DOF + 1))),
+        ("colli_point_radius", C.c_double * (2 * (DOF + 1))),
+        ("joint_pos_limit_max", C.c_double * DOF),
+        ("joint_vel_limit", C.c_double * DOF),
+        ("joint_acc_limit", C.c_double * DOF),
+        ("relative_R", C.c_double * 9),
+        ("relative_t", C.c_double * 3),
+        ("collision_matrix", C.c_int32 * (NSPHERE * NSPHERE)),
+    ]
+
+
+class LbfgsParams(C.Structure):
+    _fields_ = [
+        ("mem_size", C.c_int32), ("g_epsilon", C.c_double), ("past", C.c_int32), ("delta", C.c_double),
+        ("max_iterations", C.c_int32), ("max_linesearch", C.c_int32),
+        ("min_step", C.c_double), ("max_step", C.c_double),
+        ("f_dec_coeff", C.c_double), ("s_curv_coeff", C.c_double),
+        ("cautious_factor", C.c_double), ("machine_prec", C.c_double),
+    ]
+
+
+class OptParams(C.Structure):
+    _fields_ = [
+        ("int_K", C.c_int32), ("min_piece_num", C.c_int32), ("relu_mu", C.c_double),
+        ("sample_interval", C.c_double), ("energy_weights", C.c_double * DIM),
+        ("s1_time_weight", C.c_double), ("s1_moment_weight", C.c_double), ("s1_acc_weight", C.c_double),
+        ("s1_domega_weight", C.c_double), ("s1_mean_time_weight", C.c_double),
+        ("s1_path_pos_weight", C.c_double),
+        ("s1_lbfgs_normal_past", C.c_int32), ("s1_lbfgs_shot_path_past", C.c_int32),
+        ("s1_shot_path_horizon", C.c_double), ("s1_lbfgs", LbfgsParams),
+        ("s2_time_weight", C.c_double), ("s2_moment_weight", C.c_double), ("s2_acc_weight", C.c_double),
+        ("s2_domega_weight", C.c_double), ("s2_collision_weight", C.c_double),
+        ("s2_mani_colli_weight", C.c_double), ("s2_self_colli_weight", C.c_double),
+        ("s2_mani_pos_weight", C.c_double), ("s2_mani_vel_weight", C.c_double),
+        ("s2_mani_acc_weight", C.c_double), ("s2_mean_time_weight", C.c_double),
+        ("s2_lbfgs", LbfgsParams),
+        ("alm_init_lambda", C.c_double * 2), ("alm_init_rho", C.c_double * 2),
+        ("alm_rho_max", C.c_double * 2), ("alm_gamma", C.c_double * 2),
+        ("alm_tolerance", C.c_double), ("alm_max_rounds", C.c_int32),
+    ]
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("map_size", C.c_double * 3), ("resolution", C.c_double),
+                ("chassis_colli_radius", C.c_double), ("chassis_height", C.c_double)]
+
+
+def grid_desc(map_size=(20.0, 20.0, 1.6), resolution=0.1, chassis_colli_radius=0.4, chassis_height=0.155):
+    """Defaults are src/planner/params/grid_map.yaml of the reference."""
+    d = GridDesc()
+    d.map_size[:] = map_size
+    d.resolution = resolution
+    d.chassis_colli_radius = chassis_colli_radius
+    d.chassis_height = chassis_height
+    return d
+
+
+class ProblemBatch(C.Structure):
+    _fields_ = [("n_cand", C.c_int32), ("piece_num", C.POINTER(C.c_int32)),
+                ("head_pva", C.POINTER(C.c_double)), ("tail_pva", C.POINTER(C.c_double)),
+                ("start_xy", C.POINTER(C.c_double)), ("end_xy", C.POINTER(C.c_double)),
+                ("init_inner_xy", C.POINTER(C.c_double)),
+                ("alm_lambda", C.POINTER(C.c_double)), ("alm_rho", C.POINTER(C.c_double))]
+
+
+class ResultBatch(C.Structure):
+    _fields_ = [("status", C.POINTER(C.c_int32)), ("lbfgs_code", C.POINTER(C.c_int32)),
+                ("piece_num", C.POINTER(C.c_int32)), ("iters", C.POINTER(C.c_int32)),
+                ("evals", C.POINTER(C.c_int32)), ("alm_rounds", C.POINTER(C.c_int32)),
+                ("cost", C.POINTER(C.c_double)), ("duration", C.POINTER(C.c_double)),
+                ("T", C.POINTER(C.c_double)), ("coeff", C.POINTER(C.c_double)),
+                ("final_xy_err", C.POINTER(C.c_double)), ("x", C.POINTER(C.c_double))]
+
+
+class SolverStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("ticks", C.c_int64), ("evals_total", C.c_int64),
+                ("ms_total", C.c_float), ("ms_eval", C.c_float), ("eval_launches", C.c_int64),
+                ("eval_nodes", C.c_int64)]
+
+
+def num_vars(piece_num):
+    return 10 * piece_num - 8
