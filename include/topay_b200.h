@@ -212,6 +212,9 @@ int topay_field_download(topay_field* f, int which, double* esdf_out);
  * carries DBL_MAX (no source cell on the whole grid). Either pointer may be NULL. */
 int topay_field_download_sqdist(topay_field* f, int which, int32_t* pos_sq, int32_t* neg_sq);
 int topay_field_download_occupancy(topay_field* f, int which, int8_t* occ_out);
+/* Whether topay_field_rebuild also stores the integer grids (default 1). Turning it off
+ * removes 8 B/voxel of writes from the last pass; download_sqdist then fails. */
+int topay_field_set_keep_sqdist(topay_field* f, int keep);
 /* Device time of the last topay_field_rebuild, measured with CUDA events on the
  * field's stream; ms_3d is the 3-D part alone. */
 int topay_field_last_rebuild_ms(topay_field* f, float* ms_total, float* ms_3d);

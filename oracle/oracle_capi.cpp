@@ -223,6 +223,34 @@ void oracle_eval(const topay_opt_params* opt, const topay_robot_params* rp, void
     }
 }
 
+// Penalty part only (calFirst/SecondStagePenalGrad outputs) for given coefficients: used to check
+// the device's per-node maths in isolation. coeff: 6N x 9, T: N.
+void oracle_penalty_only(const topay_opt_params* opt, const topay_robot_params* rp, void* field, int stage, int N,
+                         const double* coeff, const double* T, const double* sxy, const double* exy,
+                         const double* inner_xy, const double* lambda, const double* rho, double* cost, double* gdC,
+                         double* gdT, double* terms, double* final_xy) {
+    TrajOpt t;
+    t.opt = *opt;
+    t.rp = *rp;
+    t.grid = (Field*)field;
+    t.exact_chain = g_exact_chain;
+    double head[27] = {0}, tail[27] = {0};
+    t.set_problem(N, head, tail, sxy, exy, inner_xy, lambda, rho);
+    t.times.assign(T, T + N);
+    t.minco.c.assign(coeff, coeff + (size_t)6 * N * 9);
+    for (int i = 0; i < TOPAY_NTERMS; i++) t.terms[i] = 0.0;
+    Vec gc, gt;
+    if (stage == 1)
+        t.first_stage_penalty(*cost, gc, gt);
+    else
+        t.second_stage_penalty(*cost, gc, gt);
+    std::memcpy(gdC, gc.data(), gc.size() * sizeof(double));
+    std::memcpy(gdT, gt.data(), gt.size() * sizeof(double));
+    std::memcpy(terms, t.terms, sizeof(t.terms));
+    final_xy[0] = t.final_xy_error[0];
+    final_xy[1] = t.final_xy_error[1];
+}
+
 struct OracleSolveOut {
     int32_t status, lbfgs_code, piece_num, iters, evals, alm_rounds;
     double cost, duration, final_xy_err[2];

@@ -1,0 +1,213 @@
+// TEST HARNESS ONLY — compiled by tests/test_device_math_host.py into a scratch library.
+//
+// Instantiates the TP_HD per-thread functions of topay_b200/csrc/*.cuh on the CPU and walks
+// them in the same dataflow as the kernels (k_integrate -> k_penalty -> k_chain), serially,
+// so that the lane-level maths can be compared with the oracle without a GPU. This is not
+// a CPU path of the product: libtopay_b200.so neither contains nor calls any of it.
+#include <cstring>
+#include <vector>
+
+#include "../topay_b200/csrc/hd.cuh"
+#include "../topay_b200/csrc/field_query.cuh"
+#include "../topay_b200/csrc/node.cuh"
+#include "../topay_b200/csrc/robot.cuh"
+
+extern "C" {
+
+void hh_make_params(const topay_opt_params* opt, const topay_robot_params* rp, TpParams* out) {
+    std::memset(out, 0, sizeof(*out));
+    out->robot = *rp;
+    out->opt = *opt;
+    tp_derive_params(*out);
+}
+int hh_params_size() { return (int)sizeof(TpParams); }
+
+void hh_make_grid(const topay_grid_desc* d, const double* e3, const double* e2, const double* e2i, const double* e2c,
+                  TpGrid* g) {
+    g->resolution = d->resolution;
+    g->resolution_inv = 1.0 / d->resolution;
+    for (int i = 0; i < 3; i++) {
+        g->min_boundary[i] = -d->map_size[i] / 2.0;
+        g->max_boundary[i] = d->map_size[i] / 2.0;
+    }
+    g->min_boundary[2] = 0.0;
+    g->max_boundary[2] = d->map_size[2];
+    for (int i = 0; i < 3; i++) {
+        g->origin[i] = g->min_boundary[i];
+        g->dims[i] = (int)ceil(d->map_size[i] / d->resolution);
+    }
+    g->ready = 1;
+    g->esdf3d = e3;
+    g->esdf2d = e2;
+    g->esdf2d_inflate = e2i;
+    g->esdf2d_critical = e2c;
+}
+int hh_grid_size() { return (int)sizeof(TpGrid); }
+
+void hh_query3d(const TpGrid* g, const double* pos, int64_t n, double* dist, double* grad) {
+    for (int64_t i = 0; i < n; i++) tp_query3d(*g, pos + 3 * i, dist[i], grad + 3 * i);
+}
+void hh_query2d(const TpGrid* g, int which, const double* pos, int64_t n, double* dist, double* grad) {
+    const double* buf = which == 2 ? g->esdf2d_critical : which == 1 ? g->esdf2d_inflate : g->esdf2d;
+    for (int64_t i = 0; i < n; i++) tp_query2d(*g, buf, pos + 2 * i, dist[i], grad + 2 * i);
+}
+
+void hh_fk(const TpParams* P, const double* pos10, double* pts36) {
+    TpFK fk;
+    double pts[TOPAY_NSPHERE][3];
+    tp_fk(*P, pos10, fk, pts);
+    std::memcpy(pts36, pts, sizeof(pts));
+}
+void hh_fk_adjoint(const TpParams* P, const double* pos10, const double* g36, double* out10) {
+    TpFK fk;
+    double pts[TOPAY_NSPHERE][3], g[TOPAY_NSPHERE][3];
+    tp_fk(*P, pos10, fk, pts);
+    std::memcpy(g, g36, sizeof(g));
+    tp_fk_adjoint(*P, fk, g, out10);
+}
+
+// Penalty part of one evaluation of one candidate, walking the kernels' dataflow serially.
+// coeff: 6N x 9, T: N. Outputs: gdC (6N x 9), gdT (N) [both without the jerk part, mean-time
+// included in gdT], terms[13] (penalty terms only), final_xy[2].
+void hh_penalty_eval(const TpParams* Pp, const TpGrid* Gp, int stage, int N, const double* coeff, const double* T,
+                     const double* start_xy, const double* end_xy, const double* init_inner_xy, const double* lambda,
+                     const double* rho, double* gdC, double* gdT, double* terms, double* final_xy) {
+    const TpParams& P = *Pp;
+    const TpGrid& G = *Gp;
+    const int K = P.opt.int_K, L = 2 * K + 1;
+    std::vector<double> Ix((size_t)N * K), Iy((size_t)N * K), totx(N), toty(N);
+    double b0[6], b1[6], b2[6];
+    // ---- k_integrate
+    for (int i = 0; i < N; i++) {
+        const double* c = coeff + (size_t)6 * i * 9;
+        const double step = T[i] / K, half_step = step / 2.0, cf = step / 6.0;
+        std::vector<TpSlot> sl(L);
+        for (int j = 0; j < L; j++) tp_slot(c, j * half_step, sl[j], b0, b1, b2);
+        double sx = 0, sy = 0;
+        for (int k = 0; k < K; k++) {
+            const int j = 2 * k;
+            double ix = cf * sl[j].ds * sl[j].cy, iy = cf * sl[j].ds * sl[j].sy;
+            ix += 4 * cf * sl[j + 1].ds * sl[j + 1].cy;
+            iy += 4 * cf * sl[j + 1].ds * sl[j + 1].sy;
+            ix += cf * sl[j + 2].ds * sl[j + 2].cy;
+            iy += cf * sl[j + 2].ds * sl[j + 2].sy;
+            Ix[(size_t)i * K + k] = ix;
+            Iy[(size_t)i * K + k] = iy;
+            sx += ix;
+            sy += iy;
+        }
+        totx[i] = sx;
+        toty[i] = sy;
+    }
+    // ---- k_penalty
+    std::memset(gdC, 0, sizeof(double) * 6 * N * 9);
+    std::memset(gdT, 0, sizeof(double) * N);
+    for (int t = 0; t < TOPAY_NTERMS; t++) terms[t] = 0.0;
+    std::vector<double> gx((size_t)N * (K + 1), 0.0), gy((size_t)N * (K + 1), 0.0);
+    for (int i = 0; i < N; i++) {
+        const double* c = coeff + (size_t)6 * i * 9;
+        double px = start_xy[0], py = start_xy[1];
+        for (int p = 0; p < i; p++) {
+            px += totx[p];
+            py += toty[p];
+        }
+        for (int jn = 0; jn <= K; jn++) {
+            double xy[2] = {px, py};
+            for (int k = 0; k < jn; k++) {
+                xy[0] += Ix[(size_t)i * K + k];
+                xy[1] += Iy[(size_t)i * K + k];
+            }
+            TpNodeOut o;
+            if (stage == 1)
+                tp_node_stage1(P, c, T[i], K, 2 * jn, o, b0, b1, b2);
+            else
+                tp_node_stage2(P, G, c, T[i], K, 2 * jn, xy, o, b0, b1, b2);
+            for (int k = 0; k < 6; k++)
+                for (int d = 0; d < 9; d++)
+                    gdC[((size_t)6 * i + k) * 9 + d] += b0[k] * o.G0[d] + b1[k] * o.G1[d] + b2[k] * o.G2[d];
+            gdT[i] += o.gdT;
+            for (int t = 0; t < TOPAY_NTERMS; t++) terms[t] += o.terms[t];
+            gx[(size_t)i * (K + 1) + jn] = o.gx;
+            gy[(size_t)i * (K + 1) + jn] = o.gy;
+        }
+    }
+    // ---- k_chain
+    std::vector<double> Fx(N + 1), Fy(N + 1);
+    Fx[0] = start_xy[0];
+    Fy[0] = start_xy[1];
+    for (int i = 0; i < N; i++) {
+        Fx[i + 1] = Fx[i] + totx[i];
+        Fy[i + 1] = Fy[i] + toty[i];
+    }
+    final_xy[0] = Fx[N] - end_xy[0];
+    final_xy[1] = Fy[N] - end_xy[1];
+    for (int i = 0; i < N; i++) {
+        double wx = 0, wy = 0;
+        if (stage == 1) {
+            for (int p = i + 1; p < N; p++) {
+                wx += P.opt.s1_path_pos_weight * 2.0 * (Fx[p + 1] - init_inner_xy[2 * p]);
+                wy += P.opt.s1_path_pos_weight * 2.0 * (Fy[p + 1] - init_inner_xy[2 * p + 1]);
+            }
+        } else {
+            wx = rho[0] * (final_xy[0] + lambda[0] / rho[0]);
+            wy = rho[1] * (final_xy[1] + lambda[1] / rho[1]);
+            for (int p = i + 1; p < N; p++)
+                for (int jn = 0; jn <= K; jn++) {
+                    wx += gx[(size_t)p * (K + 1) + jn];
+                    wy += gy[(size_t)p * (K + 1) + jn];
+                }
+        }
+        const double* c = coeff + (size_t)6 * i * 9;
+        const double half_step = (T[i] / K) / 2.0;
+        double gth[6] = {0}, gar[6] = {0}, gdt = 0.0;
+        for (int j = 0; j < L; j++) {
+            double sx = 0, sy = 0;   // adjoints of this piece's nodes at or after slot j
+            for (int jn = 0; jn <= K; jn++)
+                if (2 * jn >= j) {
+                    sx += gx[(size_t)i * (K + 1) + jn];
+                    sy += gy[(size_t)i * (K + 1) + jn];
+                }
+            const double icc = (j == 0 || j == 2 * K) ? 1.0 : (j % 2 ? 4.0 : 2.0);
+            TpSlot sl;
+            tp_slot(c, j * half_step, sl, b0, b1, b2);
+            tp_chain_slot(sl, b0, b1, T[i], K, j, (wx + sx) * icc, (wy + sy) * icc, gth, gar, gdt);
+        }
+        for (int k = 0; k < 6; k++) {
+            gdC[((size_t)6 * i + k) * 9 + 0] += gth[k];
+            gdC[((size_t)6 * i + k) * 9 + 1] += gar[k];
+        }
+        gdT[i] += gdt;
+    }
+    // ---- k_cand's share of the penalty: end-point / path terms and the mean-time penalty
+    if (stage == 1) {
+        double cp = 0.0;
+        for (int i = 0; i < N; i++) {
+            const double ex = Fx[i + 1] - init_inner_xy[2 * i], ey = Fy[i + 1] - init_inner_xy[2 * i + 1];
+            cp += P.opt.s1_path_pos_weight * (ex * ex + ey * ey);
+        }
+        terms[TOPAY_TERM_ENDP] = cp;
+    } else {
+        double avg = 0.0;
+        for (int i = 0; i < N; i++) avg += T[i];
+        avg /= N;
+        const double w = P.opt.s2_mean_time_weight;
+        double all = 0.0;
+        for (int i = 0; i < N; i++) {
+            if (T[i] < avg * 0.5) {
+                terms[TOPAY_TERM_MEAN_TIME] += w * (T[i] - avg * 0.5) * (T[i] - avg * 0.5);
+                all += w * 2.0 * (T[i] - avg * 0.5) * (-0.5 / N);
+                gdT[i] += w * 2.0 * (T[i] - avg * 0.5);
+            }
+            if (T[i] > avg * 2.0) {
+                terms[TOPAY_TERM_MEAN_TIME] += w * (T[i] - avg * 2.0) * (T[i] - avg * 2.0);
+                all += w * 2.0 * (T[i] - avg * 2.0) * (-2.0 / N);
+                gdT[i] += w * 2.0 * (T[i] - avg * 2.0);
+            }
+        }
+        for (int i = 0; i < N; i++) gdT[i] += all;
+        terms[TOPAY_TERM_ENDP] = 0.5 * (rho[0] * (final_xy[0] + lambda[0] / rho[0]) * (final_xy[0] + lambda[0] / rho[0]) +
+                                        rho[1] * (final_xy[1] + lambda[1] / rho[1]) * (final_xy[1] + lambda[1] / rho[1]));
+    }
+}
+
+}  // extern "C"

@@ -251,3 +251,12 @@ def solve_batch(opt, rp, field: Field, paths, bvel, bacc, n_threads, wall_cap_s=
                              _p(bacc), C.c_double(wall_cap_s), n_threads, outs)
     return [dict(status=o.status, lbfgs_code=o.lbfgs_code, piece_num=o.piece_num, iters=o.iters, evals=o.evals,
                  alm_rounds=o.alm_rounds, cost=o.cost, duration=o.duration) for o in outs]
+
+
+def penalty_only(opt, rp, field: Field, stage, N, coeff, T, sxy, exy, inner_xy, lam, rho):
+    coeff, T, sxy, exy, inner_xy, lam, rho = map(_f64, (coeff, T, sxy, exy, inner_xy, lam, rho))
+    cost = C.c_double()
+    gdC, gdT, terms, fxy = np.zeros((6 * N, 9)), np.zeros(N), np.zeros(NTERMS), np.zeros(2)
+    lib().oracle_penalty_only(C.byref(opt), C.byref(rp), field.h, stage, N, _p(coeff), _p(T), _p(sxy), _p(exy),
+                              _p(inner_xy), _p(lam), _p(rho), C.byref(cost), _p(gdC), _p(gdT), _p(terms), _p(fxy))
+    return cost.value, gdC, gdT, terms, fxy

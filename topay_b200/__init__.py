@@ -1,0 +1,14 @@
+"""topay_b200 — B200-native (CUDA sm_100a, fp64) hot path of the TopAY planner.
+
+The product is topay_b200/libtopay_b200.so (kernels in csrc/, C ABI in include/topay_b200.h);
+this package is the host-side mirror of the two reference interfaces it replaces:
+GridMap (field.py) and MomaTrajOpt (optimizer.py).
+"""
+from ._structs import (MAP2D_CRITICAL, MAP2D_FLAT, MAP2D_INFLATE, MAP3D, TERM_NAMES, GridDesc, OptParams,
+                       RobotParams, grid_desc, num_vars)
+from .field import GridMap, robot_params_default
+from .optimizer import MomaTraj, MomaTrajOpt, opt_params_default, prepare_candidate
+
+__all__ = ["GridMap", "MomaTrajOpt", "MomaTraj", "grid_desc", "GridDesc", "OptParams", "RobotParams",
+           "robot_params_default", "opt_params_default", "prepare_candidate", "num_vars", "TERM_NAMES",
+           "MAP2D_FLAT", "MAP2D_INFLATE", "MAP2D_CRITICAL", "MAP3D"]

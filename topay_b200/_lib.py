@@ -1,0 +1,95 @@
+"""Loader of the in-tree CUDA library (topay_b200/libtopay_b200.so) and its C-ABI prototypes.
+
+The library is the product: there is no Python/NumPy fallback. Import works without a GPU (so
+that the ABI can be inspected on a CPU box) but every compute entry point returns
+TOPAY_ERR_NO_DEVICE there and the wrappers raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+from ._structs import GridDesc, OptParams, ProblemBatch, ResultBatch, RobotParams, SolverStats
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libtopay_b200.so")
+
+OK, ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_ALLOC, ERR_TOO_LARGE, ERR_NOT_READY = 0, -1, -2, -3, -4, -5, -6
+
+
+class TopayError(RuntimeError):
+    def __init__(self, code, what, detail):
+        super().__init__(f"{what}: {detail} (code {code})")
+        self.code = code
+
+
+def build(verbose=False):
+    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc")]
+    out = subprocess.run(cmd, capture_output=not verbose, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("building libtopay_b200.so failed:\n" + (out.stdout or "") + (out.stderr or ""))
+    return SO_PATH
+
+
+_lib = None
+_dp, _ip, _i8p, _fp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int8), C.POINTER(C.c_float)
+
+# name -> (restype, argtypes); every symbol include/topay_b200.h declares
+PROTOTYPES = {
+    "topay_strerror": (C.c_char_p, [C.c_int]),
+    "topay_last_error": (C.c_char_p, []),
+    "topay_version": (C.c_char_p, []),
+    "topay_robot_params_default": (None, [C.POINTER(RobotParams)]),
+    "topay_opt_params_default": (None, [C.POINTER(OptParams)]),
+    "topay_field_create": (C.c_int, [C.POINTER(GridDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    "topay_field_destroy": (None, [C.c_void_p]),
+    "topay_field_dims": (C.c_int, [C.c_void_p, _ip]),
+    "topay_field_set_occupancy": (C.c_int, [C.c_void_p, _i8p, _i8p, _i8p]),
+    "topay_field_clear": (C.c_int, [C.c_void_p, C.c_int]),
+    "topay_field_rasterize_points": (C.c_int, [C.c_void_p, _fp, C.c_int64]),
+    "topay_field_rebuild": (C.c_int, [C.c_void_p]),
+    "topay_field_query3d": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp]),
+    "topay_field_query2d": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int, _dp, _dp]),
+    "topay_field_distance3d": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp]),
+    "topay_field_distance2d": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp]),
+    "topay_field_whole_body_collision": (C.c_int, [C.c_void_p, C.POINTER(RobotParams), _dp, C.c_int64, _i8p]),
+    "topay_field_query3d_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "topay_field_sync": (C.c_int, [C.c_void_p]),
+    "topay_field_download": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "topay_field_download_sqdist": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip]),
+    "topay_field_download_occupancy": (C.c_int, [C.c_void_p, C.c_int, _i8p]),
+    "topay_field_set_keep_sqdist": (C.c_int, [C.c_void_p, C.c_int]),
+    "topay_field_last_rebuild_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "topay_solver_create": (C.c_int, [C.POINTER(OptParams), C.POINTER(RobotParams), C.c_void_p, C.c_int, C.c_int,
+                                      C.POINTER(C.c_void_p)]),
+    "topay_solver_destroy": (None, [C.c_void_p]),
+    "topay_solver_eval": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ProblemBatch), _dp, C.c_int, _dp, _dp, _dp, _dp,
+                                    _dp]),
+    "topay_prepare_candidate": (C.c_int, [C.POINTER(OptParams), C.POINTER(RobotParams), _dp, C.c_int, _dp, _dp,
+                                          C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
+    "topay_solver_solve_batch": (C.c_int, [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp, C.POINTER(ResultBatch), _ip,
+                                           _ip]),
+    "topay_solver_upload": (C.c_int, [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp]),
+    "topay_solver_run": (C.c_int, [C.c_void_p]),
+    "topay_solver_download": (C.c_int, [C.c_void_p, C.POINTER(ResultBatch), _ip, _ip]),
+    "topay_solver_last_stats": (C.c_int, [C.c_void_p, C.POINTER(SolverStats)]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        _lib = C.CDLL(SO_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(_lib, name)
+            fn.restype, fn.argtypes = res, args
+    return _lib
+
+
+def check(code, what):
+    if code != OK:
+        l = lib()
+        raise TopayError(code, what, (l.topay_last_error() or l.topay_strerror(code)).decode())

@@ -1,0 +1,26 @@
+// Host-side helpers shared by field.cu and solver.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "hd.cuh"
+
+void tp_set_error(const std::string& msg);
+// TOPAY_OK when `device` is a usable CUDA device, else TOPAY_ERR_NO_DEVICE (the
+// product path never falls back to the CPU).
+int tp_require_device(int device);
+
+int tp_field_device(const topay_field* f);
+bool tp_field_ready(const topay_field* f);
+void tp_field_grid(const topay_field* f, TpGrid* out);
+
+#define TP_CUDA_OK(call, cleanup)                                                              \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            tp_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+            cleanup;                                                                           \
+            return TOPAY_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)

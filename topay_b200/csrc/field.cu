@@ -1,0 +1,684 @@
+// topay_field: the dense occupancy / ESDF grid of the reference's GridMap in HBM.
+//
+//   rasterise   GridMap::regenerateMap ingest         src/map/src/grid_map.cpp:733-747
+//   rebuild     GridMap::updateESDF + fillESDF        src/map/src/grid_map.cpp:89-123, 125-521
+//   queries     getDisWithGradI2d/3d, getDistance2d/3d, isWholeBodyCollision
+//                                                      src/map/include/map/grid_map.h:256-509, 613-650
+//
+// The distance transform is exact and integer: each separable pass computes
+// min_v (q - v)^2 + f(v) over a line, which is what the reference's lower-envelope
+// routine evaluates (its intermediates are exact integers in double), so
+// the squared-distance grids are bit-identical; the final `res * sqrt(v)` and the
+// sign combine are evaluated with explicit round-to-nearest intrinsics (no FMA
+// contraction) so the fp64 grids are bit-identical too.
+//
+// Layout (as the reference): 3-D x*Ny*Nz + y*Nz + z, 2-D x*Ny + y.
+// Pass 1 runs along the contiguous axis from the binary occupancy (two sweeps per line in
+// shared memory, positive and negative transform together, output packed int16 pairs);
+// passes 2/3 run along a strided axis on tiles of 16 contiguous cells x the whole line
+// staged in shared memory, every global access a 64-128 B contiguous segment.
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common_host.h"
+#include "field_query.cuh"
+#include "robot.cuh"
+
+#define TP_INF16 16383
+#define TP_INF32 (1 << 29)
+
+static thread_local std::string g_last_error;
+void tp_set_error(const std::string& msg) { g_last_error = msg; }
+extern "C" const char* topay_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* topay_version(void) { return "topay_b200 0.1 (sm_100a)"; }
+extern "C" const char* topay_strerror(int code) {
+    switch (code) {
+        case TOPAY_OK: return "ok";
+        case TOPAY_ERR_INVALID_ARG: return "invalid argument";
+        case TOPAY_ERR_NO_DEVICE: return "no usable CUDA device (the B200 path has no CPU fallback)";
+        case TOPAY_ERR_CUDA: return "CUDA runtime error";
+        case TOPAY_ERR_ALLOC: return "device allocation failed";
+        case TOPAY_ERR_TOO_LARGE: return "problem larger than the configured capacity";
+        case TOPAY_ERR_NOT_READY: return "field not built";
+        default: return "unknown error";
+    }
+}
+
+int tp_require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        tp_set_error("no usable CUDA device: libtopay_b200 runs on the GPU only");
+        return TOPAY_ERR_NO_DEVICE;
+    }
+    return TOPAY_OK;
+}
+
+struct topay_field {
+    topay_grid_desc desc;
+    int device;
+    cudaStream_t stream;
+    TpGrid grid;            // device pointers + geometry
+    int nx, ny, nz;
+    size_t n2, n3;
+    int8_t *occ3d, *occ2d, *occ2d_crit, *src2d;
+    double *esdf3d, *esdf2d, *esdf2d_inflate, *esdf2d_crit;
+    short2* packed;         // pass-1 output (3-D sized)
+    int32_t *tmp_pos, *tmp_neg;   // pass-2 output (3-D sized)
+    int32_t *sq_pos[4], *sq_neg[4];
+    bool keep_sq;
+    bool ready;
+    cudaEvent_t ev0, ev1, ev2;
+    float ms_total, ms_3d;
+};
+
+int tp_field_device(const topay_field* f) { return f->device; }
+bool tp_field_ready(const topay_field* f) { return f->ready; }
+void tp_field_grid(const topay_field* f, TpGrid* out) { *out = f->grid; }
+
+// ------------------------------------------------------------------ kernels
+
+// grid_map.cpp:733-747: one thread per float32 point.
+__global__ void k_rasterize(const float* __restrict__ xyz, int64_t n, TpGrid g, double chassis_height,
+                            int8_t* occ3d, int8_t* occ2d, int8_t* occ2d_crit) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+    const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+    const int ix = (int)floor(((double)px - g.origin[0]) * g.resolution_inv);
+    const int iy = (int)floor(((double)py - g.origin[1]) * g.resolution_inv);
+    const int iz = (int)floor(((double)pz - g.origin[2]) * g.resolution_inv);
+    if (ix >= 0 && iy >= 0 && ix <= nx - 1 && iy <= ny - 1) {
+        occ2d_crit[(size_t)ix * ny + iy] = 1;
+        if ((double)pz < chassis_height) occ2d[(size_t)ix * ny + iy] = 1;
+        if (iz >= 0 && iz <= nz - 1) occ3d[((size_t)ix * ny + iy) * nz + iz] = 1;
+    }
+}
+
+// inflated maps: source = previous ESDF below the chassis radius (grid_map.cpp:288, 360)
+__global__ void k_threshold(const double* __restrict__ esdf, double thr, int8_t* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = esdf[i] < thr ? 1 : 0;
+}
+
+// Pass 1, along the contiguous axis: 1-D distance to the nearest source (pos) and to the
+// nearest non-source (neg) cell of each line, as int16 (TP_INF16 = none on this line).
+// One thread per line; the block's lines are staged in shared memory both ways so global
+// traffic is coalesced. dynamic smem: lines*in_stride bytes + lines*out_stride*4 bytes.
+__global__ void k_edt_contig(const int8_t* __restrict__ src, short2* __restrict__ out, int64_t n_lines, int C,
+                             int in_stride, int out_stride) {
+    extern __shared__ unsigned char smraw[];
+    const int LPB = blockDim.x;
+    unsigned char* s_in = smraw;
+    short2* s_out = (short2*)(smraw + (((size_t)LPB * in_stride + 15) & ~(size_t)15));
+    const int64_t line0 = (int64_t)blockIdx.x * LPB;
+    const int lines = (int)min((int64_t)LPB, n_lines - line0);
+    const int8_t* gsrc = src + line0 * C;
+    for (int e = threadIdx.x; e < lines * C; e += LPB) s_in[(e / C) * in_stride + (e % C)] = (unsigned char)gsrc[e];
+    __syncthreads();
+    if ((int)threadIdx.x < lines) {
+        const unsigned char* in = s_in + threadIdx.x * in_stride;
+        short2* o = s_out + (size_t)threadIdx.x * out_stride;
+        int dp = TP_INF16, dn = TP_INF16;
+        for (int c = 0; c < C; c++) {
+            const bool occ = in[c] == 1;
+            dp = occ ? 0 : min(dp + 1, TP_INF16);
+            dn = occ ? min(dn + 1, TP_INF16) : 0;
+            o[c] = make_short2((short)dp, (short)dn);
+        }
+        dp = TP_INF16;
+        dn = TP_INF16;
+        for (int c = C - 1; c >= 0; c--) {
+            const bool occ = in[c] == 1;
+            dp = occ ? 0 : min(dp + 1, TP_INF16);
+            dn = occ ? min(dn + 1, TP_INF16) : 0;
+            short2 v = o[c];
+            v.x = (short)min((int)v.x, dp);
+            v.y = (short)min((int)v.y, dn);
+            o[c] = v;
+        }
+    }
+    __syncthreads();
+    short2* gout = out + line0 * C;
+    for (int e = threadIdx.x; e < lines * C; e += LPB) gout[e] = s_out[(size_t)(e / C) * out_stride + (e % C)];
+}
+
+// exact 1-D squared-distance envelope by outward search with the d*d >= best cut-off
+__device__ __forceinline__ int tp_line_min(const int* __restrict__ col, int stride, int n, int l) {
+    int best = col[(size_t)l * stride];
+    for (int d = 1; d < n; d++) {
+        const int dd = d * d;
+        if (dd >= best) break;
+        if (l - d >= 0) best = min(best, dd + col[(size_t)(l - d) * stride]);
+        if (l + d < n) best = min(best, dd + col[(size_t)(l + d) * stride]);
+    }
+    return best;
+}
+
+// Passes 2 and 3, along a strided axis. Block = one outer index x TZ contiguous inner cells;
+// the whole line (n_line) of both transforms is staged in shared memory as int32 squared
+// distances. IN16: input is pass 1's packed int16 1-D distances (squared on load).
+// FINAL: writes the fp64 ESDF (grid_map.cpp:457, 503, 515-517) and optionally the integer grids.
+template <bool IN16, bool FINAL>
+__global__ void k_edt_strided(const short2* __restrict__ in16, const int32_t* __restrict__ in_pos,
+                              const int32_t* __restrict__ in_neg, int32_t* __restrict__ out_pos,
+                              int32_t* __restrict__ out_neg, double* __restrict__ esdf, int n_line,
+                              size_t line_stride, size_t outer_stride, int n_inner, int tiles, double res) {
+    extern __shared__ int sm_i[];
+    const int TZ = blockDim.x, TY = blockDim.y;
+    int* s_pos = sm_i;
+    int* s_neg = sm_i + (size_t)n_line * TZ;
+    const int outer = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+    const int c = tile * TZ + threadIdx.x;
+    const bool cvalid = c < n_inner;
+    const size_t base = (size_t)outer * outer_stride + c;
+    for (int l = threadIdx.y; l < n_line; l += TY) {
+        int p = TP_INF32, q = TP_INF32;
+        if (cvalid) {
+            const size_t idx = base + (size_t)l * line_stride;
+            if (IN16) {
+                const short2 v = in16[idx];
+                p = v.x >= TP_INF16 ? TP_INF32 : (int)v.x * (int)v.x;
+                q = v.y >= TP_INF16 ? TP_INF32 : (int)v.y * (int)v.y;
+            } else {
+                p = in_pos[idx];
+                q = in_neg[idx];
+            }
+        }
+        s_pos[(size_t)l * TZ + threadIdx.x] = p;
+        s_neg[(size_t)l * TZ + threadIdx.x] = q;
+    }
+    __syncthreads();
+    if (!cvalid) return;
+    for (int l = threadIdx.y; l < n_line; l += TY) {
+        int bp = tp_line_min(s_pos + threadIdx.x, TZ, n_line, l);
+        int bn = tp_line_min(s_neg + threadIdx.x, TZ, n_line, l);
+        if (bp >= TP_INF32) bp = FINAL ? INT32_MAX : TP_INF32;
+        if (bn >= TP_INF32) bn = FINAL ? INT32_MAX : TP_INF32;
+        const size_t idx = base + (size_t)l * line_stride;
+        if (FINAL) {
+            const double vp = bp == INT32_MAX ? DBL_MAX : (double)bp;
+            const double vn = bn == INT32_MAX ? DBL_MAX : (double)bn;
+            const double dp = __dmul_rn(res, __dsqrt_rn(vp));
+            const double dn = __dmul_rn(res, __dsqrt_rn(vn));
+            double d = dp;
+            if (dn > 0.0) d = __dadd_rn(d, __dadd_rn(-dn, res));
+            esdf[idx] = d;
+            if (out_pos) {
+                out_pos[idx] = bp;
+                out_neg[idx] = bn;
+            }
+        } else {
+            out_pos[idx] = bp;
+            out_neg[idx] = bn;
+        }
+    }
+}
+
+__global__ void k_query3d(TpGrid g, const double* __restrict__ pos, int64_t n, double* dist, double* grad,
+                          int value_only) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double p[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+    if (value_only) {
+        dist[i] = tp_distance3d(g, p);
+        return;
+    }
+    double d, gr[3];
+    tp_query3d(g, p, d, gr);
+    dist[i] = d;
+    if (grad) {
+        grad[3 * i] = gr[0];
+        grad[3 * i + 1] = gr[1];
+        grad[3 * i + 2] = gr[2];
+    }
+}
+
+__global__ void k_query2d(TpGrid g, const double* __restrict__ buf, const double* __restrict__ pos, int64_t n,
+                          double* dist, double* grad, int value_only) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double p[2] = {pos[2 * i], pos[2 * i + 1]};
+    if (value_only) {
+        dist[i] = tp_distance2d(g, p);
+        return;
+    }
+    double d, gr[2];
+    tp_query2d(g, buf, p, d, gr);
+    dist[i] = d;
+    if (grad) {
+        grad[2 * i] = gr[0];
+        grad[2 * i + 1] = gr[1];
+    }
+}
+
+// GridMap::isWholeBodyCollision (grid_map.h:613-650), one thread per 10-D state.
+__global__ void k_whole_body(TpGrid g, TpParams P, const double* __restrict__ states, int64_t n, int8_t* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* s = states + 10 * i;
+    const topay_robot_params& rp = P.robot;
+    bool hit = false;
+    for (int q = 0; q < TOPAY_DOF; q++)
+        if (s[3 + q] > rp.joint_pos_limit_max[q] || s[3 + q] < -rp.joint_pos_limit_max[q]) hit = true;
+    if (!hit) {
+        const double p2[2] = {s[0], s[1]};
+        if (!tp_in_map2(g, p2) || tp_distance2d(g, p2) < rp.chassis_colli_radius) hit = true;
+    }
+    if (!hit) {
+        double pos[10];
+        for (int k = 0; k < 10; k++) pos[k] = s[k];
+        TpFK fk;
+        double pts[TOPAY_NSPHERE][3];
+        tp_fk(P, pos, fk, pts);
+        for (int a = 0; a < P.n_sphere && !hit; a++) {
+            const double r = P.sphere_r[a];
+            if (!tp_in_map3(g, pts[a]) || tp_distance3d(g, pts[a]) < r) hit = true;
+            if (a > 2 && pts[a][2] < rp.chassis_height + r) {
+                const double dx = pts[a][0] - s[0], dy = pts[a][1] - s[1];
+                if (sqrt(dx * dx + dy * dy) < rp.chassis_colli_radius + r) hit = true;
+            }
+            for (int b = a + 1; b < P.n_sphere; b++) {
+                const double dx = pts[a][0] - pts[b][0], dy = pts[a][1] - pts[b][1], dz = pts[a][2] - pts[b][2];
+                if (sqrt(dx * dx + dy * dy + dz * dz) < r + P.sphere_r[b] && ((P.pair_mask[a] >> b) & 1u)) hit = true;
+            }
+        }
+    }
+    out[i] = hit ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ host
+
+namespace {
+
+template <typename T>
+int fmalloc(T** p, size_t count) {
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        tp_set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        *p = nullptr;
+        return TOPAY_ERR_ALLOC;
+    }
+    return TOPAY_OK;
+}
+
+// One signed transform over a [A][B][C] array (C contiguous): pass 1 along C, pass 2 along B
+// and, when A > 1, pass 3 along A. The last pass writes `esdf` (+ the integer grids).
+int signed_edt(topay_field* f, const int8_t* src, int A, int B, int C, double* esdf, int32_t* sqp, int32_t* sqn) {
+    cudaStream_t q = f->stream;
+    const int64_t n_lines = (int64_t)A * B;
+    // pass 1
+    {
+        int in_stride = (C + 3) & ~3;
+        if (((in_stride / 4) & 1) == 0) in_stride += 4;
+        const int out_stride = C | 1;
+        int lpb = 128;
+        auto need = [&](int l) { return (((size_t)l * in_stride + 15) & ~(size_t)15) + (size_t)l * out_stride * 4; };
+        while (lpb > 32 && need(lpb) > 96 * 1024) lpb >>= 1;
+        if (need(lpb) > 200 * 1024) {
+            tp_set_error("grid line too long for the pass-1 staging buffer");
+            return TOPAY_ERR_TOO_LARGE;
+        }
+        TP_CUDA_OK(cudaFuncSetAttribute(k_edt_contig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(lpb)), {});
+        const unsigned blocks = (unsigned)((n_lines + lpb - 1) / lpb);
+        k_edt_contig<<<blocks, lpb, need(lpb), q>>>(src, f->packed, n_lines, C, in_stride, out_stride);
+    }
+    auto strided = [&](bool in16, bool fin, int n_line, size_t line_stride, int n_outer, size_t outer_stride,
+                       int n_inner) -> int {
+        int TZ = 16;
+        while (TZ > 1 && (size_t)n_line * TZ * 8 > 100 * 1024) TZ >>= 1;
+        const size_t smem = (size_t)n_line * TZ * 8;
+        if (smem > 200 * 1024) {
+            tp_set_error("grid line too long for the strided-pass staging buffer");
+            return TOPAY_ERR_TOO_LARGE;
+        }
+        const int TY = std::max(1, std::min(512 / TZ, n_line));
+        const int tiles = (n_inner + TZ - 1) / TZ;
+        dim3 blk(TZ, TY);
+        const unsigned blocks = (unsigned)n_outer * tiles;
+        int32_t* op = fin ? (f->keep_sq ? sqp : nullptr) : f->tmp_pos;
+        int32_t* on = fin ? (f->keep_sq ? sqn : nullptr) : f->tmp_neg;
+#define TP_LAUNCH_STRIDED(I16, FIN)                                                                                \
+    do {                                                                                                           \
+        TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided<I16, FIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                        (int)smem), {});                                                           \
+        k_edt_strided<I16, FIN><<<blocks, blk, smem, q>>>(f->packed, f->tmp_pos, f->tmp_neg, op, on, esdf, n_line, \
+                                                          line_stride, outer_stride, n_inner, tiles,               \
+                                                          f->desc.resolution);                                     \
+    } while (0)
+        if (in16 && fin) TP_LAUNCH_STRIDED(true, true);
+        else if (in16) TP_LAUNCH_STRIDED(true, false);
+        else TP_LAUNCH_STRIDED(false, true);
+#undef TP_LAUNCH_STRIDED
+        return TOPAY_OK;
+    };
+    int rc;
+    if (A == 1) {
+        rc = strided(true, true, B, (size_t)C, 1, 0, C);
+    } else {
+        rc = strided(true, false, B, (size_t)C, A, (size_t)B * C, C);
+        if (rc != TOPAY_OK) return rc;
+        rc = strided(false, true, A, (size_t)B * C, B, (size_t)C, C);
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int topay_field_create(const topay_grid_desc* desc, int device, topay_field** out) {
+    if (!desc || !out || desc->resolution <= 0.0) return TOPAY_ERR_INVALID_ARG;
+    int rc = tp_require_device(device);
+    if (rc != TOPAY_OK) return rc;
+    topay_field* f = new topay_field();
+    memset(f, 0, sizeof(*f));
+    f->desc = *desc;
+    f->device = device;
+    f->keep_sq = true;
+    cudaSetDevice(device);
+    // grid_map.cpp:33-54
+    TpGrid& g = f->grid;
+    g.resolution = desc->resolution;
+    g.resolution_inv = 1.0 / desc->resolution;
+    for (int i = 0; i < 3; i++) {
+        g.min_boundary[i] = -desc->map_size[i] / 2.0;
+        g.max_boundary[i] = desc->map_size[i] / 2.0;
+    }
+    g.min_boundary[2] = 0.0;
+    g.max_boundary[2] = desc->map_size[2];
+    for (int i = 0; i < 3; i++) {
+        g.origin[i] = g.min_boundary[i];
+        g.dims[i] = (int)ceil(desc->map_size[i] / desc->resolution);
+    }
+    f->nx = g.dims[0];
+    f->ny = g.dims[1];
+    f->nz = g.dims[2];
+    if (f->nx < 1 || f->ny < 1 || f->nz < 1 || f->nx >= TP_INF16 || f->ny >= TP_INF16 || f->nz >= TP_INF16) {
+        delete f;
+        tp_set_error("grid dimensions out of range");
+        return TOPAY_ERR_INVALID_ARG;
+    }
+    f->n2 = (size_t)f->nx * f->ny;
+    f->n3 = f->n2 * f->nz;
+    TP_CUDA_OK(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking), { delete f; });
+#define FA(p, n)                                  \
+    if ((rc = fmalloc(&(p), (n))) != TOPAY_OK) {  \
+        topay_field_destroy(f);                   \
+        return rc;                                \
+    }
+    FA(f->occ3d, f->n3);
+    FA(f->occ2d, f->n2);
+    FA(f->occ2d_crit, f->n2);
+    FA(f->src2d, f->n2);
+    FA(f->esdf3d, f->n3);
+    FA(f->esdf2d, f->n2);
+    FA(f->esdf2d_inflate, f->n2);
+    FA(f->esdf2d_crit, f->n2);
+    FA(f->packed, f->n3);
+    FA(f->tmp_pos, f->n3);
+    FA(f->tmp_neg, f->n3);
+    for (int w = 0; w < 3; w++) {
+        FA(f->sq_pos[w], f->n2);
+        FA(f->sq_neg[w], f->n2);
+    }
+    FA(f->sq_pos[3], f->n3);
+    FA(f->sq_neg[3], f->n3);
+#undef FA
+    cudaMemsetAsync(f->occ3d, 0, f->n3, f->stream);
+    cudaMemsetAsync(f->occ2d, 0, f->n2, f->stream);
+    cudaMemsetAsync(f->occ2d_crit, 0, f->n2, f->stream);
+    cudaMemsetAsync(f->esdf3d, 0, f->n3 * 8, f->stream);
+    cudaMemsetAsync(f->esdf2d, 0, f->n2 * 8, f->stream);
+    cudaMemsetAsync(f->esdf2d_inflate, 0, f->n2 * 8, f->stream);
+    cudaMemsetAsync(f->esdf2d_crit, 0, f->n2 * 8, f->stream);
+    g.esdf3d = f->esdf3d;
+    g.esdf2d = f->esdf2d;
+    g.esdf2d_inflate = f->esdf2d_inflate;
+    g.esdf2d_critical = f->esdf2d_crit;
+    g.ready = 0;
+    cudaEventCreate(&f->ev0);
+    cudaEventCreate(&f->ev1);
+    cudaEventCreate(&f->ev2);
+    TP_CUDA_OK(cudaStreamSynchronize(f->stream), { topay_field_destroy(f); });
+    *out = f;
+    return TOPAY_OK;
+}
+
+extern "C" void topay_field_destroy(topay_field* f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    if (f->stream) cudaStreamSynchronize(f->stream);
+    void* ptrs[] = {f->occ3d, f->occ2d, f->occ2d_crit, f->src2d, f->esdf3d, f->esdf2d, f->esdf2d_inflate,
+                    f->esdf2d_crit, f->packed, f->tmp_pos, f->tmp_neg, f->sq_pos[0], f->sq_pos[1], f->sq_pos[2],
+                    f->sq_pos[3], f->sq_neg[0], f->sq_neg[1], f->sq_neg[2], f->sq_neg[3]};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (f->ev0) cudaEventDestroy(f->ev0);
+    if (f->ev1) cudaEventDestroy(f->ev1);
+    if (f->ev2) cudaEventDestroy(f->ev2);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+}
+
+extern "C" int topay_field_dims(const topay_field* f, int32_t dims[3]) {
+    if (!f || !dims) return TOPAY_ERR_INVALID_ARG;
+    dims[0] = f->nx;
+    dims[1] = f->ny;
+    dims[2] = f->nz;
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_set_keep_sqdist(topay_field* f, int keep) {
+    if (!f) return TOPAY_ERR_INVALID_ARG;
+    f->keep_sq = keep != 0;
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_set_occupancy(topay_field* f, const int8_t* occ3d, const int8_t* occ2d,
+                                         const int8_t* occ2d_critical) {
+    if (!f) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(f->device);
+    if (occ3d) TP_CUDA_OK(cudaMemcpyAsync(f->occ3d, occ3d, f->n3, cudaMemcpyHostToDevice, f->stream), {});
+    if (occ2d) TP_CUDA_OK(cudaMemcpyAsync(f->occ2d, occ2d, f->n2, cudaMemcpyHostToDevice, f->stream), {});
+    if (occ2d_critical)
+        TP_CUDA_OK(cudaMemcpyAsync(f->occ2d_crit, occ2d_critical, f->n2, cudaMemcpyHostToDevice, f->stream), {});
+    TP_CUDA_OK(cudaStreamSynchronize(f->stream), {});
+    f->ready = false;
+    f->grid.ready = 0;
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_clear(topay_field* f, int clear_critical) {
+    if (!f) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(f->device);
+    cudaMemsetAsync(f->occ3d, 0, f->n3, f->stream);
+    cudaMemsetAsync(f->occ2d, 0, f->n2, f->stream);
+    if (clear_critical) cudaMemsetAsync(f->occ2d_crit, 0, f->n2, f->stream);
+    f->ready = false;
+    f->grid.ready = 0;
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_rasterize_points(topay_field* f, const float* xyz, int64_t n) {
+    if (!f || (!xyz && n > 0) || n < 0) return TOPAY_ERR_INVALID_ARG;
+    if (n == 0) return TOPAY_OK;
+    cudaSetDevice(f->device);
+    float* d = nullptr;
+    TP_CUDA_OK(cudaMalloc(&d, (size_t)n * 3 * sizeof(float)), {});
+    TP_CUDA_OK(cudaMemcpyAsync(d, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, f->stream), { cudaFree(d); });
+    k_rasterize<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(d, n, f->grid, f->desc.chassis_height, f->occ3d,
+                                                                  f->occ2d, f->occ2d_crit);
+    TP_CUDA_OK(cudaStreamSynchronize(f->stream), { cudaFree(d); });
+    cudaFree(d);
+    f->ready = false;
+    f->grid.ready = 0;
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_rebuild(topay_field* f) {
+    if (!f) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(f->device);
+    cudaStream_t q = f->stream;
+    const unsigned tb = (unsigned)((f->n2 + 255) / 256);
+    int rc;
+    cudaEventRecord(f->ev0, q);
+    // the four 2-D maps, in the reference's order (grid_map.cpp:138-423)
+    if ((rc = signed_edt(f, f->occ2d, 1, f->nx, f->ny, f->esdf2d, f->sq_pos[0], f->sq_neg[0])) != TOPAY_OK) return rc;
+    if ((rc = signed_edt(f, f->occ2d_crit, 1, f->nx, f->ny, f->esdf2d_crit, f->sq_pos[2], f->sq_neg[2])) != TOPAY_OK)
+        return rc;
+    k_threshold<<<tb, 256, 0, q>>>(f->esdf2d_crit, f->desc.chassis_colli_radius, f->src2d, f->n2);
+    if ((rc = signed_edt(f, f->src2d, 1, f->nx, f->ny, f->esdf2d_crit, f->sq_pos[2], f->sq_neg[2])) != TOPAY_OK)
+        return rc;
+    k_threshold<<<tb, 256, 0, q>>>(f->esdf2d, f->desc.chassis_colli_radius, f->src2d, f->n2);
+    if ((rc = signed_edt(f, f->src2d, 1, f->nx, f->ny, f->esdf2d_inflate, f->sq_pos[1], f->sq_neg[1])) != TOPAY_OK)
+        return rc;
+    cudaEventRecord(f->ev1, q);
+    // the 3-D map (grid_map.cpp:425-518): z, y, x
+    if ((rc = signed_edt(f, f->occ3d, f->nx, f->ny, f->nz, f->esdf3d, f->sq_pos[3], f->sq_neg[3])) != TOPAY_OK)
+        return rc;
+    cudaEventRecord(f->ev2, q);
+    TP_CUDA_OK(cudaStreamSynchronize(q), {});
+    TP_CUDA_OK(cudaGetLastError(), {});
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, f->ev0, f->ev1);
+    cudaEventElapsedTime(&b, f->ev1, f->ev2);
+    f->ms_total = a + b;
+    f->ms_3d = b;
+    f->ready = true;
+    f->grid.ready = 1;
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_last_rebuild_ms(topay_field* f, float* ms_total, float* ms_3d) {
+    if (!f) return TOPAY_ERR_INVALID_ARG;
+    if (ms_total) *ms_total = f->ms_total;
+    if (ms_3d) *ms_3d = f->ms_3d;
+    return TOPAY_OK;
+}
+
+static int query_common(topay_field* f, const double* pos, int64_t n, int dim, int which, double* dist,
+                        double* grad, int value_only) {
+    if (!f || (!pos && n > 0) || !dist || n < 0) return TOPAY_ERR_INVALID_ARG;
+    if (!f->ready) {
+        tp_set_error("field not built: call topay_field_rebuild first");
+        return TOPAY_ERR_NOT_READY;
+    }
+    if (n == 0) return TOPAY_OK;
+    cudaSetDevice(f->device);
+    double *dpos = nullptr, *dd = nullptr, *dg = nullptr;
+    TP_CUDA_OK(cudaMalloc(&dpos, (size_t)n * dim * 8), {});
+    TP_CUDA_OK(cudaMalloc(&dd, (size_t)n * 8), { cudaFree(dpos); });
+    if (grad) TP_CUDA_OK(cudaMalloc(&dg, (size_t)n * dim * 8), { cudaFree(dpos); cudaFree(dd); });
+    cudaMemcpyAsync(dpos, pos, (size_t)n * dim * 8, cudaMemcpyHostToDevice, f->stream);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (dim == 3)
+        k_query3d<<<blocks, 256, 0, f->stream>>>(f->grid, dpos, n, dd, dg, value_only);
+    else {
+        const double* buf = which == TOPAY_MAP2D_CRITICAL ? f->esdf2d_crit
+                            : which == TOPAY_MAP2D_INFLATE ? f->esdf2d_inflate : f->esdf2d;
+        k_query2d<<<blocks, 256, 0, f->stream>>>(f->grid, buf, dpos, n, dd, dg, value_only);
+    }
+    cudaMemcpyAsync(dist, dd, (size_t)n * 8, cudaMemcpyDeviceToHost, f->stream);
+    if (grad) cudaMemcpyAsync(grad, dg, (size_t)n * dim * 8, cudaMemcpyDeviceToHost, f->stream);
+    cudaError_t e = cudaStreamSynchronize(f->stream);
+    cudaFree(dpos);
+    cudaFree(dd);
+    if (dg) cudaFree(dg);
+    TP_CUDA_OK(e, {});
+    TP_CUDA_OK(cudaGetLastError(), {});
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_query3d(topay_field* f, const double* pos, int64_t n, double* dist, double* grad) {
+    return query_common(f, pos, n, 3, TOPAY_MAP3D, dist, grad, 0);
+}
+extern "C" int topay_field_query2d(topay_field* f, const double* pos, int64_t n, int which, double* dist,
+                                   double* grad) {
+    if (which < 0 || which > 2) return TOPAY_ERR_INVALID_ARG;
+    return query_common(f, pos, n, 2, which, dist, grad, 0);
+}
+extern "C" int topay_field_distance3d(topay_field* f, const double* pos, int64_t n, double* dist) {
+    return query_common(f, pos, n, 3, TOPAY_MAP3D, dist, nullptr, 1);
+}
+extern "C" int topay_field_distance2d(topay_field* f, const double* pos, int64_t n, double* dist) {
+    return query_common(f, pos, n, 2, TOPAY_MAP2D_FLAT, dist, nullptr, 1);
+}
+
+extern "C" int topay_field_query3d_dev(topay_field* f, const double* pos_dev, int64_t n, double* dist_dev,
+                                       double* grad_dev) {
+    if (!f || !pos_dev || !dist_dev || n < 0) return TOPAY_ERR_INVALID_ARG;
+    if (!f->ready) return TOPAY_ERR_NOT_READY;
+    if (n == 0) return TOPAY_OK;
+    cudaSetDevice(f->device);
+    k_query3d<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(f->grid, pos_dev, n, dist_dev, grad_dev, 0);
+    TP_CUDA_OK(cudaGetLastError(), {});
+    return TOPAY_OK;
+}
+extern "C" int topay_field_sync(topay_field* f) {
+    if (!f) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(f->device);
+    TP_CUDA_OK(cudaStreamSynchronize(f->stream), {});
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_whole_body_collision(topay_field* f, const topay_robot_params* robot,
+                                                const double* states, int64_t n, int8_t* out) {
+    if (!f || !robot || (!states && n > 0) || !out || n < 0) return TOPAY_ERR_INVALID_ARG;
+    if (!f->ready) return TOPAY_ERR_NOT_READY;
+    if (n == 0) return TOPAY_OK;
+    cudaSetDevice(f->device);
+    TpParams P;
+    memset(&P, 0, sizeof(P));
+    P.robot = *robot;
+    topay_opt_params_default(&P.opt);
+    tp_derive_params(P);
+    double* ds = nullptr;
+    int8_t* dout = nullptr;
+    TP_CUDA_OK(cudaMalloc(&ds, (size_t)n * 10 * 8), {});
+    TP_CUDA_OK(cudaMalloc(&dout, (size_t)n), { cudaFree(ds); });
+    cudaMemcpyAsync(ds, states, (size_t)n * 10 * 8, cudaMemcpyHostToDevice, f->stream);
+    k_whole_body<<<(unsigned)((n + 127) / 128), 128, 0, f->stream>>>(f->grid, P, ds, n, dout);
+    cudaMemcpyAsync(out, dout, (size_t)n, cudaMemcpyDeviceToHost, f->stream);
+    cudaError_t e = cudaStreamSynchronize(f->stream);
+    cudaFree(ds);
+    cudaFree(dout);
+    TP_CUDA_OK(e, {});
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_download(topay_field* f, int which, double* esdf_out) {
+    if (!f || !esdf_out || which < 0 || which > 3) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(f->device);
+    const double* src = which == TOPAY_MAP3D ? f->esdf3d
+                        : which == TOPAY_MAP2D_CRITICAL ? f->esdf2d_crit
+                        : which == TOPAY_MAP2D_INFLATE ? f->esdf2d_inflate : f->esdf2d;
+    const size_t n = which == TOPAY_MAP3D ? f->n3 : f->n2;
+    TP_CUDA_OK(cudaMemcpy(esdf_out, src, n * 8, cudaMemcpyDeviceToHost), {});
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_download_sqdist(topay_field* f, int which, int32_t* pos_sq, int32_t* neg_sq) {
+    if (!f || which < 0 || which > 3) return TOPAY_ERR_INVALID_ARG;
+    if (!f->keep_sq) {
+        tp_set_error("integer grids were not kept (topay_field_set_keep_sqdist(f, 0))");
+        return TOPAY_ERR_NOT_READY;
+    }
+    cudaSetDevice(f->device);
+    const size_t n = which == TOPAY_MAP3D ? f->n3 : f->n2;
+    if (pos_sq) TP_CUDA_OK(cudaMemcpy(pos_sq, f->sq_pos[which], n * 4, cudaMemcpyDeviceToHost), {});
+    if (neg_sq) TP_CUDA_OK(cudaMemcpy(neg_sq, f->sq_neg[which], n * 4, cudaMemcpyDeviceToHost), {});
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_download_occupancy(topay_field* f, int which, int8_t* occ_out) {
+    if (!f || !occ_out || which < 0 || which > 3 || which == TOPAY_MAP2D_INFLATE) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(f->device);
+    const int8_t* src = which == TOPAY_MAP3D ? f->occ3d : which == TOPAY_MAP2D_CRITICAL ? f->occ2d_crit : f->occ2d;
+    const size_t n = which == TOPAY_MAP3D ? f->n3 : f->n2;
+    TP_CUDA_OK(cudaMemcpy(occ_out, src, n, cudaMemcpyDeviceToHost), {});
+    return TOPAY_OK;
+}

@@ -1,0 +1,116 @@
+// Dense-grid distance lookups — GridMap::getDisWithGradI2d/3d and getDistance2d/3d
+// (src/map/include/map/grid_map.h:256-509) with the index helpers of :727-868.
+// Addressing: 3-D x*Ny*Nz + y*Nz + z (grid_map.h:808-816); 2-D x*Ny + y (:798-806).
+#pragma once
+#include "hd.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define TP_LDG(p) __ldg(p)
+#else
+#define TP_LDG(p) (*(p))
+#endif
+
+TP_HD bool tp_in_map2(const TpGrid& g, const double* p) {
+    if (p[0] < g.min_boundary[0] + 1e-4 || p[1] < g.min_boundary[1] + 1e-4) return false;
+    if (p[0] > g.max_boundary[0] - 1e-4 || p[1] > g.max_boundary[1] - 1e-4) return false;
+    return true;
+}
+TP_HD bool tp_in_map3(const TpGrid& g, const double* p) {
+    if (p[0] < g.min_boundary[0] + 1e-4 || p[1] < g.min_boundary[1] + 1e-4 || p[2] < g.min_boundary[2] + 1e-4)
+        return false;
+    if (p[0] > g.max_boundary[0] - 1e-4 || p[1] > g.max_boundary[1] - 1e-4 || p[2] > g.max_boundary[2] - 1e-4)
+        return false;
+    return true;
+}
+TP_HD int tp_clampi(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+
+// Anchor cell + fractional offsets of the interpolation (grid_map.h:472-480).
+TP_HD void tp_anchor(const TpGrid& g, double pos, int axis, int& idx, double& diff) {
+    const double pm = pos - 0.5 * g.resolution;
+    idx = (int)floor((pm - g.origin[axis]) * g.resolution_inv);
+    const double centre = (idx + 0.5) * g.resolution + g.origin[axis];
+    diff = (pos - centre) * g.resolution_inv;
+}
+
+// getDisWithGradI3d (grid_map.h:443-509). grad may be null.
+TP_HD void tp_query3d(const TpGrid& g, const double* pos, double& distance, double* grad) {
+    if (!tp_in_map3(g, pos)) {
+        distance = 0.0;
+        if (grad) grad[0] = grad[1] = grad[2] = 0.0;
+        return;
+    }
+    int ix, iy, iz;
+    double dx, dy, dz;
+    tp_anchor(g, pos[0], 0, ix, dx);
+    tp_anchor(g, pos[1], 1, iy, dy);
+    tp_anchor(g, pos[2], 2, iz, dz);
+    const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+    const int x0 = tp_clampi(ix, nx - 1), x1 = tp_clampi(ix + 1, nx - 1);
+    const int y0 = tp_clampi(iy, ny - 1), y1 = tp_clampi(iy + 1, ny - 1);
+    const int z0 = tp_clampi(iz, nz - 1), z1 = tp_clampi(iz + 1, nz - 1);
+    const double* b = g.esdf3d;
+    const size_t sx = (size_t)ny * nz, sy = (size_t)nz;
+    const double v000 = TP_LDG(b + x0 * sx + y0 * sy + z0), v001 = TP_LDG(b + x0 * sx + y0 * sy + z1);
+    const double v010 = TP_LDG(b + x0 * sx + y1 * sy + z0), v011 = TP_LDG(b + x0 * sx + y1 * sy + z1);
+    const double v100 = TP_LDG(b + x1 * sx + y0 * sy + z0), v101 = TP_LDG(b + x1 * sx + y0 * sy + z1);
+    const double v110 = TP_LDG(b + x1 * sx + y1 * sy + z0), v111 = TP_LDG(b + x1 * sx + y1 * sy + z1);
+    const double v00 = v000 * (1 - dx) + v100 * dx;
+    const double v01 = v001 * (1 - dx) + v101 * dx;
+    const double v10 = v010 * (1 - dx) + v110 * dx;
+    const double v11 = v011 * (1 - dx) + v111 * dx;
+    const double v0 = v00 * (1 - dy) + v10 * dy;
+    const double v1 = v01 * (1 - dy) + v11 * dy;
+    distance = v0 * (1.0 - dz) + v1 * dz;
+    if (grad) {
+        grad[2] = (v1 - v0) * g.resolution_inv;
+        grad[1] = ((v10 - v00) * (1.0 - dz) + (v11 - v01) * dz) * g.resolution_inv;
+        double gx = (1.0 - dz) * (1 - dy) * (v100 - v000);
+        gx += (1.0 - dz) * dy * (v110 - v010);
+        gx += dz * (1 - dy) * (v101 - v001);
+        gx += dz * dy * (v111 - v011);
+        grad[0] = gx * g.resolution_inv;
+    }
+}
+
+// getDistance3d (grid_map.h:307-362): value only, 1e10 outside the map.
+TP_HD double tp_distance3d(const TpGrid& g, const double* pos) {
+    if (!tp_in_map3(g, pos)) return 1e+10;
+    double d;
+    tp_query3d(g, pos, d, nullptr);
+    return d;
+}
+
+// getDisWithGradI2d (grid_map.h:364-441) on one of the three 2-D buffers.
+TP_HD void tp_query2d(const TpGrid& g, const double* buf, const double* pos, double& distance, double* grad) {
+    if (!tp_in_map2(g, pos)) {
+        distance = 0.0;
+        if (grad) grad[0] = grad[1] = 0.0;
+        return;
+    }
+    int ix, iy;
+    double dx, dy;
+    tp_anchor(g, pos[0], 0, ix, dx);
+    tp_anchor(g, pos[1], 1, iy, dy);
+    const int nx = g.dims[0], ny = g.dims[1];
+    const int x0 = tp_clampi(ix, nx - 1), x1 = tp_clampi(ix + 1, nx - 1);
+    const int y0 = tp_clampi(iy, ny - 1), y1 = tp_clampi(iy + 1, ny - 1);
+    const double v00 = TP_LDG(buf + (size_t)x0 * ny + y0), v01 = TP_LDG(buf + (size_t)x0 * ny + y1);
+    const double v10 = TP_LDG(buf + (size_t)x1 * ny + y0), v11 = TP_LDG(buf + (size_t)x1 * ny + y1);
+    const double v0 = v00 * (1 - dx) + v10 * dx;
+    const double v1 = v01 * (1 - dx) + v11 * dx;
+    distance = v0 * (1 - dy) + v1 * dy;
+    if (grad) {
+        grad[1] = (v1 - v0) * g.resolution_inv;
+        double gx = (1 - dy) * (v10 - v00);
+        gx += dy * (v11 - v01);
+        grad[0] = gx * g.resolution_inv;
+    }
+}
+
+// getDistance2d (grid_map.h:256-305): flat map only, 1e10 outside.
+TP_HD double tp_distance2d(const TpGrid& g, const double* pos) {
+    if (!tp_in_map2(g, pos)) return 1e+10;
+    double d;
+    tp_query2d(g, g.esdf2d, pos, d, nullptr);
+    return d;
+}

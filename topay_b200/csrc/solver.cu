@@ -1,0 +1,432 @@
+// Host side of topay_solver: allocation, candidate upload, the tick loop and downloads.
+// Replaces the per-thread MomaTrajOpt instances of the reference
+// (src/planner/src/planner.cpp:59-66, 847-918) with one batched device solve.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common_host.h"
+#include "solver_kernels.cuh"
+
+struct topay_solver {
+    TpSolverDev dev;
+    TpParams params;
+    topay_field* field;
+    int device;
+    cudaStream_t stream;
+    int n_cand;          // candidates of the uploaded batch
+    int max_N;           // largest piece count in the batch
+    std::vector<TpCandState> h_state;
+    std::vector<void*> allocs;
+    int32_t* h_active;   // pinned
+    unsigned long long* h_nodes;  // pinned
+    int slots;
+    std::vector<cudaEvent_t> ev;  // event pool for the penalty kernel timing
+    cudaEvent_t ev_begin, ev_end;
+    topay_solver_stats stats;
+    size_t smem_cand;
+    // initial state kept on the host for repeated runs
+    std::vector<double> h_x0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(topay_solver* s, T** p, size_t count) {
+    void* q = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) {
+        tp_set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        return TOPAY_ERR_ALLOC;
+    }
+    cudaMemsetAsync(q, 0, count * sizeof(T), s->stream);
+    s->allocs.push_back(q);
+    *p = (T*)q;
+    return TOPAY_OK;
+}
+
+int kpad_of(int K) {
+    int p = 4;
+    while (p < K) p <<= 1;
+    return p;
+}
+
+void launch_eval(topay_solver* s, bool timed, int tick_in_batch) {
+    const TpSolverDev& D = s->dev;
+    const int groups = (s->max_N + D.ppw - 1) / D.ppw;
+    const int end_warps = D.end_tasks ? (s->max_N + 31) / 32 : 0;
+    dim3 blk(TP_WARPS_PER_BLOCK * 32);
+    dim3 g1((groups + TP_WARPS_PER_BLOCK - 1) / TP_WARPS_PER_BLOCK, s->n_cand);
+    dim3 g2((groups + end_warps + TP_WARPS_PER_BLOCK - 1) / TP_WARPS_PER_BLOCK, s->n_cand);
+    const size_t sm_int = (size_t)TP_WARPS_PER_BLOCK * D.ppw * 3 * (2 * D.K + 1) * sizeof(double);
+    TpGrid G;
+    tp_field_grid(s->field, &G);
+    k_integrate<<<g1, blk, sm_int, s->stream>>>(D);
+    if (timed) cudaEventRecord(s->ev[2 * tick_in_batch], s->stream);
+    k_penalty<<<g2, blk, 0, s->stream>>>(D, s->params, G, groups);
+    if (timed) cudaEventRecord(s->ev[2 * tick_in_batch + 1], s->stream);
+    k_chain<<<g1, blk, 0, s->stream>>>(D, s->params);
+    s->stats.kernel_launches += 3;
+    s->stats.eval_launches += 1;
+}
+
+void launch_cand(topay_solver* s, int mode, int slot) {
+    k_cand<<<s->n_cand, 32, s->smem_cand, s->stream>>>(s->dev, s->params, mode, slot);
+    s->stats.kernel_launches += 1;
+}
+
+}  // namespace
+
+extern "C" int topay_solver_create(const topay_opt_params* opt, const topay_robot_params* robot,
+                                   topay_field* field, int max_cand, int max_pieces, topay_solver** out) {
+    if (!opt || !robot || !field || !out || max_cand < 1 || max_pieces < 1) return TOPAY_ERR_INVALID_ARG;
+    if (opt->int_K < 1 || opt->int_K > TP_MAX_K) {
+        tp_set_error("int_K must be in [1, 32]");
+        return TOPAY_ERR_TOO_LARGE;
+    }
+    if (opt->s1_lbfgs_normal_past > TP_LBFGS_MAX_PAST || opt->s1_lbfgs_shot_path_past > TP_LBFGS_MAX_PAST ||
+        opt->s2_lbfgs.past > TP_LBFGS_MAX_PAST) {
+        tp_set_error("lbfgs past above the supported ring size");
+        return TOPAY_ERR_TOO_LARGE;
+    }
+    int rc = tp_require_device(tp_field_device(field));
+    if (rc != TOPAY_OK) return rc;
+    topay_solver* s = new topay_solver();
+    s->field = field;
+    s->device = tp_field_device(field);
+    s->n_cand = 0;
+    s->max_N = 0;
+    s->slots = 16;
+    memset(&s->stats, 0, sizeof(s->stats));
+    cudaSetDevice(s->device);
+    TP_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), { delete s; });
+    memset(&s->params, 0, sizeof(s->params));
+    s->params.robot = *robot;
+    s->params.opt = *opt;
+    tp_derive_params(s->params);
+    TpSolverDev& D = s->dev;
+    memset(&D, 0, sizeof(D));
+    D.max_cand = max_cand;
+    D.max_pieces = max_pieces;
+    D.K = opt->int_K;
+    D.Kpad = kpad_of(D.K);
+    D.ppw = 32 / D.Kpad;
+    D.end_tasks = D.K == D.Kpad ? 1 : 0;
+    D.xs = (topay_num_vars(max_pieces) + 3) & ~3;
+    D.mem = std::max(1, std::max(opt->s1_lbfgs.mem_size, opt->s2_lbfgs.mem_size));
+    const size_t C = max_cand, NP = max_pieces, K = D.K;
+#define ALLOC(ptr, count)                                    \
+    if ((rc = dev_alloc(s, &(ptr), (count))) != TOPAY_OK) {  \
+        topay_solver_destroy(s);                             \
+        return rc;                                           \
+    }
+    ALLOC(D.st, C);
+    ALLOC(D.head_pva, C * 27);
+    ALLOC(D.tail_pva, C * 27);
+    ALLOC(D.start_xy, C * 2);
+    ALLOC(D.end_xy, C * 2);
+    ALLOC(D.init_inner_xy, C * NP * 2);
+    ALLOC(D.x, C * D.xs);
+    ALLOC(D.g, C * D.xs);
+    ALLOC(D.xp, C * D.xs);
+    ALLOC(D.gp, C * D.xs);
+    ALLOC(D.d, C * D.xs);
+    ALLOC(D.lm_s, C * D.mem * D.xs);
+    ALLOC(D.lm_y, C * D.mem * D.xs);
+    ALLOC(D.lm_ys, C * D.mem);
+    ALLOC(D.lm_alpha, C * D.mem);
+    ALLOC(D.T, C * NP);
+    ALLOC(D.coeff, C * 6 * NP * 9);
+    ALLOC(D.lu, C * 6 * NP * TP_BAND);
+    ALLOC(D.Ixy, C * NP * K * 2);
+    ALLOC(D.tot, C * NP * 2);
+    ALLOC(D.gnode, C * NP * (K + 1) * 2);
+    ALLOC(D.gsum, C * NP * 2);
+    ALLOC(D.gdC, C * 6 * NP * 9);
+    ALLOC(D.gdC_end, C * NP * 54);
+    ALLOC(D.gdT, C * NP);
+    ALLOC(D.gdT_end, C * NP);
+    ALLOC(D.terms, C * NP * TOPAY_NTERMS);
+    ALLOC(D.terms_end, C * NP * TOPAY_NTERMS);
+    ALLOC(D.f, C);
+    ALLOC(D.term_out, C * TOPAY_NTERMS);
+    ALLOC(D.n_active, (size_t)s->slots);
+    ALLOC(D.node_count, 1);
+#undef ALLOC
+    TP_CUDA_OK(cudaMallocHost(&s->h_active, s->slots * sizeof(int32_t)), { topay_solver_destroy(s); });
+    TP_CUDA_OK(cudaMallocHost(&s->h_nodes, sizeof(unsigned long long)), { topay_solver_destroy(s); });
+    s->ev.resize(2 * s->slots);
+    for (auto& e : s->ev) cudaEventCreate(&e);
+    cudaEventCreate(&s->ev_begin);
+    cudaEventCreate(&s->ev_end);
+    s->smem_cand = (size_t)6 * NP * (TP_BAND + 9 + 9) * sizeof(double);
+    if (s->smem_cand > 227 * 1024) {
+        tp_set_error("max_pieces too large for the per-candidate shared-memory working set");
+        topay_solver_destroy(s);
+        return TOPAY_ERR_TOO_LARGE;
+    }
+    TP_CUDA_OK(cudaFuncSetAttribute(k_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_cand),
+               { topay_solver_destroy(s); });
+    const size_t sm_int = (size_t)TP_WARPS_PER_BLOCK * D.ppw * 3 * (2 * D.K + 1) * sizeof(double);
+    TP_CUDA_OK(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_int),
+               { topay_solver_destroy(s); });
+    TP_CUDA_OK(cudaStreamSynchronize(s->stream), { topay_solver_destroy(s); });
+    *out = s;
+    return TOPAY_OK;
+}
+
+extern "C" void topay_solver_destroy(topay_solver* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void* p : s->allocs) cudaFree(p);
+    if (s->h_active) cudaFreeHost(s->h_active);
+    if (s->h_nodes) cudaFreeHost(s->h_nodes);
+    for (auto& e : s->ev) cudaEventDestroy(e);
+    if (s->ev_begin) cudaEventDestroy(s->ev_begin);
+    if (s->ev_end) cudaEventDestroy(s->ev_end);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+// Uploads problem data + x and (re)initialises the per-candidate state.
+static int upload_problem(topay_solver* s, int n_cand, const int32_t* piece_num, const double* head,
+                          const double* tail, const double* sxy, const double* exy, const double* inner_xy,
+                          const double* x, int x_stride, const int32_t* s1_past, int phase, const double* lambda,
+                          const double* rho) {
+    TpSolverDev& D = s->dev;
+    if (n_cand < 1 || n_cand > D.max_cand) {
+        tp_set_error("n_cand above the solver capacity");
+        return TOPAY_ERR_TOO_LARGE;
+    }
+    int maxN = 0;
+    for (int c = 0; c < n_cand; c++) {
+        if (piece_num[c] < 1 || piece_num[c] > D.max_pieces) {
+            tp_set_error("piece_num above the solver capacity");
+            return TOPAY_ERR_TOO_LARGE;
+        }
+        maxN = std::max(maxN, piece_num[c]);
+    }
+    cudaSetDevice(s->device);
+    s->n_cand = n_cand;
+    s->max_N = maxN;
+    s->h_state.assign(n_cand, TpCandState());
+    std::vector<double> xs((size_t)n_cand * D.xs, 0.0);
+    for (int c = 0; c < n_cand; c++) {
+        TpCandState& st = s->h_state[c];
+        memset(&st, 0, sizeof(st));
+        st.phase = phase;
+        st.N = piece_num[c];
+        st.n = topay_num_vars(piece_num[c]);
+        st.ls_init = 1;
+        st.s1_past = s1_past ? s1_past[c] : s->params.opt.s1_lbfgs.past;
+        st.lambda[0] = lambda ? lambda[2 * c] : s->params.opt.alm_init_lambda[0];
+        st.lambda[1] = lambda ? lambda[2 * c + 1] : s->params.opt.alm_init_lambda[1];
+        st.rho[0] = rho ? rho[2 * c] : s->params.opt.alm_init_rho[0];
+        st.rho[1] = rho ? rho[2 * c + 1] : s->params.opt.alm_init_rho[1];
+        memcpy(&xs[(size_t)c * D.xs], x + (size_t)c * x_stride, st.n * sizeof(double));
+    }
+    s->h_x0 = xs;
+    cudaStream_t q = s->stream;
+    TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state.data(), n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.head_pva, head, (size_t)n_cand * 27 * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.tail_pva, tail, (size_t)n_cand * 27 * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.start_xy, sxy, (size_t)n_cand * 2 * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.end_xy, exy, (size_t)n_cand * 2 * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.init_inner_xy, inner_xy, (size_t)n_cand * D.max_pieces * 2 * 8,
+                               cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.x, xs.data(), xs.size() * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaStreamSynchronize(q), {});
+    return TOPAY_OK;
+}
+
+extern "C" int topay_solver_eval(topay_solver* s, int stage, const topay_problem_batch* prob, const double* x,
+                                 int x_stride, double* cost, double* grad, double* term_costs, double* coeff_out,
+                                 double* final_xy_out) {
+    if (!s || !prob || !x || !cost || !grad || (stage != 1 && stage != 2)) return TOPAY_ERR_INVALID_ARG;
+    if (!tp_field_ready(s->field)) {
+        tp_set_error("field not built: call topay_field_rebuild first");
+        return TOPAY_ERR_NOT_READY;
+    }
+    int rc = upload_problem(s, prob->n_cand, prob->piece_num, prob->head_pva, prob->tail_pva, prob->start_xy,
+                            prob->end_xy, prob->init_inner_xy, x, x_stride, nullptr, stage, prob->alm_lambda,
+                            prob->alm_rho);
+    if (rc != TOPAY_OK) return rc;
+    const TpSolverDev& D = s->dev;
+    const int n = prob->n_cand;
+    cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), s->stream);
+    launch_cand(s, TP_MODE_GEN, 0);
+    launch_eval(s, false, 0);
+    launch_cand(s, TP_MODE_ADJ, 1);
+    TP_CUDA_OK(cudaStreamSynchronize(s->stream), {});
+    TP_CUDA_OK(cudaGetLastError(), {});
+    std::vector<double> g((size_t)n * D.xs);
+    TP_CUDA_OK(cudaMemcpy(cost, D.f, n * 8, cudaMemcpyDeviceToHost), {});
+    TP_CUDA_OK(cudaMemcpy(g.data(), D.g, g.size() * 8, cudaMemcpyDeviceToHost), {});
+    for (int c = 0; c < n; c++)
+        memcpy(grad + (size_t)c * x_stride, &g[(size_t)c * D.xs], topay_num_vars(prob->piece_num[c]) * 8);
+    if (term_costs) TP_CUDA_OK(cudaMemcpy(term_costs, D.term_out, (size_t)n * TOPAY_NTERMS * 8, cudaMemcpyDeviceToHost), {});
+    if (coeff_out)
+        TP_CUDA_OK(cudaMemcpy(coeff_out, D.coeff, (size_t)n * 6 * D.max_pieces * 9 * 8, cudaMemcpyDeviceToHost), {});
+    if (final_xy_out) {
+        TP_CUDA_OK(cudaMemcpy(s->h_state.data(), D.st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), {});
+        for (int c = 0; c < n; c++) {
+            final_xy_out[2 * c] = s->h_state[c].final_xy[0];
+            final_xy_out[2 * c + 1] = s->h_state[c].final_xy[1];
+        }
+    }
+    return TOPAY_OK;
+}
+
+extern "C" int topay_solver_upload(topay_solver* s, int n_cand, const int32_t* path_len, const double* init_paths,
+                                   const double* bvel, const double* bacc) {
+    if (!s || !path_len || !init_paths || !bvel || !bacc) return TOPAY_ERR_INVALID_ARG;
+    const TpSolverDev& D = s->dev;
+    if (n_cand < 1 || n_cand > D.max_cand) {
+        tp_set_error("n_cand above the solver capacity");
+        return TOPAY_ERR_TOO_LARGE;
+    }
+    const int NP = D.max_pieces, xstride = topay_num_vars(NP);
+    std::vector<int32_t> pn(n_cand), past(n_cand);
+    std::vector<double> head((size_t)n_cand * 27), tail((size_t)n_cand * 27), sxy((size_t)n_cand * 2),
+        exy((size_t)n_cand * 2), ixy((size_t)n_cand * NP * 2), x((size_t)n_cand * xstride, 0.0);
+    size_t off = 0;
+    for (int c = 0; c < n_cand; c++) {
+        int rc = topay_prepare_candidate(&s->params.opt, &s->params.robot, init_paths + off * 10, path_len[c],
+                                         bvel + (size_t)c * 20, bacc + (size_t)c * 20, NP, &pn[c], &head[c * 27],
+                                         &tail[c * 27], &sxy[c * 2], &exy[c * 2], &ixy[(size_t)c * NP * 2],
+                                         &x[(size_t)c * xstride], &past[c]);
+        if (rc != TOPAY_OK) {
+            tp_set_error("candidate needs more pieces than max_pieces");
+            return rc;
+        }
+        off += path_len[c];
+    }
+    return upload_problem(s, n_cand, pn.data(), head.data(), tail.data(), sxy.data(), exy.data(), ixy.data(),
+                          x.data(), xstride, past.data(), 1, nullptr, nullptr);
+}
+
+extern "C" int topay_solver_run(topay_solver* s) {
+    if (!s || s->n_cand < 1) return TOPAY_ERR_INVALID_ARG;
+    if (!tp_field_ready(s->field)) {
+        tp_set_error("field not built: call topay_field_rebuild first");
+        return TOPAY_ERR_NOT_READY;
+    }
+    cudaSetDevice(s->device);
+    TpSolverDev& D = s->dev;
+    cudaStream_t q = s->stream;
+    memset(&s->stats, 0, sizeof(s->stats));
+    // reset to the uploaded initial state so that repeated runs do identical work
+    TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state.data(), s->n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.x, s->h_x0.data(), s->h_x0.size() * 8, cudaMemcpyHostToDevice, q), {});
+    cudaMemsetAsync(D.node_count, 0, sizeof(unsigned long long), q);
+    cudaEventRecord(s->ev_begin, q);
+    cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), q);
+    launch_cand(s, TP_MODE_GEN, 0);
+    double ms_eval = 0.0;
+    // hard cap on ticks: every candidate does at most this many evaluations
+    const long long max_ticks =
+        (long long)(s->params.opt.alm_max_rounds + 1) * ((long long)s->params.opt.s2_lbfgs.max_iterations + 2) *
+        (s->params.opt.s2_lbfgs.max_linesearch + 1);
+    long long ticks = 0;
+    bool done = false;
+    while (!done && ticks < max_ticks) {
+        cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), q);
+        for (int t = 0; t < s->slots; t++) {
+            launch_eval(s, true, t);
+            launch_cand(s, TP_MODE_ADJ | TP_MODE_ADVANCE | TP_MODE_GEN, t);
+        }
+        ticks += s->slots;
+        cudaMemcpyAsync(s->h_active, D.n_active, s->slots * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
+        TP_CUDA_OK(cudaStreamSynchronize(q), {});
+        for (int t = 0; t < s->slots; t++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s->ev[2 * t], s->ev[2 * t + 1]);
+            ms_eval += ms;
+        }
+        done = s->h_active[s->slots - 1] == 0;
+    }
+    cudaEventRecord(s->ev_end, q);
+    cudaMemcpyAsync(s->h_nodes, D.node_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, q);
+    TP_CUDA_OK(cudaStreamSynchronize(q), {});
+    TP_CUDA_OK(cudaGetLastError(), {});
+    cudaEventElapsedTime(&s->stats.ms_total, s->ev_begin, s->ev_end);
+    s->stats.ms_eval = (float)ms_eval;
+    s->stats.ticks = ticks;
+    s->stats.eval_nodes = (int64_t)*s->h_nodes;
+    return TOPAY_OK;
+}
+
+extern "C" int topay_solver_download(topay_solver* s, topay_result_batch* out, int32_t* best_by_duration,
+                                     int32_t* best_by_cost) {
+    if (!s || !out || !out->status || s->n_cand < 1) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(s->device);
+    const TpSolverDev& D = s->dev;
+    const int n = s->n_cand, NP = D.max_pieces;
+    std::vector<TpCandState> st(n);
+    TP_CUDA_OK(cudaMemcpy(st.data(), D.st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), {});
+    std::vector<double> T((size_t)n * NP);
+    TP_CUDA_OK(cudaMemcpy(T.data(), D.T, T.size() * 8, cudaMemcpyDeviceToHost), {});
+    int bd = -1, bc = -1;
+    double bdv = 0, bcv = 0;
+    int64_t evals = 0;
+    for (int c = 0; c < n; c++) {
+        double dur = 0.0;
+        for (int i = 0; i < st[c].N; i++) dur += T[(size_t)c * NP + i];
+        out->status[c] = st[c].status;
+        if (out->lbfgs_code) out->lbfgs_code[c] = st[c].last_code;
+        if (out->piece_num) out->piece_num[c] = st[c].N;
+        if (out->iters) out->iters[c] = st[c].iters_total;
+        if (out->evals) out->evals[c] = st[c].evals_total;
+        if (out->alm_rounds) out->alm_rounds[c] = st[c].alm_round;
+        if (out->cost) out->cost[c] = st[c].cost;
+        if (out->duration) out->duration[c] = dur;
+        if (out->final_xy_err) {
+            out->final_xy_err[2 * c] = st[c].final_xy[0];
+            out->final_xy_err[2 * c + 1] = st[c].final_xy[1];
+        }
+        evals += st[c].evals_total;
+        if (st[c].status == 1) {
+            // planner.cpp:999-1010: first success, replaced only by a strictly shorter duration
+            if (bd < 0 || dur < bdv) {
+                bd = c;
+                bdv = dur;
+            }
+            if (bc < 0 || st[c].cost < bcv) {
+                bc = c;
+                bcv = st[c].cost;
+            }
+        }
+    }
+    s->stats.evals_total = evals;
+    if (out->T) memcpy(out->T, T.data(), T.size() * 8);
+    if (out->coeff) TP_CUDA_OK(cudaMemcpy(out->coeff, D.coeff, (size_t)n * 6 * NP * 9 * 8, cudaMemcpyDeviceToHost), {});
+    if (out->x) {
+        std::vector<double> xs((size_t)n * D.xs);
+        TP_CUDA_OK(cudaMemcpy(xs.data(), D.x, xs.size() * 8, cudaMemcpyDeviceToHost), {});
+        const int xstride = topay_num_vars(NP);
+        for (int c = 0; c < n; c++) memcpy(out->x + (size_t)c * xstride, &xs[(size_t)c * D.xs], st[c].n * 8);
+    }
+    if (best_by_duration) *best_by_duration = bd;
+    if (best_by_cost) *best_by_cost = bc;
+    return TOPAY_OK;
+}
+
+extern "C" int topay_solver_solve_batch(topay_solver* s, int n_cand, const int32_t* path_len,
+                                        const double* init_paths, const double* bvel, const double* bacc,
+                                        topay_result_batch* out, int32_t* best_by_duration, int32_t* best_by_cost) {
+    int rc = topay_solver_upload(s, n_cand, path_len, init_paths, bvel, bacc);
+    if (rc != TOPAY_OK) return rc;
+    rc = topay_solver_run(s);
+    if (rc != TOPAY_OK) return rc;
+    return topay_solver_download(s, out, best_by_duration, best_by_cost);
+}
+
+extern "C" int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out) {
+    if (!s || !out) return TOPAY_ERR_INVALID_ARG;
+    *out = s->stats;
+    return TOPAY_OK;
+}

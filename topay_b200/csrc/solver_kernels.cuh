@@ -1,0 +1,1092 @@
+// sm_100a kernels of the batched NLP solve.
+//
+// One evaluation of all candidates ("tick") is four launches:
+//   k_cand      one warp per candidate: [adjoint of the previous evaluation -> f, g] ->
+//               [line search / L-BFGS / ALM state machine -> new x] -> [x -> T, q -> banded
+//               LU -> spline coefficients]                       (a2,a3,a4,a5,a11-a15 of SURVEY §8a)
+//   k_integrate sub-warp per piece: Simpson interval integrals of (s' cos, s' sin)   (a6/a7 prefix)
+//   k_penalty   sub-warp per piece, lane per penalty node: ESDF lookups, FK, all penalties,
+//               per-piece reduction of gdC / gdT / cost terms                        (a6,a7,a8,a9,a17,a18)
+//   k_chain     sub-warp per piece: suffix sums of the xy adjoints and the contraction with
+//               the Simpson-prefix Jacobians                                         (a6 tail, :1812-1822)
+// Nothing returns to the host between ticks; finished candidates are masked.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "hd.cuh"
+#include "node.cuh"
+
+#define TP_WARPS_PER_BLOCK 4
+#define TP_BAND 16   // padded band width of a stored LU row (13 used)
+
+enum { TP_MODE_ADJ = 1, TP_MODE_ADVANCE = 2, TP_MODE_GEN = 4 };
+
+// Per-candidate scalar state of the device-side solve (lbfgs.hpp:439-722 locals,
+// line_search_lewisoverton locals :288-291, and the ALM loop state of
+// moma_traj_opt.cpp:395-460).
+struct TpCandState {
+    int32_t phase;       // 0 = idle / finished, 1 = stage 1, 2 = stage 2
+    int32_t N, n;
+    int32_t ls_init;     // the evaluation in flight is the initial one of an lbfgs run
+    int32_t k, end, bound, ls_count;
+    int32_t brackt, touched;
+    int32_t s1_past;
+    int32_t alm_round;
+    int32_t iters_total, evals_total;
+    int32_t last_code, status;
+    double stp, mu, nu, finit, dgtest, dstest, fx;
+    double pf[TP_LBFGS_MAX_PAST];
+    double lambda[2], rho[2];
+    double final_xy[2];
+    double cost;
+};
+
+// All device pointers of a solver; strides are fixed by (max_cand, max_pieces, K).
+struct TpSolverDev {
+    int32_t max_cand, max_pieces, K, Kpad, ppw, xs, mem;   // xs = stride of x-like vectors
+    int32_t end_tasks;        // 1 when K == Kpad: node j = 2K is handled by separate end-node warps
+    TpCandState* st;
+    // problem data
+    double *head_pva, *tail_pva, *start_xy, *end_xy, *init_inner_xy;
+    // vectors [max_cand][xs]
+    double *x, *g, *xp, *gp, *d;
+    // L-BFGS memory: lm_s, lm_y [max_cand][mem][xs]; lm_ys, lm_alpha [max_cand][mem]
+    double *lm_s, *lm_y, *lm_ys, *lm_alpha;
+    // spline state
+    double *T;        // [max_cand][max_pieces]
+    double *coeff;    // [max_cand][6*max_pieces][9]
+    double *lu;       // [max_cand][6*max_pieces][TP_BAND]
+    // evaluation scratch
+    double *Ixy;      // [max_cand][max_pieces][K][2]
+    double *tot;      // [max_cand][max_pieces][2]
+    double *gnode;    // [max_cand][max_pieces][K+1][2]
+    double *gsum;     // [max_cand][max_pieces][2]      sum of gnode over nodes 0..K-1 (+K when in-segment)
+    double *gdC;      // [max_cand][6*max_pieces][9]    penalty part
+    double *gdC_end;  // [max_cand][max_pieces][54]     end-node part (end_tasks only)
+    double *gdT;      // [max_cand][max_pieces]         penalty part
+    double *gdT_end;  // [max_cand][max_pieces]
+    double *terms;    // [max_cand][max_pieces][TOPAY_NTERMS]
+    double *terms_end;// [max_cand][max_pieces][TOPAY_NTERMS]
+    // outputs of an evaluation
+    double *f;        // [max_cand]
+    double *term_out; // [max_cand][TOPAY_NTERMS]
+    int32_t *n_active; // [slots] candidates still solving after tick `slot` (written by k_cand)
+    unsigned long long *node_count; // penalty nodes scheduled for evaluation so far
+};
+
+// ------------------------------------------------------------------ warp helpers
+__device__ __forceinline__ double tp_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double tp_shfl_down(double v, int d, int w) { return __shfl_down_sync(0xffffffffu, v, d, w); }
+__device__ __forceinline__ double tp_shfl_up(double v, int d, int w) { return __shfl_up_sync(0xffffffffu, v, d, w); }
+__device__ __forceinline__ double tp_shfl(double v, int src, int w) { return __shfl_sync(0xffffffffu, v, src, w); }
+// butterfly sum over aligned segments of `w` lanes (w power of two); every lane gets the sum
+__device__ __forceinline__ double tp_seg_sum(double v, int w) {
+    for (int m = w >> 1; m > 0; m >>= 1) v += tp_shfl_xor(v, m);
+    return v;
+}
+__device__ __forceinline__ double tp_warp_sum(double v) { return tp_seg_sum(v, 32); }
+__device__ __forceinline__ double tp_warp_max(double v) {
+    for (int m = 16; m > 0; m >>= 1) v = fmax(v, tp_shfl_xor(v, m));
+    return v;
+}
+
+// ------------------------------------------------------------------ k_integrate
+// Simpson interval integrals of one piece (moma_traj_opt.cpp:1282-1291, 1731-1732):
+//   I[k] = coeff v(2k) + 4 coeff v(2k+1) + coeff v(2k+2),  v = s' (cos yaw, sin yaw)
+// and the piece totals (IntegralX.sum(), :1750).
+__global__ void __launch_bounds__(TP_WARPS_PER_BLOCK * 32)
+k_integrate(const __grid_constant__ TpSolverDev S) {
+    const int cand = blockIdx.y;
+    const TpCandState& cs = S.st[cand];
+    if (cs.phase == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = S.K, Kpad = S.Kpad;
+    const int seg = lane / Kpad, jn = lane % Kpad;
+    const int piece = (blockIdx.x * TP_WARPS_PER_BLOCK + warp) * S.ppw + seg;
+    const int N = cs.N;
+    extern __shared__ double sm[];
+    // per warp: ppw segments x (2K+1) slots x 3 values
+    const int L = 2 * K + 1;
+    double* base = sm + (size_t)(warp * S.ppw + seg) * 3 * L;
+    double *s_ds = base, *s_cy = base + L, *s_sy = base + 2 * L;
+    const bool valid = piece < N;
+    double T = 1.0;
+    const double* c = S.coeff;
+    if (valid) {
+        T = S.T[(size_t)cand * S.max_pieces + piece];
+        c = S.coeff + ((size_t)cand * 6 * S.max_pieces + 6 * piece) * 9;
+    }
+    const double step = T / K, half_step = step / 2.0, coeff = step / 6.0;
+    if (valid) {
+        double b0[6], b1[6], b2[6];
+        TpSlot sl;
+        if (jn < K) {
+            for (int r = 0; r < 2; r++) {
+                const int j = 2 * jn + r;
+                tp_slot(c, j * half_step, sl, b0, b1, b2);
+                s_ds[j] = sl.ds;
+                s_cy[j] = sl.cy;
+                s_sy[j] = sl.sy;
+            }
+        }
+        const int end_lane = K < Kpad ? K : 0;
+        if (jn == end_lane) {
+            tp_slot(c, (2 * K) * half_step, sl, b0, b1, b2);
+            s_ds[2 * K] = sl.ds;
+            s_cy[2 * K] = sl.cy;
+            s_sy[2 * K] = sl.sy;
+        }
+    }
+    __syncwarp();
+    double ix = 0.0, iy = 0.0;
+    if (valid && jn < K) {
+        const int j = 2 * jn;
+        // the reference's accumulation order: even node, midpoint, next even node
+        ix = coeff * s_ds[j] * s_cy[j];
+        iy = coeff * s_ds[j] * s_sy[j];
+        ix += 4 * coeff * s_ds[j + 1] * s_cy[j + 1];
+        iy += 4 * coeff * s_ds[j + 1] * s_sy[j + 1];
+        ix += coeff * s_ds[j + 2] * s_cy[j + 2];
+        iy += coeff * s_ds[j + 2] * s_sy[j + 2];
+        double* o = S.Ixy + (((size_t)cand * S.max_pieces + piece) * K + jn) * 2;
+        o[0] = ix;
+        o[1] = iy;
+    }
+    const double tx = tp_seg_sum(ix, Kpad), ty = tp_seg_sum(iy, Kpad);
+    if (valid && jn == 0) {
+        double* o = S.tot + ((size_t)cand * S.max_pieces + piece) * 2;
+        o[0] = tx;
+        o[1] = ty;
+    }
+}
+
+// ------------------------------------------------------------------ k_penalty
+// Lane = one penalty node (even j). STAGE 1: calFirstStagePenalGrad's node body;
+// STAGE 2: calSecondStagePenalGrad's. Reduces gdC / gdT / cost terms over the piece.
+__device__ __forceinline__ void tp_penalty_node(const int STAGE, const TpParams& P, const TpGrid& G,
+                                                const TpSolverDev& S, int cand, int piece, int jn, double T,
+                                                const double* c, const double* xy, TpNodeOut& o, double* b0,
+                                                double* b1, double* b2) {
+    if (STAGE == 1)
+        tp_node_stage1(P, c, T, S.K, 2 * jn, o, b0, b1, b2);
+    else
+        tp_node_stage2(P, G, c, T, S.K, 2 * jn, xy, o, b0, b1, b2);
+}
+
+__global__ void __launch_bounds__(TP_WARPS_PER_BLOCK * 32)
+k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P,
+          const __grid_constant__ TpGrid G, int n_groups) {
+    const int cand = blockIdx.y;
+    const TpCandState& cs = S.st[cand];
+    if (cs.phase == 0) return;
+    const int STAGE = cs.phase;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = S.K, Kpad = S.Kpad, N = cs.N;
+    const int task = blockIdx.x * TP_WARPS_PER_BLOCK + warp;
+    const double* start_xy = S.start_xy + (size_t)cand * 2;
+    const double* totc = S.tot + (size_t)cand * S.max_pieces * 2;
+    double b0[6], b1[6], b2[6];
+    TpNodeOut o;
+
+    if (task >= n_groups) {
+        // ---- end-node task: lane = piece, node j = 2K (only when K == Kpad) ----
+        const int piece = (task - n_groups) * 32 + lane;
+        if (piece >= N) return;
+        const double T = S.T[(size_t)cand * S.max_pieces + piece];
+        const double* c = S.coeff + ((size_t)cand * 6 * S.max_pieces + 6 * piece) * 9;
+        double xy[2] = {start_xy[0], start_xy[1]};
+        if (STAGE == 2)
+            for (int i = 0; i <= piece; i++) {
+                xy[0] += totc[2 * i];
+                xy[1] += totc[2 * i + 1];
+            }
+        tp_penalty_node(STAGE, P, G, S, cand, piece, K, T, c, xy, o, b0, b1, b2);
+        double* gc = S.gdC_end + ((size_t)cand * S.max_pieces + piece) * 54;
+        for (int k = 0; k < 6; k++)
+            for (int d = 0; d < 9; d++) gc[k * 9 + d] = b0[k] * o.G0[d] + b1[k] * o.G1[d] + b2[k] * o.G2[d];
+        S.gdT_end[(size_t)cand * S.max_pieces + piece] = o.gdT;
+        double* tm = S.terms_end + ((size_t)cand * S.max_pieces + piece) * TOPAY_NTERMS;
+        for (int t = 0; t < TOPAY_NTERMS; t++) tm[t] = o.terms[t];
+        double* gn = S.gnode + (((size_t)cand * S.max_pieces + piece) * (K + 1) + K) * 2;
+        gn[0] = o.gx;
+        gn[1] = o.gy;
+        return;
+    }
+
+    // ---- piece task: segment of Kpad lanes per piece ----
+    const int seg = lane / Kpad, jn = lane % Kpad;
+    const int piece = task * S.ppw + seg;
+    const bool pvalid = piece < N;
+    const int n_nodes = S.end_tasks ? K : K + 1;   // nodes handled inside the segment
+    const bool active = pvalid && jn < n_nodes;
+    double T = 1.0;
+    const double* c = S.coeff;
+    if (pvalid) {
+        T = S.T[(size_t)cand * S.max_pieces + piece];
+        c = S.coeff + ((size_t)cand * 6 * S.max_pieces + 6 * piece) * 9;
+    }
+    double xy[2] = {0.0, 0.0};
+    if (STAGE == 2) {
+        // CurrentXY (moma_traj_opt.cpp:1302): start + all earlier intervals
+        double px = 0.0, py = 0.0;
+        if (pvalid)
+            for (int i = jn; i < piece; i += Kpad) {
+                px += totc[2 * i];
+                py += totc[2 * i + 1];
+            }
+        px = tp_seg_sum(px, Kpad);
+        py = tp_seg_sum(py, Kpad);
+        // inclusive scan of this piece's intervals; node jn sees intervals 0..jn-1
+        double ix = 0.0, iy = 0.0;
+        if (pvalid && jn < K) {
+            const double* I = S.Ixy + (((size_t)cand * S.max_pieces + piece) * K + jn) * 2;
+            ix = I[0];
+            iy = I[1];
+        }
+        for (int dlt = 1; dlt < Kpad; dlt <<= 1) {
+            const double ux = tp_shfl_up(ix, dlt, Kpad), uy = tp_shfl_up(iy, dlt, Kpad);
+            if (jn >= dlt) {
+                ix += ux;
+                iy += uy;
+            }
+        }
+        const double ex = tp_shfl_up(ix, 1, Kpad), ey = tp_shfl_up(iy, 1, Kpad);
+        xy[0] = start_xy[0] + px + (jn > 0 ? ex : 0.0);
+        xy[1] = start_xy[1] + py + (jn > 0 ? ey : 0.0);
+    }
+    if (active)
+        tp_penalty_node(STAGE, P, G, S, cand, piece, jn, T, c, xy, o, b0, b1, b2);
+    else {
+        tp_node_clear(o);
+        for (int k = 0; k < 6; k++) b0[k] = b1[k] = b2[k] = 0.0;
+    }
+    // per-node xy adjoint, kept for the suffix sums of k_chain
+    if (STAGE == 2 && active) {
+        double* gn = S.gnode + (((size_t)cand * S.max_pieces + piece) * (K + 1) + jn) * 2;
+        gn[0] = o.gx;
+        gn[1] = o.gy;
+    }
+    // reductions over the piece
+    const size_t prow = (size_t)cand * S.max_pieces + piece;
+    const int dmax = STAGE == 1 ? 2 : 9;
+    for (int k = 0; k < 6; k++)
+        for (int d = 0; d < dmax; d++) {
+            double v = b0[k] * o.G0[d] + b1[k] * o.G1[d] + b2[k] * o.G2[d];
+            v = tp_seg_sum(v, Kpad);
+            if (pvalid && jn == 0) S.gdC[(prow * 6 + k) * 9 + d] = v;
+        }
+    if (STAGE == 1 && pvalid && jn == 0)
+        for (int k = 0; k < 6; k++)
+            for (int d = 2; d < 9; d++) S.gdC[(prow * 6 + k) * 9 + d] = 0.0;
+    {
+        const double v = tp_seg_sum(o.gdT, Kpad);
+        if (pvalid && jn == 0) S.gdT[prow] = v;
+    }
+    for (int t = 0; t < TOPAY_NTERMS; t++) {
+        const double v = tp_seg_sum(o.terms[t], Kpad);
+        if (pvalid && jn == 0) S.terms[prow * TOPAY_NTERMS + t] = v;
+    }
+    if (STAGE == 2) {
+        const double sx = tp_seg_sum(o.gx, Kpad), sy = tp_seg_sum(o.gy, Kpad);
+        if (pvalid && jn == 0) {
+            S.gsum[prow * 2] = sx;
+            S.gsum[prow * 2 + 1] = sy;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ k_chain
+// Chain weights of every node slot and their contraction with the prefix Jacobians.
+// Stage 2: weight of slot (i, j) = sum of the xy adjoints of all penalty nodes at or after it
+// (the reference's `head(i*(2K+1)+j+1) +=`, moma_traj_opt.cpp:1313, 1667) + the ALM term (:1809).
+// Stage 1: weight of every slot of piece p = sum over pieces i > p of 2 w (F_{i+1} - target_i)
+// (`head(i*(2K+1))`, :1175 — piece i itself excluded, reference quirk 1).
+__global__ void __launch_bounds__(TP_WARPS_PER_BLOCK * 32)
+k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P) {
+    const int cand = blockIdx.y;
+    const TpCandState& cs = S.st[cand];
+    if (cs.phase == 0) return;
+    const int STAGE = cs.phase;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = S.K, Kpad = S.Kpad, N = cs.N;
+    const int seg = lane / Kpad, jn = lane % Kpad;
+    const int piece = (blockIdx.x * TP_WARPS_PER_BLOCK + warp) * S.ppw + seg;
+    const bool pvalid = piece < N;
+    const size_t prow = (size_t)cand * S.max_pieces + piece;
+    const double* totc = S.tot + (size_t)cand * S.max_pieces * 2;
+
+    // trajectory end point of every piece, accumulated piece by piece like VecTrajFinalXY
+    // (moma_traj_opt.cpp:1750): F_{i+1} = F_i + tot_i
+    double wx = 0.0, wy = 0.0;   // weight common to all slots of this piece
+    {
+        double fx = S.start_xy[(size_t)cand * 2], fy = S.start_xy[(size_t)cand * 2 + 1];
+        if (STAGE == 1) {
+            const double w = P.opt.s1_path_pos_weight;
+            const double* tgt = S.init_inner_xy + (size_t)cand * S.max_pieces * 2;
+            for (int i = 0; i < N; i++) {
+                fx += totc[2 * i];
+                fy += totc[2 * i + 1];
+                if (i > piece) {
+                    wx += w * 2.0 * (fx - tgt[2 * i]);
+                    wy += w * 2.0 * (fy - tgt[2 * i + 1]);
+                }
+            }
+        } else {
+            for (int i = 0; i < N; i++) {
+                fx += totc[2 * i];
+                fy += totc[2 * i + 1];
+            }
+            const double ex = fx - S.end_xy[(size_t)cand * 2], ey = fy - S.end_xy[(size_t)cand * 2 + 1];
+            wx = cs.rho[0] * (ex + cs.lambda[0] / cs.rho[0]);
+            wy = cs.rho[1] * (ey + cs.lambda[1] / cs.rho[1]);
+            // adjoints of all later pieces
+            double lx = 0.0, ly = 0.0;
+            if (pvalid)
+                for (int i = piece + 1 + jn; i < N; i += Kpad) {
+                    const size_t r = (size_t)cand * S.max_pieces + i;
+                    lx += S.gsum[r * 2];
+                    ly += S.gsum[r * 2 + 1];
+                    if (S.end_tasks) {
+                        lx += S.gnode[(r * (K + 1) + K) * 2];
+                        ly += S.gnode[(r * (K + 1) + K) * 2 + 1];
+                    }
+                }
+            wx += tp_seg_sum(lx, Kpad);
+            wy += tp_seg_sum(ly, Kpad);
+        }
+    }
+    // stage 2: suffix sums of this piece's own node adjoints
+    double suf_x = 0.0, suf_y = 0.0;     // sum over nodes jn' >= jn (incl. node K)
+    double sufn_x = 0.0, sufn_y = 0.0;   // sum over nodes jn' >  jn
+    if (STAGE == 2) {
+        double gx = 0.0, gy = 0.0;
+        if (pvalid && jn < K) {
+            const double* gn = S.gnode + ((prow * (K + 1)) + jn) * 2;
+            gx = gn[0];
+            gy = gn[1];
+        }
+        double ex = 0.0, ey = 0.0;
+        if (pvalid) {
+            const double* gn = S.gnode + ((prow * (K + 1)) + K) * 2;
+            ex = gn[0];
+            ey = gn[1];
+        }
+        double sx = gx, sy = gy;
+        for (int dlt = 1; dlt < Kpad; dlt <<= 1) {
+            const double ux = tp_shfl_down(sx, dlt, Kpad), uy = tp_shfl_down(sy, dlt, Kpad);
+            if (jn + dlt < Kpad) {
+                sx += ux;
+                sy += uy;
+            }
+        }
+        suf_x = sx + ex;
+        suf_y = sy + ey;
+        sufn_x = suf_x - gx;
+        sufn_y = suf_y - gy;
+        // exact value of the "after" sum without the subtraction's rounding: shift instead
+        const double nx = tp_shfl_down(sx, 1, Kpad), ny = tp_shfl_down(sy, 1, Kpad);
+        if (jn + 1 < Kpad) {
+            sufn_x = nx + ex;
+            sufn_y = ny + ey;
+        } else {
+            sufn_x = ex;
+            sufn_y = ey;
+        }
+    }
+    double gth[6], gar[6], gdt = 0.0;
+    for (int k = 0; k < 6; k++) gth[k] = gar[k] = 0.0;
+    if (pvalid) {
+        const double T = S.T[prow];
+        const double* c = S.coeff + (prow * 6) * 9;
+        const double half_step = (T / K) / 2.0;
+        double b0[6], b1[6], b2[6];
+        TpSlot sl;
+        if (jn < K) {
+            {   // even slot j = 2 jn: Simpson pattern weight 1 at j = 0, else 2
+                const int j = 2 * jn;
+                const double icc = j == 0 ? 1.0 : 2.0;
+                tp_slot(c, j * half_step, sl, b0, b1, b2);
+                tp_chain_slot(sl, b0, b1, T, K, j, (wx + suf_x) * icc, (wy + suf_y) * icc, gth, gar, gdt);
+            }
+            {   // midpoint j = 2 jn + 1: weight 4
+                const int j = 2 * jn + 1;
+                tp_slot(c, j * half_step, sl, b0, b1, b2);
+                tp_chain_slot(sl, b0, b1, T, K, j, (wx + sufn_x) * 4.0, (wy + sufn_y) * 4.0, gth, gar, gdt);
+            }
+        }
+        const int end_lane = K < Kpad ? K : 0;
+        if (jn == end_lane) {   // last slot j = 2K: weight 1, only its own node is at/after it
+            double ex = 0.0, ey = 0.0;
+            if (STAGE == 2) {
+                const double* gn = S.gnode + ((prow * (K + 1)) + K) * 2;
+                ex = gn[0];
+                ey = gn[1];
+            }
+            tp_slot(c, (2 * K) * half_step, sl, b0, b1, b2);
+            tp_chain_slot(sl, b0, b1, T, K, 2 * K, wx + ex, wy + ey, gth, gar, gdt);
+        }
+    }
+    for (int k = 0; k < 6; k++) {
+        const double a = tp_seg_sum(gth[k], Kpad), b = tp_seg_sum(gar[k], Kpad);
+        if (pvalid && jn == 0) {
+            double* row = S.gdC + (prow * 6 + k) * 9;
+            row[0] += a;
+            row[1] += b;
+        }
+    }
+    gdt = tp_seg_sum(gdt, Kpad);
+    if (pvalid && jn == 0) S.gdT[prow] += gdt;
+    // fold the end-node contributions into the piece
+    __syncwarp();
+    if (S.end_tasks && pvalid) {
+        const double* ge = S.gdC_end + prow * 54;
+        for (int e = jn; e < 54; e += Kpad) S.gdC[prow * 54 + e] += ge[e];
+        if (jn == 0) {
+            S.gdT[prow] += S.gdT_end[prow];
+            for (int t = 0; t < TOPAY_NTERMS; t++) S.terms[prow * TOPAY_NTERMS + t] += S.terms_end[prow * TOPAY_NTERMS + t];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ k_cand
+// One warp per candidate. Shared memory: the banded LU (6N x TP_BAND), the spline
+// coefficients (6N x 9) and one 6N x 9 work matrix.
+//
+// Banded storage: row i holds A(i, i-6 .. i+6) at lu[i*TP_BAND + (j - i + 6)]; same
+// no-pivot elimination, zero tests and operation order per element as
+// BandedSystem::factorizeLU / solve / solveAdj (banded_system.hpp:66-145).
+#define LU_AT(i, j) lu[(i) * TP_BAND + ((j) - (i) + 6)]
+
+// MinJerkOpt<9>::generate (minco.hpp:824-906): fill A and the right-hand side.
+__device__ __forceinline__ void tp_fill_system(int N, const double* T, const double* head, const double* tail,
+                                               const double* xin, const TpParams& P, double* lu, double* cf,
+                                               int lane) {
+    const int n = 6 * N;
+    for (int e = lane; e < n * TP_BAND; e += 32) lu[e] = 0.0;
+    for (int e = lane; e < n * 9; e += 32) cf[e] = 0.0;
+    __syncwarp();
+    // x layout (moma_traj_opt.cpp:324-344): tau(N) | theta(N-1) | arc(N) | vq(7 x (N-1), column-major)
+    const double* Theta = xin + N;
+    const double* Arc = Theta + (N - 1);
+    const double* Vq = Arc + N;
+    for (int r = lane; r < n; r += 32) {
+        if (r < 3) {
+            LU_AT(r, r) = r == 2 ? 2.0 : 1.0;
+            for (int d = 0; d < 9; d++) cf[r * 9 + d] = head[d * 3 + r];
+        } else if (r >= n - 3) {
+            const int i = N - 1;
+            const double t1 = T[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
+            const int q = r - (n - 3);
+            const int c0 = 6 * N - 6;
+            if (q == 0) {
+                LU_AT(r, c0) = 1.0; LU_AT(r, c0 + 1) = t1; LU_AT(r, c0 + 2) = t2;
+                LU_AT(r, c0 + 3) = t3; LU_AT(r, c0 + 4) = t4; LU_AT(r, c0 + 5) = t5;
+            } else if (q == 1) {
+                LU_AT(r, c0 + 1) = 1.0; LU_AT(r, c0 + 2) = 2 * t1; LU_AT(r, c0 + 3) = 3 * t2;
+                LU_AT(r, c0 + 4) = 4 * t3; LU_AT(r, c0 + 5) = 5 * t4;
+            } else {
+                LU_AT(r, c0 + 2) = 2; LU_AT(r, c0 + 3) = 6 * t1; LU_AT(r, c0 + 4) = 12 * t2;
+                LU_AT(r, c0 + 5) = 20 * t3;
+            }
+            for (int d = 0; d < 9; d++) {
+                double v = tail[d * 3 + q];
+                if (d == 1 && q == 0) v = Arc[N - 1];   // minco_end_state(1,0) = Arc[N-1], :905
+                cf[r * 9 + d] = v;
+            }
+        } else {
+            const int i = (r - 3) / 6, q = (r - 3) % 6;   // row 6i+3+q
+            const double t1 = T[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
+            const int c0 = 6 * i;
+            switch (q) {
+                case 0:
+                    LU_AT(r, c0 + 3) = 6.0; LU_AT(r, c0 + 4) = 24.0 * t1; LU_AT(r, c0 + 5) = 60.0 * t2;
+                    LU_AT(r, c0 + 9) = -6.0;
+                    break;
+                case 1:
+                    LU_AT(r, c0 + 4) = 24.0; LU_AT(r, c0 + 5) = 120.0 * t1; LU_AT(r, c0 + 10) = -24.0;
+                    break;
+                case 2:
+                    LU_AT(r, c0) = 1.0; LU_AT(r, c0 + 1) = t1; LU_AT(r, c0 + 2) = t2; LU_AT(r, c0 + 3) = t3;
+                    LU_AT(r, c0 + 4) = t4; LU_AT(r, c0 + 5) = t5;
+                    cf[r * 9 + 0] = Theta[i];
+                    cf[r * 9 + 1] = Arc[i];
+                    for (int j = 0; j < TOPAY_DOF; j++)
+                        cf[r * 9 + 2 + j] = tp_sigmoidC2(Vq[(size_t)i * TOPAY_DOF + j], P.robot.joint_pos_limit_max[j]);
+                    break;
+                case 3:
+                    LU_AT(r, c0) = 1.0; LU_AT(r, c0 + 1) = t1; LU_AT(r, c0 + 2) = t2; LU_AT(r, c0 + 3) = t3;
+                    LU_AT(r, c0 + 4) = t4; LU_AT(r, c0 + 5) = t5; LU_AT(r, c0 + 6) = -1.0;
+                    break;
+                case 4:
+                    LU_AT(r, c0 + 1) = 1.0; LU_AT(r, c0 + 2) = 2 * t1; LU_AT(r, c0 + 3) = 3 * t2;
+                    LU_AT(r, c0 + 4) = 4 * t3; LU_AT(r, c0 + 5) = 5 * t4; LU_AT(r, c0 + 7) = -1.0;
+                    break;
+                default:
+                    LU_AT(r, c0 + 2) = 2.0; LU_AT(r, c0 + 3) = 6 * t1; LU_AT(r, c0 + 4) = 12 * t2;
+                    LU_AT(r, c0 + 5) = 20 * t3; LU_AT(r, c0 + 8) = -2.0;
+                    break;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// factorizeLU + solve, fused: the forward substitution of step k uses the multipliers
+// of step k as soon as they exist (same arithmetic per element as running solve() after
+// factorizeLU()).
+__device__ __forceinline__ void tp_lu_solve(int n, double* lu, double* b, int lane) {
+    for (int k = 0; k <= n - 2; k++) {
+        const int iM = min(k + 6, n - 1);
+        const int rows = iM - k;
+        if (lane < rows) {
+            const int i = k + 1 + lane;
+            const double a = LU_AT(i, k);
+            if (a != 0.0) LU_AT(i, k) = a / LU_AT(k, k);
+        }
+        __syncwarp();
+        for (int e = lane; e < rows * 15; e += 32) {
+            const int i = k + 1 + e / 15, t = e % 15;
+            const double l = LU_AT(i, k);
+            if (l != 0.0) {
+                if (t < 6) {
+                    const int j = k + 1 + t;
+                    if (j <= iM) {
+                        const double cv = LU_AT(k, j);
+                        if (cv != 0.0) LU_AT(i, j) -= l * cv;
+                    }
+                } else {
+                    const int cc = t - 6;
+                    b[i * 9 + cc] -= l * b[k * 9 + cc];
+                }
+            }
+        }
+        __syncwarp();
+    }
+    for (int j = n - 1; j >= 0; j--) {
+        if (lane < 9) b[j * 9 + lane] /= LU_AT(j, j);
+        __syncwarp();
+        const int i0 = max(0, j - 6);
+        const int rows = j - i0;
+        for (int e = lane; e < rows * 9; e += 32) {
+            const int i = i0 + e / 9, cc = e % 9;
+            const double a = LU_AT(i, j);
+            if (a != 0.0) b[i * 9 + cc] -= a * b[j * 9 + cc];
+        }
+        __syncwarp();
+    }
+}
+
+// solveAdj (banded_system.hpp:123-145)
+__device__ __forceinline__ void tp_lu_solve_adj(int n, const double* lu, double* b, int lane) {
+    for (int j = 0; j <= n - 1; j++) {
+        if (lane < 9) b[j * 9 + lane] /= LU_AT(j, j);
+        __syncwarp();
+        const int iM = min(j + 6, n - 1);
+        const int rows = iM - j;
+        for (int e = lane; e < rows * 9; e += 32) {
+            const int i = j + 1 + e / 9, cc = e % 9;
+            const double a = LU_AT(j, i);
+            if (a != 0.0) b[i * 9 + cc] -= a * b[j * 9 + cc];
+        }
+        __syncwarp();
+    }
+    for (int j = n - 1; j >= 0; j--) {
+        const int i0 = max(0, j - 6);
+        const int rows = j - i0;
+        for (int e = lane; e < rows * 9; e += 32) {
+            const int i = i0 + e / 9, cc = e % 9;
+            const double a = LU_AT(j, i);
+            if (a != 0.0) b[i * 9 + cc] -= a * b[j * 9 + cc];
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ double tp_dot(const double* a, const double* b, int n, int lane) {
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += a[i] * b[i];
+    return tp_warp_sum(s);
+}
+__device__ __forceinline__ double tp_absmax(const double* a, int n, int lane) {
+    double m = 0.0;
+    for (int i = lane; i < n; i += 32) m = fmax(m, fabs(a[i]));
+    return tp_warp_max(m);
+}
+__device__ __forceinline__ bool tp_ok_code(int r) {
+    return r == TOPAY_LBFGS_CONVERGENCE || r == TOPAY_LBFGS_CANCELED || r == TOPAY_LBFGS_STOP ||
+           r == TOPAY_LBFGSERR_MAXIMUMITERATION;
+}
+
+__global__ void __launch_bounds__(32)
+k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P, int mode, int slot) {
+    const int cand = blockIdx.x;
+    const int lane = threadIdx.x;
+    TpCandState* gs = S.st + cand;
+    if (gs->phase == 0) return;
+    TpCandState st = *gs;          // uniform copy per lane
+    __syncwarp();
+    const int N = st.N, n = st.n, n6 = 6 * N;
+    const int stage = st.phase;
+    extern __shared__ double sm[];
+    double* lu = sm;
+    double* cf = lu + (size_t)6 * S.max_pieces * TP_BAND;
+    double* wk = cf + (size_t)6 * S.max_pieces * 9;
+    double* x = S.x + (size_t)cand * S.xs;
+    double* g = S.g + (size_t)cand * S.xs;
+    double* xp = S.xp + (size_t)cand * S.xs;
+    double* gp = S.gp + (size_t)cand * S.xs;
+    double* dv = S.d + (size_t)cand * S.xs;
+    double* Tg = S.T + (size_t)cand * S.max_pieces;
+    double* cg = S.coeff + (size_t)cand * 6 * S.max_pieces * 9;
+    double* lug = S.lu + (size_t)cand * 6 * S.max_pieces * TP_BAND;
+    const topay_lbfgs_params& lp = stage == 1 ? P.opt.s1_lbfgs : P.opt.s2_lbfgs;
+    const int past = stage == 1 ? st.s1_past : lp.past;
+    double f_eval = 0.0;
+
+    // ================= adjoint half of the evaluation in flight =================
+    if (mode & TP_MODE_ADJ) {
+        for (int e = lane; e < n6 * TP_BAND; e += 32) lu[e] = lug[e];
+        for (int e = lane; e < n6 * 9; e += 32) cf[e] = cg[e];
+        __syncwarp();
+        const double* gdCp = S.gdC + (size_t)cand * 6 * S.max_pieces * 9;
+        const double* gdTp = S.gdT + (size_t)cand * S.max_pieces;
+        const double* tmp = S.terms + (size_t)cand * S.max_pieces * TOPAY_NTERMS;
+        const double* totc = S.tot + (size_t)cand * S.max_pieces * 2;
+        // cost terms: pieces in order
+        double terms[TOPAY_NTERMS];
+        for (int t = 0; t < TOPAY_NTERMS; t++) {
+            double s = 0.0;
+            for (int i = 0; i < N; i++) s += tmp[i * TOPAY_NTERMS + t];
+            terms[t] = s;
+        }
+        // end point, VecTrajFinalXY order (:1750)
+        double fx = S.start_xy[cand * 2], fy = S.start_xy[cand * 2 + 1];
+        double cost_path = 0.0;
+        const double* tgt = S.init_inner_xy + (size_t)cand * S.max_pieces * 2;
+        for (int i = 0; i < N; i++) {
+            fx += totc[2 * i];
+            fy += totc[2 * i + 1];
+            if (stage == 1) {
+                const double ex = fx - tgt[2 * i], ey = fy - tgt[2 * i + 1];
+                cost_path += P.opt.s1_path_pos_weight * (ex * ex + ey * ey);
+            }
+        }
+        st.final_xy[0] = fx - S.end_xy[cand * 2];
+        st.final_xy[1] = fy - S.end_xy[cand * 2 + 1];
+        // mean-time penalty (:1752-1769, hard-coded 0.5 / 2.0) — stage 2 only
+        double avg_time = 0.0;
+        for (int i = 0; i < N; i++) avg_time += Tg[i];
+        avg_time /= N;
+        double mt_all = 0.0;
+        if (stage == 2) {
+            const double w_mt = P.opt.s2_mean_time_weight;
+            for (int i = 0; i < N; i++) {
+                const double ti = Tg[i];
+                if (ti < avg_time * 0.5) {
+                    terms[TOPAY_TERM_MEAN_TIME] += w_mt * (ti - avg_time * 0.5) * (ti - avg_time * 0.5);
+                    mt_all += w_mt * 2.0 * (ti - avg_time * 0.5) * (-0.5 / N);
+                }
+                if (ti > avg_time * 2.0) {
+                    terms[TOPAY_TERM_MEAN_TIME] += w_mt * (ti - avg_time * 2.0) * (ti - avg_time * 2.0);
+                    mt_all += w_mt * 2.0 * (ti - avg_time * 2.0) * (-2.0 / N);
+                }
+            }
+            terms[TOPAY_TERM_ENDP] =
+                0.5 * (st.rho[0] * (st.final_xy[0] + st.lambda[0] / st.rho[0]) * (st.final_xy[0] + st.lambda[0] / st.rho[0]) +
+                       st.rho[1] * (st.final_xy[1] + st.lambda[1] / st.rho[1]) * (st.final_xy[1] + st.lambda[1] / st.rho[1]));
+        } else {
+            terms[TOPAY_TERM_ENDP] = cost_path;
+        }
+        double pen = 0.0;
+        bool bad = false;
+        for (int t = TOPAY_TERM_CHASSIS_COLLI; t < TOPAY_NTERMS; t++) {
+            pen += terms[t];
+            if (isinf(terms[t]) || isnan(terms[t])) bad = true;
+        }
+        if (stage == 1) bad = false;          // the guard exists in stage 2 only (:1790-1807)
+        if (bad) pen = 1.0e+22;
+        // gdC = jerk part (minco.hpp:951-977) + penalty part -> wk ; jerk cost (:923-942)
+        double jerk = 0.0;
+        {
+            double js = 0.0;
+            for (int i = lane; i < N; i += 32) {
+                const double t1 = Tg[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
+                const double *c3 = cf + (6 * i + 3) * 9, *c4 = c3 + 9, *c5 = c4 + 9;
+                double d33 = 0, d43 = 0, d44 = 0, d53 = 0, d54 = 0, d55 = 0;
+                for (int d = 0; d < 9; d++) {
+                    const double w = P.opt.energy_weights[d];
+                    d33 += (c3[d] * w) * c3[d];
+                    d43 += (c4[d] * w) * c3[d];
+                    d44 += (c4[d] * w) * c4[d];
+                    d53 += (c5[d] * w) * c3[d];
+                    d54 += (c5[d] * w) * c4[d];
+                    d55 += (c5[d] * w) * c5[d];
+                }
+                js += 36.0 * d33 * t1 + 144.0 * d43 * t2 + 192.0 * d44 * t3 + 240.0 * d53 * t3 + 720.0 * d54 * t4 +
+                      720.0 * d55 * t5;
+                // gdT jerk part, kept in wk's tail for the moment: written below
+            }
+            jerk = tp_warp_sum(js);
+        }
+        for (int e = lane; e < n6 * 9; e += 32) {
+            const int r = e / 9, d = e % 9, i = r / 6, q = r % 6;
+            const double t1 = Tg[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
+            const double w = P.opt.energy_weights[d];
+            const double c3 = cf[(6 * i + 3) * 9 + d], c4 = cf[(6 * i + 4) * 9 + d], c5 = cf[(6 * i + 5) * 9 + d];
+            double v = 0.0;
+            if (q == 5) v = 240.0 * c3 * w * t3 + 720.0 * c4 * w * t4 + 1440.0 * c5 * w * t5;
+            else if (q == 4) v = 144.0 * c3 * w * t2 + 384.0 * c4 * w * t3 + 720.0 * c5 * w * t4;
+            else if (q == 3) v = 72.0 * c3 * w * t1 + 144.0 * c4 * w * t2 + 240.0 * c5 * w * t3;
+            wk[e] = v + (bad ? 0.0 : gdCp[e]);
+        }
+        __syncwarp();
+        tp_lu_solve_adj(n6, lu, wk, lane);
+        // gradients w.r.t. the variables (:939-948) with calGradCTtoQT's gdT part (minco.hpp:1016-1067)
+        const double tw = stage == 1 ? P.opt.s1_time_weight : P.opt.s2_time_weight;
+        const double* Tau = x;
+        const double* Vq = x + N + (N - 1) + N;
+        double* gTau = g;
+        double* gTheta = g + N;
+        double* gArc = gTheta + (N - 1);
+        double* gVq = gArc + N;
+        double tsum = 0.0;
+        for (int i = 0; i < N; i++) tsum += Tg[i];
+        for (int i = lane; i < N; i += 32) {
+            const double t1 = Tg[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2;
+            const double *c1 = cf + (6 * i + 1) * 9, *c2 = c1 + 9, *c3 = c2 + 9, *c4 = c3 + 9, *c5 = c4 + 9;
+            double d33 = 0, d43 = 0, d44 = 0, d53 = 0, d54 = 0, d55 = 0;
+            for (int d = 0; d < 9; d++) {
+                const double w = P.opt.energy_weights[d];
+                d33 += (c3[d] * w) * c3[d];
+                d43 += (c4[d] * w) * c3[d];
+                d44 += (c4[d] * w) * c4[d];
+                d53 += (c5[d] * w) * c3[d];
+                d54 += (c5[d] * w) * c4[d];
+                d55 += (c5[d] * w) * c5[d];
+            }
+            double gt = 36.0 * d33 + 288.0 * d43 * t1 + 576.0 * d44 * t2 + 720.0 * d53 * t2 + 2880.0 * d54 * t3 +
+                        3600.0 * d55 * t4;
+            if (!bad) gt += gdTp[i] + mt_all;
+            if (!bad && stage == 2) {
+                const double w_mt = P.opt.s2_mean_time_weight;
+                if (t1 < avg_time * 0.5) gt += w_mt * 2.0 * (t1 - avg_time * 0.5);
+                if (t1 > avg_time * 2.0) gt += w_mt * 2.0 * (t1 - avg_time * 2.0);
+            }
+            double s = 0.0;
+            if (i < N - 1) {
+                for (int d = 0; d < 9; d++) {
+                    const double vel = -(c1[d] + 2.0 * t1 * c2[d] + 3.0 * t2 * c3[d] + 4.0 * t3 * c4[d] + 5.0 * t4 * c5[d]);
+                    const double acc = -(2.0 * c2[d] + 6.0 * t1 * c3[d] + 12.0 * t2 * c4[d] + 20.0 * t3 * c5[d]);
+                    const double jer = -(6.0 * c3[d] + 24.0 * t1 * c4[d] + 60.0 * t2 * c5[d]);
+                    const double snp = -(24.0 * c4[d] + 120.0 * t1 * c5[d]);
+                    const double crk = -120.0 * c5[d];
+                    const double* a = wk + (6 * i + 3) * 9 + d;
+                    s += snp * a[0] + crk * a[9] + vel * a[18] + vel * a[27] + acc * a[36] + jer * a[45];
+                }
+            } else {
+                for (int d = 0; d < 9; d++) {
+                    const double vel = -(c1[d] + 2.0 * t1 * c2[d] + 3.0 * t2 * c3[d] + 4.0 * t3 * c4[d] + 5.0 * t4 * c5[d]);
+                    const double acc = -(2.0 * c2[d] + 6.0 * t1 * c3[d] + 12.0 * t2 * c4[d] + 20.0 * t3 * c5[d]);
+                    const double jer = -(6.0 * c3[d] + 24.0 * t1 * c4[d] + 60.0 * t2 * c5[d]);
+                    const double* a = wk + (6 * N - 3) * 9 + d;
+                    s += vel * a[0] + acc * a[9] + jer * a[18];
+                }
+            }
+            gt += s;
+            gTau[i] = (gt + tw) * tp_dT_dtau(Tau[i]);
+            if (i < N - 1) {
+                const double* a = wk + (6 * i + 5) * 9;
+                gTheta[i] = a[0];
+                gArc[i] = a[1];
+                for (int j = 0; j < TOPAY_DOF; j++)
+                    gVq[(size_t)i * TOPAY_DOF + j] =
+                        a[2 + j] * tp_dq_dvq(Vq[(size_t)i * TOPAY_DOF + j], P.robot.joint_pos_limit_max[j]);
+            } else {
+                gArc[N - 1] = wk[(6 * N - 3) * 9 + 1];   // gdP_tail(1, 0)
+            }
+        }
+        __syncwarp();
+        terms[TOPAY_TERM_JERK] = jerk;
+        terms[TOPAY_TERM_TIME] = tw * tsum;
+        f_eval = jerk + pen + tw * tsum;
+        if (lane == 0) {
+            S.f[cand] = f_eval;
+            for (int t = 0; t < TOPAY_NTERMS; t++) S.term_out[(size_t)cand * TOPAY_NTERMS + t] = terms[t];
+        }
+        st.evals_total++;
+    }
+
+    // ================= line search / L-BFGS / ALM state machine =================
+    bool need_eval = true;
+    if (mode & TP_MODE_ADVANCE) {
+        const int m = lp.mem_size < S.mem ? lp.mem_size : S.mem;
+        double* lm_s = S.lm_s + (size_t)cand * S.mem * S.xs;
+        double* lm_y = S.lm_y + (size_t)cand * S.mem * S.xs;
+        double* lm_ys = S.lm_ys + (size_t)cand * S.mem;
+        double* lm_alpha = S.lm_alpha + (size_t)cand * S.mem;
+        int ret = 0;
+        // what happens after the evaluation that just completed
+        enum { A_NONE, A_BEGIN_LS, A_LS_DONE, A_FINISH } action = A_NONE;
+        const double f = f_eval;
+        if (st.ls_init) {
+            // lbfgs.hpp:522-554
+            st.ls_init = 0;
+            st.fx = f;
+            st.pf[0] = f;
+            for (int i = lane; i < n; i += 32) dv[i] = -g[i];
+            __syncwarp();
+            const double gn = tp_absmax(g, n, lane), xn = tp_absmax(x, n, lane);
+            st.k = 0;
+            if (gn / fmax(1.0, xn) < lp.g_epsilon) {
+                ret = TOPAY_LBFGS_CONVERGENCE;
+                action = A_FINISH;
+            } else {
+                st.stp = 1.0 / sqrt(tp_dot(dv, dv, n, lane));
+                st.k = 1;
+                st.end = 0;
+                st.bound = 0;
+                action = A_BEGIN_LS;
+            }
+        } else {
+            // one trip of line_search_lewisoverton's loop, lbfgs.hpp:319-387
+            st.ls_count++;
+            st.fx = f;
+            bool done = false, fail = false;
+            if (isinf(f) || isnan(f)) {
+                ret = TOPAY_LBFGSERR_INVALID_FUNCVAL;
+                fail = true;
+            } else if (past > 0 && fabs(st.finit - f) / (fabs(st.finit) + 1.0) < lp.delta / past) {
+                done = true;   // reference-specific early accept, :327-330
+            } else {
+                if (f > st.finit + st.stp * st.dgtest) {
+                    st.nu = st.stp;
+                    st.brackt = 1;
+                } else {
+                    if (tp_dot(g, dv, n, lane) < st.dstest)
+                        st.mu = st.stp;
+                    else
+                        done = true;
+                }
+                if (!done) {
+                    if (lp.max_linesearch <= st.ls_count) {
+                        ret = TOPAY_LBFGSERR_MAXIMUMLINESEARCH;
+                        fail = true;
+                    } else if (st.brackt && (st.nu - st.mu) < lp.machine_prec * st.nu) {
+                        ret = TOPAY_LBFGSERR_WIDTHTOOSMALL;
+                        fail = true;
+                    } else {
+                        if (st.brackt)
+                            st.stp = 0.5 * (st.mu + st.nu);
+                        else
+                            st.stp *= 2.0;
+                        if (st.stp < lp.min_step) {
+                            ret = TOPAY_LBFGSERR_MINIMUMSTEP;
+                            fail = true;
+                        } else if (st.stp > lp.max_step) {
+                            if (st.touched) {
+                                ret = TOPAY_LBFGSERR_MAXIMUMSTEP;
+                                fail = true;
+                            } else {
+                                st.touched = 1;
+                                st.stp = lp.max_step;
+                            }
+                        }
+                    }
+                }
+            }
+            if (fail) {
+                // lbfgs.hpp:575-582: revert to the previous point
+                for (int i = lane; i < n; i += 32) {
+                    x[i] = xp[i];
+                    g[i] = gp[i];
+                }
+                __syncwarp();
+                action = A_FINISH;
+            } else if (done) {
+                action = A_LS_DONE;
+            } else {
+                for (int i = lane; i < n; i += 32) x[i] = xp[i] + st.stp * dv[i];
+                __syncwarp();
+            }
+        }
+        if (action == A_LS_DONE) {
+            // lbfgs.hpp:584-715
+            const int k = st.k;
+            bool fin = false;
+            if (stage == 2 && k > lp.max_iterations) {   // progress callback earlyExit, :1873
+                ret = TOPAY_LBFGS_CANCELED;
+                fin = true;
+            }
+            if (!fin) {
+                const double gn = tp_absmax(g, n, lane), xn = tp_absmax(x, n, lane);
+                if (gn / fmax(1.0, xn) < lp.g_epsilon) {
+                    ret = TOPAY_LBFGS_CONVERGENCE;
+                    fin = true;
+                }
+            }
+            if (!fin && 0 < past) {
+                if (past <= k) {
+                    const double rate = fabs(st.pf[k % past] - st.fx) / fmax(1.0, fabs(st.fx));
+                    if (rate < lp.delta) {
+                        ret = TOPAY_LBFGS_STOP;
+                        fin = true;
+                    }
+                }
+                if (!fin) st.pf[k % past] = st.fx;
+            }
+            if (!fin && lp.max_iterations != 0 && lp.max_iterations <= k) {
+                ret = TOPAY_LBFGSERR_MAXIMUMITERATION;
+                fin = true;
+            }
+            if (fin) {
+                action = A_FINISH;
+            } else {
+                st.k = k + 1;
+                double* se = lm_s + (size_t)st.end * S.xs;
+                double* ye = lm_y + (size_t)st.end * S.xs;
+                double ys = 0.0, yy = 0.0, ss = 0.0, gg = 0.0;
+                for (int i = lane; i < n; i += 32) {
+                    const double sv = x[i] - xp[i], yv = g[i] - gp[i];
+                    se[i] = sv;
+                    ye[i] = yv;
+                    ys += yv * sv;
+                    yy += yv * yv;
+                    ss += sv * sv;
+                    gg += gp[i] * gp[i];
+                    dv[i] = -g[i];
+                }
+                ys = tp_warp_sum(ys);
+                yy = tp_warp_sum(yy);
+                ss = tp_warp_sum(ss);
+                gg = tp_warp_sum(gg);
+                if (lane == 0) lm_ys[st.end] = ys;
+                __syncwarp();
+                const double cau = ss * sqrt(gg) * lp.cautious_factor;
+                if (ys > cau) {
+                    st.bound = st.bound + 1 < m ? st.bound + 1 : m;
+                    st.end = (st.end + 1) % m;
+                    int j = st.end;
+                    for (int i = 0; i < st.bound; ++i) {
+                        j = (j + m - 1) % m;
+                        const double* sj = lm_s + (size_t)j * S.xs;
+                        const double* yj = lm_y + (size_t)j * S.xs;
+                        const double al = tp_dot(sj, dv, n, lane) / lm_ys[j];
+                        if (lane == 0) lm_alpha[j] = al;
+                        for (int t = lane; t < n; t += 32) dv[t] += (-al) * yj[t];
+                        __syncwarp();
+                    }
+                    const double sc = ys / yy;
+                    for (int t = lane; t < n; t += 32) dv[t] *= sc;
+                    __syncwarp();
+                    for (int i = 0; i < st.bound; ++i) {
+                        const double* sj = lm_s + (size_t)j * S.xs;
+                        const double* yj = lm_y + (size_t)j * S.xs;
+                        const double beta = tp_dot(yj, dv, n, lane) / lm_ys[j];
+                        const double a = lm_alpha[j] - beta;
+                        for (int t = lane; t < n; t += 32) dv[t] += a * sj[t];
+                        __syncwarp();
+                        j = (j + 1) % m;
+                    }
+                }
+                st.stp = 1.0;
+                action = A_BEGIN_LS;
+            }
+        }
+        if (action == A_BEGIN_LS) {
+            // lbfgs.hpp:558-573 and line search prologue :288-311
+            for (int i = lane; i < n; i += 32) {
+                xp[i] = x[i];
+                gp[i] = g[i];
+            }
+            __syncwarp();
+            st.ls_count = 0;
+            st.brackt = 0;
+            st.touched = 0;
+            st.mu = 0.0;
+            st.nu = lp.max_step;
+            if (!(st.stp > 0.0)) {
+                ret = TOPAY_LBFGSERR_INVALIDPARAMETERS;
+                action = A_FINISH;
+            } else {
+                const double dginit = tp_dot(gp, dv, n, lane);
+                if (0.0 < dginit) {
+                    ret = TOPAY_LBFGSERR_INCREASEGRADIENT;
+                    action = A_FINISH;
+                } else {
+                    st.finit = st.fx;
+                    st.dgtest = lp.f_dec_coeff * dginit;
+                    st.dstest = lp.s_curv_coeff * dginit;
+                    for (int i = lane; i < n; i += 32) x[i] = xp[i] + st.stp * dv[i];
+                    __syncwarp();
+                }
+            }
+        }
+        if (action == A_FINISH) {
+            // end of one lbfgs_optimize call; the outer logic of optimizeTraj (:362-460)
+            st.iters_total += st.k;
+            st.last_code = ret;
+            st.cost = st.fx;
+            bool next_round = false;
+            if (st.phase == 1) {
+                if (tp_ok_code(ret)) {
+                    st.phase = 2;
+                    st.lambda[0] = P.opt.alm_init_lambda[0];
+                    st.lambda[1] = P.opt.alm_init_lambda[1];
+                    st.rho[0] = P.opt.alm_init_rho[0];
+                    st.rho[1] = P.opt.alm_init_rho[1];
+                    st.alm_round = 0;
+                    next_round = true;
+                } else {
+                    st.status = 0;
+                    st.phase = 0;
+                }
+            } else {
+                if (tp_ok_code(ret) || ret == TOPAY_LBFGSERR_MAXIMUMLINESEARCH) {
+                    const double en = sqrt(st.final_xy[0] * st.final_xy[0] + st.final_xy[1] * st.final_xy[1]);
+                    if (en < P.opt.alm_tolerance) {
+                        st.status = 1;
+                        st.phase = 0;
+                    } else {
+                        st.lambda[0] += st.rho[0] * st.final_xy[0];
+                        st.lambda[1] += st.rho[1] * st.final_xy[1];
+                        st.rho[0] = fmin((1 + P.opt.alm_gamma[0]) * st.rho[0], P.opt.alm_rho_max[0]);
+                        st.rho[1] = fmin((1 + P.opt.alm_gamma[1]) * st.rho[1], P.opt.alm_rho_max[1]);
+                        next_round = true;
+                    }
+                } else {
+                    st.status = 0;
+                    st.phase = 0;
+                }
+            }
+            if (next_round) {
+                if (st.alm_round >= P.opt.alm_max_rounds) {
+                    st.status = 0;
+                    st.phase = 0;
+                } else {
+                    st.alm_round++;
+                    st.ls_init = 1;
+                }
+            }
+            need_eval = st.phase != 0;
+        }
+    }
+
+    // ================= generate half of the next evaluation =================
+    if ((mode & TP_MODE_GEN) && need_eval) {
+        for (int i = lane; i < N; i += 32) Tg[i] = tp_expC2(x[i]);
+        __syncwarp();
+        tp_fill_system(N, Tg, S.head_pva + (size_t)cand * 27, S.tail_pva + (size_t)cand * 27, x, P, lu, cf, lane);
+        tp_lu_solve(n6, lu, cf, lane);
+        for (int e = lane; e < n6 * TP_BAND; e += 32) lug[e] = lu[e];
+        for (int e = lane; e < n6 * 9; e += 32) cg[e] = cf[e];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        *gs = st;
+        if (st.phase != 0 && (mode & TP_MODE_GEN)) {
+            atomicAdd(S.n_active + slot, 1);
+            atomicAdd(S.node_count, (unsigned long long)(N * (S.K + 1)));
+        }
+    }
+}
+#undef LU_AT

@@ -1,0 +1,153 @@
+"""MomaTrajOpt — host-side mirror of the reference's trajectory optimizer over the C ABI.
+
+nmoma_planner::MomaTrajOpt (src/planner/include/planner/moma_traj_opt.h:613-675) is one
+single-threaded instance per candidate; the reference runs up to 8 of them on threads
+(planner.cpp:59-66, 921-925). Here one object owns the device state for a whole batch:
+`optimizeTraj` keeps the reference's call shape for one candidate, `optimizeTrajBatch` is the
+batched entry the planner's worker pool collapses into.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._structs import NTERMS, OptParams, ProblemBatch, ResultBatch, RobotParams, SolverStats, num_vars
+from .field import GridMap, _p, robot_params_default
+
+
+def opt_params_default():
+    o = OptParams()
+    _lib.lib().topay_opt_params_default(C.byref(o))
+    return o
+
+
+class MomaTraj:
+    """Result of one optimisation: piece durations + MINCO coefficients (row 6i+k = t^k of piece i,
+    columns theta, arc, q1..q7 — MinJerkOpt<9>::getCoeffs layout, minco.hpp:944)."""
+
+    def __init__(self, T, coeff, start_se2):
+        self.durations, self.coeff, self.start_se2 = T, coeff, start_se2
+        self.is_init = True
+
+    def getTotalDuration(self):
+        return float(np.sum(self.durations))
+
+
+class MomaTrajOpt:
+    def __init__(self, grid_map: GridMap, max_cand=8, max_pieces=16, opt_param: OptParams = None,
+                 robot: RobotParams = None):
+        self._l = _lib.lib()
+        self.grid_map = grid_map
+        self.opt_param = opt_param if opt_param is not None else opt_params_default()
+        self.moma_param = robot if robot is not None else robot_params_default()
+        self.max_cand, self.max_pieces = max_cand, max_pieces
+        self.h = C.c_void_p()
+        _lib.check(self._l.topay_solver_create(C.byref(self.opt_param), C.byref(self.moma_param), grid_map.h,
+                                               max_cand, max_pieces, C.byref(self.h)), "topay_solver_create")
+        self.traj_cost = 0.0
+        self._last = None
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self._l.topay_solver_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    # ---- parity hook: one cost/gradient evaluation per candidate ---------------
+    def evaluate(self, stage, piece_num, head_pva, tail_pva, start_xy, end_xy, init_inner_xy, x, alm_lambda=None,
+                 alm_rho=None):
+        """firstStageCostCallback / secondStageCostCallback (moma_traj_opt.cpp:817-955) for a batch.
+        x: (n, num_vars(max_pieces)) padded. Returns dict(cost, grad, terms, coeff, final_xy)."""
+        n = len(piece_num)
+        NP = self.max_pieces
+        xs = num_vars(NP)
+        pn = np.ascontiguousarray(piece_num, dtype=np.int32)
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (head_pva, tail_pva, start_xy, end_xy)]
+        ixy = np.zeros((n, NP, 2))
+        for c in range(n):
+            ixy[c, :pn[c]] = np.asarray(init_inner_xy[c])[:pn[c]]
+        lam = np.ascontiguousarray(alm_lambda if alm_lambda is not None else np.zeros((n, 2)), dtype=np.float64)
+        rho = np.ascontiguousarray(alm_rho if alm_rho is not None else np.ones((n, 2)), dtype=np.float64)
+        xb = np.zeros((n, xs))
+        for c in range(n):
+            xb[c, :num_vars(pn[c])] = np.asarray(x[c])[:num_vars(pn[c])]
+        pb = ProblemBatch(n, _p(pn, C.c_int32), _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(ixy), _p(lam),
+                          _p(rho))
+        cost, grad = np.zeros(n), np.zeros((n, xs))
+        terms, coeff, fxy = np.zeros((n, NTERMS)), np.zeros((n, 6 * NP, 9)), np.zeros((n, 2))
+        _lib.check(self._l.topay_solver_eval(self.h, stage, C.byref(pb), _p(xb), xs, _p(cost), _p(grad), _p(terms),
+                                             _p(coeff), _p(fxy)), "topay_solver_eval")
+        return dict(cost=cost, grad=grad, terms=terms, coeff=coeff, final_xy=fxy)
+
+    # ---- solve -------------------------------------------------------------------
+    def _flatten(self, paths, bvel, bacc):
+        n = len(paths)
+        plen = np.array([np.asarray(p).shape[0] for p in paths], dtype=np.int32)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64) for p in paths], axis=0))
+        bvel = np.ascontiguousarray(bvel, dtype=np.float64).reshape(n, 10, 2)
+        bacc = np.ascontiguousarray(bacc, dtype=np.float64).reshape(n, 10, 2)
+        return n, plen, flat, bvel, bacc
+
+    def upload(self, paths, bvel, bacc):
+        n, plen, flat, bvel, bacc = self._flatten(paths, bvel, bacc)
+        _lib.check(self._l.topay_solver_upload(self.h, n, _p(plen, C.c_int32), _p(flat), _p(bvel), _p(bacc)),
+                   "topay_solver_upload")
+        self._n = n
+        self._starts = [np.asarray(p)[0, :3].copy() for p in paths]
+        self.h2d_bytes = int(plen.nbytes + flat.nbytes + bvel.nbytes + bacc.nbytes)
+
+    def run(self):
+        _lib.check(self._l.topay_solver_run(self.h), "topay_solver_run")
+
+    def download(self):
+        n, NP = self._n, self.max_pieces
+        r = dict(status=np.zeros(n, np.int32), lbfgs_code=np.zeros(n, np.int32), piece_num=np.zeros(n, np.int32),
+                 iters=np.zeros(n, np.int32), evals=np.zeros(n, np.int32), alm_rounds=np.zeros(n, np.int32),
+                 cost=np.zeros(n), duration=np.zeros(n), T=np.zeros((n, NP)), coeff=np.zeros((n, 6 * NP, 9)),
+                 final_xy_err=np.zeros((n, 2)), x=np.zeros((n, num_vars(NP))))
+        rb = ResultBatch(*[_p(r[k], C.c_int32 if r[k].dtype == np.int32 else C.c_double) for k in
+                           ("status", "lbfgs_code", "piece_num", "iters", "evals", "alm_rounds", "cost", "duration",
+                            "T", "coeff", "final_xy_err", "x")])
+        bd, bc = C.c_int32(-1), C.c_int32(-1)
+        _lib.check(self._l.topay_solver_download(self.h, C.byref(rb), C.byref(bd), C.byref(bc)), "download")
+        r["best_by_duration"], r["best_by_cost"] = bd.value, bc.value
+        self.d2h_bytes = int(sum(v.nbytes for v in r.values() if isinstance(v, np.ndarray)))
+        self._last = r
+        return r
+
+    def optimizeTrajBatch(self, paths, boundary_vel, boundary_acc):
+        """All candidates of a plan in one device solve; returns the result dict of download()."""
+        self.upload(paths, boundary_vel, boundary_acc)
+        self.run()
+        return self.download()
+
+    def optimizeTraj(self, init_path, boundary_vel, boundary_acc):
+        """bool MomaTrajOpt::optimizeTraj(init_path, boundary_vel, boundary_acc) (moma_traj_opt.cpp:142)."""
+        r = self.optimizeTrajBatch([init_path], np.asarray(boundary_vel)[None], np.asarray(boundary_acc)[None])
+        self.traj_cost = float(r["cost"][0])
+        return bool(r["status"][0])
+
+    def getTraj(self, idx=0):
+        r = self._last
+        N = int(r["piece_num"][idx])
+        return MomaTraj(r["T"][idx, :N].copy(), r["coeff"][idx, :6 * N].copy(), self._starts[idx])
+
+    def stats(self):
+        s = SolverStats()
+        self._l.topay_solver_last_stats(self.h, C.byref(s))
+        return {k: getattr(s, k) for k, _ in SolverStats._fields_}
+
+
+def prepare_candidate(opt, rp, init_path, bvel, bacc, max_pieces):
+    """topay_prepare_candidate: the host pre-processing of optimizeTraj (moma_traj_opt.cpp:146-344)."""
+    init_path = np.ascontiguousarray(init_path, dtype=np.float64)
+    bvel, bacc = np.ascontiguousarray(bvel, dtype=np.float64), np.ascontiguousarray(bacc, dtype=np.float64)
+    N, past = C.c_int32(), C.c_int32()
+    head, tail, sxy, exy = np.zeros((9, 3)), np.zeros((9, 3)), np.zeros(2), np.zeros(2)
+    inner_xy, x0 = np.zeros((max_pieces, 2)), np.zeros(num_vars(max_pieces))
+    rc = _lib.lib().topay_prepare_candidate(C.byref(opt), C.byref(rp), _p(init_path), init_path.shape[0], _p(bvel),
+                                            _p(bacc), max_pieces, C.byref(N), _p(head), _p(tail), _p(sxy), _p(exy),
+                                            _p(inner_xy), _p(x0), C.byref(past))
+    return dict(rc=rc, piece_num=N.value, head_pva=head, tail_pva=tail, start_xy=sxy, end_xy=exy,
+                init_inner_xy=inner_xy, x0=x0[:num_vars(N.value)] if rc == 0 else x0, s1_past=past.value)
