@@ -316,6 +316,12 @@ typedef struct topay_solver_stats {
 } topay_solver_stats;
 int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out);
 
+/* Optional L-BFGS iterate trace (parity / debugging): when cap > 0 every accepted iteration of
+ * every candidate records (f, step, k, line-search evaluations) — the arguments the reference
+ * passes to its progress callback (lbfgs.hpp:585-592). cap = 0 turns it off. */
+int topay_solver_set_trace(topay_solver* s, int cap);
+int topay_solver_download_trace(topay_solver* s, int cand, double* out /*cap x 4*/, int cap, int32_t* len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,7 +74,7 @@ void launch_eval(topay_solver* s, bool timed, int tick_in_batch) {
 }
 
 void launch_cand(topay_solver* s, int mode, int slot) {
-    k_cand<<<s->n_cand, 32, s->smem_cand, s->stream>>>(s->dev, s->params, mode, slot);
+    k_cand<<<s->n_cand, TP_CAND_THREADS, s->smem_cand, s->stream>>>(s->dev, s->params, mode, slot);
     s->stats.kernel_launches += 1;
 }
 
@@ -90,6 +90,11 @@ extern "C" int topay_solver_create(const topay_opt_params* opt, const topay_robo
     if (opt->s1_lbfgs_normal_past > TP_LBFGS_MAX_PAST || opt->s1_lbfgs_shot_path_past > TP_LBFGS_MAX_PAST ||
         opt->s2_lbfgs.past > TP_LBFGS_MAX_PAST) {
         tp_set_error("lbfgs past above the supported ring size");
+        return TOPAY_ERR_TOO_LARGE;
+    }
+    if (topay_num_vars(max_pieces) > TP_EPT * TP_CAND_THREADS || max_pieces > 64 ||
+        std::max(opt->s1_lbfgs.mem_size, opt->s2_lbfgs.mem_size) > 256) {
+        tp_set_error("max_pieces above 64 or lbfgs mem_size above 256 is not supported");
         return TOPAY_ERR_TOO_LARGE;
     }
     int rc = tp_require_device(tp_field_device(field));
@@ -183,6 +188,8 @@ extern "C" void topay_solver_destroy(topay_solver* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (void* p : s->allocs) cudaFree(p);
+    if (s->dev.trace) cudaFree(s->dev.trace);
+    if (s->dev.trace_len) cudaFree(s->dev.trace_len);
     if (s->h_active) cudaFreeHost(s->h_active);
     if (s->h_nodes) cudaFreeHost(s->h_nodes);
     for (auto& e : s->ev) cudaEventDestroy(e);
@@ -323,6 +330,7 @@ extern "C" int topay_solver_run(topay_solver* s) {
     TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state.data(), s->n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
     TP_CUDA_OK(cudaMemcpyAsync(D.x, s->h_x0.data(), s->h_x0.size() * 8, cudaMemcpyHostToDevice, q), {});
     cudaMemsetAsync(D.node_count, 0, sizeof(unsigned long long), q);
+    if (D.trace) cudaMemsetAsync(D.trace_len, 0, (size_t)D.max_cand * sizeof(int32_t), q);
     cudaEventRecord(s->ev_begin, q);
     cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), q);
     launch_cand(s, TP_MODE_GEN, 0);
@@ -423,6 +431,39 @@ extern "C" int topay_solver_solve_batch(topay_solver* s, int n_cand, const int32
     rc = topay_solver_run(s);
     if (rc != TOPAY_OK) return rc;
     return topay_solver_download(s, out, best_by_duration, best_by_cost);
+}
+
+extern "C" int topay_solver_set_trace(topay_solver* s, int cap) {
+    if (!s || cap < 0) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(s->device);
+    TpSolverDev& D = s->dev;
+    if (D.trace) {
+        cudaFree(D.trace);
+        cudaFree(D.trace_len);
+        D.trace = nullptr;
+        D.trace_len = nullptr;
+    }
+    D.trace_cap = cap;
+    if (cap > 0) {
+        TP_CUDA_OK(cudaMalloc(&D.trace, (size_t)D.max_cand * cap * 4 * sizeof(double)), {});
+        TP_CUDA_OK(cudaMalloc(&D.trace_len, (size_t)D.max_cand * sizeof(int32_t)), {});
+        cudaMemset(D.trace_len, 0, (size_t)D.max_cand * sizeof(int32_t));
+    }
+    return TOPAY_OK;
+}
+
+extern "C" int topay_solver_download_trace(topay_solver* s, int cand, double* out, int cap, int32_t* len) {
+    if (!s || !out || !len || cand < 0 || cand >= s->dev.max_cand) return TOPAY_ERR_INVALID_ARG;
+    const TpSolverDev& D = s->dev;
+    if (!D.trace) return TOPAY_ERR_NOT_READY;
+    cudaSetDevice(s->device);
+    int32_t n = 0;
+    TP_CUDA_OK(cudaMemcpy(&n, D.trace_len + cand, sizeof(int32_t), cudaMemcpyDeviceToHost), {});
+    n = std::min(n, cap);
+    TP_CUDA_OK(cudaMemcpy(out, D.trace + (size_t)cand * D.trace_cap * 4, (size_t)n * 4 * sizeof(double),
+                          cudaMemcpyDeviceToHost), {});
+    *len = n;
+    return TOPAY_OK;
 }
 
 extern "C" int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out) {

@@ -72,6 +72,10 @@ struct TpSolverDev {
     double *term_out; // [max_cand][TOPAY_NTERMS]
     int32_t *n_active; // [slots] candidates still solving after tick `slot` (written by k_cand)
     unsigned long long *node_count; // penalty nodes scheduled for evaluation so far
+    // optional L-BFGS iterate trace (debug / parity): 4 doubles (f, step, k, ls) per accepted iteration
+    double *trace;        // [max_cand][trace_cap][4] or null
+    int32_t *trace_len;   // [max_cand]
+    int32_t trace_cap;
 };
 
 // ------------------------------------------------------------------ warp helpers
@@ -449,27 +453,67 @@ k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams 
 }
 
 // ------------------------------------------------------------------ k_cand
-// One warp per candidate. Shared memory: the banded LU (6N x TP_BAND), the spline
-// coefficients (6N x 9) and one 6N x 9 work matrix.
+// One CTA of TP_CAND_THREADS threads per candidate. Shared memory: the banded LU
+// (6N x TP_BAND), the spline coefficients (6N x 9) and one 6N x 9 work matrix.
 //
 // Banded storage: row i holds A(i, i-6 .. i+6) at lu[i*TP_BAND + (j - i + 6)]; same
 // no-pivot elimination, zero tests and operation order per element as
-// BandedSystem::factorizeLU / solve / solveAdj (banded_system.hpp:66-145).
+// BandedSystem::factorizeLU / solve / solveAdj (banded_system.hpp:66-145). The 9
+// right-hand-side columns are independent, so the substitutions run on three warps of
+// three columns each; the L-BFGS vectors live in registers (thread t owns elements
+// t, t+128, ...), only the dot products cross threads.
+#define TP_CAND_THREADS 128
+#define TP_CAND_WARPS (TP_CAND_THREADS / 32)
+#define TP_EPT 5      // vector elements per thread: n <= TP_EPT * TP_CAND_THREADS (N <= 64)
 #define LU_AT(i, j) lu[(i) * TP_BAND + ((j) - (i) + 6)]
+
+// block-wide sums of up to 4 values; every thread gets the results. `red` is a
+// [2][4][TP_CAND_WARPS] scratch, `flip` alternates so one barrier per call suffices.
+template <int NV>
+__device__ __forceinline__ void tp_block_sum(double* v, double* red, int& flip) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* r = red + flip * 4 * TP_CAND_WARPS;
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+        const double w = tp_warp_sum(v[q]);
+        if (lane == 0) r[q * TP_CAND_WARPS + warp] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+        double a = r[q * TP_CAND_WARPS];
+#pragma unroll
+        for (int w = 1; w < TP_CAND_WARPS; w++) a += r[q * TP_CAND_WARPS + w];
+        v[q] = a;
+    }
+    flip ^= 1;
+}
+__device__ __forceinline__ double tp_block_max(double v, double* red, int& flip) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* r = red + flip * 4 * TP_CAND_WARPS;
+    const double w = tp_warp_max(v);
+    if (lane == 0) r[warp] = w;
+    __syncthreads();
+    double a = r[0];
+#pragma unroll
+    for (int q = 1; q < TP_CAND_WARPS; q++) a = fmax(a, r[q]);
+    flip ^= 1;
+    return a;
+}
 
 // MinJerkOpt<9>::generate (minco.hpp:824-906): fill A and the right-hand side.
 __device__ __forceinline__ void tp_fill_system(int N, const double* T, const double* head, const double* tail,
-                                               const double* xin, const TpParams& P, double* lu, double* cf,
-                                               int lane) {
+                                               const double* xin, const TpParams& P, double* lu, double* cf) {
     const int n = 6 * N;
-    for (int e = lane; e < n * TP_BAND; e += 32) lu[e] = 0.0;
-    for (int e = lane; e < n * 9; e += 32) cf[e] = 0.0;
-    __syncwarp();
+    const int tid = threadIdx.x;
+    for (int e = tid; e < n * TP_BAND; e += TP_CAND_THREADS) lu[e] = 0.0;
+    for (int e = tid; e < n * 9; e += TP_CAND_THREADS) cf[e] = 0.0;
+    __syncthreads();
     // x layout (moma_traj_opt.cpp:324-344): tau(N) | theta(N-1) | arc(N) | vq(7 x (N-1), column-major)
     const double* Theta = xin + N;
     const double* Arc = Theta + (N - 1);
     const double* Vq = Arc + N;
-    for (int r = lane; r < n; r += 32) {
+    for (int r = tid; r < n; r += TP_CAND_THREADS) {
         if (r < 3) {
             LU_AT(r, r) = r == 2 ? 2.0 : 1.0;
             for (int d = 0; d < 9; d++) cf[r * 9 + d] = head[d * 3 + r];
@@ -528,73 +572,92 @@ __device__ __forceinline__ void tp_fill_system(int N, const double* T, const dou
             }
         }
     }
-    __syncwarp();
+    __syncthreads();
 }
 
-// factorizeLU + solve, fused: the forward substitution of step k uses the multipliers
-// of step k as soon as they exist (same arithmetic per element as running solve() after
-// factorizeLU()).
-__device__ __forceinline__ void tp_lu_solve(int n, double* lu, double* b, int lane) {
+// factorizeLU (banded_system.hpp:66-91) on one warp. Each lane that updates A(i, j) forms the
+// multiplier A(i,k)/A(k,k) itself (same value the reference stores), so a step needs a single
+// warp barrier. 6 x 7 elements per step: column 0 of the window stores the multiplier.
+__device__ __forceinline__ void tp_lu_factor(int n, double* lu, int lane) {
     for (int k = 0; k <= n - 2; k++) {
         const int iM = min(k + 6, n - 1);
         const int rows = iM - k;
-        if (lane < rows) {
-            const int i = k + 1 + lane;
+        const double piv = LU_AT(k, k);
+        for (int e = lane; e < rows * 7; e += 32) {
+            const int i = k + 1 + e / 7, t = e % 7;
             const double a = LU_AT(i, k);
-            if (a != 0.0) LU_AT(i, k) = a / LU_AT(k, k);
-        }
-        __syncwarp();
-        for (int e = lane; e < rows * 15; e += 32) {
-            const int i = k + 1 + e / 15, t = e % 15;
-            const double l = LU_AT(i, k);
-            if (l != 0.0) {
-                if (t < 6) {
-                    const int j = k + 1 + t;
+            if (a != 0.0) {
+                const double l = a / piv;
+                if (t == 0) {
+                    // written after every lane of this pass has read A(i, k): see the barrier below
+                } else {
+                    const int j = k + t;
                     if (j <= iM) {
                         const double cv = LU_AT(k, j);
                         if (cv != 0.0) LU_AT(i, j) -= l * cv;
                     }
-                } else {
-                    const int cc = t - 6;
-                    b[i * 9 + cc] -= l * b[k * 9 + cc];
                 }
             }
         }
         __syncwarp();
-    }
-    for (int j = n - 1; j >= 0; j--) {
-        if (lane < 9) b[j * 9 + lane] /= LU_AT(j, j);
+        if (lane < rows) {
+            const int i = k + 1 + lane;
+            const double a = LU_AT(i, k);
+            if (a != 0.0) LU_AT(i, k) = a / piv;
+        }
         __syncwarp();
-        const int i0 = max(0, j - 6);
-        const int rows = j - i0;
-        for (int e = lane; e < rows * 9; e += 32) {
-            const int i = i0 + e / 9, cc = e % 9;
+    }
+}
+
+// solve (banded_system.hpp:96-118) for the 3 columns [c0, c0+3) on one warp.
+__device__ __forceinline__ void tp_lu_subst(int n, const double* lu, double* b, int c0, int lane) {
+    const int cc = c0 + lane % 3;
+    for (int j = 0; j <= n - 2; j++) {
+        const int iM = min(j + 6, n - 1);
+        const int rows = iM - j;
+        if (lane < rows * 3) {
+            const int i = j + 1 + lane / 3;
             const double a = LU_AT(i, j);
             if (a != 0.0) b[i * 9 + cc] -= a * b[j * 9 + cc];
         }
         __syncwarp();
     }
+    for (int j = n - 1; j >= 0; j--) {
+        const int i0 = max(0, j - 6);
+        const int rows = j - i0;
+        const double v = b[j * 9 + cc] / LU_AT(j, j);
+        __syncwarp();
+        if (lane < rows * 3) {
+            const int i = i0 + lane / 3;
+            const double a = LU_AT(i, j);
+            if (a != 0.0) b[i * 9 + cc] -= a * v;
+        }
+        if (lane >= 18 && lane < 21) b[j * 9 + cc] = v;
+        __syncwarp();
+    }
 }
 
-// solveAdj (banded_system.hpp:123-145)
-__device__ __forceinline__ void tp_lu_solve_adj(int n, const double* lu, double* b, int lane) {
+// solveAdj (banded_system.hpp:123-145) for the 3 columns [c0, c0+3) on one warp.
+__device__ __forceinline__ void tp_lu_subst_adj(int n, const double* lu, double* b, int c0, int lane) {
+    const int cc = c0 + lane % 3;
     for (int j = 0; j <= n - 1; j++) {
-        if (lane < 9) b[j * 9 + lane] /= LU_AT(j, j);
-        __syncwarp();
         const int iM = min(j + 6, n - 1);
         const int rows = iM - j;
-        for (int e = lane; e < rows * 9; e += 32) {
-            const int i = j + 1 + e / 9, cc = e % 9;
+        const double v = b[j * 9 + cc] / LU_AT(j, j);
+        __syncwarp();
+        if (lane < rows * 3) {
+            const int i = j + 1 + lane / 3;
             const double a = LU_AT(j, i);
-            if (a != 0.0) b[i * 9 + cc] -= a * b[j * 9 + cc];
+            if (a != 0.0) b[i * 9 + cc] -= a * v;
         }
+        if (lane >= 18 && lane < 21) b[j * 9 + cc] = v;
         __syncwarp();
     }
     for (int j = n - 1; j >= 0; j--) {
         const int i0 = max(0, j - 6);
         const int rows = j - i0;
-        for (int e = lane; e < rows * 9; e += 32) {
-            const int i = i0 + e / 9, cc = e % 9;
+        if (lane < rows * 3) {
+            const int i = i0 + lane / 3;
             const double a = LU_AT(j, i);
             if (a != 0.0) b[i * 9 + cc] -= a * b[j * 9 + cc];
         }
@@ -602,35 +665,28 @@ __device__ __forceinline__ void tp_lu_solve_adj(int n, const double* lu, double*
     }
 }
 
-__device__ __forceinline__ double tp_dot(const double* a, const double* b, int n, int lane) {
-    double s = 0.0;
-    for (int i = lane; i < n; i += 32) s += a[i] * b[i];
-    return tp_warp_sum(s);
-}
-__device__ __forceinline__ double tp_absmax(const double* a, int n, int lane) {
-    double m = 0.0;
-    for (int i = lane; i < n; i += 32) m = fmax(m, fabs(a[i]));
-    return tp_warp_max(m);
-}
 __device__ __forceinline__ bool tp_ok_code(int r) {
     return r == TOPAY_LBFGS_CONVERGENCE || r == TOPAY_LBFGS_CANCELED || r == TOPAY_LBFGS_STOP ||
            r == TOPAY_LBFGSERR_MAXIMUMITERATION;
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(TP_CAND_THREADS)
 k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P, int mode, int slot) {
     const int cand = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     TpCandState* gs = S.st + cand;
     if (gs->phase == 0) return;
-    TpCandState st = *gs;          // uniform copy per lane
-    __syncwarp();
+    TpCandState st = *gs;          // uniform copy per thread
     const int N = st.N, n = st.n, n6 = 6 * N;
     const int stage = st.phase;
     extern __shared__ double sm[];
     double* lu = sm;
     double* cf = lu + (size_t)6 * S.max_pieces * TP_BAND;
     double* wk = cf + (size_t)6 * S.max_pieces * 9;
+    __shared__ double red[2 * 4 * TP_CAND_WARPS];
+    __shared__ double s_small[4 * 64 + 2 * TOPAY_NTERMS];   // T, totals (x,y), scratch
+    __shared__ double s_alpha[256], s_ys[256];
+    int flip = 0;
     double* x = S.x + (size_t)cand * S.xs;
     double* g = S.g + (size_t)cand * S.xs;
     double* xp = S.xp + (size_t)cand * S.xs;
@@ -645,57 +701,82 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
 
     // ================= adjoint half of the evaluation in flight =================
     if (mode & TP_MODE_ADJ) {
-        for (int e = lane; e < n6 * TP_BAND; e += 32) lu[e] = lug[e];
-        for (int e = lane; e < n6 * 9; e += 32) cf[e] = cg[e];
-        __syncwarp();
+        for (int e = tid; e < n6 * TP_BAND; e += TP_CAND_THREADS) lu[e] = lug[e];
+        for (int e = tid; e < n6 * 9; e += TP_CAND_THREADS) cf[e] = cg[e];
         const double* gdCp = S.gdC + (size_t)cand * 6 * S.max_pieces * 9;
         const double* gdTp = S.gdT + (size_t)cand * S.max_pieces;
         const double* tmp = S.terms + (size_t)cand * S.max_pieces * TOPAY_NTERMS;
         const double* totc = S.tot + (size_t)cand * S.max_pieces * 2;
-        // cost terms: pieces in order
-        double terms[TOPAY_NTERMS];
-        for (int t = 0; t < TOPAY_NTERMS; t++) {
-            double s = 0.0;
-            for (int i = 0; i < N; i++) s += tmp[i * TOPAY_NTERMS + t];
-            terms[t] = s;
+        double* sT = s_small;
+        double* sTot = s_small + 64;
+        double* sTerm = s_small + 192;
+        double* sMisc = sTerm + TOPAY_NTERMS;   // fx, fy, cost_path, avg_time, tsum, mt_all
+        for (int i = tid; i < N; i += TP_CAND_THREADS) {
+            sT[i] = Tg[i];
+            sTot[2 * i] = totc[2 * i];
+            sTot[2 * i + 1] = totc[2 * i + 1];
         }
-        // end point, VecTrajFinalXY order (:1750)
-        double fx = S.start_xy[cand * 2], fy = S.start_xy[cand * 2 + 1];
-        double cost_path = 0.0;
-        const double* tgt = S.init_inner_xy + (size_t)cand * S.max_pieces * 2;
-        for (int i = 0; i < N; i++) {
-            fx += totc[2 * i];
-            fy += totc[2 * i + 1];
-            if (stage == 1) {
-                const double ex = fx - tgt[2 * i], ey = fy - tgt[2 * i + 1];
-                cost_path += P.opt.s1_path_pos_weight * (ex * ex + ey * ey);
-            }
+        // cost terms: fixed-tree sum over pieces, one warp per term
+        for (int t = warp; t < TOPAY_NTERMS; t += TP_CAND_WARPS) {
+            double a = 0.0;
+            for (int i = lane; i < N; i += 32) a += tmp[i * TOPAY_NTERMS + t];
+            a = tp_warp_sum(a);
+            if (lane == 0) sTerm[t] = a;
         }
-        st.final_xy[0] = fx - S.end_xy[cand * 2];
-        st.final_xy[1] = fy - S.end_xy[cand * 2 + 1];
-        // mean-time penalty (:1752-1769, hard-coded 0.5 / 2.0) — stage 2 only
-        double avg_time = 0.0;
-        for (int i = 0; i < N; i++) avg_time += Tg[i];
-        avg_time /= N;
-        double mt_all = 0.0;
-        if (stage == 2) {
-            const double w_mt = P.opt.s2_mean_time_weight;
+        __syncthreads();
+        if (tid == 0) {
+            // end point, VecTrajFinalXY order (:1750); stage-1 path cost (:1173-1178)
+            double fx = S.start_xy[cand * 2], fy = S.start_xy[cand * 2 + 1];
+            double cost_path = 0.0, avg = 0.0;
+            const double* tgt = S.init_inner_xy + (size_t)cand * S.max_pieces * 2;
             for (int i = 0; i < N; i++) {
-                const double ti = Tg[i];
-                if (ti < avg_time * 0.5) {
-                    terms[TOPAY_TERM_MEAN_TIME] += w_mt * (ti - avg_time * 0.5) * (ti - avg_time * 0.5);
-                    mt_all += w_mt * 2.0 * (ti - avg_time * 0.5) * (-0.5 / N);
-                }
-                if (ti > avg_time * 2.0) {
-                    terms[TOPAY_TERM_MEAN_TIME] += w_mt * (ti - avg_time * 2.0) * (ti - avg_time * 2.0);
-                    mt_all += w_mt * 2.0 * (ti - avg_time * 2.0) * (-2.0 / N);
+                fx += sTot[2 * i];
+                fy += sTot[2 * i + 1];
+                avg += sT[i];
+                if (stage == 1) {
+                    const double ex = fx - tgt[2 * i], ey = fy - tgt[2 * i + 1];
+                    cost_path += P.opt.s1_path_pos_weight * (ex * ex + ey * ey);
                 }
             }
+            const double tsum = avg;
+            avg /= N;
+            // mean-time penalty (:1752-1769, hard-coded 0.5 / 2.0) — stage 2 only
+            double mt_all = 0.0, mt_cost = 0.0;
+            if (stage == 2) {
+                const double w_mt = P.opt.s2_mean_time_weight;
+                for (int i = 0; i < N; i++) {
+                    const double ti = sT[i];
+                    if (ti < avg * 0.5) {
+                        mt_cost += w_mt * (ti - avg * 0.5) * (ti - avg * 0.5);
+                        mt_all += w_mt * 2.0 * (ti - avg * 0.5) * (-0.5 / N);
+                    }
+                    if (ti > avg * 2.0) {
+                        mt_cost += w_mt * (ti - avg * 2.0) * (ti - avg * 2.0);
+                        mt_all += w_mt * 2.0 * (ti - avg * 2.0) * (-2.0 / N);
+                    }
+                }
+            }
+            sMisc[0] = fx - S.end_xy[cand * 2];
+            sMisc[1] = fy - S.end_xy[cand * 2 + 1];
+            sMisc[2] = cost_path;
+            sMisc[3] = avg;
+            sMisc[4] = tsum;
+            sMisc[5] = mt_all;
+            sMisc[6] = mt_cost;
+        }
+        __syncthreads();
+        st.final_xy[0] = sMisc[0];
+        st.final_xy[1] = sMisc[1];
+        const double avg_time = sMisc[3], tsum = sMisc[4], mt_all = sMisc[5];
+        double terms[TOPAY_NTERMS];
+        for (int t = 0; t < TOPAY_NTERMS; t++) terms[t] = sTerm[t];
+        if (stage == 2) {
+            terms[TOPAY_TERM_MEAN_TIME] += sMisc[6];
             terms[TOPAY_TERM_ENDP] =
                 0.5 * (st.rho[0] * (st.final_xy[0] + st.lambda[0] / st.rho[0]) * (st.final_xy[0] + st.lambda[0] / st.rho[0]) +
                        st.rho[1] * (st.final_xy[1] + st.lambda[1] / st.rho[1]) * (st.final_xy[1] + st.lambda[1] / st.rho[1]));
         } else {
-            terms[TOPAY_TERM_ENDP] = cost_path;
+            terms[TOPAY_TERM_ENDP] = sMisc[2];
         }
         double pen = 0.0;
         bool bad = false;
@@ -705,32 +786,30 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         }
         if (stage == 1) bad = false;          // the guard exists in stage 2 only (:1790-1807)
         if (bad) pen = 1.0e+22;
-        // gdC = jerk part (minco.hpp:951-977) + penalty part -> wk ; jerk cost (:923-942)
-        double jerk = 0.0;
-        {
-            double js = 0.0;
-            for (int i = lane; i < N; i += 32) {
-                const double t1 = Tg[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
-                const double *c3 = cf + (6 * i + 3) * 9, *c4 = c3 + 9, *c5 = c4 + 9;
-                double d33 = 0, d43 = 0, d44 = 0, d53 = 0, d54 = 0, d55 = 0;
-                for (int d = 0; d < 9; d++) {
-                    const double w = P.opt.energy_weights[d];
-                    d33 += (c3[d] * w) * c3[d];
-                    d43 += (c4[d] * w) * c3[d];
-                    d44 += (c4[d] * w) * c4[d];
-                    d53 += (c5[d] * w) * c3[d];
-                    d54 += (c5[d] * w) * c4[d];
-                    d55 += (c5[d] * w) * c5[d];
-                }
-                js += 36.0 * d33 * t1 + 144.0 * d43 * t2 + 192.0 * d44 * t3 + 240.0 * d53 * t3 + 720.0 * d54 * t4 +
-                      720.0 * d55 * t5;
-                // gdT jerk part, kept in wk's tail for the moment: written below
+        // jerk cost (minco.hpp:923-942)
+        double js[1] = {0.0};
+        for (int i = tid; i < N; i += TP_CAND_THREADS) {
+            const double t1 = sT[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
+            const double *c3 = cf + (6 * i + 3) * 9, *c4 = c3 + 9, *c5 = c4 + 9;
+            double d33 = 0, d43 = 0, d44 = 0, d53 = 0, d54 = 0, d55 = 0;
+            for (int d = 0; d < 9; d++) {
+                const double w = P.opt.energy_weights[d];
+                d33 += (c3[d] * w) * c3[d];
+                d43 += (c4[d] * w) * c3[d];
+                d44 += (c4[d] * w) * c4[d];
+                d53 += (c5[d] * w) * c3[d];
+                d54 += (c5[d] * w) * c4[d];
+                d55 += (c5[d] * w) * c5[d];
             }
-            jerk = tp_warp_sum(js);
+            js[0] += 36.0 * d33 * t1 + 144.0 * d43 * t2 + 192.0 * d44 * t3 + 240.0 * d53 * t3 + 720.0 * d54 * t4 +
+                     720.0 * d55 * t5;
         }
-        for (int e = lane; e < n6 * 9; e += 32) {
+        tp_block_sum<1>(js, red, flip);
+        const double jerk = js[0];
+        // gdC = jerk part (minco.hpp:951-977) + penalty part -> wk
+        for (int e = tid; e < n6 * 9; e += TP_CAND_THREADS) {
             const int r = e / 9, d = e % 9, i = r / 6, q = r % 6;
-            const double t1 = Tg[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
+            const double t1 = sT[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
             const double w = P.opt.energy_weights[d];
             const double c3 = cf[(6 * i + 3) * 9 + d], c4 = cf[(6 * i + 4) * 9 + d], c5 = cf[(6 * i + 5) * 9 + d];
             double v = 0.0;
@@ -739,8 +818,9 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             else if (q == 3) v = 72.0 * c3 * w * t1 + 144.0 * c4 * w * t2 + 240.0 * c5 * w * t3;
             wk[e] = v + (bad ? 0.0 : gdCp[e]);
         }
-        __syncwarp();
-        tp_lu_solve_adj(n6, lu, wk, lane);
+        __syncthreads();
+        if (warp < 3) tp_lu_subst_adj(n6, lu, wk, 3 * warp, lane);
+        __syncthreads();
         // gradients w.r.t. the variables (:939-948) with calGradCTtoQT's gdT part (minco.hpp:1016-1067)
         const double tw = stage == 1 ? P.opt.s1_time_weight : P.opt.s2_time_weight;
         const double* Tau = x;
@@ -749,10 +829,8 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         double* gTheta = g + N;
         double* gArc = gTheta + (N - 1);
         double* gVq = gArc + N;
-        double tsum = 0.0;
-        for (int i = 0; i < N; i++) tsum += Tg[i];
-        for (int i = lane; i < N; i += 32) {
-            const double t1 = Tg[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2;
+        for (int i = tid; i < N; i += TP_CAND_THREADS) {
+            const double t1 = sT[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2;
             const double *c1 = cf + (6 * i + 1) * 9, *c2 = c1 + 9, *c3 = c2 + 9, *c4 = c3 + 9, *c5 = c4 + 9;
             double d33 = 0, d43 = 0, d44 = 0, d53 = 0, d54 = 0, d55 = 0;
             for (int d = 0; d < 9; d++) {
@@ -805,11 +883,11 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                 gArc[N - 1] = wk[(6 * N - 3) * 9 + 1];   // gdP_tail(1, 0)
             }
         }
-        __syncwarp();
+        __syncthreads();
         terms[TOPAY_TERM_JERK] = jerk;
         terms[TOPAY_TERM_TIME] = tw * tsum;
         f_eval = jerk + pen + tw * tsum;
-        if (lane == 0) {
+        if (tid == 0) {
             S.f[cand] = f_eval;
             for (int t = 0; t < TOPAY_NTERMS; t++) S.term_out[(size_t)cand * TOPAY_NTERMS + t] = terms[t];
         }
@@ -823,9 +901,19 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         double* lm_s = S.lm_s + (size_t)cand * S.mem * S.xs;
         double* lm_y = S.lm_y + (size_t)cand * S.mem * S.xs;
         double* lm_ys = S.lm_ys + (size_t)cand * S.mem;
-        double* lm_alpha = S.lm_alpha + (size_t)cand * S.mem;
+        // this thread's elements of the five vectors
+        double rx[TP_EPT], rg[TP_EPT], rxp[TP_EPT], rgp[TP_EPT], rd[TP_EPT];
+#pragma unroll
+        for (int e = 0; e < TP_EPT; e++) {
+            const int i = tid + e * TP_CAND_THREADS;
+            const bool in = i < n;
+            rx[e] = in ? x[i] : 0.0;
+            rg[e] = in ? g[i] : 0.0;
+            rxp[e] = in ? xp[i] : 0.0;
+            rgp[e] = in ? gp[i] : 0.0;
+            rd[e] = in ? dv[i] : 0.0;
+        }
         int ret = 0;
-        // what happens after the evaluation that just completed
         enum { A_NONE, A_BEGIN_LS, A_LS_DONE, A_FINISH } action = A_NONE;
         const double f = f_eval;
         if (st.ls_init) {
@@ -833,15 +921,23 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             st.ls_init = 0;
             st.fx = f;
             st.pf[0] = f;
-            for (int i = lane; i < n; i += 32) dv[i] = -g[i];
-            __syncwarp();
-            const double gn = tp_absmax(g, n, lane), xn = tp_absmax(x, n, lane);
+            double gm = 0.0, xm = 0.0, dd[1] = {0.0};
+#pragma unroll
+            for (int e = 0; e < TP_EPT; e++) {
+                rd[e] = -rg[e];
+                gm = fmax(gm, fabs(rg[e]));
+                xm = fmax(xm, fabs(rx[e]));
+                dd[0] += rd[e] * rd[e];
+            }
+            gm = tp_block_max(gm, red, flip);
+            xm = tp_block_max(xm, red, flip);
             st.k = 0;
-            if (gn / fmax(1.0, xn) < lp.g_epsilon) {
+            if (gm / fmax(1.0, xm) < lp.g_epsilon) {
                 ret = TOPAY_LBFGS_CONVERGENCE;
                 action = A_FINISH;
             } else {
-                st.stp = 1.0 / sqrt(tp_dot(dv, dv, n, lane));
+                tp_block_sum<1>(dd, red, flip);
+                st.stp = 1.0 / sqrt(dd[0]);
                 st.k = 1;
                 st.end = 0;
                 st.bound = 0;
@@ -862,7 +958,11 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     st.nu = st.stp;
                     st.brackt = 1;
                 } else {
-                    if (tp_dot(g, dv, n, lane) < st.dstest)
+                    double gs_[1] = {0.0};
+#pragma unroll
+                    for (int e = 0; e < TP_EPT; e++) gs_[0] += rg[e] * rd[e];
+                    tp_block_sum<1>(gs_, red, flip);
+                    if (gs_[0] < st.dstest)
                         st.mu = st.stp;
                     else
                         done = true;
@@ -896,30 +996,48 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             }
             if (fail) {
                 // lbfgs.hpp:575-582: revert to the previous point
-                for (int i = lane; i < n; i += 32) {
-                    x[i] = xp[i];
-                    g[i] = gp[i];
+#pragma unroll
+                for (int e = 0; e < TP_EPT; e++) {
+                    rx[e] = rxp[e];
+                    rg[e] = rgp[e];
                 }
-                __syncwarp();
                 action = A_FINISH;
             } else if (done) {
                 action = A_LS_DONE;
             } else {
-                for (int i = lane; i < n; i += 32) x[i] = xp[i] + st.stp * dv[i];
-                __syncwarp();
+#pragma unroll
+                for (int e = 0; e < TP_EPT; e++) rx[e] = rxp[e] + st.stp * rd[e];
             }
         }
         if (action == A_LS_DONE) {
             // lbfgs.hpp:584-715
             const int k = st.k;
             bool fin = false;
+            if (S.trace && tid == 0) {   // where the reference calls proc_progress (:585-592)
+                const int tl = S.trace_len[cand];
+                if (tl < S.trace_cap) {
+                    double* tr = S.trace + ((size_t)cand * S.trace_cap + tl) * 4;
+                    tr[0] = st.fx;
+                    tr[1] = st.stp;
+                    tr[2] = (double)k;
+                    tr[3] = (double)st.ls_count;
+                    S.trace_len[cand] = tl + 1;
+                }
+            }
             if (stage == 2 && k > lp.max_iterations) {   // progress callback earlyExit, :1873
                 ret = TOPAY_LBFGS_CANCELED;
                 fin = true;
             }
-            if (!fin) {
-                const double gn = tp_absmax(g, n, lane), xn = tp_absmax(x, n, lane);
-                if (gn / fmax(1.0, xn) < lp.g_epsilon) {
+            if (!fin && lp.g_epsilon > 0.0) {
+                double gm = 0.0, xm = 0.0;
+#pragma unroll
+                for (int e = 0; e < TP_EPT; e++) {
+                    gm = fmax(gm, fabs(rg[e]));
+                    xm = fmax(xm, fabs(rx[e]));
+                }
+                gm = tp_block_max(gm, red, flip);
+                xm = tp_block_max(xm, red, flip);
+                if (gm / fmax(1.0, xm) < lp.g_epsilon) {
                     ret = TOPAY_LBFGS_CONVERGENCE;
                     fin = true;
                 }
@@ -944,47 +1062,106 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                 st.k = k + 1;
                 double* se = lm_s + (size_t)st.end * S.xs;
                 double* ye = lm_y + (size_t)st.end * S.xs;
-                double ys = 0.0, yy = 0.0, ss = 0.0, gg = 0.0;
-                for (int i = lane; i < n; i += 32) {
-                    const double sv = x[i] - xp[i], yv = g[i] - gp[i];
-                    se[i] = sv;
-                    ye[i] = yv;
-                    ys += yv * sv;
-                    yy += yv * yv;
-                    ss += sv * sv;
-                    gg += gp[i] * gp[i];
-                    dv[i] = -g[i];
+                double q4[4] = {0.0, 0.0, 0.0, 0.0};   // ys, yy, ss, gg
+#pragma unroll
+                for (int e = 0; e < TP_EPT; e++) {
+                    const int i = tid + e * TP_CAND_THREADS;
+                    const double sv = rx[e] - rxp[e], yv = rg[e] - rgp[e];
+                    if (i < n) {
+                        se[i] = sv;
+                        ye[i] = yv;
+                    }
+                    q4[0] += yv * sv;
+                    q4[1] += yv * yv;
+                    q4[2] += sv * sv;
+                    q4[3] += rgp[e] * rgp[e];
+                    rd[e] = -rg[e];
                 }
-                ys = tp_warp_sum(ys);
-                yy = tp_warp_sum(yy);
-                ss = tp_warp_sum(ss);
-                gg = tp_warp_sum(gg);
-                if (lane == 0) lm_ys[st.end] = ys;
-                __syncwarp();
-                const double cau = ss * sqrt(gg) * lp.cautious_factor;
+                for (int j = tid; j < m; j += TP_CAND_THREADS) s_ys[j] = lm_ys[j];
+                tp_block_sum<4>(q4, red, flip);
+                const double ys = q4[0], yy = q4[1];
+                if (tid == 0) {
+                    lm_ys[st.end] = ys;
+                    s_ys[st.end] = ys;
+                }
+                const double cau = q4[2] * sqrt(q4[3]) * lp.cautious_factor;
                 if (ys > cau) {
                     st.bound = st.bound + 1 < m ? st.bound + 1 : m;
                     st.end = (st.end + 1) % m;
+                    __syncthreads();   // s_ys / the new history row are visible
+                    // two-loop recursion (lbfgs.hpp:691-710); rows prefetched one step ahead
                     int j = st.end;
-                    for (int i = 0; i < st.bound; ++i) {
+                    double ps[TP_EPT], py[TP_EPT];
+                    {
+                        const int j0 = (j + m - 1) % m;
+#pragma unroll
+                        for (int e = 0; e < TP_EPT; e++) {
+                            const int i = tid + e * TP_CAND_THREADS;
+                            ps[e] = i < n ? lm_s[(size_t)j0 * S.xs + i] : 0.0;
+                            py[e] = i < n ? lm_y[(size_t)j0 * S.xs + i] : 0.0;
+                        }
+                    }
+                    for (int it = 0; it < st.bound; ++it) {
                         j = (j + m - 1) % m;
-                        const double* sj = lm_s + (size_t)j * S.xs;
-                        const double* yj = lm_y + (size_t)j * S.xs;
-                        const double al = tp_dot(sj, dv, n, lane) / lm_ys[j];
-                        if (lane == 0) lm_alpha[j] = al;
-                        for (int t = lane; t < n; t += 32) dv[t] += (-al) * yj[t];
-                        __syncwarp();
+                        double cs[TP_EPT], cy[TP_EPT];
+#pragma unroll
+                        for (int e = 0; e < TP_EPT; e++) {
+                            cs[e] = ps[e];
+                            cy[e] = py[e];
+                        }
+                        if (it + 1 < st.bound) {
+                            const int jn = (j + m - 1) % m;
+#pragma unroll
+                            for (int e = 0; e < TP_EPT; e++) {
+                                const int i = tid + e * TP_CAND_THREADS;
+                                ps[e] = i < n ? lm_s[(size_t)jn * S.xs + i] : 0.0;
+                                py[e] = i < n ? lm_y[(size_t)jn * S.xs + i] : 0.0;
+                            }
+                        }
+                        double a1[1] = {0.0};
+#pragma unroll
+                        for (int e = 0; e < TP_EPT; e++) a1[0] += cs[e] * rd[e];
+                        tp_block_sum<1>(a1, red, flip);
+                        const double al = a1[0] / s_ys[j];
+                        if (tid == 0) s_alpha[j] = al;
+#pragma unroll
+                        for (int e = 0; e < TP_EPT; e++) rd[e] += (-al) * cy[e];
                     }
                     const double sc = ys / yy;
-                    for (int t = lane; t < n; t += 32) dv[t] *= sc;
-                    __syncwarp();
-                    for (int i = 0; i < st.bound; ++i) {
-                        const double* sj = lm_s + (size_t)j * S.xs;
-                        const double* yj = lm_y + (size_t)j * S.xs;
-                        const double beta = tp_dot(yj, dv, n, lane) / lm_ys[j];
-                        const double a = lm_alpha[j] - beta;
-                        for (int t = lane; t < n; t += 32) dv[t] += a * sj[t];
-                        __syncwarp();
+#pragma unroll
+                    for (int e = 0; e < TP_EPT; e++) rd[e] *= sc;
+                    __syncthreads();   // s_alpha complete
+                    {
+#pragma unroll
+                        for (int e = 0; e < TP_EPT; e++) {
+                            const int i = tid + e * TP_CAND_THREADS;
+                            ps[e] = i < n ? lm_s[(size_t)j * S.xs + i] : 0.0;
+                            py[e] = i < n ? lm_y[(size_t)j * S.xs + i] : 0.0;
+                        }
+                    }
+                    for (int it = 0; it < st.bound; ++it) {
+                        double cs[TP_EPT], cy[TP_EPT];
+#pragma unroll
+                        for (int e = 0; e < TP_EPT; e++) {
+                            cs[e] = ps[e];
+                            cy[e] = py[e];
+                        }
+                        if (it + 1 < st.bound) {
+                            const int jn = (j + 1) % m;
+#pragma unroll
+                            for (int e = 0; e < TP_EPT; e++) {
+                                const int i = tid + e * TP_CAND_THREADS;
+                                ps[e] = i < n ? lm_s[(size_t)jn * S.xs + i] : 0.0;
+                                py[e] = i < n ? lm_y[(size_t)jn * S.xs + i] : 0.0;
+                            }
+                        }
+                        double b1[1] = {0.0};
+#pragma unroll
+                        for (int e = 0; e < TP_EPT; e++) b1[0] += cy[e] * rd[e];
+                        tp_block_sum<1>(b1, red, flip);
+                        const double a = s_alpha[j] - b1[0] / s_ys[j];
+#pragma unroll
+                        for (int e = 0; e < TP_EPT; e++) rd[e] += a * cs[e];
                         j = (j + 1) % m;
                     }
                 }
@@ -994,11 +1171,11 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         }
         if (action == A_BEGIN_LS) {
             // lbfgs.hpp:558-573 and line search prologue :288-311
-            for (int i = lane; i < n; i += 32) {
-                xp[i] = x[i];
-                gp[i] = g[i];
+#pragma unroll
+            for (int e = 0; e < TP_EPT; e++) {
+                rxp[e] = rx[e];
+                rgp[e] = rg[e];
             }
-            __syncwarp();
             st.ls_count = 0;
             st.brackt = 0;
             st.touched = 0;
@@ -1008,7 +1185,11 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                 ret = TOPAY_LBFGSERR_INVALIDPARAMETERS;
                 action = A_FINISH;
             } else {
-                const double dginit = tp_dot(gp, dv, n, lane);
+                double dg[1] = {0.0};
+#pragma unroll
+                for (int e = 0; e < TP_EPT; e++) dg[0] += rgp[e] * rd[e];
+                tp_block_sum<1>(dg, red, flip);
+                const double dginit = dg[0];
                 if (0.0 < dginit) {
                     ret = TOPAY_LBFGSERR_INCREASEGRADIENT;
                     action = A_FINISH;
@@ -1016,8 +1197,8 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     st.finit = st.fx;
                     st.dgtest = lp.f_dec_coeff * dginit;
                     st.dstest = lp.s_curv_coeff * dginit;
-                    for (int i = lane; i < n; i += 32) x[i] = xp[i] + st.stp * dv[i];
-                    __syncwarp();
+#pragma unroll
+                    for (int e = 0; e < TP_EPT; e++) rx[e] = rxp[e] + st.stp * rd[e];
                 }
             }
         }
@@ -1069,19 +1250,39 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             }
             need_eval = st.phase != 0;
         }
+        // write this thread's elements back
+#pragma unroll
+        for (int e = 0; e < TP_EPT; e++) {
+            const int i = tid + e * TP_CAND_THREADS;
+            if (i < n) {
+                x[i] = rx[e];
+                g[i] = rg[e];
+                xp[i] = rxp[e];
+                gp[i] = rgp[e];
+                dv[i] = rd[e];
+            }
+        }
+        __syncthreads();
     }
 
     // ================= generate half of the next evaluation =================
     if ((mode & TP_MODE_GEN) && need_eval) {
-        for (int i = lane; i < N; i += 32) Tg[i] = tp_expC2(x[i]);
-        __syncwarp();
-        tp_fill_system(N, Tg, S.head_pva + (size_t)cand * 27, S.tail_pva + (size_t)cand * 27, x, P, lu, cf, lane);
-        tp_lu_solve(n6, lu, cf, lane);
-        for (int e = lane; e < n6 * TP_BAND; e += 32) lug[e] = lu[e];
-        for (int e = lane; e < n6 * 9; e += 32) cg[e] = cf[e];
+        double* sT = s_small;
+        for (int i = tid; i < N; i += TP_CAND_THREADS) {
+            const double t = tp_expC2(x[i]);
+            sT[i] = t;
+            Tg[i] = t;
+        }
+        __syncthreads();
+        tp_fill_system(N, sT, S.head_pva + (size_t)cand * 27, S.tail_pva + (size_t)cand * 27, x, P, lu, cf);
+        if (warp == 0) tp_lu_factor(n6, lu, lane);
+        __syncthreads();
+        if (warp < 3) tp_lu_subst(n6, lu, cf, 3 * warp, lane);
+        __syncthreads();
+        for (int e = tid; e < n6 * TP_BAND; e += TP_CAND_THREADS) lug[e] = lu[e];
+        for (int e = tid; e < n6 * 9; e += TP_CAND_THREADS) cg[e] = cf[e];
     }
-    __syncwarp();
-    if (lane == 0) {
+    if (tid == 0) {
         *gs = st;
         if (st.phase != 0 && (mode & TP_MODE_GEN)) {
             atomicAdd(S.n_active + slot, 1);

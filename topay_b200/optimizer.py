@@ -133,6 +133,17 @@ class MomaTrajOpt:
         N = int(r["piece_num"][idx])
         return MomaTraj(r["T"][idx, :N].copy(), r["coeff"][idx, :6 * N].copy(), self._starts[idx])
 
+    def set_trace(self, cap):
+        _lib.check(self._l.topay_solver_set_trace(self.h, cap), "topay_solver_set_trace")
+        self._trace_cap = cap
+
+    def trace(self, cand):
+        """(m, 4) array: f, step, k, ls of every accepted L-BFGS iteration of candidate `cand`."""
+        out = np.zeros((self._trace_cap, 4))
+        n = C.c_int32()
+        _lib.check(self._l.topay_solver_download_trace(self.h, cand, _p(out), self._trace_cap, C.byref(n)), "trace")
+        return out[:n.value].copy()
+
     def stats(self):
         s = SolverStats()
         self._l.topay_solver_last_stats(self.h, C.byref(s))
