@@ -54,15 +54,15 @@ void hh_query2d(const TpGrid* g, int which, const double* pos, int64_t n, double
 
 void hh_fk(const TpParams* P, const double* pos10, double* pts36) {
     TpFK fk;
-    double pts[TOPAY_NSPHERE][3];
+    TpSphereStoreLocal pts;
     tp_fk(*P, pos10, fk, pts);
-    std::memcpy(pts36, pts, sizeof(pts));
+    std::memcpy(pts36, pts.a, sizeof(pts.a));
 }
 void hh_fk_adjoint(const TpParams* P, const double* pos10, const double* g36, double* out10) {
     TpFK fk;
-    double pts[TOPAY_NSPHERE][3], g[TOPAY_NSPHERE][3];
+    TpSphereStoreLocal pts, g;
     tp_fk(*P, pos10, fk, pts);
-    std::memcpy(g, g36, sizeof(g));
+    std::memcpy(g.a, g36, sizeof(g.a));
     tp_fk_adjoint(*P, fk, g, out10);
 }
 
@@ -120,8 +120,10 @@ void hh_penalty_eval(const TpParams* Pp, const TpGrid* Gp, int stage, int N, con
             TpNodeOut o;
             if (stage == 1)
                 tp_node_stage1(P, c, T[i], K, 2 * jn, o, b0, b1, b2);
-            else
-                tp_node_stage2(P, G, c, T[i], K, 2 * jn, xy, o, b0, b1, b2);
+            else {
+                TpSphereStoreLocal pts, pg;
+                tp_node_stage2(P, G, c, T[i], K, 2 * jn, xy, o, b0, b1, b2, pts, pg);
+            }
             for (int k = 0; k < 6; k++)
                 for (int d = 0; d < 9; d++)
                     gdC[((size_t)6 * i + k) * 9 + d] += b0[k] * o.G0[d] + b1[k] * o.G1[d] + b2[k] * o.G2[d];

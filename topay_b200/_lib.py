@@ -11,7 +11,7 @@ import subprocess
 from ._structs import GridDesc, OptParams, ProblemBatch, ResultBatch, RobotParams, SolverStats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libtopay_b200.so")
+SO_PATH = os.environ.get("TOPAY_B200_LIB", os.path.join(_HERE, "libtopay_b200.so"))
 
 OK, ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_ALLOC, ERR_TOO_LARGE, ERR_NOT_READY = 0, -1, -2, -3, -4, -5, -6
 

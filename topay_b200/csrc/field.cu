@@ -274,17 +274,18 @@ __global__ void k_whole_body(TpGrid g, TpParams P, const double* __restrict__ st
         double pos[10];
         for (int k = 0; k < 10; k++) pos[k] = s[k];
         TpFK fk;
-        double pts[TOPAY_NSPHERE][3];
+        TpSphereStoreLocal pts;
         tp_fk(P, pos, fk, pts);
         for (int a = 0; a < P.n_sphere && !hit; a++) {
             const double r = P.sphere_r[a];
-            if (!tp_in_map3(g, pts[a]) || tp_distance3d(g, pts[a]) < r) hit = true;
-            if (a > 2 && pts[a][2] < rp.chassis_height + r) {
-                const double dx = pts[a][0] - s[0], dy = pts[a][1] - s[1];
+            const double pa[3] = {pts.at(a, 0), pts.at(a, 1), pts.at(a, 2)};
+            if (!tp_in_map3(g, pa) || tp_distance3d(g, pa) < r) hit = true;
+            if (a > 2 && pa[2] < rp.chassis_height + r) {
+                const double dx = pa[0] - s[0], dy = pa[1] - s[1];
                 if (sqrt(dx * dx + dy * dy) < rp.chassis_colli_radius + r) hit = true;
             }
             for (int b = a + 1; b < P.n_sphere; b++) {
-                const double dx = pts[a][0] - pts[b][0], dy = pts[a][1] - pts[b][1], dz = pts[a][2] - pts[b][2];
+                const double dx = pa[0] - pts.at(b, 0), dy = pa[1] - pts.at(b, 1), dz = pa[2] - pts.at(b, 2);
                 if (sqrt(dx * dx + dy * dy + dz * dz) < r + P.sphere_r[b] && ((P.pair_mask[a] >> b) & 1u)) hit = true;
             }
         }

@@ -44,6 +44,7 @@ struct TpParams {
     double  sphere_off[TOPAY_NSPHERE];     // offset along the frame's z axis
     double  sphere_r[TOPAY_NSPHERE];
     int32_t n_sphere;
+    int32_t slot_sphere[2 * (TOPAY_DOF + 1)];  // sphere index of (frame i, slot j) or -1
     uint32_t pair_mask[TOPAY_NSPHERE];     // bit c2 set => pair (c, c2), c2 > c, is checked
 };
 
@@ -57,8 +58,10 @@ TP_HD void tp_derive_params(TpParams& p) {
     int n = 0;
     for (int i = 0; i < TOPAY_DOF + 1; i++)
         for (int j = 0; j < 2; j++) {
+            p.slot_sphere[i * 2 + j] = -1;
             if (p.robot.colli_points[i * 2 + j] == 0.0) continue;
             if (n < TOPAY_NSPHERE) {
+                p.slot_sphere[i * 2 + j] = n;
                 p.sphere_frame[n] = i;
                 p.sphere_off[n] = p.robot.colli_points[i * 2 + j];
                 p.sphere_r[n] = p.robot.colli_point_radius[i * 2 + j];

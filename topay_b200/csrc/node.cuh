@@ -24,9 +24,12 @@ TP_HD void tp_basis(double s1, double* b0, double* b1, double* b2, double* b3) {
 
 // c is the 6 x 9 coefficient block of one piece, row k = coefficient of t^k.
 // out[d] = sum_k c[k][d] * b[k] for d in [d0, d1).
-TP_HD void tp_rows(const double* c, const double* b, int d0, int d1, double* out) {
-    for (int d = d0; d < d1; d++) {
+template <int D0, int D1>
+TP_HD void tp_rows(const double* c, const double* b, double* out) {
+#pragma unroll
+    for (int d = D0; d < D1; d++) {
         double s = 0.0;
+#pragma unroll
         for (int k = 0; k < 6; k++) s += c[k * 9 + d] * b[k];
         out[d] = s;
     }
@@ -41,9 +44,9 @@ struct TpSlot {
 TP_HD void tp_slot(const double* c, double t, TpSlot& o, double* b0, double* b1, double* b2) {
     tp_basis(t, b0, b1, b2, nullptr);
     double st[2], d1[2], d2[2];
-    tp_rows(c, b0, 0, 2, st);
-    tp_rows(c, b1, 0, 2, d1);
-    tp_rows(c, b2, 0, 2, d2);
+    tp_rows<0, 2>(c, b0, st);
+    tp_rows<0, 2>(c, b1, d1);
+    tp_rows<0, 2>(c, b2, d2);
     o.sy = sin(st[0]);
     o.cy = cos(st[0]);
     o.dth = d1[0];
@@ -62,6 +65,7 @@ TP_HD void tp_chain_slot(const TpSlot& s, const double* b0, const double* b1, do
     const double coeff = step / 6.0;
     const double alpha = 1.0 / (2 * K) * j;
     const int int_6K = 6 * K;
+#pragma unroll
     for (int k = 0; k < 6; k++) {
         const double xth = (-s.ds * b0[k] * s.sy) * coeff;
         const double xar = (b1[k] * s.cy) * coeff;
@@ -84,9 +88,11 @@ struct TpNodeOut {
 };
 
 TP_HD void tp_node_clear(TpNodeOut& o) {
+#pragma unroll
     for (int d = 0; d < 9; d++) o.G0[d] = o.G1[d] = o.G2[d] = 0.0;
     o.gdT = 0.0;
     o.gx = o.gy = 0.0;
+#pragma unroll
     for (int t = 0; t < TOPAY_NTERMS; t++) o.terms[t] = 0.0;
 }
 
@@ -96,8 +102,10 @@ TP_HD void tp_base_limits(const TpParams& P, double w_m, double w_a, double w_dw
                           double real_alpha, const double* dst, const double* d2st, const double* d3st,
                           TpNodeOut& o) {
     const topay_robot_params& rp = P.robot;
+#pragma unroll
     for (int half = 0; half < 2; half++) {
         const double sw = half == 0 ? 1.0 : -1.0;   // sign of the max_w term
+#pragma unroll
         for (int omg_sym = -1; omg_sym <= 1; omg_sym += 2) {
             const double v = omg_sym * rp.max_v * dst[0] + sw * rp.max_w * dst[1] - rp.max_v * rp.max_w;
             if (v > 0) {
@@ -139,9 +147,9 @@ TP_HD void tp_node_stage1(const TpParams& P, const double* c, double T, int K, i
     const double t = j * (step / 2.0);
     tp_basis(t, b0, b1, b2, b3);
     double dst[2], d2st[2], d3st[2];
-    tp_rows(c, b1, 0, 2, dst);
-    tp_rows(c, b2, 0, 2, d2st);
-    tp_rows(c, b3, 0, 2, d3st);
+    tp_rows<0, 2>(c, b1, dst);
+    tp_rows<0, 2>(c, b2, d2st);
+    tp_rows<0, 2>(c, b3, d3st);
     const double omg = (j == 0 || j == 2 * K) ? 0.5 : 1.0;
     const double real_alpha = 1.0 / K * ((double)j / 2.0);
     tp_node_clear(o);
@@ -150,9 +158,12 @@ TP_HD void tp_node_stage1(const TpParams& P, const double* c, double T, int K, i
 }
 
 // Stage-2 penalty node (even j), moma_traj_opt.cpp:1261-1713. xy is the Simpson
-// prefix position CurrentXY at this node.
+// prefix position CurrentXY at this node. pts / pg are per-thread sphere stores (centres and
+// their gradients).
+template <class Store>
 TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, double T, int K, int j,
-                          const double* xy, TpNodeOut& o, double* b0, double* b1, double* b2) {
+                          const double* xy, TpNodeOut& o, double* b0, double* b1, double* b2, Store& pts,
+                          Store& pg) {
     const topay_robot_params& rp = P.robot;
     const topay_opt_params& op = P.opt;
     double b3[6];
@@ -160,10 +171,10 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
     const double t = j * (step / 2.0);
     tp_basis(t, b0, b1, b2, b3);
     double st[9], dst[9], d2st[9], d3st[9];
-    tp_rows(c, b0, 0, 9, st);
-    tp_rows(c, b1, 0, 9, dst);
-    tp_rows(c, b2, 0, 9, d2st);
-    tp_rows(c, b3, 0, 9, d3st);
+    tp_rows<0, 9>(c, b0, st);
+    tp_rows<0, 9>(c, b1, dst);
+    tp_rows<0, 9>(c, b2, d2st);
+    tp_rows<0, 9>(c, b3, d3st);
     const double omg = (j == 0 || j == 2 * K) ? 0.5 : 1.0;
     const double real_alpha = 1.0 / K * ((double)j / 2.0);
     tp_node_clear(o);
@@ -191,62 +202,80 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
     pos[0] = xy[0];
     pos[1] = xy[1];
     pos[2] = st[0];
+#pragma unroll
     for (int q = 0; q < TOPAY_DOF; q++) pos[3 + q] = st[2 + q];
     TpFK fk;
-    double pts[TOPAY_NSPHERE][3];
     tp_fk(P, pos, fk, pts);
-    double pg[TOPAY_NSPHERE][3];
     const double cost_scale = 10.0;
     const double w_mc = op.s2_mani_colli_weight, w_sc = op.s2_self_colli_weight;
+    // sphere vs the 3-D field (:1477-1520) and vs the chassis top (:1525-1564)
     for (int ci = 0; ci < P.n_sphere; ci++) {
+        const double pc[3] = {pts.at(ci, 0), pts.at(ci, 1), pts.at(ci, 2)};
         double sdf, gp[3];
-        tp_query3d(g, pts[ci], sdf, gp);
+        tp_query3d(g, pc, sdf, gp);
         const double v = P.sphere_r[ci] * cost_scale * 1.1 - sdf * cost_scale;
-        pg[ci][0] = pg[ci][1] = pg[ci][2] = 0.0;
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
         if (v > 0) {
             double f, df;
             tp_smoothL1(P, v, f, df);
-            for (int d = 0; d < 3; d++) pg[ci][d] = -omg * step * w_mc * df * gp[d] * cost_scale;
+            const double k = -omg * step * w_mc * df;
+            g0 = k * gp[0] * cost_scale;
+            g1 = k * gp[1] * cost_scale;
+            g2 = k * gp[2] * cost_scale;
             o.gdT += omg * w_mc * (f / K);
             o.terms[TOPAY_TERM_MANI_COLLI] += omg * step * w_mc * f;
         }
-    }
-    for (int ci = 0; ci < P.n_sphere; ci++) {
-        if (ci > 2) {  // sphere vs chassis top (:1525-1564)
-            const double height = rp.chassis_height + rp.relative_t[2] + P.sphere_r[ci] - pts[ci][2];
+        if (ci > 2) {
+            const double height = rp.chassis_height + rp.relative_t[2] + P.sphere_r[ci] - pc[2];
             if (height > 0) {
                 double f, df;
                 tp_smoothL1(P, height, f, df);
-                pg[ci][2] += -omg * step * w_sc * df;
+                g2 += -omg * step * w_sc * df;
                 o.gdT += omg * w_sc * (f / K);
                 o.terms[TOPAY_TERM_SELF_COLLI] += omg * step * w_sc * f;
             }
         }
+        pg.at(ci, 0) = g0;
+        pg.at(ci, 1) = g1;
+        pg.at(ci, 2) = g2;
+    }
+    // link vs link (:1566-1611)
+    for (int ci = 0; ci < P.n_sphere; ci++) {
         const uint32_t mask = P.pair_mask[ci];
-        for (int cj = ci + 1; cj < P.n_sphere; cj++) {  // link vs link (:1566-1611)
+        if (mask == 0u) continue;
+        const double pi0 = pts.at(ci, 0), pi1 = pts.at(ci, 1), pi2 = pts.at(ci, 2);
+        const double ri = P.sphere_r[ci];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int cj = ci + 1; cj < P.n_sphere; cj++) {
             if (!((mask >> cj) & 1u)) continue;
-            const double dx = pts[ci][0] - pts[cj][0], dy = pts[ci][1] - pts[cj][1], dz = pts[ci][2] - pts[cj][2];
-            const double rs = P.sphere_r[ci] + P.sphere_r[cj];
+            const double dx = pi0 - pts.at(cj, 0), dy = pi1 - pts.at(cj, 1), dz = pi2 - pts.at(cj, 2);
+            const double rs = ri + P.sphere_r[cj];
             const double dist = rs * rs - (dx * dx + dy * dy + dz * dz);
             if (dist > 0) {
                 double f, df;
                 tp_smoothL1(P, dist, f, df);
                 const double k = -omg * step * w_sc * df;
-                const double g1[3] = {k * dx * 2.0, k * dy * 2.0, k * dz * 2.0};
+                const double h0 = k * dx * 2.0, h1 = k * dy * 2.0, h2 = k * dz * 2.0;
                 o.gdT += omg * w_sc * (f / K);
                 o.terms[TOPAY_TERM_SELF_COLLI] += omg * step * w_sc * f;
-                for (int d = 0; d < 3; d++) {
-                    pg[ci][d] += g1[d];
-                    pg[cj][d] -= g1[d];
-                }
+                a0 += h0;
+                a1 += h1;
+                a2 += h2;
+                pg.at(cj, 0) -= h0;
+                pg.at(cj, 1) -= h1;
+                pg.at(cj, 2) -= h2;
             }
         }
+        pg.at(ci, 0) += a0;
+        pg.at(ci, 1) += a1;
+        pg.at(ci, 2) += a2;
     }
     double mu[10];
     tp_fk_adjoint(P, fk, pg, mu);
 
     // joint position limits (:1616-1666)
     const double w_mp = op.s2_mani_pos_weight;
+#pragma unroll
     for (int ji = 0; ji < TOPAY_DOF; ji++) {
         double v = pos[ji + 3] - rp.joint_pos_limit_max[ji];
         if (v > 0) {
@@ -271,6 +300,7 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
     o.G0[0] += mu[2];
     o.gdT += mu[2] * dst[0] * real_alpha;
     double dsum = 0.0;
+#pragma unroll
     for (int q = 0; q < TOPAY_DOF; q++) {
         o.G0[2 + q] = mu[3 + q];
         dsum += mu[3 + q] * dst[2 + q];
@@ -278,6 +308,7 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
     o.gdT += dsum * real_alpha;
     // joint velocity / acceleration limits (:1674-1710)
     const double w_mv = op.s2_mani_vel_weight, w_ma = op.s2_mani_acc_weight;
+#pragma unroll
     for (int q = 0; q < TOPAY_DOF; q++) {
         const double dq = dst[2 + q], d2q = d2st[2 + q], d3q = d3st[2 + q];
         const double vdq = dq * dq - rp.joint_vel_limit[q] * rp.joint_vel_limit[q];

@@ -54,19 +54,30 @@ int kpad_of(int K) {
     return p;
 }
 
+size_t penalty_smem() {
+    return (size_t)(72 * TP_PEN_WARPS * 32 + TP_PEN_WARPS * 8 * 54) * sizeof(double);
+}
+
 void launch_eval(topay_solver* s, bool timed, int tick_in_batch) {
     const TpSolverDev& D = s->dev;
     const int groups = (s->max_N + D.ppw - 1) / D.ppw;
     const int end_warps = D.end_tasks ? (s->max_N + 31) / 32 : 0;
     dim3 blk(TP_WARPS_PER_BLOCK * 32);
     dim3 g1((groups + TP_WARPS_PER_BLOCK - 1) / TP_WARPS_PER_BLOCK, s->n_cand);
-    dim3 g2((groups + end_warps + TP_WARPS_PER_BLOCK - 1) / TP_WARPS_PER_BLOCK, s->n_cand);
+    dim3 blk2(TP_PEN_WARPS * 32);
+    dim3 g2((groups + end_warps + TP_PEN_WARPS - 1) / TP_PEN_WARPS, s->n_cand);
     const size_t sm_int = (size_t)TP_WARPS_PER_BLOCK * D.ppw * 3 * (2 * D.K + 1) * sizeof(double);
+    const size_t sm_pen = penalty_smem();
     TpGrid G;
     tp_field_grid(s->field, &G);
     k_integrate<<<g1, blk, sm_int, s->stream>>>(D);
     if (timed) cudaEventRecord(s->ev[2 * tick_in_batch], s->stream);
-    k_penalty<<<g2, blk, 0, s->stream>>>(D, s->params, G, groups);
+    switch (D.Kpad) {
+        case 4: k_penalty<4><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
+        case 8: k_penalty<8><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
+        case 16: k_penalty<16><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
+        default: k_penalty<32><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
+    }
     if (timed) cudaEventRecord(s->ev[2 * tick_in_batch + 1], s->stream);
     k_chain<<<g1, blk, 0, s->stream>>>(D, s->params);
     s->stats.kernel_launches += 3;
@@ -178,6 +189,13 @@ extern "C" int topay_solver_create(const topay_opt_params* opt, const topay_robo
     const size_t sm_int = (size_t)TP_WARPS_PER_BLOCK * D.ppw * 3 * (2 * D.K + 1) * sizeof(double);
     TP_CUDA_OK(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_int),
                { topay_solver_destroy(s); });
+    {
+        const int smp = (int)penalty_smem();
+        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp), { topay_solver_destroy(s); });
+        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp), { topay_solver_destroy(s); });
+        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp), { topay_solver_destroy(s); });
+        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp), { topay_solver_destroy(s); });
+    }
     TP_CUDA_OK(cudaStreamSynchronize(s->stream), { topay_solver_destroy(s); });
     *out = s;
     return TOPAY_OK;

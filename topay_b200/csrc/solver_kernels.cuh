@@ -165,19 +165,40 @@ k_integrate(const __grid_constant__ TpSolverDev S) {
 }
 
 // ------------------------------------------------------------------ k_penalty
-// Lane = one penalty node (even j). STAGE 1: calFirstStagePenalGrad's node body;
-// STAGE 2: calSecondStagePenalGrad's. Reduces gdC / gdT / cost terms over the piece.
-__device__ __forceinline__ void tp_penalty_node(const int STAGE, const TpParams& P, const TpGrid& G,
-                                                const TpSolverDev& S, int cand, int piece, int jn, double T,
-                                                const double* c, const double* xy, TpNodeOut& o, double* b0,
-                                                double* b1, double* b2) {
-    if (STAGE == 1)
-        tp_node_stage1(P, c, T, S.K, 2 * jn, o, b0, b1, b2);
-    else
-        tp_node_stage2(P, G, c, T, S.K, 2 * jn, xy, o, b0, b1, b2);
+// Lane = one penalty node (even j). Stage 1: calFirstStagePenalGrad's node body; stage 2:
+// calSecondStagePenalGrad's. The piece's 6 x 9 spline coefficients are staged in shared
+// memory; the per-thread sphere centres / gradients (dynamically indexed) live in shared
+// memory too, everything else in registers.
+#define TP_PEN_WARPS 2
+#ifndef TP_PEN_MIN_BLOCKS
+#define TP_PEN_MIN_BLOCKS 5
+#endif
+
+// Sum of 64 values per lane over an aligned segment of KPAD lanes with 64/KPAD results per lane
+// ("transpose-reduce": each butterfly step halves the values a lane still carries, so the whole
+// reduction costs ~64 shuffles instead of 64 x log2(KPAD)). On return v[i], i < 64/KPAD, holds
+// the segment sum of element (64/KPAD) * jn + i.
+template <int KPAD>
+__device__ __forceinline__ void tp_transpose_reduce64(double* v, int jn) {
+    int cnt = 64;
+#pragma unroll
+    for (int m = KPAD >> 1; m > 0; m >>= 1) {
+        const bool hi = (jn & m) != 0;
+        const int half = cnt >> 1;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            if (i < half) {
+                const double send = hi ? v[i] : v[i + half];
+                const double keep = hi ? v[i + half] : v[i];
+                v[i] = keep + tp_shfl_xor(send, m);
+            }
+        }
+        cnt = half;
+    }
 }
 
-__global__ void __launch_bounds__(TP_WARPS_PER_BLOCK * 32)
+template <int KPAD>
+__global__ void __launch_bounds__(TP_PEN_WARPS * 32, TP_PEN_MIN_BLOCKS)
 k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P,
           const __grid_constant__ TpGrid G, int n_groups) {
     const int cand = blockIdx.y;
@@ -185,31 +206,46 @@ k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParam
     if (cs.phase == 0) return;
     const int STAGE = cs.phase;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int K = S.K, Kpad = S.Kpad, N = cs.N;
-    const int task = blockIdx.x * TP_WARPS_PER_BLOCK + warp;
+    const int K = S.K, N = cs.N;
+    constexpr int PPW = 32 / KPAD;
+    const int task = blockIdx.x * TP_PEN_WARPS + warp;
     const double* start_xy = S.start_xy + (size_t)cand * 2;
     const double* totc = S.tot + (size_t)cand * S.max_pieces * 2;
+    extern __shared__ double sm[];
+    // [2 stores][36][block threads] sphere stores, then per-warp coefficient staging
+    TpSphereStoreStrided pts{sm + threadIdx.x, TP_PEN_WARPS * 32};
+    TpSphereStoreStrided pg{sm + 36 * TP_PEN_WARPS * 32 + threadIdx.x, TP_PEN_WARPS * 32};
+    double* s_c = sm + 72 * TP_PEN_WARPS * 32 + warp * (8 * 54);   // up to 8 pieces x 54 per warp
     double b0[6], b1[6], b2[6];
     TpNodeOut o;
 
     if (task >= n_groups) {
-        // ---- end-node task: lane = piece, node j = 2K (only when K == Kpad) ----
+        // ---- end-node task: lane = piece, node j = 2K (only when K == KPAD) ----
         const int piece = (task - n_groups) * 32 + lane;
         if (piece >= N) return;
         const double T = S.T[(size_t)cand * S.max_pieces + piece];
         const double* c = S.coeff + ((size_t)cand * 6 * S.max_pieces + 6 * piece) * 9;
         double xy[2] = {start_xy[0], start_xy[1]};
-        if (STAGE == 2)
+        if (STAGE == 2) {
+            double ax = 0.0, ay = 0.0;
             for (int i = 0; i <= piece; i++) {
-                xy[0] += totc[2 * i];
-                xy[1] += totc[2 * i + 1];
+                ax += totc[2 * i];
+                ay += totc[2 * i + 1];
             }
-        tp_penalty_node(STAGE, P, G, S, cand, piece, K, T, c, xy, o, b0, b1, b2);
+            xy[0] += ax;
+            xy[1] += ay;
+            tp_node_stage2(P, G, c, T, K, 2 * K, xy, o, b0, b1, b2, pts, pg);
+        } else {
+            tp_node_stage1(P, c, T, K, 2 * K, o, b0, b1, b2);
+        }
         double* gc = S.gdC_end + ((size_t)cand * S.max_pieces + piece) * 54;
+#pragma unroll
         for (int k = 0; k < 6; k++)
+#pragma unroll
             for (int d = 0; d < 9; d++) gc[k * 9 + d] = b0[k] * o.G0[d] + b1[k] * o.G1[d] + b2[k] * o.G2[d];
         S.gdT_end[(size_t)cand * S.max_pieces + piece] = o.gdT;
         double* tm = S.terms_end + ((size_t)cand * S.max_pieces + piece) * TOPAY_NTERMS;
+#pragma unroll
         for (int t = 0; t < TOPAY_NTERMS; t++) tm[t] = o.terms[t];
         double* gn = S.gnode + (((size_t)cand * S.max_pieces + piece) * (K + 1) + K) * 2;
         gn[0] = o.gx;
@@ -217,29 +253,31 @@ k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParam
         return;
     }
 
-    // ---- piece task: segment of Kpad lanes per piece ----
-    const int seg = lane / Kpad, jn = lane % Kpad;
-    const int piece = task * S.ppw + seg;
+    // ---- piece task: segment of KPAD lanes per piece ----
+    const int seg = lane / KPAD, jn = lane % KPAD;
+    const int piece = task * PPW + seg;
     const bool pvalid = piece < N;
     const int n_nodes = S.end_tasks ? K : K + 1;   // nodes handled inside the segment
     const bool active = pvalid && jn < n_nodes;
     double T = 1.0;
-    const double* c = S.coeff;
+    double* c = s_c + seg * 54;
     if (pvalid) {
         T = S.T[(size_t)cand * S.max_pieces + piece];
-        c = S.coeff + ((size_t)cand * 6 * S.max_pieces + 6 * piece) * 9;
+        const double* cgl = S.coeff + ((size_t)cand * 6 * S.max_pieces + 6 * piece) * 9;
+        for (int e = jn; e < 54; e += KPAD) c[e] = cgl[e];
     }
+    __syncwarp();
     double xy[2] = {0.0, 0.0};
     if (STAGE == 2) {
         // CurrentXY (moma_traj_opt.cpp:1302): start + all earlier intervals
         double px = 0.0, py = 0.0;
         if (pvalid)
-            for (int i = jn; i < piece; i += Kpad) {
+            for (int i = jn; i < piece; i += KPAD) {
                 px += totc[2 * i];
                 py += totc[2 * i + 1];
             }
-        px = tp_seg_sum(px, Kpad);
-        py = tp_seg_sum(py, Kpad);
+        px = tp_seg_sum(px, KPAD);
+        py = tp_seg_sum(py, KPAD);
         // inclusive scan of this piece's intervals; node jn sees intervals 0..jn-1
         double ix = 0.0, iy = 0.0;
         if (pvalid && jn < K) {
@@ -247,54 +285,70 @@ k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParam
             ix = I[0];
             iy = I[1];
         }
-        for (int dlt = 1; dlt < Kpad; dlt <<= 1) {
-            const double ux = tp_shfl_up(ix, dlt, Kpad), uy = tp_shfl_up(iy, dlt, Kpad);
+#pragma unroll
+        for (int dlt = 1; dlt < KPAD; dlt <<= 1) {
+            const double ux = tp_shfl_up(ix, dlt, KPAD), uy = tp_shfl_up(iy, dlt, KPAD);
             if (jn >= dlt) {
                 ix += ux;
                 iy += uy;
             }
         }
-        const double ex = tp_shfl_up(ix, 1, Kpad), ey = tp_shfl_up(iy, 1, Kpad);
+        const double ex = tp_shfl_up(ix, 1, KPAD), ey = tp_shfl_up(iy, 1, KPAD);
         xy[0] = start_xy[0] + px + (jn > 0 ? ex : 0.0);
         xy[1] = start_xy[1] + py + (jn > 0 ? ey : 0.0);
     }
-    if (active)
-        tp_penalty_node(STAGE, P, G, S, cand, piece, jn, T, c, xy, o, b0, b1, b2);
-    else {
+    if (active) {
+        if (STAGE == 2)
+            tp_node_stage2(P, G, c, T, K, 2 * jn, xy, o, b0, b1, b2, pts, pg);
+        else
+            tp_node_stage1(P, c, T, K, 2 * jn, o, b0, b1, b2);
+    } else {
         tp_node_clear(o);
+#pragma unroll
         for (int k = 0; k < 6; k++) b0[k] = b1[k] = b2[k] = 0.0;
     }
-    // per-node xy adjoint, kept for the suffix sums of k_chain
-    if (STAGE == 2 && active) {
-        double* gn = S.gnode + (((size_t)cand * S.max_pieces + piece) * (K + 1) + jn) * 2;
-        gn[0] = o.gx;
-        gn[1] = o.gy;
-    }
-    // reductions over the piece
     const size_t prow = (size_t)cand * S.max_pieces + piece;
-    const int dmax = STAGE == 1 ? 2 : 9;
-    for (int k = 0; k < 6; k++)
-        for (int d = 0; d < dmax; d++) {
-            double v = b0[k] * o.G0[d] + b1[k] * o.G1[d] + b2[k] * o.G2[d];
-            v = tp_seg_sum(v, Kpad);
-            if (pvalid && jn == 0) S.gdC[(prow * 6 + k) * 9 + d] = v;
-        }
-    if (STAGE == 1 && pvalid && jn == 0)
-        for (int k = 0; k < 6; k++)
-            for (int d = 2; d < 9; d++) S.gdC[(prow * 6 + k) * 9 + d] = 0.0;
-    {
-        const double v = tp_seg_sum(o.gdT, Kpad);
-        if (pvalid && jn == 0) S.gdT[prow] = v;
-    }
-    for (int t = 0; t < TOPAY_NTERMS; t++) {
-        const double v = tp_seg_sum(o.terms[t], Kpad);
-        if (pvalid && jn == 0) S.terms[prow * TOPAY_NTERMS + t] = v;
-    }
+    // per-node xy adjoint, kept for the suffix sums of k_chain, and its sum over the piece
     if (STAGE == 2) {
-        const double sx = tp_seg_sum(o.gx, Kpad), sy = tp_seg_sum(o.gy, Kpad);
+        if (active) {
+            double* gn = S.gnode + ((prow * (K + 1)) + jn) * 2;
+            gn[0] = o.gx;
+            gn[1] = o.gy;
+        }
+        const double sx = tp_seg_sum(o.gx, KPAD), sy = tp_seg_sum(o.gy, KPAD);
         if (pvalid && jn == 0) {
             S.gsum[prow * 2] = sx;
             S.gsum[prow * 2 + 1] = sy;
+        }
+    }
+    // reduction over the piece of gdC (54), gdT (1) and the 9 per-node cost terms
+    double v[64];
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+#pragma unroll
+        for (int d = 0; d < 9; d++) v[k * 9 + d] = b0[k] * o.G0[d] + b1[k] * o.G1[d] + b2[k] * o.G2[d];
+    v[54] = o.gdT;
+#pragma unroll
+    for (int t = 0; t < 9; t++) v[55 + t] = o.terms[TOPAY_TERM_CHASSIS_COLLI + t];
+    tp_transpose_reduce64<KPAD>(v, jn);
+    if (pvalid) {
+        constexpr int PER = 64 / KPAD;
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int idx = PER * jn + i;
+            if (idx < 54)
+                S.gdC[prow * 54 + idx] = v[i];
+            else if (idx == 54)
+                S.gdT[prow] = v[i];
+            else
+                S.terms[prow * TOPAY_NTERMS + TOPAY_TERM_CHASSIS_COLLI + (idx - 55)] = v[i];
+        }
+        if (jn == 0) {
+            double* tm = S.terms + prow * TOPAY_NTERMS;
+            tm[TOPAY_TERM_JERK] = 0.0;
+            tm[TOPAY_TERM_TIME] = 0.0;
+            tm[TOPAY_TERM_MEAN_TIME] = 0.0;
+            tm[TOPAY_TERM_ENDP] = 0.0;
         }
     }
 }
@@ -318,50 +372,74 @@ k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams 
     const bool pvalid = piece < N;
     const size_t prow = (size_t)cand * S.max_pieces + piece;
     const double* totc = S.tot + (size_t)cand * S.max_pieces * 2;
+    __shared__ double s_w[TP_WARPS_PER_BLOCK][2 * 64 + 2];   // stage 1: per-piece suffix weights
 
-    // trajectory end point of every piece, accumulated piece by piece like VecTrajFinalXY
-    // (moma_traj_opt.cpp:1750): F_{i+1} = F_i + tot_i
     double wx = 0.0, wy = 0.0;   // weight common to all slots of this piece
-    {
-        double fx = S.start_xy[(size_t)cand * 2], fy = S.start_xy[(size_t)cand * 2 + 1];
-        if (STAGE == 1) {
-            const double w = P.opt.s1_path_pos_weight;
-            const double* tgt = S.init_inner_xy + (size_t)cand * S.max_pieces * 2;
-            for (int i = 0; i < N; i++) {
-                fx += totc[2 * i];
-                fy += totc[2 * i + 1];
-                if (i > piece) {
-                    wx += w * 2.0 * (fx - tgt[2 * i]);
-                    wy += w * 2.0 * (fy - tgt[2 * i + 1]);
-                }
-            }
-        } else {
-            for (int i = 0; i < N; i++) {
-                fx += totc[2 * i];
-                fy += totc[2 * i + 1];
-            }
-            const double ex = fx - S.end_xy[(size_t)cand * 2], ey = fy - S.end_xy[(size_t)cand * 2 + 1];
-            wx = cs.rho[0] * (ex + cs.lambda[0] / cs.rho[0]);
-            wy = cs.rho[1] * (ey + cs.lambda[1] / cs.rho[1]);
-            // adjoints of all later pieces
-            double lx = 0.0, ly = 0.0;
-            if (pvalid)
-                for (int i = piece + 1 + jn; i < N; i += Kpad) {
-                    const size_t r = (size_t)cand * S.max_pieces + i;
-                    lx += S.gsum[r * 2];
-                    ly += S.gsum[r * 2 + 1];
-                    if (S.end_tasks) {
-                        lx += S.gnode[(r * (K + 1) + K) * 2];
-                        ly += S.gnode[(r * (K + 1) + K) * 2 + 1];
-                    }
-                }
-            wx += tp_seg_sum(lx, Kpad);
-            wy += tp_seg_sum(ly, Kpad);
+    if (STAGE == 1) {
+        // F_{i+1} = F_i + tot_i in piece order (VecTrajFinalXY, :1173), then the suffix sums of
+        // 2 w (F_{i+1} - target_i); lane 0 of the warp walks the <= 64 pieces once.
+        double* w = s_w[warp];
+        for (int i = lane; i < N; i += 32) {
+            w[2 * i] = totc[2 * i];
+            w[2 * i + 1] = totc[2 * i + 1];
         }
+        __syncwarp();
+        if (lane == 0) {
+            const double wgt = P.opt.s1_path_pos_weight;
+            const double* tgt = S.init_inner_xy + (size_t)cand * S.max_pieces * 2;
+            double fx = S.start_xy[(size_t)cand * 2], fy = S.start_xy[(size_t)cand * 2 + 1];
+            for (int i = 0; i < N; i++) {
+                fx += w[2 * i];
+                fy += w[2 * i + 1];
+                w[2 * i] = wgt * 2.0 * (fx - tgt[2 * i]);
+                w[2 * i + 1] = wgt * 2.0 * (fy - tgt[2 * i + 1]);
+            }
+            double sx = 0.0, sy = 0.0;     // suffix over pieces i > p, accumulated in increasing i
+            for (int p = N - 1; p >= 0; p--) {
+                const double ax = w[2 * p], ay = w[2 * p + 1];
+                w[2 * p] = sx;
+                w[2 * p + 1] = sy;
+                sx += ax;
+                sy += ay;
+            }
+        }
+        __syncwarp();
+        if (pvalid) {
+            wx = w[2 * piece];
+            wy = w[2 * piece + 1];
+        }
+    } else {
+        // trajectory end point -> ALM weight (:1786-1810)
+        double tx = 0.0, ty = 0.0;
+        for (int i = jn; i < N; i += Kpad) {
+            tx += totc[2 * i];
+            ty += totc[2 * i + 1];
+        }
+        tx = tp_seg_sum(tx, Kpad);
+        ty = tp_seg_sum(ty, Kpad);
+        const double ex = S.start_xy[(size_t)cand * 2] + tx - S.end_xy[(size_t)cand * 2];
+        const double ey = S.start_xy[(size_t)cand * 2 + 1] + ty - S.end_xy[(size_t)cand * 2 + 1];
+        wx = cs.rho[0] * (ex + cs.lambda[0] / cs.rho[0]);
+        wy = cs.rho[1] * (ey + cs.lambda[1] / cs.rho[1]);
+        // adjoints of all later pieces
+        double lx = 0.0, ly = 0.0;
+        if (pvalid)
+            for (int i = piece + 1 + jn; i < N; i += Kpad) {
+                const size_t r = (size_t)cand * S.max_pieces + i;
+                lx += S.gsum[r * 2];
+                ly += S.gsum[r * 2 + 1];
+                if (S.end_tasks) {
+                    lx += S.gnode[(r * (K + 1) + K) * 2];
+                    ly += S.gnode[(r * (K + 1) + K) * 2 + 1];
+                }
+            }
+        wx += tp_seg_sum(lx, Kpad);
+        wy += tp_seg_sum(ly, Kpad);
     }
     // stage 2: suffix sums of this piece's own node adjoints
     double suf_x = 0.0, suf_y = 0.0;     // sum over nodes jn' >= jn (incl. node K)
     double sufn_x = 0.0, sufn_y = 0.0;   // sum over nodes jn' >  jn
+    double end_x = 0.0, end_y = 0.0;     // node K alone
     if (STAGE == 2) {
         double gx = 0.0, gy = 0.0;
         if (pvalid && jn < K) {
@@ -369,11 +447,10 @@ k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams 
             gx = gn[0];
             gy = gn[1];
         }
-        double ex = 0.0, ey = 0.0;
         if (pvalid) {
             const double* gn = S.gnode + ((prow * (K + 1)) + K) * 2;
-            ex = gn[0];
-            ey = gn[1];
+            end_x = gn[0];
+            end_y = gn[1];
         }
         double sx = gx, sy = gy;
         for (int dlt = 1; dlt < Kpad; dlt <<= 1) {
@@ -383,21 +460,19 @@ k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams 
                 sy += uy;
             }
         }
-        suf_x = sx + ex;
-        suf_y = sy + ey;
-        sufn_x = suf_x - gx;
-        sufn_y = suf_y - gy;
-        // exact value of the "after" sum without the subtraction's rounding: shift instead
+        suf_x = sx + end_x;
+        suf_y = sy + end_y;
         const double nx = tp_shfl_down(sx, 1, Kpad), ny = tp_shfl_down(sy, 1, Kpad);
         if (jn + 1 < Kpad) {
-            sufn_x = nx + ex;
-            sufn_y = ny + ey;
+            sufn_x = nx + end_x;
+            sufn_y = ny + end_y;
         } else {
-            sufn_x = ex;
-            sufn_y = ey;
+            sufn_x = end_x;
+            sufn_y = end_y;
         }
     }
     double gth[6], gar[6], gdt = 0.0;
+#pragma unroll
     for (int k = 0; k < 6; k++) gth[k] = gar[k] = 0.0;
     if (pvalid) {
         const double T = S.T[prow];
@@ -420,16 +495,11 @@ k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams 
         }
         const int end_lane = K < Kpad ? K : 0;
         if (jn == end_lane) {   // last slot j = 2K: weight 1, only its own node is at/after it
-            double ex = 0.0, ey = 0.0;
-            if (STAGE == 2) {
-                const double* gn = S.gnode + ((prow * (K + 1)) + K) * 2;
-                ex = gn[0];
-                ey = gn[1];
-            }
             tp_slot(c, (2 * K) * half_step, sl, b0, b1, b2);
-            tp_chain_slot(sl, b0, b1, T, K, 2 * K, wx + ex, wy + ey, gth, gar, gdt);
+            tp_chain_slot(sl, b0, b1, T, K, 2 * K, wx + end_x, wy + end_y, gth, gar, gdt);
         }
     }
+#pragma unroll
     for (int k = 0; k < 6; k++) {
         const double a = tp_seg_sum(gth[k], Kpad), b = tp_seg_sum(gar[k], Kpad);
         if (pvalid && jn == 0) {
@@ -466,6 +536,20 @@ k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams 
 #define TP_CAND_WARPS (TP_CAND_THREADS / 32)
 #define TP_EPT 5      // vector elements per thread: n <= TP_EPT * TP_CAND_THREADS (N <= 64)
 #define LU_AT(i, j) lu[(i) * TP_BAND + ((j) - (i) + 6)]
+#define LU_DINV(i) lu[(i) * TP_BAND + 13]   // 1 / U(i,i), kept in the row's padding
+
+// 1/x to within ~1 ulp without the IEEE division sequence: hardware seed + 3 Newton steps.
+// The banded solves multiply by the reciprocal pivot where the reference divides
+// (banded_system.hpp:75,109,128); the difference is <= 2 ulp per operation, far inside the
+// 1e-9 parity tolerance, and takes the divide off the 6N-step critical path.
+__device__ __forceinline__ double tp_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
 
 // block-wide sums of up to 4 values; every thread gets the results. `red` is a
 // [2][4][TP_CAND_WARPS] scratch, `flip` alternates so one barrier per call suffices.
@@ -575,35 +659,26 @@ __device__ __forceinline__ void tp_fill_system(int N, const double* T, const dou
     __syncthreads();
 }
 
-// factorizeLU (banded_system.hpp:66-91) on one warp. Each lane that updates A(i, j) forms the
-// multiplier A(i,k)/A(k,k) itself (same value the reference stores), so a step needs a single
-// warp barrier. 6 x 7 elements per step: column 0 of the window stores the multiplier.
+// factorizeLU (banded_system.hpp:66-91) on one warp; every lane forms the multiplier itself.
 __device__ __forceinline__ void tp_lu_factor(int n, double* lu, int lane) {
-    for (int k = 0; k <= n - 2; k++) {
+    for (int k = 0; k <= n - 1; k++) {
         const int iM = min(k + 6, n - 1);
         const int rows = iM - k;
-        const double piv = LU_AT(k, k);
-        for (int e = lane; e < rows * 7; e += 32) {
-            const int i = k + 1 + e / 7, t = e % 7;
+        const double rinv = tp_rcp(LU_AT(k, k));
+        if (lane == 31) LU_DINV(k) = rinv;
+        for (int e = lane; e < rows * 6; e += 32) {
+            const int i = k + 1 + e / 6, j = k + 1 + e % 6;
             const double a = LU_AT(i, k);
-            if (a != 0.0) {
-                const double l = a / piv;
-                if (t == 0) {
-                    // written after every lane of this pass has read A(i, k): see the barrier below
-                } else {
-                    const int j = k + t;
-                    if (j <= iM) {
-                        const double cv = LU_AT(k, j);
-                        if (cv != 0.0) LU_AT(i, j) -= l * cv;
-                    }
-                }
+            if (a != 0.0 && j <= iM) {
+                const double cv = LU_AT(k, j);
+                if (cv != 0.0) LU_AT(i, j) -= (a * rinv) * cv;
             }
         }
         __syncwarp();
         if (lane < rows) {
             const int i = k + 1 + lane;
             const double a = LU_AT(i, k);
-            if (a != 0.0) LU_AT(i, k) = a / piv;
+            if (a != 0.0) LU_AT(i, k) = a * rinv;
         }
         __syncwarp();
     }
@@ -625,7 +700,7 @@ __device__ __forceinline__ void tp_lu_subst(int n, const double* lu, double* b, 
     for (int j = n - 1; j >= 0; j--) {
         const int i0 = max(0, j - 6);
         const int rows = j - i0;
-        const double v = b[j * 9 + cc] / LU_AT(j, j);
+        const double v = b[j * 9 + cc] * LU_DINV(j);
         __syncwarp();
         if (lane < rows * 3) {
             const int i = i0 + lane / 3;
@@ -643,7 +718,7 @@ __device__ __forceinline__ void tp_lu_subst_adj(int n, const double* lu, double*
     for (int j = 0; j <= n - 1; j++) {
         const int iM = min(j + 6, n - 1);
         const int rows = iM - j;
-        const double v = b[j * 9 + cc] / LU_AT(j, j);
+        const double v = b[j * 9 + cc] * LU_DINV(j);
         __syncwarp();
         if (lane < rows * 3) {
             const int i = j + 1 + lane / 3;
@@ -1291,3 +1366,4 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
     }
 }
 #undef LU_AT
+#undef LU_DINV
