@@ -1,0 +1,88 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/topay_b200.h declares,
+agrees with the oracle on the pure-host entry points, and refuses to compute without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "topay_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(topay_[a-z0-9_]+)\s*\(", src))
+    names.discard("topay_num_vars")     # static inline
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    from topay_b200 import _lib
+    lib = _lib.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in topay_b200.h but not exported"
+    assert set(_lib.PROTOTYPES) == set(syms), set(_lib.PROTOTYPES) ^ set(syms)
+    assert b"sm_100a" in lib.topay_version()
+
+
+def test_struct_sizes_match_the_compiler():
+    import subprocess
+    import tempfile
+    from topay_b200 import _structs as S
+    prog = ('#include "topay_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+            "sizeof(topay_robot_params),sizeof(topay_lbfgs_params),sizeof(topay_opt_params),sizeof(topay_grid_desc),"
+            "sizeof(topay_problem_batch),sizeof(topay_result_batch),sizeof(topay_solver_stats));return 0;}")
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "a.c"), "w").write(prog)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "a"),
+                               os.path.join(d, "a.c")])
+        sizes = list(map(int, subprocess.check_output([os.path.join(d, "a")]).split()))
+    want = [C.sizeof(x) for x in (S.RobotParams, S.LbfgsParams, S.OptParams, S.GridDesc, S.ProblemBatch,
+                                  S.ResultBatch, S.SolverStats)]
+    assert sizes == want
+
+
+def test_host_entry_points_match_the_oracle(oracle):
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    assert bytes(tp.robot_params_default()) == bytes(oracle.robot_defaults())
+    assert bytes(tp.opt_params_default()) == bytes(oracle.opt_defaults())
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    paths, bv, ba = scenes.short_candidates(6, 3)
+    paths += scenes.synthetic_batch(2, 5)[0]
+    for p in paths:
+        a = tp.prepare_candidate(opt, rp, p, bv[0], ba[0], 64)
+        b = oracle.prepare_candidate(opt, rp, p, bv[0], ba[0], 64)
+        assert a["piece_num"] == b["piece_num"] and a["s1_past"] == b["s1_past"] and a["rc"] == b["rc"] == 0
+        for k in ("head_pva", "tail_pva", "start_xy", "end_xy", "init_inner_xy", "x0"):
+            assert np.array_equal(a[k], b[k]), k
+
+
+def test_compute_fails_loudly_without_a_device():
+    import pytest
+    import topay_b200 as tp
+    from topay_b200 import _lib
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.TopayError) as e:
+        tp.GridMap(tp.grid_desc())
+    assert e.value.code == _lib.ERR_NO_DEVICE
+    h = C.c_void_p()
+    assert _lib.lib().topay_field_create(C.byref(tp.grid_desc()), 0, C.byref(h)) == _lib.ERR_NO_DEVICE
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "topay_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle_lib" not in txt and "liboracle" not in txt and "oracle/" not in txt, f
