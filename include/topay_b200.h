@@ -322,6 +322,10 @@ int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out);
 int topay_solver_set_trace(topay_solver* s, int cap);
 int topay_solver_download_trace(topay_solver* s, int cand, double* out /*cap x 4*/, int cap, int32_t* len);
 
+/* Developer profiling: accumulated SM clock cycles of the per-candidate kernel's phases
+ * (candidate 0) since the last call; enable != 0 switches the counters on. out16 may be NULL. */
+int topay_solver_phase_clocks(topay_solver* s, int enable, long long* out16);
+
 #ifdef __cplusplus
 }
 #endif

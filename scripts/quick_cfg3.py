@@ -14,7 +14,13 @@ opt.int_K = 32; opt.min_piece_num = 64; opt.sample_interval = 1e9
 paths, bv, ba = scenes.synthetic_batch(C, 1234)
 solver = tp.MomaTrajOpt(gm, max_cand=C, max_pieces=64, opt_param=opt, robot=rp)
 t = time.time(); solver.upload(paths, bv, ba); print("upload s", time.time() - t)
+import ctypes
+solver._l.topay_solver_phase_clocks(solver.h, 1, None)
 t = time.time(); solver.run(); w = time.time() - t
+clk = (ctypes.c_longlong * 16)(); solver._l.topay_solver_phase_clocks(solver.h, 1, clk)
+names = ["adj:load+terms", "adj:misc+jerk", "adj:wk", "adj:sweeps", "adj:grad", "adv:ls+hist", "adv:loop1", "adv:loop2", "adv:rest", "gen:fill", "gen:lu", "gen:sweeps", "gen:store"]
+tk = solver.stats()["ticks"]
+print("k_cand phases of candidate 0, us per tick @1.965GHz:", {n: round(clk[i] / 1965.0 / tk, 1) for i, n in enumerate(names)}, "sum", round(sum(clk[:13]) / 1965.0 / tk, 1))
 r = solver.download(); st = solver.stats()
 print("run wall s", w, "stats", st)
 print("status ok", int(r["status"].sum()), "/", C, "pieces", set(r["piece_num"].tolist()))

@@ -451,6 +451,26 @@ extern "C" int topay_solver_solve_batch(topay_solver* s, int n_cand, const int32
     return topay_solver_download(s, out, best_by_duration, best_by_cost);
 }
 
+// Dev profiling: accumulated clock64() deltas of k_cand's phases for candidate 0 (16 slots).
+extern "C" int topay_solver_phase_clocks(topay_solver* s, int enable, long long* out16) {
+    if (!s) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(s->device);
+    TpSolverDev& D = s->dev;
+    if (enable && !D.prof) {
+        TP_CUDA_OK(cudaMalloc(&D.prof, 16 * sizeof(long long)), {});
+        cudaMemset(D.prof, 0, 16 * sizeof(long long));
+    }
+    if (out16 && D.prof) {
+        TP_CUDA_OK(cudaMemcpy(out16, D.prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost), {});
+        cudaMemset(D.prof, 0, 16 * sizeof(long long));
+    }
+    if (!enable && D.prof) {
+        cudaFree(D.prof);
+        D.prof = nullptr;
+    }
+    return TOPAY_OK;
+}
+
 extern "C" int topay_solver_set_trace(topay_solver* s, int cap) {
     if (!s || cap < 0) return TOPAY_ERR_INVALID_ARG;
     cudaSetDevice(s->device);

@@ -76,6 +76,7 @@ struct TpSolverDev {
     double *trace;        // [max_cand][trace_cap][4] or null
     int32_t *trace_len;   // [max_cand]
     int32_t trace_cap;
+    long long *prof;      // optional phase clocks of candidate 0 (dev profiling), [16] or null
 };
 
 // ------------------------------------------------------------------ warp helpers
@@ -548,7 +549,7 @@ __device__ __forceinline__ double tp_rcp(double x) {
     r = fma(fma(-x, r, 1.0), r, r);
     r = fma(fma(-x, r, 1.0), r, r);
     r = fma(fma(-x, r, 1.0), r, r);
-    return r;
+    return r;   // seed ~2^-20; three steps leave margin for subnormal-free pivots
 }
 
 // block-wide sums of up to 4 values; every thread gets the results. `red` is a
@@ -659,91 +660,137 @@ __device__ __forceinline__ void tp_fill_system(int N, const double* T, const dou
     __syncthreads();
 }
 
-// factorizeLU (banded_system.hpp:66-91) on one warp; every lane forms the multiplier itself.
+// factorizeLU (banded_system.hpp:66-91) on one warp. Step k updates the 6 x 6 block below / right of
+// the pivot: lane e owns element (k+1 + e/6, k+1 + e%6) (lanes 0..3 also own elements 32..35), loads
+// everything it needs before the reciprocal pivot is known, then does one multiply-FMA-store; the
+// lanes of column k+1 also store the multipliers. One warp barrier per step. Multiplying by an
+// exactly zero factor equals the reference's `!= 0.0` skips.
 __device__ __forceinline__ void tp_lu_factor(int n, double* lu, int lane) {
+    const int r0 = lane / 6, c0 = lane % 6;            // element 0 of this lane
+    const int r1 = (lane + 32) / 6, c1 = (lane + 32) % 6;   // element 1 (lanes 0..3 only)
     for (int k = 0; k <= n - 1; k++) {
         const int iM = min(k + 6, n - 1);
-        const int rows = iM - k;
-        const double rinv = tp_rcp(LU_AT(k, k));
+        const double piv = LU_AT(k, k);
+        const int i0 = k + 1 + r0, j0 = k + 1 + c0;
+        const bool ok0 = lane < 36 && i0 <= iM && j0 <= iM;
+        double a0 = 0.0, cv0 = 0.0, v0 = 0.0;
+        if (ok0) {
+            a0 = LU_AT(i0, k);
+            cv0 = LU_AT(k, j0);
+            v0 = LU_AT(i0, j0);
+        }
+        const int i1 = k + 1 + r1, j1 = k + 1 + c1;
+        const bool ok1 = lane < 4 && i1 <= iM && j1 <= iM;
+        double a1 = 0.0, cv1 = 0.0, v1 = 0.0;
+        if (ok1) {
+            a1 = LU_AT(i1, k);
+            cv1 = LU_AT(k, j1);
+            v1 = LU_AT(i1, j1);
+        }
+        const double rinv = tp_rcp(piv);
+        __syncwarp();                                  // every lane has read column k
         if (lane == 31) LU_DINV(k) = rinv;
-        for (int e = lane; e < rows * 6; e += 32) {
-            const int i = k + 1 + e / 6, j = k + 1 + e % 6;
-            const double a = LU_AT(i, k);
-            if (a != 0.0 && j <= iM) {
-                const double cv = LU_AT(k, j);
-                if (cv != 0.0) LU_AT(i, j) -= (a * rinv) * cv;
-            }
+        if (ok0) {
+            const double l = a0 * rinv;
+            LU_AT(i0, j0) = v0 - l * cv0;
+            if (c0 == 0) LU_AT(i0, k) = l;
         }
-        __syncwarp();
-        if (lane < rows) {
-            const int i = k + 1 + lane;
-            const double a = LU_AT(i, k);
-            if (a != 0.0) LU_AT(i, k) = a * rinv;
+        if (ok1) {
+            const double l = a1 * rinv;
+            LU_AT(i1, j1) = v1 - l * cv1;
+            if (c1 == 0) LU_AT(i1, k) = l;
         }
         __syncwarp();
     }
 }
 
-// solve (banded_system.hpp:96-118) for the 3 columns [c0, c0+3) on one warp.
-__device__ __forceinline__ void tp_lu_subst(int n, const double* lu, double* b, int c0, int lane) {
-    const int cc = c0 + lane % 3;
-    for (int j = 0; j <= n - 2; j++) {
-        const int iM = min(j + 6, n - 1);
-        const int rows = iM - j;
-        if (lane < rows * 3) {
-            const int i = j + 1 + lane / 3;
-            const double a = LU_AT(i, j);
-            if (a != 0.0) b[i * 9 + cc] -= a * b[j * 9 + cc];
-        }
-        __syncwarp();
+// The four triangular sweeps of solve / solveAdj (banded_system.hpp:96-145), row-oriented: one
+// lane per right-hand-side column walks the rows with the last six solution entries in registers.
+// Each element receives its updates in the reference's order (the column index of the factor
+// ascending in the forward sweeps, descending in the backward ones), the update with the
+// most recent neighbour comes last, so the dependent chain is one FMA (plus the reciprocal-pivot
+// multiply) per row and no lane ever waits for another. Slots of the band outside the matrix
+// hold zeros, so no bounds tests are needed; multiplying by an exact zero multiplier equals the
+// reference's `!= 0.0` skip.
+//   mode 0: L y = b   (unit lower, forward)        mode 1: U x = y   (backward)
+//   mode 2: U^T y = b (forward)                    mode 3: L^T x = y (unit, backward)
+// The triangular sweeps of solve / solveAdj (banded_system.hpp:96-145), one lane per right-hand-side
+// column, in the reference's own loop order: as soon as entry i of the solution is known it is
+// subtracted from the six rows it couples to. The six pending rows are six independent
+// accumulators in registers, so a row costs six independent FMAs and the dependent chain is one
+// FMA (+ the reciprocal-pivot multiply for the factor with the non-unit diagonal). The factor
+// entries needed when x_i is known are COLUMN i of the triangular factor, i.e. row i of the
+// transposed band:
+//   solve():    L y = b (forward)  and U x = y (backward)   want the band of A^T  (GEN transposes it in place)
+//   solveAdj(): U^T y = b (forward) and L^T x = y (backward) want the band of A    (as stored)
+// `m` is that band: row i holds the entries coupling x_i to rows i+1..i+6 in slots 7..12 and to
+// rows i-1..i-6 in slots 5..0; slot 13 is the reciprocal pivot. Slots outside the matrix are zero.
+template <bool FWD, bool SCALE>
+__device__ __forceinline__ void tp_sweep(int n, const double* __restrict__ m, double* b, int cc) {
+    double acc0, acc1, acc2, acc3, acc4, acc5;
+    if (FWD) {
+        acc0 = b[0 * 9 + cc];
+        acc1 = n > 1 ? b[1 * 9 + cc] : 0.0;
+        acc2 = n > 2 ? b[2 * 9 + cc] : 0.0;
+        acc3 = n > 3 ? b[3 * 9 + cc] : 0.0;
+        acc4 = n > 4 ? b[4 * 9 + cc] : 0.0;
+        acc5 = n > 5 ? b[5 * 9 + cc] : 0.0;
+    } else {
+        acc0 = b[(n - 1) * 9 + cc];
+        acc1 = n > 1 ? b[(n - 2) * 9 + cc] : 0.0;
+        acc2 = n > 2 ? b[(n - 3) * 9 + cc] : 0.0;
+        acc3 = n > 3 ? b[(n - 4) * 9 + cc] : 0.0;
+        acc4 = n > 4 ? b[(n - 5) * 9 + cc] : 0.0;
+        acc5 = n > 5 ? b[(n - 6) * 9 + cc] : 0.0;
     }
-    for (int j = n - 1; j >= 0; j--) {
-        const int i0 = max(0, j - 6);
-        const int rows = j - i0;
-        const double v = b[j * 9 + cc] * LU_DINV(j);
-        __syncwarp();
-        if (lane < rows * 3) {
-            const int i = i0 + lane / 3;
-            const double a = LU_AT(i, j);
-            if (a != 0.0) b[i * 9 + cc] -= a * v;
+#pragma unroll 2
+    for (int r = 0; r < n; r++) {
+        const int i = FWD ? r : n - 1 - r;
+        const double2* row = reinterpret_cast<const double2*>(m + i * TP_BAND);
+        double c1, c2, c3, c4, c5, c6, dinv;
+        if (FWD) {
+            const double2 p3 = row[3], p4 = row[4], p5 = row[5], p6 = row[6];   // slots 6..13
+            c1 = p3.y; c2 = p4.x; c3 = p4.y; c4 = p5.x; c5 = p5.y; c6 = p6.x;
+            dinv = p6.y;
+        } else {
+            const double2 p0 = row[0], p1 = row[1], p2 = row[2];                 // slots 0..5
+            c6 = p0.x; c5 = p0.y; c4 = p1.x; c3 = p1.y; c2 = p2.x; c1 = p2.y;
+            dinv = SCALE ? m[i * TP_BAND + 13] : 1.0;
         }
-        if (lane >= 18 && lane < 21) b[j * 9 + cc] = v;
-        __syncwarp();
+        const int inew = FWD ? i + 6 : i - 6;        // row entering the window
+        const double bnew = (inew >= 0 && inew < n) ? b[inew * 9 + cc] : 0.0;
+        const double x = SCALE ? acc0 * dinv : acc0;
+        b[i * 9 + cc] = x;
+        acc0 = acc1 - c1 * x;
+        acc1 = acc2 - c2 * x;
+        acc2 = acc3 - c3 * x;
+        acc3 = acc4 - c4 * x;
+        acc4 = acc5 - c5 * x;
+        acc5 = bnew - c6 * x;
     }
 }
 
-// solveAdj (banded_system.hpp:123-145) for the 3 columns [c0, c0+3) on one warp.
-__device__ __forceinline__ void tp_lu_subst_adj(int n, const double* lu, double* b, int c0, int lane) {
-    const int cc = c0 + lane % 3;
-    for (int j = 0; j <= n - 1; j++) {
-        const int iM = min(j + 6, n - 1);
-        const int rows = iM - j;
-        const double v = b[j * 9 + cc] * LU_DINV(j);
-        __syncwarp();
-        if (lane < rows * 3) {
-            const int i = j + 1 + lane / 3;
-            const double a = LU_AT(j, i);
-            if (a != 0.0) b[i * 9 + cc] -= a * v;
+// In-place transpose of the band (slots 0..12 around the diagonal); slot 13 stays.
+__device__ __forceinline__ void tp_band_transpose(int n, double* lu) {
+    for (int e = threadIdx.x; e < n * 6; e += TP_CAND_THREADS) {
+        const int i = e / 6, k = e % 6 + 1;
+        if (i + k < n) {
+            double* up = lu + i * TP_BAND + 6 + k;          // A(i, i+k)
+            double* lo = lu + (i + k) * TP_BAND + 6 - k;    // A(i+k, i)
+            const double t = *up;
+            *up = *lo;
+            *lo = t;
         }
-        if (lane >= 18 && lane < 21) b[j * 9 + cc] = v;
-        __syncwarp();
     }
-    for (int j = n - 1; j >= 0; j--) {
-        const int i0 = max(0, j - 6);
-        const int rows = j - i0;
-        if (lane < rows * 3) {
-            const int i = i0 + lane / 3;
-            const double a = LU_AT(j, i);
-            if (a != 0.0) b[i * 9 + cc] -= a * b[j * 9 + cc];
-        }
-        __syncwarp();
-    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ bool tp_ok_code(int r) {
     return r == TOPAY_LBFGS_CONVERGENCE || r == TOPAY_LBFGS_CANCELED || r == TOPAY_LBFGS_STOP ||
            r == TOPAY_LBFGSERR_MAXIMUMITERATION;
 }
+
+#define TP_PROF(slot) do { if (S.prof && cand == 0 && tid == 0) S.prof[slot] += clock64() - t_prof; t_prof = clock64(); } while (0)
 
 __global__ void __launch_bounds__(TP_CAND_THREADS)
 k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P, int mode, int slot) {
@@ -752,6 +799,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
     TpCandState* gs = S.st + cand;
     if (gs->phase == 0) return;
     TpCandState st = *gs;          // uniform copy per thread
+    long long t_prof = clock64();
     const int N = st.N, n = st.n, n6 = 6 * N;
     const int stage = st.phase;
     extern __shared__ double sm[];
@@ -799,6 +847,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             if (lane == 0) sTerm[t] = a;
         }
         __syncthreads();
+        TP_PROF(0);
         if (tid == 0) {
             // end point, VecTrajFinalXY order (:1750); stage-1 path cost (:1173-1178)
             double fx = S.start_xy[cand * 2], fy = S.start_xy[cand * 2 + 1];
@@ -881,6 +930,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         }
         tp_block_sum<1>(js, red, flip);
         const double jerk = js[0];
+        TP_PROF(1);
         // gdC = jerk part (minco.hpp:951-977) + penalty part -> wk
         for (int e = tid; e < n6 * 9; e += TP_CAND_THREADS) {
             const int r = e / 9, d = e % 9, i = r / 6, q = r % 6;
@@ -894,8 +944,13 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             wk[e] = v + (bad ? 0.0 : gdCp[e]);
         }
         __syncthreads();
-        if (warp < 3) tp_lu_subst_adj(n6, lu, wk, 3 * warp, lane);
+        TP_PROF(2);
+        if (tid < 9) {
+            tp_sweep<true, true>(n6, lu, wk, tid);     // U^T y = b  (solveAdj, first loop)
+            tp_sweep<false, false>(n6, lu, wk, tid);   // L^T x = y  (second loop)
+        }
         __syncthreads();
+        TP_PROF(3);
         // gradients w.r.t. the variables (:939-948) with calGradCTtoQT's gdT part (minco.hpp:1016-1067)
         const double tw = stage == 1 ? P.opt.s1_time_weight : P.opt.s2_time_weight;
         const double* Tau = x;
@@ -967,6 +1022,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             for (int t = 0; t < TOPAY_NTERMS; t++) S.term_out[(size_t)cand * TOPAY_NTERMS + t] = terms[t];
         }
         st.evals_total++;
+        TP_PROF(4);
     }
 
     // ================= line search / L-BFGS / ALM state machine =================
@@ -1152,14 +1208,15 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     q4[3] += rgp[e] * rgp[e];
                     rd[e] = -rg[e];
                 }
-                for (int j = tid; j < m; j += TP_CAND_THREADS) s_ys[j] = lm_ys[j];
+                for (int j = tid; j < m; j += TP_CAND_THREADS) s_ys[j] = 1.0 / lm_ys[j];   // reciprocals
                 tp_block_sum<4>(q4, red, flip);
                 const double ys = q4[0], yy = q4[1];
                 if (tid == 0) {
                     lm_ys[st.end] = ys;
-                    s_ys[st.end] = ys;
+                    s_ys[st.end] = 1.0 / ys;
                 }
                 const double cau = q4[2] * sqrt(q4[3]) * lp.cautious_factor;
+                TP_PROF(5);
                 if (ys > cau) {
                     st.bound = st.bound + 1 < m ? st.bound + 1 : m;
                     st.end = (st.end + 1) % m;
@@ -1177,7 +1234,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                         }
                     }
                     for (int it = 0; it < st.bound; ++it) {
-                        j = (j + m - 1) % m;
+                        j = j == 0 ? m - 1 : j - 1;
                         double cs[TP_EPT], cy[TP_EPT];
 #pragma unroll
                         for (int e = 0; e < TP_EPT; e++) {
@@ -1185,7 +1242,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                             cy[e] = py[e];
                         }
                         if (it + 1 < st.bound) {
-                            const int jn = (j + m - 1) % m;
+                            const int jn = j == 0 ? m - 1 : j - 1;
 #pragma unroll
                             for (int e = 0; e < TP_EPT; e++) {
                                 const int i = tid + e * TP_CAND_THREADS;
@@ -1197,12 +1254,13 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
 #pragma unroll
                         for (int e = 0; e < TP_EPT; e++) a1[0] += cs[e] * rd[e];
                         tp_block_sum<1>(a1, red, flip);
-                        const double al = a1[0] / s_ys[j];
+                        const double al = a1[0] * s_ys[j];
                         if (tid == 0) s_alpha[j] = al;
 #pragma unroll
                         for (int e = 0; e < TP_EPT; e++) rd[e] += (-al) * cy[e];
                     }
                     const double sc = ys / yy;
+                    TP_PROF(6);
 #pragma unroll
                     for (int e = 0; e < TP_EPT; e++) rd[e] *= sc;
                     __syncthreads();   // s_alpha complete
@@ -1222,7 +1280,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                             cy[e] = py[e];
                         }
                         if (it + 1 < st.bound) {
-                            const int jn = (j + 1) % m;
+                            const int jn = j + 1 == m ? 0 : j + 1;
 #pragma unroll
                             for (int e = 0; e < TP_EPT; e++) {
                                 const int i = tid + e * TP_CAND_THREADS;
@@ -1234,12 +1292,13 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
 #pragma unroll
                         for (int e = 0; e < TP_EPT; e++) b1[0] += cy[e] * rd[e];
                         tp_block_sum<1>(b1, red, flip);
-                        const double a = s_alpha[j] - b1[0] / s_ys[j];
+                        const double a = s_alpha[j] - b1[0] * s_ys[j];
 #pragma unroll
                         for (int e = 0; e < TP_EPT; e++) rd[e] += a * cs[e];
-                        j = (j + 1) % m;
+                        j = j + 1 == m ? 0 : j + 1;
                     }
                 }
+                TP_PROF(7);
                 st.stp = 1.0;
                 action = A_BEGIN_LS;
             }
@@ -1338,6 +1397,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             }
         }
         __syncthreads();
+        TP_PROF(8);
     }
 
     // ================= generate half of the next evaluation =================
@@ -1350,12 +1410,21 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         }
         __syncthreads();
         tp_fill_system(N, sT, S.head_pva + (size_t)cand * 27, S.tail_pva + (size_t)cand * 27, x, P, lu, cf);
+        TP_PROF(9);
         if (warp == 0) tp_lu_factor(n6, lu, lane);
         __syncthreads();
-        if (warp < 3) tp_lu_subst(n6, lu, cf, 3 * warp, lane);
+        TP_PROF(10);
+        tp_band_transpose(n6, lu);
+        if (tid < 9) {
+            tp_sweep<true, false>(n6, lu, cf, tid);    // L y = b   (solve, first loop)
+            tp_sweep<false, true>(n6, lu, cf, tid);    // U x = y   (second loop)
+        }
         __syncthreads();
+        tp_band_transpose(n6, lu);
+        TP_PROF(11);
         for (int e = tid; e < n6 * TP_BAND; e += TP_CAND_THREADS) lug[e] = lu[e];
         for (int e = tid; e < n6 * 9; e += TP_CAND_THREADS) cg[e] = cf[e];
+        TP_PROF(12);
     }
     if (tid == 0) {
         *gs = st;
