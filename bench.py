@@ -220,6 +220,8 @@ def main():
     batches = [scenes.synthetic_batch(n_cand, 1234 + 100000 * rank + 1000 * p) for p in range(P)]
     paths, bv, ba = batches[0]
     solvers = [tp.MomaTrajOpt(gm, max_cand=n_cand, max_pieces=N_PIECES, opt_param=opt, robot=rp) for _ in range(P)]
+    for sv in solvers:
+        sv.set_timed(True)      # CUDA events around every k_penalty launch, live in the timed region
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
     import threading
 

@@ -315,6 +315,10 @@ typedef struct topay_solver_stats {
     int64_t eval_nodes;        /* penalty nodes processed by them (active candidates only) */
 } topay_solver_stats;
 int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out);
+/* timed != 0: every k_penalty launch is bracketed by CUDA events (stats.ms_eval) and the ticks are
+ * plain launches; timed == 0 (default): a batch of 16 ticks is replayed as one CUDA graph, which
+ * removes the per-launch host cost that dominates small plans; stats.ms_eval is then 0. */
+int topay_solver_set_timed(topay_solver* s, int timed);
 
 /* Optional L-BFGS iterate trace (parity / debugging): when cap > 0 every accepted iteration of
  * every candidate records (f, step, k, line-search evaluations) — the arguments the reference

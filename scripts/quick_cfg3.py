@@ -13,6 +13,7 @@ opt, rp = tp.opt_params_default(), tp.robot_params_default()
 opt.int_K = 32; opt.min_piece_num = 64; opt.sample_interval = 1e9
 paths, bv, ba = scenes.synthetic_batch(C, 1234)
 solver = tp.MomaTrajOpt(gm, max_cand=C, max_pieces=64, opt_param=opt, robot=rp)
+solver.set_timed(os.environ.get('TIMED', '1') == '1')
 t = time.time(); solver.upload(paths, bv, ba); print("upload s", time.time() - t)
 import ctypes
 solver._l.topay_solver_phase_clocks(solver.h, 1, None)

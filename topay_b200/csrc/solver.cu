@@ -29,6 +29,11 @@ struct topay_solver {
     size_t smem_cand;
     // initial state kept on the host for repeated runs
     std::vector<double> h_x0;
+    // one batch of `slots` ticks as a CUDA graph (launch-bound small plans); rebuilt when the
+    // launch geometry or a captured pointer changes
+    bool timed;                 // per-launch CUDA events around k_penalty (plain launches, no graph)
+    cudaGraphExec_t graph_exec;
+    int graph_n_cand, graph_max_N;
 };
 
 namespace {
@@ -116,6 +121,9 @@ extern "C" int topay_solver_create(const topay_opt_params* opt, const topay_robo
     s->n_cand = 0;
     s->max_N = 0;
     s->slots = 16;
+    s->timed = false;
+    s->graph_exec = nullptr;
+    s->graph_n_cand = s->graph_max_N = -1;
     memset(&s->stats, 0, sizeof(s->stats));
     cudaSetDevice(s->device);
     TP_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), { delete s; });
@@ -205,6 +213,7 @@ extern "C" void topay_solver_destroy(topay_solver* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     for (void* p : s->allocs) cudaFree(p);
     if (s->dev.trace) cudaFree(s->dev.trace);
     if (s->dev.trace_len) cudaFree(s->dev.trace_len);
@@ -359,20 +368,49 @@ extern "C" int topay_solver_run(topay_solver* s) {
         (s->params.opt.s2_lbfgs.max_linesearch + 1);
     long long ticks = 0;
     bool done = false;
-    while (!done && ticks < max_ticks) {
+    const bool use_graph = !s->timed;
+    if (use_graph && (!s->graph_exec || s->graph_n_cand != s->n_cand || s->graph_max_N != s->max_N)) {
+        if (s->graph_exec) {
+            cudaGraphExecDestroy(s->graph_exec);
+            s->graph_exec = nullptr;
+        }
+        cudaGraph_t g = nullptr;
+        const topay_solver_stats keep = s->stats;
+        TP_CUDA_OK(cudaStreamBeginCapture(q, cudaStreamCaptureModeThreadLocal), {});
         cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), q);
         for (int t = 0; t < s->slots; t++) {
-            launch_eval(s, true, t);
+            launch_eval(s, false, t);
             launch_cand(s, TP_MODE_ADJ | TP_MODE_ADVANCE | TP_MODE_GEN, t);
         }
-        ticks += s->slots;
         cudaMemcpyAsync(s->h_active, D.n_active, s->slots * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
-        TP_CUDA_OK(cudaStreamSynchronize(q), {});
-        for (int t = 0; t < s->slots; t++) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, s->ev[2 * t], s->ev[2 * t + 1]);
-            ms_eval += ms;
+        TP_CUDA_OK(cudaStreamEndCapture(q, &g), {});
+        TP_CUDA_OK(cudaGraphInstantiate(&s->graph_exec, g, 0), { cudaGraphDestroy(g); });
+        cudaGraphDestroy(g);
+        s->graph_n_cand = s->n_cand;
+        s->graph_max_N = s->max_N;
+        s->stats = keep;   // the capture pass launched nothing
+    }
+    while (!done && ticks < max_ticks) {
+        if (use_graph) {
+            TP_CUDA_OK(cudaGraphLaunch(s->graph_exec, q), {});
+            s->stats.kernel_launches += 4 * s->slots;
+            s->stats.eval_launches += s->slots;
+        } else {
+            cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), q);
+            for (int t = 0; t < s->slots; t++) {
+                launch_eval(s, true, t);
+                launch_cand(s, TP_MODE_ADJ | TP_MODE_ADVANCE | TP_MODE_GEN, t);
+            }
+            cudaMemcpyAsync(s->h_active, D.n_active, s->slots * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
         }
+        ticks += s->slots;
+        TP_CUDA_OK(cudaStreamSynchronize(q), {});
+        if (!use_graph)
+            for (int t = 0; t < s->slots; t++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, s->ev[2 * t], s->ev[2 * t + 1]);
+                ms_eval += ms;
+            }
         done = s->h_active[s->slots - 1] == 0;
     }
     cudaEventRecord(s->ev_end, q);
@@ -456,6 +494,7 @@ extern "C" int topay_solver_phase_clocks(topay_solver* s, int enable, long long*
     if (!s) return TOPAY_ERR_INVALID_ARG;
     cudaSetDevice(s->device);
     TpSolverDev& D = s->dev;
+    s->graph_n_cand = -1;   // captured kernel arguments change
     if (enable && !D.prof) {
         TP_CUDA_OK(cudaMalloc(&D.prof, 16 * sizeof(long long)), {});
         cudaMemset(D.prof, 0, 16 * sizeof(long long));
@@ -471,10 +510,17 @@ extern "C" int topay_solver_phase_clocks(topay_solver* s, int enable, long long*
     return TOPAY_OK;
 }
 
+extern "C" int topay_solver_set_timed(topay_solver* s, int timed) {
+    if (!s) return TOPAY_ERR_INVALID_ARG;
+    s->timed = timed != 0;
+    return TOPAY_OK;
+}
+
 extern "C" int topay_solver_set_trace(topay_solver* s, int cap) {
     if (!s || cap < 0) return TOPAY_ERR_INVALID_ARG;
     cudaSetDevice(s->device);
     TpSolverDev& D = s->dev;
+    s->graph_n_cand = -1;   // captured kernel arguments change
     if (D.trace) {
         cudaFree(D.trace);
         cudaFree(D.trace_len);

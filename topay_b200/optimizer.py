@@ -133,6 +133,10 @@ class MomaTrajOpt:
         N = int(r["piece_num"][idx])
         return MomaTraj(r["T"][idx, :N].copy(), r["coeff"][idx, :6 * N].copy(), self._starts[idx])
 
+    def set_timed(self, timed):
+        """Per-launch CUDA-event timing of the penalty kernel (plain launches) instead of graph replay."""
+        _lib.check(self._l.topay_solver_set_timed(self.h, int(timed)), "topay_solver_set_timed")
+
     def set_trace(self, cap):
         _lib.check(self._l.topay_solver_set_trace(self.h, cap), "topay_solver_set_trace")
         self._trace_cap = cap
