@@ -220,8 +220,9 @@ def main():
     batches = [scenes.synthetic_batch(n_cand, 1234 + 100000 * rank + 1000 * p) for p in range(P)]
     paths, bv, ba = batches[0]
     solvers = [tp.MomaTrajOpt(gm, max_cand=n_cand, max_pieces=N_PIECES, opt_param=opt, robot=rp) for _ in range(P)]
-    for sv in solvers:
-        sv.set_timed(True)      # CUDA events around every k_penalty launch, live in the timed region
+    # plan slot 0 brackets every k_penalty launch with CUDA events (plain launches), live in the timed
+    # region and under the same concurrent load; the other slots replay their ticks as CUDA graphs
+    solvers[0].set_timed(os.environ.get("TOPAY_BENCH_TIMED", "1") == "1")
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
     import threading
 
@@ -255,10 +256,12 @@ def main():
         with lock:
             acc["launches"] += st["kernel_launches"]
             acc["ticks"] += st["ticks"]
-            acc["evals_launch"] += st["eval_launches"]
-            acc["nodes"] += st["eval_nodes"]
-            acc["ms_eval"] += st["ms_eval"]
             acc["ms_dev"] += st["ms_total"]
+            if st["ms_eval"] > 0:      # the timed slot
+                acc["evals_launch"] += st["eval_launches"]
+                acc["nodes"] += st["eval_nodes"]
+                acc["ms_eval"] += st["ms_eval"]
+                acc["ms_dev_timed"] = acc.get("ms_dev_timed", 0.0) + st["ms_total"]
 
     run_steps(max(args.warmup, 0), lambda slot: solvers[slot].run())
     torch.cuda.synchronize()
@@ -297,6 +300,7 @@ def main():
     pen_ms = ms_eval / max(evals_launch, 1)
     nodes_per_launch = nodes / max(evals_launch, 1)
     alg_bytes = nodes_per_launch * NODE_BYTES
+    pen_ms = max(pen_ms, 1e-9)
     achieved = alg_bytes / (pen_ms * 1e-3) / 1e9
     mids_per_launch = nodes_per_launch * INT_K / (INT_K + 1)
     flop = nodes_per_launch * NODE_FLOP + mids_per_launch * MID_FLOP
@@ -318,7 +322,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_penalty", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "avg_launch_ms": pen_ms, "nodes_per_launch": nodes_per_launch,
-                     "share_of_step": ms_eval / max(ms_dev, 1e-9),
+                     "share_of_step": ms_eval / max(acc.get("ms_dev_timed", ms_dev), 1e-9),
                      "fp64": {"achieved_tflops": flop / (pen_ms * 1e-3) / 1e12, "nominal_peak_tflops": 40.0,
                               "note": "the kernel is FP64-pipe/latency bound, not HBM bound: 4.0 kflop per "
                                       "penalty node against 800 algorithmic bytes"}},
