@@ -106,69 +106,305 @@ __global__ void k_threshold(const double* __restrict__ esdf, double thr, int8_t*
     if (i < n) out[i] = esdf[i] < thr ? 1 : 0;
 }
 
-// Pass 1, along the contiguous axis: 1-D distance to the nearest source (pos) and to the
-// nearest non-source (neg) cell of each line, as int16 (TP_INF16 = none on this line).
-// One thread per line; the block's lines are staged in shared memory both ways so global
-// traffic is coalesced. dynamic smem: lines*in_stride bytes + lines*out_stride*4 bytes.
-__global__ void k_edt_contig(const int8_t* __restrict__ src, short2* __restrict__ out, int64_t n_lines, int C,
-                             int in_stride, int out_stride) {
-    extern __shared__ unsigned char smraw[];
-    const int LPB = blockDim.x;
-    unsigned char* s_in = smraw;
-    short2* s_out = (short2*)(smraw + (((size_t)LPB * in_stride + 15) & ~(size_t)15));
-    const int64_t line0 = (int64_t)blockIdx.x * LPB;
-    const int lines = (int)min((int64_t)LPB, n_lines - line0);
-    const int8_t* gsrc = src + line0 * C;
-    for (int e = threadIdx.x; e < lines * C; e += LPB) s_in[(e / C) * in_stride + (e % C)] = (unsigned char)gsrc[e];
-    __syncthreads();
-    if ((int)threadIdx.x < lines) {
-        const unsigned char* in = s_in + threadIdx.x * in_stride;
-        short2* o = s_out + (size_t)threadIdx.x * out_stride;
-        int dp = TP_INF16, dn = TP_INF16;
-        for (int c = 0; c < C; c++) {
-            const bool occ = in[c] == 1;
-            dp = occ ? 0 : min(dp + 1, TP_INF16);
-            dn = occ ? min(dn + 1, TP_INF16) : 0;
-            o[c] = make_short2((short)dp, (short)dn);
-        }
-        dp = TP_INF16;
-        dn = TP_INF16;
-        for (int c = C - 1; c >= 0; c--) {
-            const bool occ = in[c] == 1;
-            dp = occ ? 0 : min(dp + 1, TP_INF16);
-            dn = occ ? min(dn + 1, TP_INF16) : 0;
-            short2 v = o[c];
-            v.x = (short)min((int)v.x, dp);
-            v.y = (short)min((int)v.y, dn);
-            o[c] = v;
-        }
+// Pass 1, along the contiguous axis: 1-D distance to the nearest source (pos) and to the nearest
+// non-source (neg) cell of each line, as int16 (TP_INF16 = none on this line). One warp per line,
+// four consecutive cells per lane (one 4-byte load, one 16-byte store when C % 4 == 0): the index of
+// the last source at or before a cell is a running max inside the lane, a warp max-scan across
+// lanes and a carry across the 128-cell chunks; the next source at or after it is the mirror image.
+// Lines of up to 128 cells (the z axis of the 3-D grid) take a single chunk, everything in
+// registers; longer lines (the 2-D maps) make a forward and a backward pass over their chunks.
+#define TP_NEG_BIG (-(1 << 28))
+#define TP_POS_BIG (1 << 28)
+
+__device__ __forceinline__ int tp_scan_max_excl(int v, int lane) {
+    // exclusive max-scan over lower lanes; identity TP_NEG_BIG
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x = max(x, y);
     }
-    __syncthreads();
-    short2* gout = out + line0 * C;
-    for (int e = threadIdx.x; e < lines * C; e += LPB) gout[e] = s_out[(size_t)(e / C) * out_stride + (e % C)];
+    const int e = __shfl_up_sync(0xffffffffu, x, 1);
+    return lane == 0 ? TP_NEG_BIG : e;
+}
+__device__ __forceinline__ int tp_scan_min_excl_rev(int v, int lane) {
+    // exclusive min-scan over higher lanes; identity TP_POS_BIG
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_down_sync(0xffffffffu, x, d);
+        if (lane + d < 32) x = min(x, y);
+    }
+    const int e = __shfl_down_sync(0xffffffffu, x, 1);
+    return lane == 31 ? TP_POS_BIG : e;
 }
 
-// exact 1-D squared-distance envelope by outward search with the d*d >= best cut-off
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k_edt_contig(const int8_t* __restrict__ src, short2* __restrict__ out, int64_t n_lines, int C) {
+    const int lane = threadIdx.x & 31;
+    const int64_t line = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (line >= n_lines) return;
+    const int8_t* in = src + line * C;
+    short2* o = out + line * C;
+    const int nchunk = (C + 127) >> 7;
+    auto load4 = [&](int c0, bool occ[4]) {
+        if (VEC) {
+            uchar4 v = make_uchar4(0, 0, 0, 0);
+            if (c0 < C) v = *reinterpret_cast<const uchar4*>(in + c0);
+            occ[0] = v.x == 1; occ[1] = v.y == 1; occ[2] = v.z == 1; occ[3] = v.w == 1;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) occ[k] = (c0 + k < C) && in[c0 + k] == 1;
+        }
+    };
+    // forward: last source / last free cell at or before each cell
+    int carry_p = TP_NEG_BIG, carry_n = TP_NEG_BIG;
+    int fp[4], fn[4];           // kept for the single-chunk case
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int c0 = (ch << 7) + lane * 4;
+        bool occ[4];
+        load4(c0, occ);
+        int lp = TP_NEG_BIG, ln = TP_NEG_BIG, lastp[4], lastn[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool in_line = c0 + k < C;
+            if (in_line && occ[k]) lp = c0 + k;
+            if (in_line && !occ[k]) ln = c0 + k;
+            lastp[k] = lp;
+            lastn[k] = ln;
+        }
+        const int ep = max(tp_scan_max_excl(lp, lane), carry_p);
+        const int en = max(tp_scan_max_excl(ln, lane), carry_n);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = c0 + k;
+            const int a = max(lastp[k], ep), b = max(lastn[k], en);
+            fp[k] = a < 0 ? TP_INF16 : min(c - a, TP_INF16);
+            fn[k] = b < 0 ? TP_INF16 : min(c - b, TP_INF16);
+        }
+        carry_p = max(carry_p, __shfl_sync(0xffffffffu, max(lp, ep), 31));
+        carry_n = max(carry_n, __shfl_sync(0xffffffffu, max(ln, en), 31));
+        if (nchunk > 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (c0 + k < C) o[c0 + k] = make_short2((short)fp[k], (short)fn[k]);
+        }
+    }
+    // backward: next source / next free cell at or after each cell, min with the forward result
+    carry_p = TP_POS_BIG;
+    carry_n = TP_POS_BIG;
+    for (int ch = nchunk - 1; ch >= 0; ch--) {
+        const int c0 = (ch << 7) + lane * 4;
+        bool occ[4];
+        load4(c0, occ);
+        int np_ = TP_POS_BIG, nn_ = TP_POS_BIG, nextp[4], nextn[4];
+#pragma unroll
+        for (int k = 3; k >= 0; k--) {
+            const bool in_line = c0 + k < C;
+            if (in_line && occ[k]) np_ = c0 + k;
+            if (in_line && !occ[k]) nn_ = c0 + k;
+            nextp[k] = np_;
+            nextn[k] = nn_;
+        }
+        const int ep = min(tp_scan_min_excl_rev(np_, lane), carry_p);
+        const int en = min(tp_scan_min_excl_rev(nn_, lane), carry_n);
+        short2 res[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = c0 + k;
+            const int a = min(nextp[k], ep), b = min(nextn[k], en);
+            int bp = a >= TP_POS_BIG ? TP_INF16 : min(a - c, TP_INF16);
+            int bn = b >= TP_POS_BIG ? TP_INF16 : min(b - c, TP_INF16);
+            if (nchunk > 1) {
+                if (c < C) {
+                    const short2 f = o[c];
+                    bp = min(bp, (int)f.x);
+                    bn = min(bn, (int)f.y);
+                }
+            } else {
+                bp = min(bp, fp[k]);
+                bn = min(bn, fn[k]);
+            }
+            res[k] = make_short2((short)bp, (short)bn);
+        }
+        carry_p = min(carry_p, __shfl_sync(0xffffffffu, min(np_, ep), 0));
+        carry_n = min(carry_n, __shfl_sync(0xffffffffu, min(nn_, en), 0));
+        if (VEC) {
+            if (c0 < C) *reinterpret_cast<uint4*>(o + c0) = *reinterpret_cast<const uint4*>(res);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (c0 + k < C) o[c0 + k] = res[k];
+        }
+    }
+}
+
+// Exact 1-D squared-distance envelope  min_v (l - v)^2 + f(v)  of one line staged in shared memory
+// (stride = tile width), by outward search with the d*d >= best cut-off: a candidate at distance d
+// cannot improve once d^2 >= best. Two-sided steps are unrolled by four with one cut-off test per
+// group; add+min is a single DPX instruction (__viaddmin_s32).
 __device__ __forceinline__ int tp_line_min(const int* __restrict__ col, int stride, int n, int l) {
     int best = col[(size_t)l * stride];
-    for (int d = 1; d < n; d++) {
+    const int dlim = min(l, n - 1 - l);
+    int d = 1;
+    for (; d + 3 <= dlim; d += 4) {
+        int dd = d * d;
+        if (dd >= best) return best;
+        const int* lo = col + (size_t)(l - d) * stride;
+        const int* hi = col + (size_t)(l + d) * stride;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            best = __viaddmin_s32(dd, lo[-k * stride], best);
+            best = __viaddmin_s32(dd, hi[k * stride], best);
+            dd += 2 * (d + k) + 1;
+        }
+    }
+    for (; d <= dlim; d++) {
         const int dd = d * d;
-        if (dd >= best) break;
-        if (l - d >= 0) best = min(best, dd + col[(size_t)(l - d) * stride]);
-        if (l + d < n) best = min(best, dd + col[(size_t)(l + d) * stride]);
+        if (dd >= best) return best;
+        best = __viaddmin_s32(dd, col[(size_t)(l - d) * stride], best);
+        best = __viaddmin_s32(dd, col[(size_t)(l + d) * stride], best);
+    }
+    if (l > n - 1 - l) {
+        for (; d <= l; d++) {
+            const int dd = d * d;
+            if (dd >= best) return best;
+            best = __viaddmin_s32(dd, col[(size_t)(l - d) * stride], best);
+        }
+    } else {
+        for (; d <= n - 1 - l; d++) {
+            const int dd = d * d;
+            if (dd >= best) return best;
+            best = __viaddmin_s32(dd, col[(size_t)(l + d) * stride], best);
+        }
     }
     return best;
 }
 
-// Passes 2 and 3, along a strided axis. Block = one outer index x TZ contiguous inner cells;
-// the whole line (n_line) of both transforms is staged in shared memory as int32 squared
-// distances. IN16: input is pass 1's packed int16 1-D distances (squared on load).
-// FINAL: writes the fp64 ESDF (grid_map.cpp:457, 503, 515-517) and optionally the integer grids.
-template <bool IN16, bool FINAL>
-__global__ void k_edt_strided(const short2* __restrict__ in16, const int32_t* __restrict__ in_pos,
-                              const int32_t* __restrict__ in_neg, int32_t* __restrict__ out_pos,
-                              int32_t* __restrict__ out_neg, double* __restrict__ esdf, int n_line,
-                              size_t line_stride, size_t outer_stride, int n_inner, int tiles, double res) {
+__device__ __forceinline__ void tp_edt_store(bool FINAL, int bp, int bn, size_t idx, double res,
+                                             int32_t* __restrict__ out_pos, int32_t* __restrict__ out_neg,
+                                             double* __restrict__ esdf) {
+    if (bp >= TP_INF32) bp = FINAL ? INT32_MAX : TP_INF32;
+    if (bn >= TP_INF32) bn = FINAL ? INT32_MAX : TP_INF32;
+    if (FINAL) {
+        // grid_map.cpp:457, 503, 515-517 — round-to-nearest, no FMA contraction
+        const double vp = bp == INT32_MAX ? DBL_MAX : (double)bp;
+        const double vn = bn == INT32_MAX ? DBL_MAX : (double)bn;
+        const double dp = __dmul_rn(res, __dsqrt_rn(vp));
+        const double dn = __dmul_rn(res, __dsqrt_rn(vn));
+        double d = dp;
+        if (dn > 0.0) d = __dadd_rn(d, __dadd_rn(-dn, res));
+        esdf[idx] = d;
+        if (out_pos) {
+            out_pos[idx] = bp;
+            out_neg[idx] = bn;
+        }
+    } else {
+        out_pos[idx] = bp;
+        out_neg[idx] = bn;
+    }
+}
+
+// Pass 2 (and the last pass of the 2-D maps): input is pass 1's packed int16 1-D distances.
+// Most entries of the positive transform are "no source on this line" (columns without any
+// obstacle), so each column's finite entries are compacted — (index << 16 | distance), in order —
+// and an output only walks its finite neighbours outwards, nearest first, with the same cut-off.
+// The negative transform (sources = free cells, dense and mostly zero) keeps the dense search.
+// smem: tile [n_line][TZ+1] short2 | compact [TZ][n_line] int32 | rank [n_line][TZ+1] int16 | cnt [TZ]
+template <bool FINAL>
+__global__ void k_edt_strided16(const short2* __restrict__ in16, int32_t* __restrict__ out_pos,
+                                int32_t* __restrict__ out_neg, double* __restrict__ esdf, int n_line,
+                                size_t line_stride, size_t outer_stride, int n_inner, int tiles, double res) {
+    extern __shared__ int sm_i[];
+    const int TZ = blockDim.x, TY = blockDim.y, RS = TZ + 1;
+    short2* s_in = reinterpret_cast<short2*>(sm_i);
+    int* s_cv = sm_i + (size_t)n_line * RS;
+    short* s_rank = reinterpret_cast<short*>(s_cv + (size_t)TZ * n_line);
+    int* s_cnt = reinterpret_cast<int*>(s_rank + (((size_t)n_line * RS + 1) & ~(size_t)1));
+    const int outer = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+    const int c = tile * TZ + threadIdx.x;
+    const bool cvalid = c < n_inner;
+    const size_t base = (size_t)outer * outer_stride + c;
+    for (int l = threadIdx.y; l < n_line; l += TY) {
+        short2 v = make_short2(TP_INF16, TP_INF16);
+        if (cvalid) v = in16[base + (size_t)l * line_stride];
+        s_in[(size_t)l * RS + threadIdx.x] = v;
+    }
+    __syncthreads();
+    // compaction: one warp per column at a time
+    const int tid = threadIdx.y * TZ + threadIdx.x, nthreads = TZ * TY;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+    for (int col = warp; col < TZ; col += max(nwarps, 1)) {
+        int count = 0;
+        for (int l0 = 0; l0 < n_line; l0 += 32) {
+            const int l = l0 + lane;
+            const int v = l < n_line ? (int)s_in[(size_t)l * RS + col].x : TP_INF16;
+            const bool fin = v < TP_INF16;
+            const unsigned m = __ballot_sync(0xffffffffu, fin);
+            const int before = count + __popc(m & ((1u << lane) - 1u));
+            if (l < n_line) s_rank[(size_t)l * RS + col] = (short)before;
+            if (fin) s_cv[(size_t)col * n_line + before] = (l << 16) | v;
+            count += __popc(m);
+        }
+        if (lane == 0) s_cnt[col] = count;
+    }
+    __syncthreads();
+    if (!cvalid) return;
+    const int cnt = s_cnt[threadIdx.x];
+    const int* cv = s_cv + (size_t)threadIdx.x * n_line;
+    for (int l = threadIdx.y; l < n_line; l += TY) {
+        // positive transform: walk the finite entries outwards from l, the nearer side first
+        int bp = TP_INF32;
+        {
+            const int b0 = s_rank[(size_t)l * RS + threadIdx.x];
+            const bool right_first = b0 < cnt && (b0 == 0 || (cv[b0] >> 16) - l <= l - (cv[b0 - 1] >> 16));
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                if ((side == 0) == right_first) {
+                    for (int b = b0; b < cnt; b++) {
+                        const int e = cv[b], d = (e >> 16) - l, v = e & 0xffff;
+                        const int dd = d * d;
+                        if (dd >= bp) break;
+                        bp = min(bp, dd + v * v);
+                    }
+                } else {
+                    for (int a = b0 - 1; a >= 0; a--) {
+                        const int e = cv[a], d = l - (e >> 16), v = e & 0xffff;
+                        const int dd = d * d;
+                        if (dd >= bp) break;
+                        bp = min(bp, dd + v * v);
+                    }
+                }
+            }
+        }
+        // negative transform: dense outward search on the packed tile
+        int bn;
+        {
+            const short2* colp = s_in + threadIdx.x;
+            auto at = [&](int q) {
+                const int v = colp[(size_t)q * RS].y;
+                return v >= TP_INF16 ? TP_INF32 : v * v;
+            };
+            bn = at(l);
+            for (int d = 1; d < n_line; d++) {
+                const int dd = d * d;
+                if (dd >= bn) break;
+                if (l - d >= 0) bn = __viaddmin_s32(dd, at(l - d), bn);
+                if (l + d < n_line) bn = __viaddmin_s32(dd, at(l + d), bn);
+            }
+        }
+        tp_edt_store(FINAL, bp, bn, base + (size_t)l * line_stride, res, out_pos, out_neg, esdf);
+    }
+}
+
+// Pass 3 (3-D maps): input = pass 2's int32 squared distances of both transforms, dense. Block = one
+// outer index x TZ contiguous inner cells; the whole line is staged in shared memory.
+template <bool FINAL>
+__global__ void k_edt_strided32(const int32_t* __restrict__ in_pos, const int32_t* __restrict__ in_neg,
+                                int32_t* __restrict__ out_pos, int32_t* __restrict__ out_neg,
+                                double* __restrict__ esdf, int n_line, size_t line_stride, size_t outer_stride,
+                                int n_inner, int tiles, double res) {
     extern __shared__ int sm_i[];
     const int TZ = blockDim.x, TY = blockDim.y;
     int* s_pos = sm_i;
@@ -181,14 +417,8 @@ __global__ void k_edt_strided(const short2* __restrict__ in16, const int32_t* __
         int p = TP_INF32, q = TP_INF32;
         if (cvalid) {
             const size_t idx = base + (size_t)l * line_stride;
-            if (IN16) {
-                const short2 v = in16[idx];
-                p = v.x >= TP_INF16 ? TP_INF32 : (int)v.x * (int)v.x;
-                q = v.y >= TP_INF16 ? TP_INF32 : (int)v.y * (int)v.y;
-            } else {
-                p = in_pos[idx];
-                q = in_neg[idx];
-            }
+            p = in_pos[idx];
+            q = in_neg[idx];
         }
         s_pos[(size_t)l * TZ + threadIdx.x] = p;
         s_neg[(size_t)l * TZ + threadIdx.x] = q;
@@ -196,27 +426,9 @@ __global__ void k_edt_strided(const short2* __restrict__ in16, const int32_t* __
     __syncthreads();
     if (!cvalid) return;
     for (int l = threadIdx.y; l < n_line; l += TY) {
-        int bp = tp_line_min(s_pos + threadIdx.x, TZ, n_line, l);
-        int bn = tp_line_min(s_neg + threadIdx.x, TZ, n_line, l);
-        if (bp >= TP_INF32) bp = FINAL ? INT32_MAX : TP_INF32;
-        if (bn >= TP_INF32) bn = FINAL ? INT32_MAX : TP_INF32;
-        const size_t idx = base + (size_t)l * line_stride;
-        if (FINAL) {
-            const double vp = bp == INT32_MAX ? DBL_MAX : (double)bp;
-            const double vn = bn == INT32_MAX ? DBL_MAX : (double)bn;
-            const double dp = __dmul_rn(res, __dsqrt_rn(vp));
-            const double dn = __dmul_rn(res, __dsqrt_rn(vn));
-            double d = dp;
-            if (dn > 0.0) d = __dadd_rn(d, __dadd_rn(-dn, res));
-            esdf[idx] = d;
-            if (out_pos) {
-                out_pos[idx] = bp;
-                out_neg[idx] = bn;
-            }
-        } else {
-            out_pos[idx] = bp;
-            out_neg[idx] = bn;
-        }
+        const int bp = tp_line_min(s_pos + threadIdx.x, TZ, n_line, l);
+        const int bn = tp_line_min(s_neg + threadIdx.x, TZ, n_line, l);
+        tp_edt_store(FINAL, bp, bn, base + (size_t)l * line_stride, res, out_pos, out_neg, esdf);
     }
 }
 
@@ -315,47 +527,51 @@ int signed_edt(topay_field* f, const int8_t* src, int A, int B, int C, double* e
     const int64_t n_lines = (int64_t)A * B;
     // pass 1
     {
-        int in_stride = (C + 3) & ~3;
-        if (((in_stride / 4) & 1) == 0) in_stride += 4;
-        const int out_stride = C | 1;
-        int lpb = 128;
-        auto need = [&](int l) { return (((size_t)l * in_stride + 15) & ~(size_t)15) + (size_t)l * out_stride * 4; };
-        while (lpb > 32 && need(lpb) > 96 * 1024) lpb >>= 1;
-        if (need(lpb) > 200 * 1024) {
-            tp_set_error("grid line too long for the pass-1 staging buffer");
-            return TOPAY_ERR_TOO_LARGE;
-        }
-        TP_CUDA_OK(cudaFuncSetAttribute(k_edt_contig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(lpb)), {});
-        const unsigned blocks = (unsigned)((n_lines + lpb - 1) / lpb);
-        k_edt_contig<<<blocks, lpb, need(lpb), q>>>(src, f->packed, n_lines, C, in_stride, out_stride);
+        const int wpb = 8;
+        const unsigned blocks = (unsigned)((n_lines + wpb - 1) / wpb);
+        if (C % 4 == 0)
+            k_edt_contig<true><<<blocks, wpb * 32, 0, q>>>(src, f->packed, n_lines, C);
+        else
+            k_edt_contig<false><<<blocks, wpb * 32, 0, q>>>(src, f->packed, n_lines, C);
     }
     auto strided = [&](bool in16, bool fin, int n_line, size_t line_stride, int n_outer, size_t outer_stride,
                        int n_inner) -> int {
+        auto smem_of = [&](int tz) -> size_t {
+            if (!in16) return (size_t)n_line * tz * 8;
+            const size_t rs = tz + 1;
+            return (size_t)n_line * rs * 4 + (size_t)tz * n_line * 4 + ((((size_t)n_line * rs + 1) & ~(size_t)1) * 2) +
+                   (size_t)tz * 4 + 16;
+        };
         int TZ = 16;
-        while (TZ > 1 && (size_t)n_line * TZ * 8 > 100 * 1024) TZ >>= 1;
-        const size_t smem = (size_t)n_line * TZ * 8;
+        while (TZ > 1 && smem_of(TZ) > (in16 ? 140 : 104) * 1024) TZ >>= 1;
+        // small grids (the 2-D maps): narrower tiles so that the blocks cover all SMs
+        while (TZ > 2 && (long long)n_outer * ((n_inner + TZ - 1) / TZ) < 296) TZ >>= 1;
+        const size_t smem = smem_of(TZ);
         if (smem > 200 * 1024) {
             tp_set_error("grid line too long for the strided-pass staging buffer");
             return TOPAY_ERR_TOO_LARGE;
         }
-        const int TY = std::max(1, std::min(512 / TZ, n_line));
+        int TY = std::max(1, std::min(512 / TZ, n_line));
+        while ((TZ * TY) % 32 != 0 && TY < 1024 / TZ) TY++;     // whole warps (the compaction uses ballots)
         const int tiles = (n_inner + TZ - 1) / TZ;
         dim3 blk(TZ, TY);
         const unsigned blocks = (unsigned)n_outer * tiles;
         int32_t* op = fin ? (f->keep_sq ? sqp : nullptr) : f->tmp_pos;
         int32_t* on = fin ? (f->keep_sq ? sqn : nullptr) : f->tmp_neg;
-#define TP_LAUNCH_STRIDED(I16, FIN)                                                                                \
-    do {                                                                                                           \
-        TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided<I16, FIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                        (int)smem), {});                                                           \
-        k_edt_strided<I16, FIN><<<blocks, blk, smem, q>>>(f->packed, f->tmp_pos, f->tmp_neg, op, on, esdf, n_line, \
-                                                          line_stride, outer_stride, n_inner, tiles,               \
-                                                          f->desc.resolution);                                     \
-    } while (0)
-        if (in16 && fin) TP_LAUNCH_STRIDED(true, true);
-        else if (in16) TP_LAUNCH_STRIDED(true, false);
-        else TP_LAUNCH_STRIDED(false, true);
-#undef TP_LAUNCH_STRIDED
+        const double res = f->desc.resolution;
+        if (in16 && fin) {
+            TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), {});
+            k_edt_strided16<true><<<blocks, blk, smem, q>>>(f->packed, op, on, esdf, n_line, line_stride, outer_stride,
+                                                           n_inner, tiles, res);
+        } else if (in16) {
+            TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), {});
+            k_edt_strided16<false><<<blocks, blk, smem, q>>>(f->packed, op, on, esdf, n_line, line_stride, outer_stride,
+                                                            n_inner, tiles, res);
+        } else {
+            TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), {});
+            k_edt_strided32<true><<<blocks, blk, smem, q>>>(f->tmp_pos, f->tmp_neg, op, on, esdf, n_line, line_stride,
+                                                           outer_stride, n_inner, tiles, res);
+        }
         return TOPAY_OK;
     };
     int rc;
