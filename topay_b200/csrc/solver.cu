@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -405,6 +407,14 @@ extern "C" int topay_solver_run(topay_solver* s) {
         }
         ticks += s->slots;
         TP_CUDA_OK(cudaStreamSynchronize(q), {});
+        if (getenv("TOPAY_TICK_LOG")) {   // dev: wall time of each 16-tick batch vs candidates still active
+            static thread_local double t_prev = 0.0;
+            timespec ts;
+            clock_gettime(CLOCK_MONOTONIC, &ts);
+            const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+            if (ticks > s->slots) fprintf(stderr, "TICKLOG %lld %d %.1f\n", ticks, s->h_active[s->slots - 1], (now - t_prev) * 1e6 / s->slots);
+            t_prev = now;
+        }
         if (!use_graph)
             for (int t = 0; t < s->slots; t++) {
                 float ms = 0.f;

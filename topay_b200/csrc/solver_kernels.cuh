@@ -552,6 +552,32 @@ __device__ __forceinline__ double tp_rcp(double x) {
     return r;   // seed ~2^-20; three steps leave margin for subnormal-free pivots
 }
 
+// ---- TMA bulk copies (cp.async.bulk) of L-BFGS history rows into a shared-memory ring ----
+#define TP_RING_STAGES 8
+__device__ __forceinline__ uint32_t tp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tp_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tp_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tp_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tp_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tp_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tp_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(tp_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tp_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(tp_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 // block-wide sums of up to 4 values; every thread gets the results. `red` is a
 // [2][4][TP_CAND_WARPS] scratch, `flip` alternates so one barrier per call suffices.
 template <int NV>
@@ -802,13 +828,19 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
     long long t_prof = clock64();
     const int N = st.N, n = st.n, n6 = 6 * N;
     const int stage = st.phase;
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     double* lu = sm;
     double* cf = lu + (size_t)6 * S.max_pieces * TP_BAND;
     double* wk = cf + (size_t)6 * S.max_pieces * 9;
     __shared__ double red[2 * 4 * TP_CAND_WARPS];
     __shared__ double s_small[4 * 64 + 2 * TOPAY_NTERMS];   // T, totals (x,y), scratch
     __shared__ double s_alpha[256], s_ys[256];
+    __shared__ uint64_t s_bar[TP_RING_STAGES];
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < TP_RING_STAGES; q++) tp_mbar_init(&s_bar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     int flip = 0;
     double* x = S.x + (size_t)cand * S.xs;
     double* g = S.g + (size_t)cand * S.xs;
@@ -1220,83 +1252,83 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                 if (ys > cau) {
                     st.bound = st.bound + 1 < m ? st.bound + 1 : m;
                     st.end = (st.end + 1) % m;
+                    // this thread's part of the new history row must be visible to the bulk-copy engine
+                    asm volatile("fence.proxy.async;" ::: "memory");
                     __syncthreads();   // s_ys / the new history row are visible
-                    // two-loop recursion (lbfgs.hpp:691-710); rows prefetched one step ahead
-                    int j = st.end;
-                    double ps[TP_EPT], py[TP_EPT];
-                    {
-                        const int j0 = (j + m - 1) % m;
-#pragma unroll
-                        for (int e = 0; e < TP_EPT; e++) {
-                            const int i = tid + e * TP_CAND_THREADS;
-                            ps[e] = i < n ? lm_s[(size_t)j0 * S.xs + i] : 0.0;
-                            py[e] = i < n ? lm_y[(size_t)j0 * S.xs + i] : 0.0;
-                        }
+                    // two-loop recursion (lbfgs.hpp:691-710). The 2*bound history rows it walks —
+                    // newest to oldest, then oldest to newest — are streamed by TMA bulk copies
+                    // into a ring of shared-memory stages (the LU / coefficient region is free
+                    // during this phase), TP_RING_STAGES rows of (s_j, y_j) ahead of their use.
+                    const int total = 2 * st.bound;
+                    const uint32_t row_bytes = (uint32_t)(S.xs * sizeof(double));
+                    double* ring = sm;
+                    // row of step t: (end-1-t) mod m in the first loop, (end-bound+u) mod m in the second;
+                    // all operands are within (-2m, 2m), so two conditional wraps replace the modulo
+                    auto row_of = [&](int t) {
+                        int j = t < st.bound ? st.end - 1 - t : st.end - st.bound + (t - st.bound);
+                        j = j < 0 ? j + m : j;
+                        j = j < 0 ? j + m : j;
+                        return j >= m ? j - m : j;
+                    };
+                    auto issue = [&](int t) {
+                        const int sg = t % TP_RING_STAGES;
+                        const int j = row_of(t);
+                        tp_mbar_expect_tx(&s_bar[sg], 2 * row_bytes);
+                        tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs, lm_s + (size_t)j * S.xs, row_bytes, &s_bar[sg]);
+                        tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs + S.xs, lm_y + (size_t)j * S.xs, row_bytes, &s_bar[sg]);
+                    };
+                    if (tid == 0) {
+                        // the ring region was last written through the generic proxy and this block's
+                        // new history row has to be visible to the bulk-copy engine
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        for (int t = 0; t < min(total, TP_RING_STAGES); t++) issue(t);
                     }
-                    for (int it = 0; it < st.bound; ++it) {
-                        j = j == 0 ? m - 1 : j - 1;
+                    for (int t = 0; t < total; t++) {
+                        const int sg = t % TP_RING_STAGES;
+                        const int j = row_of(t);
+                        tp_mbar_wait(&s_bar[sg], (uint32_t)((t / TP_RING_STAGES) & 1));
+                        const double* rs_ = ring + (size_t)sg * 2 * S.xs;
+                        const double* ry_ = rs_ + S.xs;
                         double cs[TP_EPT], cy[TP_EPT];
 #pragma unroll
                         for (int e = 0; e < TP_EPT; e++) {
-                            cs[e] = ps[e];
-                            cy[e] = py[e];
+                            const int i = tid + e * TP_CAND_THREADS;
+                            cs[e] = i < n ? rs_[i] : 0.0;
+                            cy[e] = i < n ? ry_[i] : 0.0;
                         }
-                        if (it + 1 < st.bound) {
-                            const int jn = j == 0 ? m - 1 : j - 1;
+                        if (t == st.bound) {
+                            // between the loops: d *= ys / yy (lbfgs.hpp:701)
+                            const double sc = ys / yy;
 #pragma unroll
-                            for (int e = 0; e < TP_EPT; e++) {
-                                const int i = tid + e * TP_CAND_THREADS;
-                                ps[e] = i < n ? lm_s[(size_t)jn * S.xs + i] : 0.0;
-                                py[e] = i < n ? lm_y[(size_t)jn * S.xs + i] : 0.0;
-                            }
+                            for (int e = 0; e < TP_EPT; e++) rd[e] *= sc;
                         }
                         double a1[1] = {0.0};
+                        if (t < st.bound) {
 #pragma unroll
-                        for (int e = 0; e < TP_EPT; e++) a1[0] += cs[e] * rd[e];
-                        tp_block_sum<1>(a1, red, flip);
-                        const double al = a1[0] * s_ys[j];
-                        if (tid == 0) s_alpha[j] = al;
+                            for (int e = 0; e < TP_EPT; e++) a1[0] += cs[e] * rd[e];
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < TP_EPT; e++) rd[e] += (-al) * cy[e];
-                    }
-                    const double sc = ys / yy;
-                    TP_PROF(6);
+                            for (int e = 0; e < TP_EPT; e++) a1[0] += cy[e] * rd[e];
+                        }
+                        tp_block_sum<1>(a1, red, flip);      // one barrier: every thread has read stage sg
+                        if (tid == 0 && t + TP_RING_STAGES < total) issue(t + TP_RING_STAGES);
+                        if (t < st.bound) {
+                            const double al = a1[0] * s_ys[j];
+                            if (tid == 0) s_alpha[j] = al;
 #pragma unroll
-                    for (int e = 0; e < TP_EPT; e++) rd[e] *= sc;
-                    __syncthreads();   // s_alpha complete
-                    {
+                            for (int e = 0; e < TP_EPT; e++) rd[e] += (-al) * cy[e];
+                        } else {
+                            const double a = s_alpha[j] - a1[0] * s_ys[j];
 #pragma unroll
-                        for (int e = 0; e < TP_EPT; e++) {
-                            const int i = tid + e * TP_CAND_THREADS;
-                            ps[e] = i < n ? lm_s[(size_t)j * S.xs + i] : 0.0;
-                            py[e] = i < n ? lm_y[(size_t)j * S.xs + i] : 0.0;
+                            for (int e = 0; e < TP_EPT; e++) rd[e] += a * cs[e];
                         }
                     }
-                    for (int it = 0; it < st.bound; ++it) {
-                        double cs[TP_EPT], cy[TP_EPT];
+                    if (total == 0) {
+                        const double sc = ys / yy;
 #pragma unroll
-                        for (int e = 0; e < TP_EPT; e++) {
-                            cs[e] = ps[e];
-                            cy[e] = py[e];
-                        }
-                        if (it + 1 < st.bound) {
-                            const int jn = j + 1 == m ? 0 : j + 1;
-#pragma unroll
-                            for (int e = 0; e < TP_EPT; e++) {
-                                const int i = tid + e * TP_CAND_THREADS;
-                                ps[e] = i < n ? lm_s[(size_t)jn * S.xs + i] : 0.0;
-                                py[e] = i < n ? lm_y[(size_t)jn * S.xs + i] : 0.0;
-                            }
-                        }
-                        double b1[1] = {0.0};
-#pragma unroll
-                        for (int e = 0; e < TP_EPT; e++) b1[0] += cy[e] * rd[e];
-                        tp_block_sum<1>(b1, red, flip);
-                        const double a = s_alpha[j] - b1[0] * s_ys[j];
-#pragma unroll
-                        for (int e = 0; e < TP_EPT; e++) rd[e] += a * cs[e];
-                        j = j + 1 == m ? 0 : j + 1;
+                        for (int e = 0; e < TP_EPT; e++) rd[e] *= sc;
                     }
+                    __syncthreads();
                 }
                 TP_PROF(7);
                 st.stp = 1.0;
