@@ -132,7 +132,81 @@ def cpu_baseline(opt, rp, pts, paths, bv, ba, cores, desc):
     t0 = time.perf_counter()
     res = O.solve_batch(opt, rp, of, paths[:m], bv[:m], ba[:m], n_threads=cores)
     dt = time.perf_counter() - t0
-    return m / dt, m, dt, sum(r["status"] for r in res)
+    # single-plan latency of the same algorithm at the reference's default scale (8 candidates on 8 threads,
+    # planner.cpp:921-925), same plans as latency_probe
+    from topay_b200 import scenes
+    o2, lat = O.opt_defaults(), []
+    for plan in range(8):
+        p8, bv8, ba8 = scenes.short_candidates(8, 5005 + plan)
+        t1 = time.perf_counter()
+        O.solve_batch(o2, rp, of, p8, bv8, ba8, n_threads=min(8, cores))
+        lat.append((time.perf_counter() - t1) * 1e3)
+    return m / dt, m, dt, sum(r["status"] for r in res), float(np.median(lat))
+
+
+def latency_probe(tp, scenes, gm, n_plans=120):
+    """Second headline metric: p50 single-plan latency, upload candidates -> best trajectory on the
+    host, at the reference's default scale (BASELINE configs[0]/[1]: <= 8 candidates per plan,
+    int_K = 12, sample_interval 1.5 s -> 3-10 pieces), one plan at a time through the public API."""
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    solver = tp.MomaTrajOpt(gm, max_cand=8, max_pieces=16, opt_param=opt, robot=rp)
+    lat, ok = [], 0
+    for plan in range(n_plans + 5):
+        paths, bv, ba = scenes.short_candidates(8, 5000 + plan)
+        t0 = time.perf_counter()
+        r = solver.optimizeTrajBatch(paths, bv, ba)
+        dt = (time.perf_counter() - t0) * 1e3
+        if plan >= 5:
+            lat.append(dt)
+            ok += int(r["best_by_duration"] >= 0)
+    lat = np.array(lat)
+    solver.close()
+    return {"p50_ms": float(np.median(lat)), "p90_ms": float(np.percentile(lat, 90)), "plans": n_plans,
+            "plans_with_a_feasible_winner": ok,
+            "workload": "8 candidates per plan, int_K 12, 3-10 pieces, cuboids scene 200x200x16 (reference scale)"}
+
+
+def field_probe(tp, scenes, device, hbm_peak):
+    """BASELINE configs[3]: ESDF rebuild + query on the 40 x 40 x 4 m grid at 0.05 m (800 x 800 x 80)."""
+    import torch
+    desc = tp.grid_desc(map_size=(40.0, 40.0, 4.0), resolution=0.05)
+    gm = tp.GridMap(desc, device=device)
+    pts, _ = scenes.cuboids_scene(7, size_x=40.0, size_y=40.0, scale=2.0)
+    gm.regenerateMap(pts)
+    gm.set_keep_sqdist(False)
+    t3 = []
+    for _ in range(5):
+        gm.updateESDF()
+        t3.append(gm.last_rebuild_ms())
+    tot, d3 = np.median([a for a, _ in t3]), np.median([b for _, b in t3])
+    vox = 800 * 800 * 80
+    # resident queries: 10^7 uniformly random in-map points (seed 7), value + gradient
+    n = 10_000_000
+    g = torch.Generator(device=f"cuda:{device}").manual_seed(7)
+    lo = torch.tensor([-20.0, -20.0, 0.0], device=f"cuda:{device}", dtype=torch.float64)
+    hi = torch.tensor([20.0, 20.0, 4.0], device=f"cuda:{device}", dtype=torch.float64)
+    pos = lo + (hi - lo) * torch.rand((n, 3), generator=g, device=f"cuda:{device}", dtype=torch.float64)
+    dist = torch.empty(n, device=f"cuda:{device}", dtype=torch.float64)
+    grad = torch.empty((n, 3), device=f"cuda:{device}", dtype=torch.float64)
+    import ctypes as C
+    from topay_b200 import _lib
+    l = _lib.lib()
+    qms = []
+    for _ in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _lib.check(l.topay_field_query3d_dev(gm.h, C.c_void_p(pos.data_ptr()), n, C.c_void_p(dist.data_ptr()),
+                                             C.c_void_p(grad.data_ptr())), "query3d_dev")
+        _lib.check(l.topay_field_sync(gm.h), "sync")
+        qms.append((time.perf_counter() - t0) * 1e3)
+    q = float(np.median(qms[1:]))
+    gm.close()
+    return {"grid": "800x800x80 @0.05 m", "rebuild_ms_total": float(tot), "rebuild_ms_3d": float(d3),
+            "rebuild_algorithmic_GBps": vox * 9 / (d3 * 1e-3) / 1e9, "rebuild_frac_of_hbm_peak": vox * 9 / (d3 * 1e-3) / 1e9 / hbm_peak,
+            "query_ms_1e7": q, "query_Gpoints_per_s": n / (q * 1e-3) / 1e9,
+            "query_algorithmic_GBps": n * (24 + 64 + 32) / (q * 1e-3) / 1e9,
+            "note": "rebuild: 9 B/voxel algorithmic (1 B occupancy in, 8 B ESDF out); query: 24 B position + "
+                    "8 taps x 8 B + 32 B result per point, points resident in HBM"}
 
 
 def run_reference(args):
@@ -191,12 +265,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="topay_b200", choices=["topay_b200", "reference"])
     ap.add_argument("--candidates", type=int, default=N_CAND, help="candidates per GPU (dev only; bench = 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (dev only)")
-    ap.add_argument("--plans", type=int, default=3,
+    ap.add_argument("--no-extras", action="store_true", help="skip the latency and field sub-benchmarks")
+    ap.add_argument("--plans", type=int, default=8,
                     help="plans (256-candidate batches) in flight per GPU, each on its own stream")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -220,9 +295,9 @@ def main():
     batches = [scenes.synthetic_batch(n_cand, 1234 + 100000 * rank + 1000 * p) for p in range(P)]
     paths, bv, ba = batches[0]
     solvers = [tp.MomaTrajOpt(gm, max_cand=n_cand, max_pieces=N_PIECES, opt_param=opt, robot=rp) for _ in range(P)]
-    # plan slot 0 brackets every k_penalty launch with CUDA events (plain launches), live in the timed
-    # region and under the same concurrent load; the other slots replay their ticks as CUDA graphs
-    solvers[0].set_timed(os.environ.get("TOPAY_BENCH_TIMED", "1") == "1")
+    # throughput region: every slot replays its ticks as CUDA graphs. The roofline of the dominant
+    # kernel is measured right after it, live, with CUDA events around every k_penalty launch of one
+    # plan running alone (under 8-way concurrency a launch's duration says nothing about the kernel).
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
     import threading
 
@@ -279,6 +354,17 @@ def main():
     launches, ticks, evals_launch, nodes = acc["launches"], acc["ticks"], acc["evals_launch"], acc["nodes"]
     ms_eval, ms_dev = acc["ms_eval"], acc["ms_dev"]
 
+    # ---- roofline pass: one plan alone, plain launches, CUDA events around every k_penalty launch
+    acc.update({"evals_launch": 0, "nodes": 0, "ms_eval": 0.0, "ms_dev_timed": 0.0})
+    solvers[0].set_timed(True)
+    flush.zero_()
+    solvers[0].run()
+    st = solvers[0].stats()
+    acc["evals_launch"], acc["nodes"], acc["ms_eval"], acc["ms_dev_timed"] = (st["eval_launches"], st["eval_nodes"],
+                                                                              st["ms_eval"], st["ms_total"])
+    solvers[0].set_timed(False)
+    evals_launch, nodes, ms_eval = acc["evals_launch"], acc["nodes"], acc["ms_eval"]
+
     # ---- end-to-end arm: host buffers in, host results out, through the public API every step
     barrier_max(dist, local, 0.0)
     flush.zero_()
@@ -320,20 +406,29 @@ def main():
         "gpu_launches": int(launches),
         "device_ms_per_step": ms_dev / args.steps, "ticks_per_step": ticks / args.steps,
         "roofline": {"bound": "hbm", "kernel": "k_penalty", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": 19.9e6, "peak_source": peak_src,
+                     "traffic_source": "ncu --set full, dram__bytes_read+write per launch at 256 candidates "
+                                       "(profiles/r01_summary.md): the 5 MB field is served from L1/L2",
                      "avg_launch_ms": pen_ms, "nodes_per_launch": nodes_per_launch,
+                     "measured_on": "one 256-candidate plan running alone right after the timed region (CUDA "
+                                    "events around each of its k_penalty launches)",
                      "share_of_step": ms_eval / max(acc.get("ms_dev_timed", ms_dev), 1e-9),
                      "fp64": {"achieved_tflops": flop / (pen_ms * 1e-3) / 1e12, "nominal_peak_tflops": 40.0,
                               "note": "the kernel is FP64-pipe/latency bound, not HBM bound: 4.0 kflop per "
                                       "penalty node against 800 algorithmic bytes"}},
         "clocks": clocks,
     }
+    if not args.no_extras:
+        line["latency"] = latency_probe(tp, scenes, gm)
+        line["field"] = field_probe(tp, scenes, local, peak)
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, m, secs, ok = cpu_baseline(opt, rp, pts, paths, bv, ba, cores, desc)
+        v, m, secs, ok, lat50 = cpu_baseline(opt, rp, pts, paths, bv, ba, cores, desc)
         line["cpu_baseline"] = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port",
                                 "sample": f"{m} of the {n_cand} candidates, one per host core (thread per "
-                                          f"candidate), {secs:.1f} s, {ok} succeeded"}
+                                          f"candidate), {secs:.1f} s, {ok} succeeded",
+                                "latency_p50_ms": lat50,
+                                "latency_sample": "8 plans of 8 candidates on 8 threads, reference scale"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
