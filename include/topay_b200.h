@@ -219,6 +219,71 @@ int topay_field_set_keep_sqdist(topay_field* f, int keep);
  * field's stream; ms_3d is the 3-D part alone. */
 int topay_field_last_rebuild_ms(topay_field* f, float* ms_total, float* ms_3d);
 
+/* ---------------------------------------------------------- ROG-Map field */
+
+/* The sliding ring-buffer distance field the reference uses when
+ * grid_map/use_rog is true: rog_map::ESDFMap (src/rog_map/include/rog_map/
+ * esdf_map.h) on top of CounterMap and SlidingMap, ORIGIN_AT_CORNER
+ * discretisation (src/rog_map/CMakeLists.txt:14). The arguments are those of
+ * ESDFMap::initESDFMap (esdf_map.cpp:28-57) as ProbMap passes them
+ * (prob_map.cpp:48-58). */
+typedef struct topay_rog_desc {
+    int32_t half_prob_map_size_i[3];   /* cfg_.half_map_size_i (config.hpp:336-382) */
+    double  prob_resolution;           /* cfg_.resolution */
+    double  esdf_resolution;           /* cfg_.esdf_resolution */
+    double  local_update_box[3];       /* cfg_.esdf_local_update_box, metres */
+    int32_t map_sliding_en;
+    double  fix_map_origin[3];         /* origin when map_sliding_en == 0 */
+    double  unk_thresh;                /* ratio in [0,1] (counter_map.cpp:83-85) */
+} topay_rog_desc;
+
+typedef struct topay_rogfield topay_rogfield;
+
+/* rog_map::GridType (include/utils/common_lib.hpp:74-81) */
+enum { TOPAY_ROG_UNDEFINED = 0, TOPAY_ROG_UNKNOWN = 1, TOPAY_ROG_OUT_OF_MAP = 2, TOPAY_ROG_OCCUPIED = 3,
+       TOPAY_ROG_KNOWN_FREE = 4 };
+
+/* which quantity topay_rogfield_query evaluates */
+enum {
+    TOPAY_ROG_Q_EDT = 0,            /* evaluateEDT + evaluateFirstGrad = getValueGrad (esdf_map.cpp:951-1003) */
+    TOPAY_ROG_Q_FLAT = 1,           /* getValueGrad2d        (esdf_map.cpp:1053-1097) */
+    TOPAY_ROG_Q_CRITICAL = 2,       /* getCriticalValueGrad  (esdf_map.cpp:1005-1051) */
+    TOPAY_ROG_Q_CELL = 3,           /* getDistance(pos)         nearest cell, grad untouched (esdf_map.cpp:78-80) */
+    TOPAY_ROG_Q_CELL_FLAT = 4,      /* getDistance2d(pos)       (esdf_map.cpp:104-111) */
+    TOPAY_ROG_Q_CELL_CRITICAL = 5   /* getCriticalDistance(pos) (esdf_map.cpp:86-93) */
+};
+/* buffers topay_rogfield_download returns */
+enum { TOPAY_ROG_BUF_DIST3 = 0, TOPAY_ROG_BUF_NEG3 = 1, TOPAY_ROG_BUF_CRITICAL = 2, TOPAY_ROG_BUF_FLAT = 3 };
+
+/* initESDFMap: sizes derived as CounterMap::initCounterMap does (counter_map.cpp:31-91,
+ * inflation_step 0), buffers in HBM, counters reset (esdf_map.cpp:72-76). */
+int topay_rogfield_create(const topay_rog_desc* desc, int device, topay_rogfield** out);
+void topay_rogfield_destroy(topay_rogfield* f);
+/* half_map_size_i, map_size_i (= 2*half+1), resolution, local origin index, half update box. */
+int topay_rogfield_geometry(const topay_rogfield* f, int32_t half[3], int32_t size[3], double* resolution,
+                            int32_t origin_i[3], int32_t half_box_i[3]);
+/* SlidingMap::mapSliding (sliding_map.cpp:113-166): moves the local origin to the cell of
+ * odom and clears the slabs that left the map (both counters, counter_map.h:127-131). */
+int topay_rogfield_slide(topay_rogfield* f, const double odom[3]);
+/* CounterMap::updateGridCounter (counter_map.cpp:94-151) for n positions (n x 3), applied
+ * in order; from_type / to_type are GridType values, one byte each. */
+int topay_rogfield_update_counters(topay_rogfield* f, const double* pos, const uint8_t* from_type,
+                                   const uint8_t* to_type, int64_t n);
+/* Whole-buffer access to md_.occupied_cnt (ring-memory layout x*Sy*Sz + y*Sz + z). */
+int topay_rogfield_set_occupied_cnt(topay_rogfield* f, const int16_t* cnt);
+int topay_rogfield_download_counters(topay_rogfield* f, int16_t* occupied_cnt, int16_t* unknown_cnt);
+/* ESDFMap::updateESDF3D (esdf_map.cpp:154-500): signed EDT of the local update box around
+ * cur_odom with the ring wrap, then the critical and flat 2-D maps. */
+int topay_rogfield_update_esdf(topay_rogfield* f, const double cur_odom[3]);
+/* Batched queries; pos is n x 3 (z is ignored by the 2-D kinds except for the ring index of
+ * the taps, as in the reference). dist: n; grad: n x 3 or NULL. */
+int topay_rogfield_query(topay_rogfield* f, int kind, const double* pos, int64_t n, double* dist, double* grad);
+/* ESDFMap::isLineFree2d (esdf_map.cpp:122-152): start/end are n x 2, out[i] = 1 when free. */
+int topay_rogfield_is_line_free2d(topay_rogfield* f, const double* start, const double* end, int64_t n,
+                                  double threshold, int8_t* out);
+int topay_rogfield_download(topay_rogfield* f, int which, double* out);
+int topay_rogfield_last_update_ms(topay_rogfield* f, float* ms_total, float* ms_3d);
+
 /* ------------------------------------------------------------------ solver */
 
 /* One solver = the device-side state for up to max_cand candidates of up to

@@ -8,6 +8,7 @@
 
 #include "oracle_field.hpp"
 #include "oracle_robot.hpp"
+#include "oracle_rog.hpp"
 #include "oracle_solve.hpp"
 
 using namespace oracle;
@@ -338,6 +339,71 @@ int oracle_eval_batch(const topay_opt_params* opt, const topay_robot_params* rp,
     for (int t = 0; t < std::max(1, n_threads); t++) th.emplace_back(worker);
     for (auto& t : th) t.join();
     return 0;
+}
+
+// ---------------------------------------------------------------- ROG-Map field (oracle_rog.hpp)
+void* oracle_rog_create(const topay_rog_desc* d) {
+    RogEsdf* r = new RogEsdf();
+    r->init(d->half_prob_map_size_i, d->prob_resolution, d->esdf_resolution, d->local_update_box,
+            d->map_sliding_en != 0, d->fix_map_origin, d->unk_thresh);
+    return r;
+}
+void oracle_rog_destroy(void* h) { delete (RogEsdf*)h; }
+void oracle_rog_geometry(void* h, int32_t* half, int32_t* size, double* res, int32_t* origin_i, int32_t* half_box) {
+    RogEsdf* r = (RogEsdf*)h;
+    for (int i = 0; i < 3; i++) {
+        half[i] = r->half[i];
+        size[i] = r->size[i];
+        origin_i[i] = r->origin_i[i];
+        half_box[i] = r->half_box_i[i];
+    }
+    *res = r->res;
+}
+void oracle_rog_slide(void* h, const double* odom) { ((RogEsdf*)h)->slide(odom); }
+void oracle_rog_update_counters(void* h, const double* pos, const uint8_t* from, const uint8_t* to, int64_t n) {
+    for (int64_t i = 0; i < n; i++) ((RogEsdf*)h)->update_counter(pos + 3 * i, from[i], to[i]);
+}
+void oracle_rog_set_occupied_cnt(void* h, const int16_t* cnt) {
+    RogEsdf* r = (RogEsdf*)h;
+    std::memcpy(r->occupied_cnt.data(), cnt, r->vox * sizeof(int16_t));
+}
+void oracle_rog_download_counters(void* h, int16_t* occ, int16_t* unk) {
+    RogEsdf* r = (RogEsdf*)h;
+    if (occ) std::memcpy(occ, r->occupied_cnt.data(), r->vox * sizeof(int16_t));
+    if (unk) std::memcpy(unk, r->unknown_cnt.data(), r->vox * sizeof(int16_t));
+}
+void oracle_rog_update_esdf(void* h, const double* odom) { ((RogEsdf*)h)->update_esdf(odom); }
+void oracle_rog_query(void* h, int kind, const double* pos, int64_t n, double* dist, double* grad) {
+    RogEsdf* r = (RogEsdf*)h;
+    for (int64_t i = 0; i < n; i++) {
+        const double* p = pos + 3 * i;
+        double d = 0, g[3] = {0, 0, 0};
+        bool has_grad = true;
+        switch (kind) {
+            case TOPAY_ROG_Q_EDT: r->value_grad(p, d, g); break;
+            case TOPAY_ROG_Q_FLAT: r->value_grad_2d(p, false, d, g); break;
+            case TOPAY_ROG_Q_CRITICAL: r->value_grad_2d(p, true, d, g); break;
+            case TOPAY_ROG_Q_CELL: d = r->get_distance(p); has_grad = false; break;
+            case TOPAY_ROG_Q_CELL_FLAT: d = r->get_distance2d(p); has_grad = false; break;
+            default: d = r->get_critical_distance(p); has_grad = false; break;
+        }
+        dist[i] = d;
+        if (grad && has_grad)
+            for (int k = 0; k < 3; k++) grad[3 * i + k] = g[k];
+    }
+}
+void oracle_rog_evaluate_edt(void* h, const double* pos, int64_t n, double* dist) {
+    for (int64_t i = 0; i < n; i++) dist[i] = ((RogEsdf*)h)->evaluate_edt(pos + 3 * i);
+}
+void oracle_rog_is_line_free2d(void* h, const double* s, const double* e, int64_t n, double thr, int8_t* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = ((RogEsdf*)h)->is_line_free_2d(s + 2 * i, e + 2 * i, thr) ? 1 : 0;
+}
+void oracle_rog_download(void* h, int which, double* out) {
+    RogEsdf* r = (RogEsdf*)h;
+    const std::vector<double>& v = which == TOPAY_ROG_BUF_DIST3 ? r->dist3
+                                 : which == TOPAY_ROG_BUF_NEG3 ? r->tmp1
+                                 : which == TOPAY_ROG_BUF_CRITICAL ? r->dist_crit : r->dist_flat;
+    std::memcpy(out, v.data(), v.size() * sizeof(double));
 }
 
 }  // extern "C"

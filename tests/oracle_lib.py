@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from topay_b200._structs import (GridDesc, LbfgsParams, OptParams, RobotParams, NTERMS, num_vars)
+from topay_b200._structs import (GridDesc, RogDesc, LbfgsParams, OptParams, RobotParams, NTERMS, num_vars)
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_ROOT, "oracle", "liboracle.so")
@@ -17,7 +17,7 @@ _SO = os.path.join(_ROOT, "oracle", "liboracle.so")
 
 def build(force=False):
     srcs = [os.path.join(_ROOT, "oracle", f) for f in
-            ("oracle_capi.cpp", "oracle_field.hpp", "oracle_robot.hpp", "oracle_solve.hpp")]
+            ("oracle_capi.cpp", "oracle_field.hpp", "oracle_robot.hpp", "oracle_rog.hpp", "oracle_solve.hpp")]
     srcs.append(os.path.join(_ROOT, "include", "topay_b200.h"))
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "liboracle.so"])
@@ -38,6 +38,7 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
         _lib.oracle_field_create.restype = C.c_void_p
+        _lib.oracle_rog_create.restype = C.c_void_p
     return _lib
 
 
@@ -260,3 +261,77 @@ def penalty_only(opt, rp, field: Field, stage, N, coeff, T, sxy, exy, inner_xy, 
     lib().oracle_penalty_only(C.byref(opt), C.byref(rp), field.h, stage, N, _p(coeff), _p(T), _p(sxy), _p(exy),
                               _p(inner_xy), _p(lam), _p(rho), C.byref(cost), _p(gdC), _p(gdT), _p(terms), _p(fxy))
     return cost.value, gdC, gdT, terms, fxy
+
+
+class RogField:
+    """oracle_rog.hpp (the ROG-Map ESDFMap restatement)."""
+
+    def __init__(self, desc: RogDesc):
+        self.h = C.c_void_p(lib().oracle_rog_create(C.byref(desc)))
+        half, size, org, hb = ((C.c_int32 * 3)() for _ in range(4))
+        res = C.c_double()
+        lib().oracle_rog_geometry(self.h, half, size, C.byref(res), org, hb)
+        self.half, self.size, self.half_box = tuple(half), tuple(size), tuple(hb)
+        self.resolution = res.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_rog_destroy(self.h)
+            self.h = None
+
+    @property
+    def origin_i(self):
+        half, size, org, hb = ((C.c_int32 * 3)() for _ in range(4))
+        res = C.c_double()
+        lib().oracle_rog_geometry(self.h, half, size, C.byref(res), org, hb)
+        return tuple(org)
+
+    def slide(self, odom):
+        o = _f64(odom)
+        lib().oracle_rog_slide(self.h, _p(o))
+
+    def update_counters(self, pos, from_type, to_type):
+        pos = _f64(pos)
+        a = np.ascontiguousarray(from_type, dtype=np.uint8)
+        b = np.ascontiguousarray(to_type, dtype=np.uint8)
+        lib().oracle_rog_update_counters(self.h, _p(pos), _p(a, C.c_uint8), _p(b, C.c_uint8), C.c_int64(pos.shape[0]))
+
+    def set_occupied_cnt(self, cnt):
+        cnt = np.ascontiguousarray(cnt, dtype=np.int16)
+        assert cnt.size == int(np.prod(self.size))
+        lib().oracle_rog_set_occupied_cnt(self.h, _p(cnt, C.c_int16))
+
+    def download_counters(self):
+        a = np.empty(self.size, dtype=np.int16)
+        b = np.empty(self.size, dtype=np.int16)
+        lib().oracle_rog_download_counters(self.h, _p(a, C.c_int16), _p(b, C.c_int16))
+        return a, b
+
+    def update_esdf(self, odom):
+        o = _f64(odom)
+        lib().oracle_rog_update_esdf(self.h, _p(o))
+
+    def query(self, kind, pos):
+        pos = _f64(pos)
+        n = pos.shape[0]
+        d, g = np.empty(n), np.zeros((n, 3))
+        lib().oracle_rog_query(self.h, kind, _p(pos), C.c_int64(n), _p(d), _p(g))
+        return d, g
+
+    def evaluate_edt(self, pos):
+        pos = _f64(pos)
+        d = np.empty(pos.shape[0])
+        lib().oracle_rog_evaluate_edt(self.h, _p(pos), C.c_int64(pos.shape[0]), _p(d))
+        return d
+
+    def is_line_free2d(self, start, end, threshold=0.0):
+        s, e = _f64(start), _f64(end)
+        out = np.empty(s.shape[0], dtype=np.int8)
+        lib().oracle_rog_is_line_free2d(self.h, _p(s), _p(e), C.c_int64(s.shape[0]), C.c_double(threshold),
+                                        _p(out, C.c_int8))
+        return out
+
+    def download(self, which):
+        out = np.empty(self.size if which < 2 else self.size[:2])
+        lib().oracle_rog_download(self.h, which, _p(out))
+        return out

@@ -69,6 +69,28 @@ def grid_desc(map_size=(20.0, 20.0, 1.6), resolution=0.1, chassis_colli_radius=0
     return d
 
 
+class RogDesc(C.Structure):
+    _fields_ = [("half_prob_map_size_i", C.c_int32 * 3), ("prob_resolution", C.c_double),
+                ("esdf_resolution", C.c_double), ("local_update_box", C.c_double * 3),
+                ("map_sliding_en", C.c_int32), ("fix_map_origin", C.c_double * 3), ("unk_thresh", C.c_double)]
+
+
+def rog_desc(half_prob_map_size_i=(400, 400, 40), prob_resolution=0.05, esdf_resolution=0.05,
+             local_update_box=(40.0, 40.0, 4.0), map_sliding_en=False, fix_map_origin=(0.0, 0.0, 0.0),
+             unk_thresh=0.7):
+    """Arguments of ESDFMap::initESDFMap (esdf_map.cpp:28-57); the defaults give the 803x803x83 ring of
+    SURVEY.md §8 row a23 (map 40x40x4 m at 0.05 m)."""
+    d = RogDesc()
+    d.half_prob_map_size_i[:] = half_prob_map_size_i
+    d.prob_resolution = prob_resolution
+    d.esdf_resolution = esdf_resolution
+    d.local_update_box[:] = local_update_box
+    d.map_sliding_en = int(map_sliding_en)
+    d.fix_map_origin[:] = fix_map_origin
+    d.unk_thresh = unk_thresh
+    return d
+
+
 class ProblemBatch(C.Structure):
     _fields_ = [("n_cand", C.c_int32), ("piece_num", C.POINTER(C.c_int32)),
                 ("head_pva", C.POINTER(C.c_double)), ("tail_pva", C.POINTER(C.c_double)),
