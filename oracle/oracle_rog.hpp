@@ -30,7 +30,9 @@
 // initial origin in init() — the reference leaves them unset until the first
 // mapSliding(); (2) the 2-D combine loop, which walks y over the x range
 // (esdf_map.cpp:391-398), is clipped to the buffer so that a non-square map
-// cannot run off the end of the vector (undefined behaviour in the reference).
+// cannot run off the end of the vector (undefined behaviour in the reference); (3) isLineFree2d's
+// walk is capped (see is_line_free_2d); (4) update_esdf returns at once when the clipped update
+// box is empty on any axis.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -269,6 +271,8 @@ struct RogEsdf {
             lo[i] = upd_min_i[i] - bmin_i[i];
             hi[i] = upd_max_i[i] - bmin_i[i];
         }
+        for (int i = 0; i < 3; i++)
+            if (hi[i] < lo[i]) return;
         // ---- 3-D: positive transform z, y, x (:187-240)
         for (int sign = 0; sign < 2; sign++) {
             for (int x = lo[0]; x <= hi[0]; x++)
@@ -459,7 +463,10 @@ struct RogEsdf {
                 t_bound[i] = dir[i] == 0 ? DMAX : std::fabs(nb - s[i]) / dd[i];
             }
         }
-        for (;;) {
+        // a ray that steps past its end cell through rounding never terminates in the reference
+        // (deviation 3): the walk is capped at the Manhattan cell distance, after which it reports free
+        const long cap = (long)std::abs(ei[0] - si[0]) + std::abs(ei[1] - si[1]) + std::abs(ei[2] - si[2]) + 1;
+        for (long it = 0; it < cap; it++) {
             double pt[3];
             for (int i = 0; i < 3; i++) pt[i] = ((double)cur[i] + 0.5) * res;
             if (cur[0] == ei[0] && cur[1] == ei[1] && cur[2] == ei[2]) return true;
@@ -472,6 +479,7 @@ struct RogEsdf {
             }
             if (dist_flat[hash2_from_pos(pt)] < threshold) return false;
         }
+        return true;
     }
 };
 

@@ -1,0 +1,143 @@
+"""GPU parity of the ROG-Map ring-buffer field through the C ABI against
+oracle/oracle_rog.hpp: counters and the four persistent distance buffers bit-exact over a sequence of slides
+and updates (ring wrap on every axis, stale-cell quirks included), queries within 1e-12 (FMA contraction
+only), nearest-cell getters and isLineFree2d exact; at the full 803x803x83 size, properties that do not need
+the CPU transform (sign structure, 1-Lipschitz, exact distance to an isolated obstacle)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+UNK, OCC, FREE = 1, 3, 4
+
+
+def _pair(**kw):
+    import oracle_lib as O
+    import topay_b200 as tp
+    from topay_b200.rog import ESDFMap
+    d = dict(half_prob_map_size_i=(30, 22, 9), prob_resolution=0.1, esdf_resolution=0.1,
+             local_update_box=(5.0, 3.0, 1.5), map_sliding_en=True)
+    d.update(kw)
+    desc = tp.rog_desc(**d)
+    return ESDFMap(desc), O.RogField(desc)
+
+
+def _random_points(rng, origin, n, spread):
+    return origin + rng.uniform(-1, 1, (n, 3)) * np.array(spread)
+
+
+def _compare(dev, orc, tag):
+    oc, un = dev.getCounters()
+    eo, eu = orc.download_counters()
+    assert np.array_equal(oc, eo) and np.array_equal(un, eu), (tag, "counters")
+    for which, key in enumerate(("dist3", "neg3", "critical", "flat")):
+        assert np.array_equal(dev.getBuffer(which), orc.download(which)), (tag, key)
+
+
+def test_geometry_and_empty_update():
+    dev, orc = _pair()
+    assert dev.map_size_i == orc.size and dev.half_map_size_i == orc.half
+    assert dev.half_local_update_box_i == orc.half_box and dev.resolution == orc.resolution
+    dev.updateESDF3D((0.0, 0.0, 0.0))
+    orc.update_esdf((0.0, 0.0, 0.0))
+    _compare(dev, orc, "empty")          # no obstacle: res * sqrt(DBL_MAX) everywhere in the box
+
+
+def test_sequence_of_slides_and_updates_bit_exact():
+    dev, orc = _pair()
+    rng = np.random.default_rng(11)
+    path = [(0.0, 0.0, 0.0), (0.43, -0.31, 0.12), (1.27, -0.9, 0.33), (1.31, 0.55, -0.21), (-0.8, 0.2, 0.05)]
+    for step, odom in enumerate(path):
+        dev.mapSliding(odom)
+        orc.slide(odom)
+        assert dev.local_map_origin_i == orc.origin_i
+        pts = _random_points(rng, np.array(odom), 400, (2.8, 2.0, 0.8))
+        dev.updateGridCounter(pts, UNK, OCC)
+        orc.update_counters(pts, np.full(len(pts), UNK), np.full(len(pts), OCC))
+        if step == 2:      # some cells are seen free again
+            dev.updateGridCounter(pts[:150], OCC, FREE)
+            orc.update_counters(pts[:150], np.full(150, OCC), np.full(150, FREE))
+        dev.updateESDF3D(odom)
+        orc.update_esdf(odom)
+        _compare(dev, orc, step)
+
+
+def test_update_box_clipped_by_the_map_and_full_box():
+    for box in [(100.0, 100.0, 100.0), (0.45, 9.0, 0.3)]:
+        dev, orc = _pair(local_update_box=box)
+        rng = np.random.default_rng(5)
+        odom = (0.7, -0.4, 0.2)
+        for m in (dev.mapSliding, orc.slide):
+            m(odom)
+        pts = _random_points(rng, np.array(odom), 600, (3.0, 2.2, 0.9))
+        dev.updateGridCounter(pts, UNK, OCC)
+        orc.update_counters(pts, np.full(len(pts), UNK), np.full(len(pts), OCC))
+        dev.updateESDF3D((1.9, -1.0, 0.5))          # box centred off the origin: clipped on one side
+        orc.update_esdf((1.9, -1.0, 0.5))
+        _compare(dev, orc, box)
+
+
+def test_queries_and_line_checks_against_oracle():
+    dev, orc = _pair()
+    rng = np.random.default_rng(21)
+    odom = (0.43, -0.31, 0.12)
+    dev.mapSliding(odom)
+    orc.slide(odom)
+    pts = _random_points(rng, np.array(odom), 500, (2.8, 2.0, 0.8))
+    dev.updateGridCounter(pts, UNK, OCC)
+    orc.update_counters(pts, np.full(len(pts), UNK), np.full(len(pts), OCC))
+    dev.updateESDF3D(odom)
+    orc.update_esdf(odom)
+    pos = np.concatenate([_random_points(rng, np.array(odom), 4000, (2.0, 1.3, 0.6)),
+                          rng.uniform(-40, 40, (500, 3))])          # the second part wraps round the ring
+    for kind in range(6):
+        d, g = dev._query(kind, pos)
+        ed, eg = orc.query(kind, pos)
+        if kind >= 3:
+            assert np.array_equal(d, ed), kind
+        else:
+            assert np.abs(d - ed).max() <= 1e-12 * max(1.0, np.abs(ed).max()), kind
+            assert np.abs(g - eg).max() <= 1e-11 * max(1.0, np.abs(eg).max()), kind
+    assert np.array_equal(dev.evaluateEDT(pos), dev.getValueGrad(pos)[0])
+    s = _random_points(rng, np.array(odom), 3000, (2.0, 1.3, 0.0))[:, :2]
+    e = _random_points(rng, np.array(odom), 3000, (2.0, 1.3, 0.0))[:, :2]
+    e[:20] = s[:20]                                                   # same-cell rays
+    for thr in (0.0, 0.15, 0.4):
+        got = dev.isLineFree2d(s, e, thr)
+        exp = orc.is_line_free2d(s, e, thr).astype(bool)
+        assert np.array_equal(got, exp), thr
+    assert 0 < dev.isLineFree2d(s, e, 0.15).sum() < len(s)
+
+
+def test_full_size_ring_properties():
+    """803 x 803 x 83. The CPU transform of 53.5 M cells takes minutes, so the full size is
+    checked through properties: exact distances to isolated obstacles, sign structure, 1-Lipschitz."""
+    import topay_b200 as tp
+    from topay_b200.rog import ESDFMap
+    dev = ESDFMap(tp.rog_desc())
+    assert dev.map_size_i == (803, 803, 83)
+    res = dev.resolution
+    rng = np.random.default_rng(3)
+    obs = np.floor(rng.uniform([-15, -15, 0.0], [15, 15, 1.5], (40, 3)) / res)        # cell indices
+    centres = (obs + 0.5) * res
+    dev.updateGridCounter(centres, UNK, OCC)
+    dev.updateESDF3D((0.0, 0.0, 0.0))
+    ms_total, ms_3d = dev.last_update_ms()
+    assert ms_total > 0 and ms_3d > 0
+    # nearest-cell value at random cells = res * distance (in cells) to the nearest obstacle cell
+    q = np.floor(rng.uniform([-19, -19, -1.9], [19, 19, 1.9], (20000, 3)) / res)
+    d = dev.getDistance((q + 0.5) * res)
+    sq = ((q[:, None, :] - obs[None, :, :]) ** 2).sum(-1).min(1)
+    exp = res * np.sqrt(sq)
+    inside = sq == 0
+    assert np.array_equal(d[~inside], exp[~inside])
+    assert np.all(d[inside] == 0.0)          # an isolated occupied cell: pos 0, neg = res -> 0 - res + res
+    # obstacles read 0 at their own cell and the field is 1-Lipschitz between neighbouring cells
+    assert np.all(dev.getDistance(centres) == 0.0)
+    d1 = dev.getDistance((q + 0.5) * res + np.array([res, 0, 0]))
+    ok = np.abs(q[:, 0] + 1) < 399
+    assert np.all(np.abs(d1 - d)[ok] <= res + 1e-12)
+    # critical map: column distance ignores z
+    d2 = dev.getCriticalDistance((q + 0.5) * res)
+    sq2 = ((q[:, None, :2] - obs[None, :, :2]) ** 2).sum(-1).min(1)
+    assert np.array_equal(d2[sq2 > 0], (res * np.sqrt(sq2))[sq2 > 0])

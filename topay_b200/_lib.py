@@ -8,7 +8,7 @@ import ctypes as C
 import os
 import subprocess
 
-from ._structs import GridDesc, OptParams, ProblemBatch, ResultBatch, RobotParams, SolverStats
+from ._structs import GridDesc, RogDesc, OptParams, ProblemBatch, ResultBatch, RobotParams, SolverStats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("TOPAY_B200_LIB", os.path.join(_HERE, "libtopay_b200.so"))
@@ -33,6 +33,7 @@ def build(verbose=False):
 
 _lib = None
 _dp, _ip, _i8p, _fp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int8), C.POINTER(C.c_float)
+_i16p, _u8p = C.POINTER(C.c_int16), C.POINTER(C.c_uint8)
 
 # name -> (restype, argtypes); every symbol include/topay_b200.h declares
 PROTOTYPES = {
@@ -60,6 +61,18 @@ PROTOTYPES = {
     "topay_field_download_occupancy": (C.c_int, [C.c_void_p, C.c_int, _i8p]),
     "topay_field_set_keep_sqdist": (C.c_int, [C.c_void_p, C.c_int]),
     "topay_field_last_rebuild_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "topay_rogfield_create": (C.c_int, [C.POINTER(RogDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    "topay_rogfield_destroy": (None, [C.c_void_p]),
+    "topay_rogfield_geometry": (C.c_int, [C.c_void_p, _ip, _ip, _dp, _ip, _ip]),
+    "topay_rogfield_slide": (C.c_int, [C.c_void_p, _dp]),
+    "topay_rogfield_update_counters": (C.c_int, [C.c_void_p, _dp, _u8p, _u8p, C.c_int64]),
+    "topay_rogfield_set_occupied_cnt": (C.c_int, [C.c_void_p, _i16p]),
+    "topay_rogfield_download_counters": (C.c_int, [C.c_void_p, _i16p, _i16p]),
+    "topay_rogfield_update_esdf": (C.c_int, [C.c_void_p, _dp]),
+    "topay_rogfield_query": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int64, _dp, _dp]),
+    "topay_rogfield_is_line_free2d": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_double, _i8p]),
+    "topay_rogfield_download": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "topay_rogfield_last_update_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "topay_solver_create": (C.c_int, [C.POINTER(OptParams), C.POINTER(RobotParams), C.c_void_p, C.c_int, C.c_int,
                                       C.POINTER(C.c_void_p)]),
     "topay_solver_destroy": (None, [C.c_void_p]),

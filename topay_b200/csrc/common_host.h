@@ -15,6 +15,17 @@ int tp_field_device(const topay_field* f);
 bool tp_field_ready(const topay_field* f);
 void tp_field_grid(const topay_field* f, TpGrid* out);
 
+// Scratch of the separable exact EDT (field.cu), shared by the dense and the ROG-ring field.
+struct TpEdtScratch {
+    cudaStream_t stream;
+    short2* packed;               // pass-1 output, A*B*C
+    int32_t *tmp_pos, *tmp_neg;   // pass-2 output, A*B*C (3-D only)
+    bool keep_sq;                 // also store the integer squared distances
+    double res;
+};
+int tp_signed_edt(const TpEdtScratch& s, const int8_t* src, int A, int B, int C, double* esdf, int32_t* sqp,
+                  int32_t* sqn);
+
 #define TP_CUDA_OK(call, cleanup)                                                              \
     do {                                                                                       \
         cudaError_t e_ = (call);                                                               \

@@ -295,7 +295,7 @@ __device__ __forceinline__ void tp_edt_store(bool FINAL, int bp, int bn, size_t 
         const double dn = __dmul_rn(res, __dsqrt_rn(vn));
         double d = dp;
         if (dn > 0.0) d = __dadd_rn(d, __dadd_rn(-dn, res));
-        esdf[idx] = d;
+        if (esdf) esdf[idx] = d;
         if (out_pos) {
             out_pos[idx] = bp;
             out_neg[idx] = bn;
@@ -523,6 +523,17 @@ int fmalloc(T** p, size_t count) {
 // One signed transform over a [A][B][C] array (C contiguous): pass 1 along C, pass 2 along B
 // and, when A > 1, pass 3 along A. The last pass writes `esdf` (+ the integer grids).
 int signed_edt(topay_field* f, const int8_t* src, int A, int B, int C, double* esdf, int32_t* sqp, int32_t* sqn) {
+    TpEdtScratch sc{f->stream, f->packed, f->tmp_pos, f->tmp_neg, f->keep_sq, f->desc.resolution};
+    return tp_signed_edt(sc, src, A, B, C, esdf, sqp, sqn);
+}
+
+}  // namespace
+
+// One signed transform over a [A][B][C] array; shared with rogfield.cu. esdf may be NULL (integer
+// grids only, keep_sq must then be set).
+int tp_signed_edt(const TpEdtScratch& f_, const int8_t* src, int A, int B, int C, double* esdf, int32_t* sqp,
+                  int32_t* sqn) {
+    const TpEdtScratch* f = &f_;
     cudaStream_t q = f->stream;
     const int64_t n_lines = (int64_t)A * B;
     // pass 1
@@ -558,7 +569,7 @@ int signed_edt(topay_field* f, const int8_t* src, int A, int B, int C, double* e
         const unsigned blocks = (unsigned)n_outer * tiles;
         int32_t* op = fin ? (f->keep_sq ? sqp : nullptr) : f->tmp_pos;
         int32_t* on = fin ? (f->keep_sq ? sqn : nullptr) : f->tmp_neg;
-        const double res = f->desc.resolution;
+        const double res = f->res;
         if (in16 && fin) {
             TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), {});
             k_edt_strided16<true><<<blocks, blk, smem, q>>>(f->packed, op, on, esdf, n_line, line_stride, outer_stride,
@@ -584,8 +595,6 @@ int signed_edt(topay_field* f, const int8_t* src, int A, int B, int C, double* e
     }
     return rc;
 }
-
-}  // namespace
 
 extern "C" int topay_field_create(const topay_grid_desc* desc, int device, topay_field** out) {
     if (!desc || !out || desc->resolution <= 0.0) return TOPAY_ERR_INVALID_ARG;
