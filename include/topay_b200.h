@@ -284,6 +284,54 @@ int topay_rogfield_is_line_free2d(topay_rogfield* f, const double* start, const 
 int topay_rogfield_download(topay_rogfield* f, int which, double* out);
 int topay_rogfield_last_update_ms(topay_rogfield* f, float* ms_total, float* ms_3d);
 
+/* -------------------------------------- result post-processing + success gate */
+
+/* n MomaTraj inputs (moma_traj_opt.h:26-68): what MinJerkOpt<9>::getTraj hands over
+ * (minco.hpp:908-921) plus the SE(2) start. coeff rows are in the solver's layout —
+ * row 6i+k = coefficient of t^k of piece i — the reference stores the same numbers in
+ * descending order. Host pointers. */
+typedef struct topay_traj_batch {
+    int32_t n_traj;
+    int32_t max_pieces;          /* row pitch of T and coeff */
+    const int32_t* piece_num;    /* [n] */
+    const double*  T;            /* [n][max_pieces] */
+    const double*  coeff;        /* [n][6*max_pieces][9] */
+    const double*  start_se2;    /* [n][3] x, y, yaw */
+} topay_traj_batch;
+
+/* What checkFeasible / printConstraintsSituations accumulate (moma_traj_opt.h:948-1210)
+ * over samples at t = 0, 0.01, ... < duration. The max_* entries are the signed value of the
+ * first sample that attains the largest magnitude, as the reference's running update keeps
+ * it. Host pointers; any may be NULL except feasible. */
+typedef struct topay_feasibility {
+    int32_t* feasible;         /* [n] checkFeasible */
+    int32_t* feasible_print;   /* [n] printConstraintsSituations: manipulator clearance reported, not enforced (:1199) */
+    int32_t* n_samples;        /* [n] */
+    double*  max_vel;          /* [n] */
+    double*  max_acc;
+    double*  max_domega;
+    double*  max_d2omega;
+    double*  max_q;            /* [n][7] */
+    double*  max_dq;
+    double*  max_d2q;
+    double*  min_dist;         /* [n] chassis clearance (getDistance2d) */
+    double*  min_dist_mani;    /* [n][12] sphere-centre clearance (getDistance3d) */
+} topay_feasibility;
+
+/* MomaTrajOpt::checkFeasible for n trajectories at once: one thread block per trajectory. */
+int topay_traj_check_feasible(topay_field* f, const topay_robot_params* robot, const topay_traj_batch* trajs,
+                              topay_feasibility* out);
+/* MomaTraj::car_seq (moma_traj_opt.h:38-68): entries (x, y, yaw, t); len[i] entries of
+ * trajectory i are written to car_seq[i*cap*4 ...] (TOPAY_ERR_TOO_LARGE if one needs more than cap). */
+int topay_traj_car_seq(int device, const topay_traj_batch* trajs, int cap, double* car_seq, int32_t* len);
+/* MomaTraj::getState / getDState (moma_traj_opt.h:121-160) at m times per trajectory:
+ * t [n][m] -> state [n][m][10] (x, y, yaw, q1..q7), dstate [n][m][10] (v, omega, 0, dq); either output may be NULL. */
+int topay_traj_sample(int device, const topay_traj_batch* trajs, const double* t, int m, double* state,
+                      double* dstate);
+/* The planner's pick (planner.cpp:999-1010): first success, replaced by any later strictly
+ * shorter trajectory; -1 when nothing succeeded. Pure host code. */
+int topay_select_shortest(const int32_t* success, const double* duration, int n);
+
 /* ------------------------------------------------------------------ solver */
 
 /* One solver = the device-side state for up to max_cand candidates of up to
@@ -380,6 +428,11 @@ typedef struct topay_solver_stats {
     int64_t eval_nodes;        /* penalty nodes processed by them (active candidates only) */
 } topay_solver_stats;
 int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out);
+/* The worker's success gate on the device, straight from the solver's result buffers
+ * (planner.cpp:877-880): checkFeasible of every candidate of the last run. best_success is
+ * the shortest-duration candidate among those with status && feasible_print (the gate the
+ * planner applies), -1 if none. */
+int topay_solver_check_feasible(topay_solver* s, topay_feasibility* out, int32_t* best_success);
 /* timed != 0: every k_penalty launch is bracketed by CUDA events (stats.ms_eval) and the ticks are
  * plain launches; timed == 0 (default): a batch of 16 ticks is replayed as one CUDA graph, which
  * removes the per-launch host cost that dominates small plans; stats.ms_eval is then 0. */

@@ -10,6 +10,7 @@
 #include "oracle_robot.hpp"
 #include "oracle_rog.hpp"
 #include "oracle_solve.hpp"
+#include "oracle_traj.hpp"
 
 using namespace oracle;
 
@@ -405,5 +406,58 @@ void oracle_rog_download(void* h, int which, double* out) {
                                  : which == TOPAY_ROG_BUF_CRITICAL ? r->dist_crit : r->dist_flat;
     std::memcpy(out, v.data(), v.size() * sizeof(double));
 }
+
+// ---------------------------------------------------------------- MomaTraj + feasibility (oracle_traj.hpp)
+static MomaTrajO make_traj(const topay_traj_batch* b, int i) {
+    PolyTraj p;
+    p.N = b->piece_num[i];
+    p.T = b->T + (size_t)i * b->max_pieces;
+    p.c = b->coeff + (size_t)i * 6 * b->max_pieces * 9;
+    MomaTrajO t;
+    t.init(p, b->start_se2 + 3 * i);
+    return t;
+}
+int oracle_traj_car_seq(const topay_traj_batch* b, int cap, double* car_seq, int32_t* len) {
+    for (int i = 0; i < b->n_traj; i++) {
+        MomaTrajO t = make_traj(b, i);
+        const int n = (int)(t.car_seq.size() / 4);
+        len[i] = n;
+        if (n > cap) return -5;
+        std::memcpy(car_seq + (size_t)i * cap * 4, t.car_seq.data(), t.car_seq.size() * sizeof(double));
+    }
+    return 0;
+}
+void oracle_traj_sample(const topay_traj_batch* b, const double* tt, int m, double* state, double* dstate) {
+    for (int i = 0; i < b->n_traj; i++) {
+        MomaTrajO t = make_traj(b, i);
+        for (int j = 0; j < m; j++) {
+            if (state) t.get_state(tt[(size_t)i * m + j], state + ((size_t)i * m + j) * 10);
+            if (dstate) t.get_dstate(tt[(size_t)i * m + j], dstate + ((size_t)i * m + j) * 10);
+        }
+    }
+}
+void oracle_check_feasible(void* field, const topay_robot_params* rp, const topay_traj_batch* b,
+                           topay_feasibility* out) {
+    for (int i = 0; i < b->n_traj; i++) {
+        MomaTrajO t = make_traj(b, i);
+        Feasibility F = check_feasible(t, *rp, *(Field*)field);
+        out->feasible[i] = F.feasible;
+        if (out->feasible_print) out->feasible_print[i] = F.feasible_print;
+        if (out->n_samples) out->n_samples[i] = F.n_samples;
+        if (out->max_vel) out->max_vel[i] = F.max_vel;
+        if (out->max_acc) out->max_acc[i] = F.max_acc;
+        if (out->max_domega) out->max_domega[i] = F.max_domega;
+        if (out->max_d2omega) out->max_d2omega[i] = F.max_d2omega;
+        for (int k = 0; k < TOPAY_DOF; k++) {
+            if (out->max_q) out->max_q[i * TOPAY_DOF + k] = F.max_q[k];
+            if (out->max_dq) out->max_dq[i * TOPAY_DOF + k] = F.max_dq[k];
+            if (out->max_d2q) out->max_d2q[i * TOPAY_DOF + k] = F.max_d2q[k];
+        }
+        if (out->min_dist) out->min_dist[i] = F.min_dist;
+        if (out->min_dist_mani)
+            for (int k = 0; k < TOPAY_NSPHERE; k++) out->min_dist_mani[i * TOPAY_NSPHERE + k] = F.min_dist_mani[k];
+    }
+}
+int oracle_select_shortest(const int32_t* succ, const double* dur, int n) { return select_shortest(succ, dur, n); }
 
 }  // extern "C"

@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from topay_b200._structs import (GridDesc, RogDesc, LbfgsParams, OptParams, RobotParams, NTERMS, num_vars)
+from topay_b200._structs import (GridDesc, RogDesc, alloc_feasibility, pack_trajs, LbfgsParams, OptParams, RobotParams, NTERMS, num_vars)
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_ROOT, "oracle", "liboracle.so")
@@ -17,7 +17,7 @@ _SO = os.path.join(_ROOT, "oracle", "liboracle.so")
 
 def build(force=False):
     srcs = [os.path.join(_ROOT, "oracle", f) for f in
-            ("oracle_capi.cpp", "oracle_field.hpp", "oracle_robot.hpp", "oracle_rog.hpp", "oracle_solve.hpp")]
+            ("oracle_capi.cpp", "oracle_field.hpp", "oracle_robot.hpp", "oracle_rog.hpp", "oracle_solve.hpp", "oracle_traj.hpp")]
     srcs.append(os.path.join(_ROOT, "include", "topay_b200.h"))
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "liboracle.so"])
@@ -335,3 +335,35 @@ class RogField:
         out = np.empty(self.size if which < 2 else self.size[:2])
         lib().oracle_rog_download(self.h, which, _p(out))
         return out
+
+
+# ---- MomaTraj post-processing + success gate (oracle_traj.hpp) -----------------------------------------
+def traj_car_seq(trajs, cap=4096):
+    tb, keep = pack_trajs(trajs)
+    out = np.zeros((len(trajs), cap, 4))
+    ln = np.zeros(len(trajs), dtype=np.int32)
+    rc = lib().oracle_traj_car_seq(C.byref(tb), cap, _p(out), _p(ln, C.c_int32))
+    assert rc == 0
+    return [out[i, :ln[i]].copy() for i in range(len(trajs))]
+
+
+def traj_sample(trajs, t):
+    tb, keep = pack_trajs(trajs)
+    t = _f64(t)
+    n, m = t.shape
+    st, ds = np.zeros((n, m, 10)), np.zeros((n, m, 10))
+    lib().oracle_traj_sample(C.byref(tb), _p(t), m, _p(st), _p(ds))
+    return st, ds
+
+
+def check_feasible(field, rp, trajs):
+    tb, keep = pack_trajs(trajs)
+    f, arrs = alloc_feasibility(len(trajs))
+    lib().oracle_check_feasible(field.h, C.byref(rp), C.byref(tb), C.byref(f))
+    return arrs
+
+
+def select_shortest(succ, dur):
+    s = np.ascontiguousarray(succ, dtype=np.int32)
+    d = _f64(dur)
+    return lib().oracle_select_shortest(_p(s, C.c_int32), _p(d), len(s))

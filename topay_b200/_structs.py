@@ -1,6 +1,8 @@
 """ctypes mirrors of the C structs in include/topay_b200.h (field order must match)."""
 import ctypes as C
 
+import numpy as np
+
 DOF, DIM, NSPHERE, NTERMS = 7, 9, 12, 13
 TERM_NAMES = ["jerk", "time", "chassis_colli", "moment", "acc", "domega", "mani_colli",
               "self_colli", "mani_pos", "mani_vel", "mani_acc", "mean_time", "endp"]
@@ -106,6 +108,47 @@ class ResultBatch(C.Structure):
                 ("cost", C.POINTER(C.c_double)), ("duration", C.POINTER(C.c_double)),
                 ("T", C.POINTER(C.c_double)), ("coeff", C.POINTER(C.c_double)),
                 ("final_xy_err", C.POINTER(C.c_double)), ("x", C.POINTER(C.c_double))]
+
+
+class TrajBatch(C.Structure):
+    _fields_ = [("n_traj", C.c_int32), ("max_pieces", C.c_int32), ("piece_num", C.POINTER(C.c_int32)),
+                ("T", C.POINTER(C.c_double)), ("coeff", C.POINTER(C.c_double)), ("start_se2", C.POINTER(C.c_double))]
+
+
+FEAS_FIELDS = (("feasible", np.int32, ()), ("feasible_print", np.int32, ()), ("n_samples", np.int32, ()),
+               ("max_vel", np.float64, ()), ("max_acc", np.float64, ()), ("max_domega", np.float64, ()),
+               ("max_d2omega", np.float64, ()), ("max_q", np.float64, (7,)), ("max_dq", np.float64, (7,)),
+               ("max_d2q", np.float64, (7,)), ("min_dist", np.float64, ()), ("min_dist_mani", np.float64, (12,)))
+
+
+class Feasibility(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_int32 if t is np.int32 else C.c_double)) for n, t, _ in FEAS_FIELDS]
+
+
+def pack_trajs(trajs):
+    """[(durations[N], coeff[6N][9], start_se2[3]), ...] -> (TrajBatch, keep-alive arrays)."""
+    n = len(trajs)
+    pn = np.array([len(t[0]) for t in trajs], dtype=np.int32)
+    NP = int(pn.max()) if n else 1
+    T = np.zeros((n, NP))
+    cf = np.zeros((n, 6 * NP, 9))
+    st = np.zeros((n, 3))
+    for i, (d, c, s0) in enumerate(trajs):
+        T[i, :pn[i]] = d
+        cf[i, :6 * pn[i]] = np.asarray(c).reshape(6 * pn[i], 9)
+        st[i] = np.asarray(s0)[:3]
+    keep = (pn, T, cf, st)
+    tb = TrajBatch(n, NP, pn.ctypes.data_as(C.POINTER(C.c_int32)), T.ctypes.data_as(C.POINTER(C.c_double)),
+                   cf.ctypes.data_as(C.POINTER(C.c_double)), st.ctypes.data_as(C.POINTER(C.c_double)))
+    return tb, keep
+
+
+def alloc_feasibility(n):
+    """(Feasibility, dict of numpy arrays it points to)."""
+    arrs = {name: np.zeros((n,) + shape, dtype=t) for name, t, shape in FEAS_FIELDS}
+    f = Feasibility(*[arrs[name].ctypes.data_as(C.POINTER(C.c_int32 if t is np.int32 else C.c_double))
+                      for name, t, _ in FEAS_FIELDS])
+    return f, arrs
 
 
 class SolverStats(C.Structure):
