@@ -11,6 +11,7 @@
 
 #include "common_host.h"
 #include "solver_kernels.cuh"
+#include "traj_host.h"
 
 struct topay_solver {
     TpSolverDev dev;
@@ -36,6 +37,10 @@ struct topay_solver {
     bool timed;                 // per-launch CUDA events around k_penalty (plain launches, no graph)
     cudaGraphExec_t graph_exec;
     int graph_n_cand, graph_max_N;
+    // success gate (topay_solver_check_feasible): built on first use
+    TpTrajChecker* checker;
+    int32_t* d_pn;
+    double* d_start;
 };
 
 namespace {
@@ -126,6 +131,9 @@ extern "C" int topay_solver_create(const topay_opt_params* opt, const topay_robo
     s->timed = false;
     s->graph_exec = nullptr;
     s->graph_n_cand = s->graph_max_N = -1;
+    s->checker = nullptr;
+    s->d_pn = nullptr;
+    s->d_start = nullptr;
     memset(&s->stats, 0, sizeof(s->stats));
     cudaSetDevice(s->device);
     TP_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), { delete s; });
@@ -216,6 +224,7 @@ extern "C" void topay_solver_destroy(topay_solver* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    delete s->checker;
     for (void* p : s->allocs) cudaFree(p);
     if (s->dev.trace) cudaFree(s->dev.trace);
     if (s->dev.trace_len) cudaFree(s->dev.trace_len);
@@ -497,6 +506,57 @@ extern "C" int topay_solver_solve_batch(topay_solver* s, int n_cand, const int32
     rc = topay_solver_run(s);
     if (rc != TOPAY_OK) return rc;
     return topay_solver_download(s, out, best_by_duration, best_by_cost);
+}
+
+// Piece counts live in the per-candidate state and the start pose is split over start_xy and the
+// yaw slot of head_pva; gather both into the layout the trajectory kernels read.
+__global__ void k_solver_traj_view(const TpCandState* __restrict__ st, const double* __restrict__ start_xy,
+                                   const double* __restrict__ head_pva, int n, int32_t* pn, double* start) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    pn[c] = st[c].N;
+    start[3 * c] = start_xy[2 * c];
+    start[3 * c + 1] = start_xy[2 * c + 1];
+    start[3 * c + 2] = head_pva[(size_t)c * 27];
+}
+
+extern "C" int topay_solver_check_feasible(topay_solver* s, topay_feasibility* out, int32_t* best_success) {
+    if (!s || !out || !out->feasible || s->n_cand < 1) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(s->device);
+    TpSolverDev& D = s->dev;
+    const int n = s->n_cand, NP = D.max_pieces;
+    int rc;
+    if (!s->checker) {
+        if ((rc = dev_alloc(s, &s->d_pn, (size_t)D.max_cand)) != TOPAY_OK) return rc;
+        if ((rc = dev_alloc(s, &s->d_start, (size_t)D.max_cand * 3)) != TOPAY_OK) return rc;
+        s->checker = new TpTrajChecker();
+        if ((rc = s->checker->init(s->device, s->stream)) != TOPAY_OK) return rc;
+    }
+    k_solver_traj_view<<<(n + 127) / 128, 128, 0, s->stream>>>(D.st, D.start_xy, D.head_pva, n, s->d_pn, s->d_start);
+    TpTrajView V{n, NP, s->d_pn, D.T, D.coeff, s->d_start};
+    TpGrid G;
+    tp_field_grid(s->field, &G);
+    std::vector<int32_t> fp;
+    int32_t* keep_fp = out->feasible_print;
+    if (!keep_fp) {   // the gate below needs it
+        fp.resize(n);
+        out->feasible_print = fp.data();
+    }
+    rc = s->checker->check(V, s->params, G, out);
+    if (rc == TOPAY_OK && best_success) {
+        // planner.cpp:877-880 + :999-1010: optimizeTraj && printConstraintsSituations, shortest duration
+        std::vector<TpCandState> st(n);
+        TP_CUDA_OK(cudaMemcpy(st.data(), D.st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), { out->feasible_print = keep_fp; });
+        std::vector<int32_t> ok(n);
+        std::vector<double> dur(n);
+        for (int c = 0; c < n; c++) {
+            ok[c] = st[c].status == 1 && out->feasible_print[c];
+            dur[c] = s->checker->h_meta[c].total;
+        }
+        *best_success = topay_select_shortest(ok.data(), dur.data(), n);
+    }
+    out->feasible_print = keep_fp;
+    return rc;
 }
 
 // Dev profiling: accumulated clock64() deltas of k_cand's phases for candidate 0 (16 slots).

@@ -11,7 +11,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._structs import NTERMS, OptParams, ProblemBatch, ResultBatch, RobotParams, SolverStats, num_vars
+from ._structs import (NTERMS, OptParams, ProblemBatch, ResultBatch, RobotParams, SolverStats, alloc_feasibility,
+                       num_vars, pack_trajs)
 from .field import GridMap, _p, robot_params_default
 
 
@@ -22,15 +23,74 @@ def opt_params_default():
 
 
 class MomaTraj:
-    """Result of one optimisation: piece durations + MINCO coefficients (row 6i+k = t^k of piece i,
-    columns theta, arc, q1..q7 — MinJerkOpt<9>::getCoeffs layout, minco.hpp:944)."""
+    """Result of one optimisation (moma_traj_opt.h:26-247): piece durations + MINCO coefficients (row 6i+k =
+    t^k of piece i, columns theta, arc, q1..q7 — MinJerkOpt<9>::getCoeffs layout, minco.hpp:944) + the SE(2)
+    start. The pose table and the state samplers are evaluated on the device."""
 
-    def __init__(self, T, coeff, start_se2):
-        self.durations, self.coeff, self.start_se2 = T, coeff, start_se2
+    def __init__(self, T, coeff, start_se2, device=0):
+        self.durations = np.ascontiguousarray(T, dtype=np.float64)
+        self.coeff = np.ascontiguousarray(coeff, dtype=np.float64).reshape(6 * len(self.durations), 9)
+        self.start_se2 = np.ascontiguousarray(start_se2, dtype=np.float64)[:3]
+        self.device = device
         self.is_init = True
+        self._car_seq = None
+
+    def _tuple(self):
+        return (self.durations, self.coeff, self.start_se2)
 
     def getTotalDuration(self):
-        return float(np.sum(self.durations))
+        return float(sum(float(t) for t in self.durations))     # summed in piece order (minco.hpp:304-313)
+
+    @property
+    def car_seq(self):
+        """(m, 4) rows x, y, yaw, t every seq_res = 0.1 s (moma_traj_opt.h:38-68)."""
+        if self._car_seq is None:
+            tb, keep = pack_trajs([self._tuple()])
+            cap = int(self.getTotalDuration() / 0.1) + 4
+            out = np.zeros((1, cap, 4))
+            ln = np.zeros(1, dtype=np.int32)
+            _lib.check(_lib.lib().topay_traj_car_seq(self.device, C.byref(tb), cap, _p(out), _p(ln, C.c_int32)),
+                       "topay_traj_car_seq")
+            self._car_seq = out[0, :ln[0]].copy()
+        return self._car_seq
+
+    def _sample(self, t, want_state=True, want_dstate=False):
+        t = np.ascontiguousarray(np.atleast_1d(t), dtype=np.float64).reshape(1, -1)
+        tb, keep = pack_trajs([self._tuple()])
+        st = np.zeros((1, t.shape[1], 10)) if want_state else None
+        ds = np.zeros((1, t.shape[1], 10)) if want_dstate else None
+        _lib.check(_lib.lib().topay_traj_sample(self.device, C.byref(tb), _p(t), t.shape[1], _p(st), _p(ds)),
+                   "topay_traj_sample")
+        return (st[0] if want_state else None), (ds[0] if want_dstate else None)
+
+    def getState(self, t):
+        """MomaTraj::getState (moma_traj_opt.h:121-149): (x, y, yaw, q1..q7) at one time or an array of times."""
+        st = self._sample(t)[0]
+        return st[0] if np.ndim(t) == 0 else st
+
+    def getDState(self, t):
+        """MomaTraj::getDState (moma_traj_opt.h:151-160): (v, omega, 0, dq1..dq7)."""
+        ds = self._sample(t, want_state=False, want_dstate=True)[1]
+        return ds[0] if np.ndim(t) == 0 else ds
+
+    @staticmethod
+    def normYaw(yaw):
+        y = np.array(yaw, dtype=np.float64)
+        while np.any(y > np.pi):
+            y = np.where(y > np.pi, y - 2 * np.pi, y)
+        while np.any(y < -np.pi):
+            y = np.where(y < -np.pi, y + 2 * np.pi, y)
+        return y
+
+    def sampleTimePoints(self, n):
+        """moma_traj_opt.h:172-199: n rows (x, y, yaw normalised, q1..q7, cos yaw, sin yaw) at equal time steps."""
+        num = n - 2
+        total = self.getTotalDuration()
+        dt = total / (num + 1)
+        t = np.array([i * dt for i in range(num + 1)] + [total])
+        x = self.getState(t)
+        x[:, 2] = self.normYaw(x[:, 2])
+        return np.concatenate([x, np.cos(x[:, 2:3]), np.sin(x[:, 2:3])], axis=1)
 
 
 class MomaTrajOpt:
@@ -131,7 +191,38 @@ class MomaTrajOpt:
     def getTraj(self, idx=0):
         r = self._last
         N = int(r["piece_num"][idx])
-        return MomaTraj(r["T"][idx, :N].copy(), r["coeff"][idx, :6 * N].copy(), self._starts[idx])
+        return MomaTraj(r["T"][idx, :N].copy(), r["coeff"][idx, :6 * N].copy(), self._starts[idx],
+                        device=self.grid_map.device)
+
+    # ---- success gate (planner.cpp:877-880) --------------------------------------
+    def checkFeasible(self, trajs):
+        """bool MomaTrajOpt::checkFeasible(MomaTraj) (moma_traj_opt.h:948-1045) for one trajectory or a list;
+        returns the verdict(s). The accumulated metrics of the last call are in self.constraints."""
+        single = isinstance(trajs, MomaTraj)
+        lst = [trajs] if single else list(trajs)
+        tb, keep = pack_trajs([t._tuple() for t in lst])
+        f, arrs = alloc_feasibility(len(lst))
+        _lib.check(self._l.topay_traj_check_feasible(self.grid_map.h, C.byref(self.moma_param), C.byref(tb),
+                                                     C.byref(f)), "topay_traj_check_feasible")
+        self.constraints = arrs
+        return bool(arrs["feasible"][0]) if single else arrs["feasible"].astype(bool)
+
+    def printConstraintsSituations(self, trajs):
+        """moma_traj_opt.h:1047-1210: the same scan; the manipulator clearances are reported, not enforced."""
+        single = isinstance(trajs, MomaTraj)
+        self.checkFeasible(trajs)
+        v = self.constraints["feasible_print"].astype(bool)
+        return bool(v[0]) if single else v
+
+    def checkFeasibleBatch(self):
+        """The gate for every candidate of the last solve without leaving the device: returns (metrics dict,
+        index of the shortest candidate with status && printConstraintsSituations, or -1)."""
+        f, arrs = alloc_feasibility(self._n)
+        best = C.c_int32(-1)
+        _lib.check(self._l.topay_solver_check_feasible(self.h, C.byref(f), C.byref(best)),
+                   "topay_solver_check_feasible")
+        self.constraints = arrs
+        return arrs, best.value
 
     def set_timed(self, timed):
         """Per-launch CUDA-event timing of the penalty kernel (plain launches) instead of graph replay."""
