@@ -199,6 +199,18 @@ int topay_field_distance2d(topay_field* f, const double* pos, int64_t n, double*
 /* GridMap::isWholeBodyCollision (grid_map.h:613-650); states are n x 10; out 0/1. */
 int topay_field_whole_body_collision(topay_field* f, const topay_robot_params* robot,
                                      const double* states, int64_t n, int8_t* out);
+/* GridMap::isCollision2d / isCollision3d (grid_map.h:511-536, 695-724): distance below
+ * threshold, or outside the map. pos is n x 2 / n x 3, out[i] in {0,1}. */
+int topay_field_is_collision2d(topay_field* f, const double* pos, int64_t n, double threshold, int8_t* out);
+int topay_field_is_collision3d(topay_field* f, const double* pos, int64_t n, double threshold, int8_t* out);
+/* GridMap::isLineCollisionGrid2d (grid_map.h:565-611): Bresenham walk over the flat map between
+ * the cells of p1 and p2 (both n x 2), both end cells tested. */
+int topay_field_is_line_collision_grid2d(topay_field* f, const double* p1, const double* p2, int64_t n,
+                                         double threshold, int8_t* out);
+/* GridMap::getDistCoarse2d / getDistCoarse2i (grid_map.h:887-940): nearest cell (clamped to the
+ * grid) of the critical map, else of the inflated map. idx is n x 2 int32. */
+int topay_field_dist_coarse2d(topay_field* f, const double* pos, int64_t n, int critical, double* out);
+int topay_field_dist_coarse2i(topay_field* f, const int32_t* idx, int64_t n, int critical, double* out);
 /* Same queries with DEVICE pointers (inputs and outputs already in HBM), asynchronous
  * on the field's stream; used by the resident benchmark and by the solver. */
 int topay_field_query3d_dev(topay_field* f, const double* pos_dev, int64_t n, double* dist_dev,

@@ -80,6 +80,20 @@ static const std::vector<double>& esdf_of(Field* f, int which) {
         default: return f->esdf_buffer_3d;
     }
 }
+void oracle_field_is_collision(void* h, int dim, const double* pos, int64_t n, double thr, int8_t* out) {
+    Field* f = (Field*)h;
+    for (int64_t i = 0; i < n; i++)
+        out[i] = dim == 2 ? f->is_collision2d(pos + 2 * i, thr) : f->is_collision3d(pos + 3 * i, thr);
+}
+void oracle_field_dist_coarse2d(void* h, const double* pos, int64_t n, int critical, double* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = ((Field*)h)->dist_coarse2d(pos + 2 * i, critical != 0);
+}
+void oracle_field_dist_coarse2i(void* h, const int32_t* idx, int64_t n, int critical, double* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = ((Field*)h)->dist_coarse2i(idx + 2 * i, critical != 0);
+}
+void oracle_field_line_collision2d(void* h, const double* p1, const double* p2, int64_t n, double thr, int8_t* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = ((Field*)h)->is_line_collision_grid2d(p1 + 2 * i, p2 + 2 * i, thr);
+}
 void oracle_field_download(void* h, int which, double* out) {
     const std::vector<double>& b = esdf_of((Field*)h, which);
     std::memcpy(out, b.data(), b.size() * sizeof(double));

@@ -302,6 +302,57 @@ struct Field {
         ready = true;
     }
 
+    // grid_map.h:511-536
+    bool is_collision2d(const double* pos, double threshold) const {
+        if (in_map2_pos(pos)) {
+            double d;
+            distance2d(pos, d);
+            return d < threshold;
+        }
+        return true;
+    }
+    // grid_map.h:695-724
+    bool is_collision3d(const double* pos, double threshold) const {
+        if (in_map3_pos(pos)) {
+            double d;
+            distance3d(pos, d);
+            return d < threshold;
+        }
+        return true;
+    }
+    // grid_map.h:538-556 (dense branch)
+    bool is_collision_idx2d(int x, int y, double threshold) const { return esdf_buffer_2d[addr2(x, y)] < threshold; }
+    // grid_map.h:565-611: Bresenham over the flat map, both end cells included
+    bool is_line_collision_grid2d(const double* p1, const double* p2, double threshold) const {
+        int s[2], e[2];
+        pos_to_index2(p1, s);
+        pos_to_index2(p2, e);
+        const int dx = std::abs(e[0] - s[0]), dy = std::abs(e[1] - s[1]);
+        const int sx = s[0] < e[0] ? 1 : -1, sy = s[1] < e[1] ? 1 : -1;
+        int err = dx - dy, x0 = s[0], y0 = s[1];
+        for (;;) {
+            if (!in_map2_idx2(x0, y0)) return true;   // deviation: the reference reads outside the buffer here
+            if (is_collision_idx2d(x0, y0, threshold)) return true;
+            if (x0 == e[0] && y0 == e[1]) break;
+            const int e2 = 2 * err;
+            if (e2 > -dy) { err -= dy; x0 += sx; }
+            if (e2 < dx) { err += dx; y0 += sy; }
+        }
+        return false;
+    }
+    bool in_map2_idx2(int x, int y) const { return x >= 0 && y >= 0 && x <= max_idx[0] && y <= max_idx[1]; }
+    // grid_map.h:887-940 (dense branch): nearest cell, clamped, critical or inflated map
+    double dist_coarse2i(const int* id_in, bool critical) const {
+        int id[2] = {id_in[0], id_in[1]};
+        bound2(id);
+        return critical ? esdf_buffer_2d_critical[addr2(id[0], id[1])] : esdf_buffer_2d_inflate[addr2(id[0], id[1])];
+    }
+    double dist_coarse2d(const double* pos, bool critical) const {
+        int id[2];
+        pos_to_index2(pos, id);
+        return dist_coarse2i(id, critical);
+    }
+
     // grid_map.h:256-305
     void distance2d(const double* pos, double& distance) const {
         if (!in_map2_pos(pos)) {

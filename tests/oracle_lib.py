@@ -114,6 +114,32 @@ class Field:
         lib().oracle_field_distance2d(self.h, _p(pos), C.c_int64(pos.shape[0]), _p(d))
         return d
 
+    def is_collision(self, pos, threshold):
+        pos = _f64(pos)
+        out = np.empty(pos.shape[0], dtype=np.int8)
+        lib().oracle_field_is_collision(self.h, pos.shape[1], _p(pos), C.c_int64(pos.shape[0]), C.c_double(threshold),
+                                        _p(out, C.c_int8))
+        return out.astype(bool)
+
+    def dist_coarse2d(self, pos, critical=False):
+        pos = _f64(pos)
+        out = np.empty(pos.shape[0])
+        lib().oracle_field_dist_coarse2d(self.h, _p(pos), C.c_int64(pos.shape[0]), int(critical), _p(out))
+        return out
+
+    def dist_coarse2i(self, idx, critical=False):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = np.empty(idx.shape[0])
+        lib().oracle_field_dist_coarse2i(self.h, _p(idx, C.c_int32), C.c_int64(idx.shape[0]), int(critical), _p(out))
+        return out
+
+    def line_collision2d(self, p1, p2, threshold=0.0):
+        p1, p2 = _f64(p1), _f64(p2)
+        out = np.empty(p1.shape[0], dtype=np.int8)
+        lib().oracle_field_line_collision2d(self.h, _p(p1), _p(p2), C.c_int64(p1.shape[0]), C.c_double(threshold),
+                                            _p(out, C.c_int8))
+        return out.astype(bool)
+
     def whole_body_collision(self, rp, states):
         states = _f64(states)
         out = np.empty(states.shape[0], dtype=np.int8)

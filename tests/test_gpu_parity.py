@@ -275,3 +275,28 @@ def test_baseline_size_field_properties(oracle):
     gm.updateESDF()                                              # idempotent
     assert np.array_equal(gm.getESDFBuffer3d(), e)
     print("800x800x80 rebuild ms (total, 3-D part):", gm.last_rebuild_ms())
+
+
+def test_front_end_predicates_and_coarse_lookups(gpu_scene, small_scene):
+    """isCollision2d/3d, isLineCollisionGrid2d, getDistCoarse2d/2i (grid_map.h:511-611, 695-724, 887-940):
+    exact against the oracle except where an interpolated distance sits within 1e-12 of the threshold."""
+    of = small_scene["field"]
+    rng = np.random.default_rng(8)
+    p2 = rng.uniform(-10.3, 10.3, (20000, 2))
+    p3 = np.concatenate([rng.uniform(-10.3, 10.3, (20000, 2)), rng.uniform(-0.2, 1.8, (20000, 1))], axis=1)
+    for thr in (0.0, 0.25, 0.4):
+        for pos, got in ((p2, gpu_scene.isCollision2d(p2, thr)), (p3, gpu_scene.isCollision3d(p3, thr))):
+            exp = of.is_collision(pos, thr)
+            d = of.distance2d(pos) if pos.shape[1] == 2 else of.distance3d(pos)
+            near = np.abs(d - thr) < 1e-12
+            assert np.array_equal(got[~near], exp[~near]) and 0 < exp.sum() < len(exp)
+    a, b = rng.uniform(-9.9, 9.9, (5000, 2)), rng.uniform(-9.9, 9.9, (5000, 2))
+    b[:50] = a[:50]
+    b[50:100] = rng.uniform(-12, 12, (50, 2))          # leaves the map
+    for thr in (0.0, 0.3):
+        got, exp = gpu_scene.isLineCollisionGrid2d(a, b, thr), of.line_collision2d(a, b, thr)
+        assert np.array_equal(got, exp) and 0 < exp.sum() < len(exp)
+    for crit in (False, True):
+        assert np.array_equal(gpu_scene.getDistCoarse2d(p2, crit), of.dist_coarse2d(p2, crit))
+        idx = rng.integers(-5, 206, (5000, 2))
+        assert np.array_equal(gpu_scene.getDistCoarse2i(idx, crit), of.dist_coarse2i(idx, crit))

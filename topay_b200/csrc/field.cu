@@ -469,6 +469,41 @@ __global__ void k_query2d(TpGrid g, const double* __restrict__ buf, const double
     }
 }
 
+// Batched predicates and nearest-cell lookups the front-end and the feasibility check use
+// (grid_map.h:511-611, 695-724, 887-940). kind: 0 isCollision2d, 1 isCollision3d,
+// 2 isLineCollisionGrid2d (a = p1, b = p2), 3 getDistCoarse2d, 4 getDistCoarse2i (ia = indices).
+__global__ void k_field_misc(TpGrid g, int kind, const double* __restrict__ a, const double* __restrict__ b,
+                             const int32_t* __restrict__ ia, int64_t n, double threshold, int critical, int8_t* flag,
+                             double* val) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (kind) {
+        case 0: {
+            const double p[2] = {a[2 * i], a[2 * i + 1]};
+            flag[i] = tp_is_collision2d(g, p, threshold) ? 1 : 0;
+            break;
+        }
+        case 1: {
+            const double p[3] = {a[3 * i], a[3 * i + 1], a[3 * i + 2]};
+            flag[i] = tp_is_collision3d(g, p, threshold) ? 1 : 0;
+            break;
+        }
+        case 2: {
+            const double p[2] = {a[2 * i], a[2 * i + 1]}, q[2] = {b[2 * i], b[2 * i + 1]};
+            flag[i] = tp_line_collision_grid2d(g, p, q, threshold) ? 1 : 0;
+            break;
+        }
+        case 3: {
+            const double p[2] = {a[2 * i], a[2 * i + 1]};
+            int id[2];
+            tp_pos_to_index2(g, p, id);
+            val[i] = tp_dist_coarse2i(g, id[0], id[1], critical != 0);
+            break;
+        }
+        default: val[i] = tp_dist_coarse2i(g, ia[2 * i], ia[2 * i + 1], critical != 0); break;
+    }
+}
+
 // GridMap::isWholeBodyCollision (grid_map.h:613-650), one thread per 10-D state.
 __global__ void k_whole_body(TpGrid g, TpParams P, const double* __restrict__ states, int64_t n, int8_t* out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -874,6 +909,58 @@ extern "C" int topay_field_whole_body_collision(topay_field* f, const topay_robo
     cudaFree(dout);
     TP_CUDA_OK(e, {});
     return TOPAY_OK;
+}
+
+// kind as k_field_misc; in_a / in_b: n x wa doubles (host), in_i: n x 2 int32 (host)
+static int field_misc(topay_field* f, int kind, const double* in_a, int wa, const double* in_b, const int32_t* in_i,
+                      int64_t n, double threshold, int critical, int8_t* flag, double* val) {
+    if (!f || n < 0 || (n > 0 && ((kind <= 3 && !in_a) || (kind == 2 && !in_b) || (kind == 4 && !in_i) ||
+                                  (kind <= 2 && !flag) || (kind >= 3 && !val))))
+        return TOPAY_ERR_INVALID_ARG;
+    if (!f->ready) {
+        tp_set_error("field queried before topay_field_rebuild");
+        return TOPAY_ERR_NOT_READY;
+    }
+    if (n == 0) return TOPAY_OK;
+    cudaSetDevice(f->device);
+    const size_t ba = in_a ? (size_t)n * wa * 8 : 0, bb = in_b ? (size_t)n * wa * 8 : 0, bi = in_i ? (size_t)n * 8 : 0;
+    const size_t bv = (size_t)n * 8, bf = (size_t)n;
+    char* d = nullptr;
+    TP_CUDA_OK(cudaMalloc(&d, ba + bb + bi + bv + bf + 64), {});
+    double* da = (double*)d;
+    double* db = (double*)(d + ba);
+    int32_t* di = (int32_t*)(d + ba + bb);
+    double* dv = (double*)(d + ba + bb + bi);
+    int8_t* df = (int8_t*)(d + ba + bb + bi + bv);
+    if (in_a) cudaMemcpyAsync(da, in_a, ba, cudaMemcpyHostToDevice, f->stream);
+    if (in_b) cudaMemcpyAsync(db, in_b, bb, cudaMemcpyHostToDevice, f->stream);
+    if (in_i) cudaMemcpyAsync(di, in_i, bi, cudaMemcpyHostToDevice, f->stream);
+    k_field_misc<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(f->grid, kind, da, db, di, n, threshold, critical,
+                                                                    df, dv);
+    if (kind <= 2) cudaMemcpyAsync(flag, df, bf, cudaMemcpyDeviceToHost, f->stream);
+    else cudaMemcpyAsync(val, dv, bv, cudaMemcpyDeviceToHost, f->stream);
+    cudaError_t e = cudaStreamSynchronize(f->stream);
+    cudaFree(d);
+    TP_CUDA_OK(e, {});
+    TP_CUDA_OK(cudaGetLastError(), {});
+    return TOPAY_OK;
+}
+
+extern "C" int topay_field_is_collision2d(topay_field* f, const double* pos, int64_t n, double threshold, int8_t* out) {
+    return field_misc(f, 0, pos, 2, nullptr, nullptr, n, threshold, 0, out, nullptr);
+}
+extern "C" int topay_field_is_collision3d(topay_field* f, const double* pos, int64_t n, double threshold, int8_t* out) {
+    return field_misc(f, 1, pos, 3, nullptr, nullptr, n, threshold, 0, out, nullptr);
+}
+extern "C" int topay_field_is_line_collision_grid2d(topay_field* f, const double* p1, const double* p2, int64_t n,
+                                                    double threshold, int8_t* out) {
+    return field_misc(f, 2, p1, 2, p2, nullptr, n, threshold, 0, out, nullptr);
+}
+extern "C" int topay_field_dist_coarse2d(topay_field* f, const double* pos, int64_t n, int critical, double* out) {
+    return field_misc(f, 3, pos, 2, nullptr, nullptr, n, 0.0, critical, nullptr, out);
+}
+extern "C" int topay_field_dist_coarse2i(topay_field* f, const int32_t* idx, int64_t n, int critical, double* out) {
+    return field_misc(f, 4, nullptr, 2, nullptr, idx, n, 0.0, critical, nullptr, out);
 }
 
 extern "C" int topay_field_download(topay_field* f, int which, double* esdf_out) {

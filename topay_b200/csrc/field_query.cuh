@@ -114,3 +114,43 @@ TP_HD double tp_distance2d(const TpGrid& g, const double* pos) {
     tp_query2d(g, g.esdf2d, pos, d, nullptr);
     return d;
 }
+
+// isCollision2d / isCollision3d (grid_map.h:511-536, 695-724): outside the map counts as collision.
+TP_HD bool tp_is_collision2d(const TpGrid& g, const double* pos, double threshold) {
+    if (!tp_in_map2(g, pos)) return true;
+    return tp_distance2d(g, pos) < threshold;
+}
+TP_HD bool tp_is_collision3d(const TpGrid& g, const double* pos, double threshold) {
+    if (!tp_in_map3(g, pos)) return true;
+    return tp_distance3d(g, pos) < threshold;
+}
+// posToIndex2d (grid_map.h:727-735)
+TP_HD void tp_pos_to_index2(const TpGrid& g, const double* pos, int* id) {
+    id[0] = (int)floor((pos[0] - g.origin[0]) * g.resolution_inv);
+    id[1] = (int)floor((pos[1] - g.origin[1]) * g.resolution_inv);
+}
+// getDistCoarse2i / getDistCoarse2d (grid_map.h:887-940, dense branch): nearest cell, clamped
+TP_HD double tp_dist_coarse2i(const TpGrid& g, int ix, int iy, bool critical) {
+    const int x = tp_clampi(ix, g.dims[0] - 1), y = tp_clampi(iy, g.dims[1] - 1);
+    const double* b = critical ? g.esdf2d_critical : g.esdf2d_inflate;
+    return TP_LDG(b + (size_t)x * g.dims[1] + y);
+}
+// isLineCollisionGrid2d (grid_map.h:565-611): Bresenham over the flat map, both end cells tested.
+// A cell outside the grid counts as occupied (the reference reads past its buffer there).
+TP_HD bool tp_line_collision_grid2d(const TpGrid& g, const double* p1, const double* p2, double threshold) {
+    int s[2], e[2];
+    tp_pos_to_index2(g, p1, s);
+    tp_pos_to_index2(g, p2, e);
+    const int dx = abs(e[0] - s[0]), dy = abs(e[1] - s[1]);
+    const int sx = s[0] < e[0] ? 1 : -1, sy = s[1] < e[1] ? 1 : -1;
+    int err = dx - dy, x0 = s[0], y0 = s[1];
+    for (;;) {
+        if (x0 < 0 || y0 < 0 || x0 > g.dims[0] - 1 || y0 > g.dims[1] - 1) return true;
+        if (TP_LDG(g.esdf2d + (size_t)x0 * g.dims[1] + y0) < threshold) return true;
+        if (x0 == e[0] && y0 == e[1]) break;
+        const int e2 = 2 * err;
+        if (e2 > -dy) { err -= dy; x0 += sx; }
+        if (e2 < dx) { err += dx; y0 += sy; }
+    }
+    return false;
+}

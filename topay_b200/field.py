@@ -109,6 +109,45 @@ class GridMap:
                                                             _p(out, C.c_int8)), "whole_body_collision")
         return out.astype(bool)
 
+    def _flags(self, fn, name, *arrays, threshold=0.0):
+        n = arrays[0].shape[0]
+        out = np.empty(n, dtype=np.int8)
+        _lib.check(fn(self.h, *[_p(a) for a in arrays], n, C.c_double(threshold), _p(out, C.c_int8)), name)
+        return out.astype(bool)
+
+    def isCollision2d(self, pos, threshold):
+        """GridMap::isCollision2d (grid_map.h:511-536) for (n, 2) positions."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+        return self._flags(self._l.topay_field_is_collision2d, "is_collision2d", pos, threshold=threshold)
+
+    def isCollision3d(self, pos, threshold):
+        """GridMap::isCollision3d (grid_map.h:695-724) for (n, 3) positions."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        return self._flags(self._l.topay_field_is_collision3d, "is_collision3d", pos, threshold=threshold)
+
+    def isLineCollisionGrid2d(self, p1, p2, threshold=0.0):
+        """GridMap::isLineCollisionGrid2d (grid_map.h:565-611) for (n, 2) end points."""
+        p1 = np.ascontiguousarray(p1, dtype=np.float64).reshape(-1, 2)
+        p2 = np.ascontiguousarray(p2, dtype=np.float64).reshape(-1, 2)
+        return self._flags(self._l.topay_field_is_line_collision_grid2d, "is_line_collision_grid2d", p1, p2,
+                           threshold=threshold)
+
+    def getDistCoarse2d(self, pos, critical=False):
+        """GridMap::getDistCoarse2d (grid_map.h:887-912)."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+        out = np.empty(pos.shape[0])
+        _lib.check(self._l.topay_field_dist_coarse2d(self.h, _p(pos), pos.shape[0], int(critical), _p(out)),
+                   "dist_coarse2d")
+        return out
+
+    def getDistCoarse2i(self, idx, critical=False):
+        """GridMap::getDistCoarse2i (grid_map.h:914-940) for (n, 2) cell indices."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1, 2)
+        out = np.empty(idx.shape[0])
+        _lib.check(self._l.topay_field_dist_coarse2i(self.h, _p(idx, C.c_int32), idx.shape[0], int(critical), _p(out)),
+                   "dist_coarse2i")
+        return out
+
     # ---- buffers ------------------------------------------------------------
     def _shape(self, which):
         return self.voxel_num if which == MAP3D else self.voxel_num[:2]
