@@ -20,18 +20,59 @@ inline void topay_check(int rc, const char* what) {
     if (rc != TOPAY_OK) throw std::runtime_error(std::string(what) + ": " + topay_last_error());
 }
 
-// MomaTraj (moma_traj_opt.h:26-247): durations + MINCO coefficients of one optimised trajectory.
+// MomaTraj (moma_traj_opt.h:26-247): durations + MINCO coefficients of one optimised trajectory; the
+// pose table and the state samplers are evaluated on the device.
 struct MomaTraj {
     bool is_init = false;
     std::vector<double> durations;          // N
     std::vector<double> coeff;              // 6N x 9, row 6i+k = coefficient of t^k of piece i
     double start_se2[3] = {0, 0, 0};
+    int device = 0;
     double getTotalDuration() const {
         double s = 0;
         for (double d : durations) s += d;
         return s;
     }
     int getPieceNum() const { return (int)durations.size(); }
+    topay_traj_batch view(int32_t* piece_num) const {
+        *piece_num = getPieceNum();
+        topay_traj_batch b;
+        b.n_traj = 1; b.max_pieces = getPieceNum(); b.piece_num = piece_num;
+        b.T = durations.data(); b.coeff = coeff.data(); b.start_se2 = start_se2;
+        return b;
+    }
+    // std::vector<Eigen::Vector4d> car_seq (moma_traj_opt.h:36, 38-68): rows x, y, yaw, t
+    std::vector<double> car_seq() const {
+        int32_t pn, len = 0;
+        topay_traj_batch b = view(&pn);
+        const int cap = (int)(getTotalDuration() / 0.1) + 4;
+        std::vector<double> out((size_t)cap * 4);
+        topay_check(topay_traj_car_seq(device, &b, cap, out.data(), &len), "topay_traj_car_seq");
+        out.resize((size_t)len * 4);
+        return out;
+    }
+    // Eigen::VectorXd getState(double t) const (moma_traj_opt.h:121): x, y, yaw, q1..q7
+    std::vector<double> getState(double t) const {
+        int32_t pn;
+        topay_traj_batch b = view(&pn);
+        std::vector<double> st(10);
+        topay_check(topay_traj_sample(device, &b, &t, 1, st.data(), nullptr), "topay_traj_sample");
+        return st;
+    }
+    // Eigen::VectorXd getDState(double t) const (moma_traj_opt.h:151): v, omega, 0, dq1..dq7
+    std::vector<double> getDState(double t) const {
+        int32_t pn;
+        topay_traj_batch b = view(&pn);
+        std::vector<double> ds(10);
+        topay_check(topay_traj_sample(device, &b, &t, 1, nullptr, ds.data()), "topay_traj_sample");
+        return ds;
+    }
+    // many times in one launch: states is m x 10
+    void getStateBatch(const double* t, int m, double* states) const {
+        int32_t pn;
+        topay_traj_batch b = view(&pn);
+        topay_check(topay_traj_sample(device, &b, t, m, states, nullptr), "topay_traj_sample");
+    }
 };
 
 class GridMap {
@@ -97,7 +138,41 @@ public:
         topay_check(topay_field_whole_body_collision(f_, &rp, s, 1, &out), "topay_field_whole_body_collision");
         return out != 0;
     }
+    template <class V2> bool isCollision2d(const V2& pos, double threshold) {                    // grid_map.h:511
+        double p[2] = {pos[0], pos[1]};
+        int8_t out = 1;
+        topay_check(topay_field_is_collision2d(f_, p, 1, threshold, &out), "topay_field_is_collision2d");
+        return out != 0;
+    }
+    template <class V3> bool isCollision3d(const V3& pos, double threshold) {                    // grid_map.h:695
+        double p[3] = {pos[0], pos[1], pos[2]};
+        int8_t out = 1;
+        topay_check(topay_field_is_collision3d(f_, p, 1, threshold, &out), "topay_field_is_collision3d");
+        return out != 0;
+    }
+    template <class V2> bool isLineCollisionGrid2d(const V2& p1, const V2& p2, double threshold = 0.0) {   // grid_map.h:565
+        double a[2] = {p1[0], p1[1]}, b[2] = {p2[0], p2[1]};
+        int8_t out = 1;
+        topay_check(topay_field_is_line_collision_grid2d(f_, a, b, 1, threshold, &out), "is_line_collision_grid2d");
+        return out != 0;
+    }
+    template <class V2> double getDistCoarse2d(const V2& pos, bool critical = false) {           // grid_map.h:887
+        double p[2] = {pos[0], pos[1]}, d = 0;
+        topay_check(topay_field_dist_coarse2d(f_, p, 1, critical, &d), "topay_field_dist_coarse2d");
+        return d;
+    }
+    template <class V2i> double getDistCoarse2i(const V2i& id, bool critical = false) {          // grid_map.h:914
+        int32_t i2[2] = {(int32_t)id[0], (int32_t)id[1]};
+        double d = 0;
+        topay_check(topay_field_dist_coarse2i(f_, i2, 1, critical, &d), "topay_field_dist_coarse2i");
+        return d;
+    }
     // batched forms for the front-end (one launch for many samples)
+    void isWholeBodyCollisionBatch(const double* states, int64_t n, int8_t* out) {
+        topay_robot_params rp;
+        topay_robot_params_default(&rp);
+        topay_check(topay_field_whole_body_collision(f_, &rp, states, n, out), "topay_field_whole_body_collision");
+    }
     void getDisWithGradI3dBatch(const double* pos, int64_t n, double* dist, double* grad) {
         topay_check(topay_field_query3d(f_, pos, n, dist, grad), "topay_field_query3d");
     }
@@ -188,9 +263,46 @@ public:
         t.is_init = true;
         return t;
     }
+    // bool checkFeasible(MomaTraj traj) (moma_traj_opt.h:948-1045)
+    bool checkFeasible(const MomaTraj& traj) { return gate(traj, false); }
+    // bool printConstraintsSituations(MomaTraj traj) (moma_traj_opt.h:1047-1210); the accumulated
+    // metrics of the last call stay in `constraints`
+    bool printConstraintsSituations(const MomaTraj& traj) { return gate(traj, true); }
+    struct Constraints {
+        double max_vel, max_acc, max_domega, max_d2omega, max_q[7], max_dq[7], max_d2q[7], min_dist, min_dist_mani[12];
+        int32_t n_samples;
+    } constraints;
+    // The worker's gate for every candidate of the last optimizeTrajBatch, on the device:
+    // optimizeTraj && printConstraintsSituations (planner.cpp:877-880), then the shortest duration
+    // (planner.cpp:999-1010). Returns the winner or -1; success[c] is the gate per candidate.
+    int selectFeasible(std::vector<int>* success = nullptr) {
+        const int n = (int)status_.size();
+        std::vector<int32_t> f(n), fp(n);
+        topay_feasibility out = {};
+        out.feasible = f.data(); out.feasible_print = fp.data();
+        int32_t best = -1;
+        topay_check(topay_solver_check_feasible(s_, &out, &best), "topay_solver_check_feasible");
+        if (success) {
+            success->resize(n);
+            for (int c = 0; c < n; c++) (*success)[c] = status_[c] == 1 && fp[c];
+        }
+        return best;
+    }
     int32_t best_by_duration = -1, best_by_cost = -1;
 
 private:
+    bool gate(const MomaTraj& traj, bool print_rule) {
+        int32_t pn, f = 0, fp = 0;
+        topay_traj_batch b = traj.view(&pn);
+        topay_feasibility out = {};
+        out.feasible = &f; out.feasible_print = &fp; out.n_samples = &constraints.n_samples;
+        out.max_vel = &constraints.max_vel; out.max_acc = &constraints.max_acc;
+        out.max_domega = &constraints.max_domega; out.max_d2omega = &constraints.max_d2omega;
+        out.max_q = constraints.max_q; out.max_dq = constraints.max_dq; out.max_d2q = constraints.max_d2q;
+        out.min_dist = &constraints.min_dist; out.min_dist_mani = constraints.min_dist_mani;
+        topay_check(topay_traj_check_feasible(grid_map->handle(), &moma_param, &b, &out), "topay_traj_check_feasible");
+        return (print_rule ? fp : f) != 0;
+    }
     topay_robot_params moma_param;
     GridMap::Ptr grid_map;
     topay_solver* s_ = nullptr;
@@ -200,3 +312,69 @@ private:
 };
 
 }  // namespace nmoma_planner
+
+namespace rog_map {
+
+// rog_map::ESDFMap (src/rog_map/include/rog_map/esdf_map.h:34-93) with the SlidingMap / CounterMap members
+// the planner side uses; positions are "anything with operator[]".
+class ESDFMap {
+public:
+    typedef std::shared_ptr<ESDFMap> Ptr;
+    ~ESDFMap() { topay_rogfield_destroy(f_); }
+    // initESDFMap (esdf_map.cpp:28-57); sliding_thresh is the caller's business (prob_map.cpp:292-298)
+    template <class V3i, class V3>
+    void initESDFMap(const V3i& half_prob_map_size_i, double prob_map_resolution, double temp_counter_map_resolution,
+                     const V3& local_update_box, bool map_sliding_en, double /*sliding_thresh*/,
+                     const V3& fix_map_origin, double unk_thresh, int device = 0) {
+        topay_rog_desc d;
+        for (int i = 0; i < 3; i++) {
+            d.half_prob_map_size_i[i] = half_prob_map_size_i[i];
+            d.local_update_box[i] = local_update_box[i];
+            d.fix_map_origin[i] = fix_map_origin[i];
+        }
+        d.prob_resolution = prob_map_resolution; d.esdf_resolution = temp_counter_map_resolution;
+        d.map_sliding_en = map_sliding_en; d.unk_thresh = unk_thresh;
+        nmoma_planner::topay_check(topay_rogfield_create(&d, device, &f_), "topay_rogfield_create");
+    }
+    template <class V3> void mapSliding(const V3& odom) {                                   // sliding_map.cpp:113
+        double o[3] = {odom[0], odom[1], odom[2]};
+        nmoma_planner::topay_check(topay_rogfield_slide(f_, o), "topay_rogfield_slide");
+    }
+    template <class V3> void updateGridCounter(const V3& pos, int from_type, int to_type) {  // counter_map.cpp:94
+        double p[3] = {pos[0], pos[1], pos[2]};
+        uint8_t a = (uint8_t)from_type, b = (uint8_t)to_type;
+        nmoma_planner::topay_check(topay_rogfield_update_counters(f_, p, &a, &b, 1), "topay_rogfield_update_counters");
+    }
+    void updateGridCounterBatch(const double* pos, const uint8_t* from_type, const uint8_t* to_type, int64_t n) {
+        nmoma_planner::topay_check(topay_rogfield_update_counters(f_, pos, from_type, to_type, n), "update_counters");
+    }
+    template <class V3> void updateESDF3D(const V3& cur_odom) {                             // esdf_map.cpp:154
+        double o[3] = {cur_odom[0], cur_odom[1], cur_odom[2]};
+        nmoma_planner::topay_check(topay_rogfield_update_esdf(f_, o), "topay_rogfield_update_esdf");
+    }
+    template <class V3> void evaluateEDT(const V3& pos, double& dist) { q(TOPAY_ROG_Q_EDT, pos, dist, (V3*)nullptr); }
+    template <class V3> void evaluateFirstGrad(const V3& pos, V3& grad) { double d; q(TOPAY_ROG_Q_EDT, pos, d, &grad); }
+    template <class V3> void getValueGrad(const V3& pos, double& dist, V3& grad) { q(TOPAY_ROG_Q_EDT, pos, dist, &grad); }
+    template <class V3> void getValueGrad2d(const V3& pos, double& dist, V3& grad) { q(TOPAY_ROG_Q_FLAT, pos, dist, &grad); }
+    template <class V3> void getCriticalValueGrad(const V3& pos, double& dist, V3& grad) { q(TOPAY_ROG_Q_CRITICAL, pos, dist, &grad); }
+    template <class V3> double getDistance(const V3& pos) { double d; q(TOPAY_ROG_Q_CELL, pos, d, (V3*)nullptr); return d; }
+    template <class V3> double getDistance2d(const V3& pos) { double d; q(TOPAY_ROG_Q_CELL_FLAT, pos, d, (V3*)nullptr); return d; }
+    template <class V3> double getCriticalDistance(const V3& pos) { double d; q(TOPAY_ROG_Q_CELL_CRITICAL, pos, d, (V3*)nullptr); return d; }
+    template <class V2> bool isLineFree2d(const V2& start, const V2& end, double threshold = 0.0) {   // esdf_map.cpp:122
+        double a[2] = {start[0], start[1]}, b[2] = {end[0], end[1]};
+        int8_t out = 0;
+        nmoma_planner::topay_check(topay_rogfield_is_line_free2d(f_, a, b, 1, threshold, &out), "is_line_free2d");
+        return out != 0;
+    }
+    topay_rogfield* handle() const { return f_; }
+
+private:
+    template <class V3> void q(int kind, const V3& pos, double& dist, V3* grad) {
+        double p[3] = {pos[0], pos[1], pos[2]}, g[3] = {0, 0, 0};
+        nmoma_planner::topay_check(topay_rogfield_query(f_, kind, p, 1, &dist, grad ? g : nullptr), "topay_rogfield_query");
+        if (grad) { (*grad)[0] = g[0]; (*grad)[1] = g[1]; (*grad)[2] = g[2]; }
+    }
+    topay_rogfield* f_ = nullptr;
+};
+
+}  // namespace rog_map
