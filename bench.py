@@ -31,6 +31,7 @@ N_CAND, N_PIECES, INT_K = 256, 64, 32
 NODE_BYTES = 800          # algorithmic ESDF bytes per penalty node, SURVEY.md §8(d)
 NODE_FLOP = 4.0e3         # algorithmic fp64 flop per penalty node, SURVEY.md §8(d)
 MID_FLOP = 0.15e3         # ... per Simpson midpoint node
+K_CAND_DRAM_BYTES = None  # dram bytes of one k_cand launch from the ncu capture (profiles/), filled per round
 
 
 def workload_params(tp):
@@ -209,6 +210,88 @@ def field_probe(tp, scenes, device, hbm_peak):
                     "8 taps x 8 B + 32 B result per point, points resident in HBM"}
 
 
+def subpath_probe(tp, scenes, device, hbm_peak, solver, gm, rp, with_cpu):
+    """The other rows of SURVEY.md §8 next to the solve, each with the oracle timed beside it on a bounded
+    sample (single host thread — these reference routines are serial): ROG-Map ring update (a23), field
+    rebuild at the default grid (a20/a21), 3-D queries (a18), success gate (a16 + N1)."""
+    from topay_b200.rog import ESDFMap
+    out = {}
+    rng = np.random.default_rng(0)
+    # ---- ROG ring, 803 x 803 x 83 (SURVEY §8 a23)
+    rog = ESDFMap(tp.rog_desc(), device=device)
+    res = rog.resolution
+    cells = np.stack(np.meshgrid(np.arange(0, 1, res), np.arange(0, 1, res), np.arange(0, 1.5, res), indexing="ij"), -1)
+    pts = np.concatenate([rng.uniform([-18, -18, 0], [18, 18, 0.2]) + cells.reshape(-1, 3) for _ in range(60)])
+    rog.updateGridCounter(pts, 1, 3)
+    ms = []
+    for odom in [(0, 0, 0), (0, 0, 0), (0.5, 0.3, 0.0), (0.5, 0.3, 0.0), (0.5, 0.3, 0.0)]:
+        rog.mapSliding(odom)
+        rog.updateESDF3D(odom)
+        ms.append(rog.last_update_ms())
+    tot, d3 = float(np.median([a for a, _ in ms[1:]])), float(np.median([b for _, b in ms[1:]]))
+    vox = 800 * 800 * 80          # the update box (the ring is 803 x 803 x 83)
+    out["rog_update"] = {"ring": "803x803x83 @0.05 m, update box 800x800x80, ring wrap on x and y",
+                         "ms_total": tot, "ms_3d": d3, "Mvoxel_per_s": vox / (tot * 1e-3) / 1e6,
+                         "algorithmic_GBps": vox * 9 / (d3 * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": vox * 9 / (d3 * 1e-3) / 1e9 / hbm_peak}
+    rog.close()
+    # ---- success gate on the candidates of the last solve, resident
+    t = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        arrs, best = solver.checkFeasibleBatch()
+        t.append((time.perf_counter() - t0) * 1e3)
+    n = len(arrs["feasible"])
+    samples = int(arrs["n_samples"].sum())
+    out["success_gate"] = {"trajectories": n, "samples": samples, "ms": float(np.median(t[1:])),
+                           "trajectories_per_s": n / (float(np.median(t[1:])) * 1e-3),
+                           "passed": int(arrs["feasible_print"].sum()), "winner": best,
+                           "note": "checkFeasible + printConstraintsSituations of every candidate of the last "
+                                   "256-candidate solve from the solver's device buffers, verdicts to the host"}
+    if not with_cpu:
+        return out
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    # oracle: ROG ring on a bounded ring (203 x 203 x 43)
+    small = tp.rog_desc(half_prob_map_size_i=(100, 100, 20), local_update_box=(10.0, 10.0, 2.0))
+    orc = O.RogField(small)
+    p2 = pts[(np.abs(pts[:, 0]) < 4.9) & (np.abs(pts[:, 1]) < 4.9) & (pts[:, 2] < 0.95)]
+    orc.update_counters(p2, np.full(len(p2), 1), np.full(len(p2), 3))
+    t0 = time.perf_counter()
+    orc.update_esdf((0.0, 0.0, 0.0))
+    dt = time.perf_counter() - t0
+    bvox = int(np.prod([2 * h for h in orc.half_box]))
+    out["rog_update"]["cpu"] = {"Mvoxel_per_s": bvox / dt / 1e6, "ms": dt * 1e3, "cores": 1, "kind": "port",
+                                "sample": f"ring {orc.size}, update box {bvox} voxels"}
+    # oracle: dense field rebuild + queries at the default 200 x 200 x 16 grid
+    desc = tp.grid_desc()
+    of = O.Field(desc)
+    spts, _ = scenes.cuboids_scene(42)
+    of.rasterize(spts)
+    t0 = time.perf_counter()
+    of.rebuild()
+    dt = time.perf_counter() - t0
+    ms_g = []
+    for _ in range(4):
+        gm.updateESDF()
+        ms_g.append(gm.last_rebuild_ms()[0])
+    q = np.concatenate([rng.uniform(-9.9, 9.9, (200000, 2)), rng.uniform(0.01, 1.59, (200000, 1))], axis=1)
+    t0 = time.perf_counter()
+    of.query3d(q)
+    dq = time.perf_counter() - t0
+    out["field_default_grid"] = {"grid": "200x200x16 @0.1 m (4 x 2-D maps + 3-D)", "gpu_rebuild_ms": float(np.median(ms_g[1:])),
+                                 "cpu": {"rebuild_ms": dt * 1e3, "query_Mpoints_per_s": len(q) / dq / 1e6, "cores": 1,
+                                         "kind": "port", "sample": "one rebuild; 2e5 value+gradient queries"}}
+    # oracle: the gate on 8 of the solved trajectories
+    trajs = [solver.getTraj(c)._tuple() for c in range(min(8, n))]
+    t0 = time.perf_counter()
+    O.check_feasible(of, rp, trajs)
+    dt = time.perf_counter() - t0
+    out["success_gate"]["cpu"] = {"trajectories_per_s": len(trajs) / dt, "cores": 1, "kind": "port",
+                                  "sample": f"{len(trajs)} of the solved trajectories, {dt:.2f} s"}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for the path on the host cores. The
     reference's sources cannot be compiled here (they need Eigen + ROS, absent), so this is the
@@ -332,11 +415,6 @@ def main():
             acc["launches"] += st["kernel_launches"]
             acc["ticks"] += st["ticks"]
             acc["ms_dev"] += st["ms_total"]
-            if st["ms_eval"] > 0:      # the timed slot
-                acc["evals_launch"] += st["eval_launches"]
-                acc["nodes"] += st["eval_nodes"]
-                acc["ms_eval"] += st["ms_eval"]
-                acc["ms_dev_timed"] = acc.get("ms_dev_timed", 0.0) + st["ms_total"]
 
     run_steps(max(args.warmup, 0), lambda slot: solvers[slot].run())
     torch.cuda.synchronize()
@@ -351,19 +429,15 @@ def main():
     clocks = sampler.stop() if sampler else None
     res = solvers[0].download()
     n_ok = int(res["status"].sum())
-    launches, ticks, evals_launch, nodes = acc["launches"], acc["ticks"], acc["evals_launch"], acc["nodes"]
-    ms_eval, ms_dev = acc["ms_eval"], acc["ms_dev"]
+    launches, ticks, ms_dev = acc["launches"], acc["ticks"], acc["ms_dev"]
 
-    # ---- roofline pass: one plan alone, plain launches, CUDA events around every k_penalty launch
-    acc.update({"evals_launch": 0, "nodes": 0, "ms_eval": 0.0, "ms_dev_timed": 0.0})
+    # ---- roofline pass: one plan alone, plain launches, CUDA events around every kernel launch
     solvers[0].set_timed(True)
     flush.zero_()
     solvers[0].run()
-    st = solvers[0].stats()
-    acc["evals_launch"], acc["nodes"], acc["ms_eval"], acc["ms_dev_timed"] = (st["eval_launches"], st["eval_nodes"],
-                                                                              st["ms_eval"], st["ms_total"])
+    rst = solvers[0].stats()
     solvers[0].set_timed(False)
-    evals_launch, nodes, ms_eval = acc["evals_launch"], acc["nodes"], acc["ms_eval"]
+    evals_launch, nodes, ms_eval = rst["eval_launches"], rst["eval_nodes"], rst["ms_eval"]
 
     # ---- end-to-end arm: host buffers in, host results out, through the public API every step
     barrier_max(dist, local, 0.0)
@@ -382,7 +456,17 @@ def main():
     total = n_cand * world
     value = total * args.steps / dt
     peak, peak_src = measured_peaks()
-    # dominant kernel: k_penalty (ESDF gathers + FK + penalties, one lane per sample node)
+    # Live device time per kernel over the roofline pass. The dominant one is k_cand (adjoint solves,
+    # L-BFGS two-loop, banded LU): its algorithmic traffic is the L-BFGS history the two-loop
+    # recursions walk, 2 loops x bound rows x (s_j, y_j) x n x 8 B, counted on the device.
+    ticks_r = max(rst["ticks"], 1)
+    k_ms = {"k_cand": rst["ms_cand"], "k_penalty": rst["ms_eval"], "k_chain": rst["ms_chain"],
+            "k_integrate": rst["ms_integrate"]}
+    k_sum = max(sum(k_ms.values()), 1e-9)
+    cand_ms = max(rst["ms_cand"] / ticks_r, 1e-9)
+    cand_bytes = rst["hist_bytes"] / ticks_r
+    cand_achieved = cand_bytes / (cand_ms * 1e-3) / 1e9
+    # second kernel: k_penalty (ESDF gathers + FK + penalties, one lane per sample node)
     pen_ms = ms_eval / max(evals_launch, 1)
     nodes_per_launch = nodes / max(evals_launch, 1)
     alg_bytes = nodes_per_launch * NODE_BYTES
@@ -405,22 +489,35 @@ def main():
                 "h2d_bytes_per_step": solver.h2d_bytes, "d2h_bytes_per_step": solver.d2h_bytes},
         "gpu_launches": int(launches),
         "device_ms_per_step": ms_dev / args.steps, "ticks_per_step": ticks / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "k_penalty", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": 19.9e6, "peak_source": peak_src,
-                     "traffic_source": "ncu --set full, dram__bytes_read+write per launch at 256 candidates "
-                                       "(profiles/r01_summary.md): the 5 MB field is served from L1/L2",
-                     "avg_launch_ms": pen_ms, "nodes_per_launch": nodes_per_launch,
-                     "measured_on": "one 256-candidate plan running alone right after the timed region (CUDA "
-                                    "events around each of its k_penalty launches)",
-                     "share_of_step": ms_eval / max(acc.get("ms_dev_timed", ms_dev), 1e-9),
-                     "fp64": {"achieved_tflops": flop / (pen_ms * 1e-3) / 1e12, "nominal_peak_tflops": 40.0,
-                              "note": "the kernel is FP64-pipe/latency bound, not HBM bound: 4.0 kflop per "
-                                      "penalty node against 800 algorithmic bytes"}},
+        "roofline": {"bound": "hbm", "kernel": "k_cand", "achieved": cand_achieved, "peak": peak, "unit": "GB/s",
+                     "frac": cand_achieved / peak, "traffic": K_CAND_DRAM_BYTES, "peak_source": peak_src,
+                     "traffic_source": "ncu --set full, dram__bytes_read+write of one mid-solve launch at 256 "
+                                       "candidates (profiles/r01_summary.md)",
+                     "avg_launch_ms": cand_ms, "algorithmic_bytes_per_launch": cand_bytes,
+                     "algorithmic_bytes": "L-BFGS history walked by the two-loop recursions: 2 loops x bound "
+                                          "rows x (s_j, y_j) x n x 8 B per accepted iteration (5.2 MB at m = 256, "
+                                          "n = 632), counted on the device; launches without an accepted "
+                                          "iteration (line-search trials) stream nothing",
+                     "measured_on": "one 256-candidate plan running alone right after the timed region, plain "
+                                    "launches with CUDA events around every kernel launch; averages include the "
+                                    "plan's low-activity tail",
+                     "share_of_step": rst["ms_cand"] / max(rst["ms_total"], 1e-9),
+                     "kernel_shares": {k: v / k_sum for k, v in k_ms.items()}},
+        "roofline_k_penalty": {"bound": "hbm", "kernel": "k_penalty", "achieved": achieved, "peak": peak,
+                               "unit": "GB/s", "frac": achieved / peak, "traffic": 19.9e6,
+                               "traffic_source": "ncu --set full at 256 candidates: the 5 MB field is served from "
+                                                 "L1/L2", "avg_launch_ms": pen_ms,
+                               "nodes_per_launch": nodes_per_launch,
+                               "share_of_step": ms_eval / max(rst["ms_total"], 1e-9),
+                               "fp64": {"achieved_tflops": flop / (pen_ms * 1e-3) / 1e12, "nominal_peak_tflops": 40.0,
+                                        "note": "FP64-pipe/latency bound, not HBM bound: 4.0 kflop per penalty "
+                                                "node against 800 algorithmic bytes"}},
         "clocks": clocks,
     }
     if not args.no_extras:
         line["latency"] = latency_probe(tp, scenes, gm)
         line["field"] = field_probe(tp, scenes, local, peak)
+        line["subpaths"] = subpath_probe(tp, scenes, local, peak, solver, gm, rp, not args.no_cpu_baseline)
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         v, m, secs, ok, lat50 = cpu_baseline(opt, rp, pts, paths, bv, ba, cores, desc)

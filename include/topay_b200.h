@@ -438,6 +438,12 @@ typedef struct topay_solver_stats {
     float   ms_eval;           /* penalty-node kernel only */
     int64_t eval_launches;     /* launches of the penalty-node kernel */
     int64_t eval_nodes;        /* penalty nodes processed by them (active candidates only) */
+    float   ms_integrate;      /* timed mode only: device ms in k_integrate, k_chain, k_cand */
+    float   ms_chain;
+    float   ms_cand;
+    float   pad_;
+    int64_t hist_bytes;        /* algorithmic bytes of L-BFGS history the two-loop recursions walked:
+                                * 2 loops x bound rows x (s_j, y_j) x n x 8 B, summed over candidates */
 } topay_solver_stats;
 int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out);
 /* The worker's success gate on the device, straight from the solver's result buffers

@@ -32,16 +32,17 @@ def test_struct_sizes_match_the_compiler():
     import subprocess
     import tempfile
     from topay_b200 import _structs as S
-    prog = ('#include "topay_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    prog = ('#include "topay_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
             "sizeof(topay_robot_params),sizeof(topay_lbfgs_params),sizeof(topay_opt_params),sizeof(topay_grid_desc),"
-            "sizeof(topay_problem_batch),sizeof(topay_result_batch),sizeof(topay_solver_stats));return 0;}")
+            "sizeof(topay_problem_batch),sizeof(topay_result_batch),sizeof(topay_solver_stats),"
+            "sizeof(topay_rog_desc),sizeof(topay_traj_batch),sizeof(topay_feasibility));return 0;}")
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "a.c"), "w").write(prog)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "a"),
                                os.path.join(d, "a.c")])
         sizes = list(map(int, subprocess.check_output([os.path.join(d, "a")]).split()))
     want = [C.sizeof(x) for x in (S.RobotParams, S.LbfgsParams, S.OptParams, S.GridDesc, S.ProblemBatch,
-                                  S.ResultBatch, S.SolverStats)]
+                                  S.ResultBatch, S.SolverStats, S.RogDesc, S.TrajBatch, S.Feasibility)]
     assert sizes == want
 
 

@@ -154,7 +154,8 @@ def alloc_feasibility(n):
 class SolverStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("ticks", C.c_int64), ("evals_total", C.c_int64),
                 ("ms_total", C.c_float), ("ms_eval", C.c_float), ("eval_launches", C.c_int64),
-                ("eval_nodes", C.c_int64)]
+                ("eval_nodes", C.c_int64), ("ms_integrate", C.c_float), ("ms_chain", C.c_float), ("ms_cand", C.c_float),
+                ("pad_", C.c_float), ("hist_bytes", C.c_int64)]
 
 
 def num_vars(piece_num):

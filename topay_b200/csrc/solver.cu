@@ -82,16 +82,18 @@ void launch_eval(topay_solver* s, bool timed, int tick_in_batch) {
     const size_t sm_pen = penalty_smem();
     TpGrid G;
     tp_field_grid(s->field, &G);
+    if (timed) cudaEventRecord(s->ev[5 * tick_in_batch], s->stream);
     k_integrate<<<g1, blk, sm_int, s->stream>>>(D);
-    if (timed) cudaEventRecord(s->ev[2 * tick_in_batch], s->stream);
+    if (timed) cudaEventRecord(s->ev[5 * tick_in_batch + 1], s->stream);
     switch (D.Kpad) {
         case 4: k_penalty<4><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
         case 8: k_penalty<8><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
         case 16: k_penalty<16><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
         default: k_penalty<32><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
     }
-    if (timed) cudaEventRecord(s->ev[2 * tick_in_batch + 1], s->stream);
+    if (timed) cudaEventRecord(s->ev[5 * tick_in_batch + 2], s->stream);
     k_chain<<<g1, blk, 0, s->stream>>>(D, s->params);
+    if (timed) cudaEventRecord(s->ev[5 * tick_in_batch + 3], s->stream);
     s->stats.kernel_launches += 3;
     s->stats.eval_launches += 1;
 }
@@ -188,15 +190,16 @@ extern "C" int topay_solver_create(const topay_opt_params* opt, const topay_robo
     ALLOC(D.f, C);
     ALLOC(D.term_out, C * TOPAY_NTERMS);
     ALLOC(D.n_active, (size_t)s->slots);
-    ALLOC(D.node_count, 1);
+    ALLOC(D.node_count, 2);
 #undef ALLOC
     TP_CUDA_OK(cudaMallocHost(&s->h_active, s->slots * sizeof(int32_t)), { topay_solver_destroy(s); });
-    TP_CUDA_OK(cudaMallocHost(&s->h_nodes, sizeof(unsigned long long)), { topay_solver_destroy(s); });
-    s->ev.resize(2 * s->slots);
+    TP_CUDA_OK(cudaMallocHost(&s->h_nodes, 2 * sizeof(unsigned long long)), { topay_solver_destroy(s); });
+    s->ev.resize(5 * s->slots);
     for (auto& e : s->ev) cudaEventCreate(&e);
     cudaEventCreate(&s->ev_begin);
     cudaEventCreate(&s->ev_end);
-    s->smem_cand = (size_t)6 * NP * (TP_BAND + 9 + 9) * sizeof(double);
+    // LU band + one right-hand-side matrix, or the two-loop's TMA ring + its two 256-entry tables
+    s->smem_cand = std::max((size_t)6 * NP * (TP_BAND + 9), (size_t)TP_RING_STAGES * 2 * D.xs + 512) * sizeof(double);
     if (s->smem_cand > 227 * 1024) {
         tp_set_error("max_pieces too large for the per-candidate shared-memory working set");
         topay_solver_destroy(s);
@@ -367,12 +370,12 @@ extern "C" int topay_solver_run(topay_solver* s) {
     // reset to the uploaded initial state so that repeated runs do identical work
     TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state.data(), s->n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
     TP_CUDA_OK(cudaMemcpyAsync(D.x, s->h_x0.data(), s->h_x0.size() * 8, cudaMemcpyHostToDevice, q), {});
-    cudaMemsetAsync(D.node_count, 0, sizeof(unsigned long long), q);
+    cudaMemsetAsync(D.node_count, 0, 2 * sizeof(unsigned long long), q);
     if (D.trace) cudaMemsetAsync(D.trace_len, 0, (size_t)D.max_cand * sizeof(int32_t), q);
     cudaEventRecord(s->ev_begin, q);
     cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), q);
     launch_cand(s, TP_MODE_GEN, 0);
-    double ms_eval = 0.0;
+    double ms_eval = 0.0, ms_k[3] = {0.0, 0.0, 0.0};
     // hard cap on ticks: every candidate does at most this many evaluations
     const long long max_ticks =
         (long long)(s->params.opt.alm_max_rounds + 1) * ((long long)s->params.opt.s2_lbfgs.max_iterations + 2) *
@@ -411,6 +414,7 @@ extern "C" int topay_solver_run(topay_solver* s) {
             for (int t = 0; t < s->slots; t++) {
                 launch_eval(s, true, t);
                 launch_cand(s, TP_MODE_ADJ | TP_MODE_ADVANCE | TP_MODE_GEN, t);
+                cudaEventRecord(s->ev[5 * t + 4], q);
             }
             cudaMemcpyAsync(s->h_active, D.n_active, s->slots * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
         }
@@ -427,19 +431,29 @@ extern "C" int topay_solver_run(topay_solver* s) {
         if (!use_graph)
             for (int t = 0; t < s->slots; t++) {
                 float ms = 0.f;
-                cudaEventElapsedTime(&ms, s->ev[2 * t], s->ev[2 * t + 1]);
+                cudaEventElapsedTime(&ms, s->ev[5 * t + 1], s->ev[5 * t + 2]);
                 ms_eval += ms;
+                cudaEventElapsedTime(&ms, s->ev[5 * t], s->ev[5 * t + 1]);
+                ms_k[0] += ms;
+                cudaEventElapsedTime(&ms, s->ev[5 * t + 2], s->ev[5 * t + 3]);
+                ms_k[1] += ms;
+                cudaEventElapsedTime(&ms, s->ev[5 * t + 3], s->ev[5 * t + 4]);
+                ms_k[2] += ms;
             }
         done = s->h_active[s->slots - 1] == 0;
     }
     cudaEventRecord(s->ev_end, q);
-    cudaMemcpyAsync(s->h_nodes, D.node_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, q);
+    cudaMemcpyAsync(s->h_nodes, D.node_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q);
     TP_CUDA_OK(cudaStreamSynchronize(q), {});
     TP_CUDA_OK(cudaGetLastError(), {});
     cudaEventElapsedTime(&s->stats.ms_total, s->ev_begin, s->ev_end);
     s->stats.ms_eval = (float)ms_eval;
+    s->stats.ms_integrate = (float)ms_k[0];
+    s->stats.ms_chain = (float)ms_k[1];
+    s->stats.ms_cand = (float)ms_k[2];
     s->stats.ticks = ticks;
-    s->stats.eval_nodes = (int64_t)*s->h_nodes;
+    s->stats.eval_nodes = (int64_t)s->h_nodes[0];
+    s->stats.hist_bytes = (int64_t)s->h_nodes[1] * 16;   // one s_j and one y_j element per row element
     return TOPAY_OK;
 }
 

@@ -17,7 +17,7 @@
 #include "node.cuh"
 
 #define TP_WARPS_PER_BLOCK 4
-#define TP_BAND 16   // padded band width of a stored LU row (13 used)
+#define TP_BAND 14   // band width of a stored LU row: 13 band entries + the reciprocal pivot
 
 enum { TP_MODE_ADJ = 1, TP_MODE_ADVANCE = 2, TP_MODE_GEN = 4 };
 
@@ -71,7 +71,8 @@ struct TpSolverDev {
     double *f;        // [max_cand]
     double *term_out; // [max_cand][TOPAY_NTERMS]
     int32_t *n_active; // [slots] candidates still solving after tick `slot` (written by k_cand)
-    unsigned long long *node_count; // penalty nodes scheduled for evaluation so far
+    unsigned long long *node_count; // [0] penalty nodes scheduled for evaluation so far; [1] history rows x n
+                                    // walked by the two-loop recursions so far (each row = one s_j and one y_j)
     // optional L-BFGS iterate trace (debug / parity): 4 doubles (f, step, k, ls) per accepted iteration
     double *trace;        // [max_cand][trace_cap][4] or null
     int32_t *trace_len;   // [max_cand]
@@ -553,7 +554,7 @@ __device__ __forceinline__ double tp_rcp(double x) {
 }
 
 // ---- TMA bulk copies (cp.async.bulk) of L-BFGS history rows into a shared-memory ring ----
-#define TP_RING_STAGES 8
+#define TP_RING_STAGES 6
 __device__ __forceinline__ uint32_t tp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tp_mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tp_smem_u32(bar)), "r"(count));
@@ -561,11 +562,20 @@ __device__ __forceinline__ void tp_mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void tp_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tp_smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tp_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     tp_smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(tp_smem_u32(bar))
-                 : "memory");
+// The L-BFGS history is a pure stream (665 MB per plan against 126 MB of L2): its lines are marked
+// evict-first so that they do not push the small per-candidate state (coefficients, LU, adjoints,
+// 150 KB per candidate) and the field out of L2 for the other kernels of the tick.
+__device__ __forceinline__ uint64_t tp_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tp_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            tp_smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(tp_smem_u32(bar)), "l"(policy)
+        : "memory");
 }
 __device__ __forceinline__ void tp_mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -818,7 +828,7 @@ __device__ __forceinline__ bool tp_ok_code(int r) {
 
 #define TP_PROF(slot) do { if (S.prof && cand == 0 && tid == 0) S.prof[slot] += clock64() - t_prof; t_prof = clock64(); } while (0)
 
-__global__ void __launch_bounds__(TP_CAND_THREADS)
+__global__ void __launch_bounds__(TP_CAND_THREADS, 3)
 k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P, int mode, int slot) {
     const int cand = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -829,12 +839,18 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
     const int N = st.N, n = st.n, n6 = 6 * N;
     const int stage = st.phase;
     extern __shared__ __align__(16) double sm[];
+    // Dynamic shared memory (70.7 KB at 64 pieces, three CTAs per SM): the banded LU (6N x TP_BAND) and
+    // ONE 6N x 9 right-hand-side matrix — the adjoint half solves A^T on `wk`, the generate half solves A
+    // on `cf`, never at the same time; the adjoint half reads the coefficients straight from global
+    // memory (element-wise, off the sequential path). The two-loop recursion reuses the whole region as
+    // its TMA ring + the alpha / 1/ys tables.
     double* lu = sm;
     double* cf = lu + (size_t)6 * S.max_pieces * TP_BAND;
-    double* wk = cf + (size_t)6 * S.max_pieces * 9;
+    double* wk = cf;
+    double* s_alpha = sm + (size_t)TP_RING_STAGES * 2 * S.xs;
+    double* s_ys = s_alpha + 256;
     __shared__ double red[2 * 4 * TP_CAND_WARPS];
     __shared__ double s_small[4 * 64 + 2 * TOPAY_NTERMS];   // T, totals (x,y), scratch
-    __shared__ double s_alpha[256], s_ys[256];
     __shared__ uint64_t s_bar[TP_RING_STAGES];
     if (tid == 0) {
 #pragma unroll
@@ -857,7 +873,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
     // ================= adjoint half of the evaluation in flight =================
     if (mode & TP_MODE_ADJ) {
         for (int e = tid; e < n6 * TP_BAND; e += TP_CAND_THREADS) lu[e] = lug[e];
-        for (int e = tid; e < n6 * 9; e += TP_CAND_THREADS) cf[e] = cg[e];
+        const double* cfr = cg;   // coefficients of this evaluation, written by the previous launch
         const double* gdCp = S.gdC + (size_t)cand * 6 * S.max_pieces * 9;
         const double* gdTp = S.gdT + (size_t)cand * S.max_pieces;
         const double* tmp = S.terms + (size_t)cand * S.max_pieces * TOPAY_NTERMS;
@@ -946,7 +962,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         double js[1] = {0.0};
         for (int i = tid; i < N; i += TP_CAND_THREADS) {
             const double t1 = sT[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
-            const double *c3 = cf + (6 * i + 3) * 9, *c4 = c3 + 9, *c5 = c4 + 9;
+            const double *c3 = cfr + (6 * i + 3) * 9, *c4 = c3 + 9, *c5 = c4 + 9;
             double d33 = 0, d43 = 0, d44 = 0, d53 = 0, d54 = 0, d55 = 0;
             for (int d = 0; d < 9; d++) {
                 const double w = P.opt.energy_weights[d];
@@ -968,7 +984,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             const int r = e / 9, d = e % 9, i = r / 6, q = r % 6;
             const double t1 = sT[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
             const double w = P.opt.energy_weights[d];
-            const double c3 = cf[(6 * i + 3) * 9 + d], c4 = cf[(6 * i + 4) * 9 + d], c5 = cf[(6 * i + 5) * 9 + d];
+            const double c3 = cfr[(6 * i + 3) * 9 + d], c4 = cfr[(6 * i + 4) * 9 + d], c5 = cfr[(6 * i + 5) * 9 + d];
             double v = 0.0;
             if (q == 5) v = 240.0 * c3 * w * t3 + 720.0 * c4 * w * t4 + 1440.0 * c5 * w * t5;
             else if (q == 4) v = 144.0 * c3 * w * t2 + 384.0 * c4 * w * t3 + 720.0 * c5 * w * t4;
@@ -993,7 +1009,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         double* gVq = gArc + N;
         for (int i = tid; i < N; i += TP_CAND_THREADS) {
             const double t1 = sT[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2;
-            const double *c1 = cf + (6 * i + 1) * 9, *c2 = c1 + 9, *c3 = c2 + 9, *c4 = c3 + 9, *c5 = c4 + 9;
+            const double *c1 = cfr + (6 * i + 1) * 9, *c2 = c1 + 9, *c3 = c2 + 9, *c4 = c3 + 9, *c5 = c4 + 9;
             double d33 = 0, d43 = 0, d44 = 0, d53 = 0, d54 = 0, d55 = 0;
             for (int d = 0; d < 9; d++) {
                 const double w = P.opt.energy_weights[d];
@@ -1262,6 +1278,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     const int total = 2 * st.bound;
                     const uint32_t row_bytes = (uint32_t)(S.xs * sizeof(double));
                     double* ring = sm;
+                    const uint64_t pol = tp_policy_evict_first();
                     // row of step t: (end-1-t) mod m in the first loop, (end-bound+u) mod m in the second;
                     // all operands are within (-2m, 2m), so two conditional wraps replace the modulo
                     auto row_of = [&](int t) {
@@ -1274,10 +1291,11 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                         const int sg = t % TP_RING_STAGES;
                         const int j = row_of(t);
                         tp_mbar_expect_tx(&s_bar[sg], 2 * row_bytes);
-                        tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs, lm_s + (size_t)j * S.xs, row_bytes, &s_bar[sg]);
-                        tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs + S.xs, lm_y + (size_t)j * S.xs, row_bytes, &s_bar[sg]);
+                        tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs, lm_s + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
+                        tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs + S.xs, lm_y + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
                     };
                     if (tid == 0) {
+                        atomicAdd(S.node_count + 1, (unsigned long long)total * (unsigned long long)n);
                         // the ring region was last written through the generic proxy and this block's
                         // new history row has to be visible to the bulk-copy engine
                         asm volatile("fence.proxy.async;" ::: "memory");
