@@ -1287,58 +1287,116 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                         j = j < 0 ? j + m : j;
                         return j >= m ? j - m : j;
                     };
-                    auto issue = [&](int t) {
+                    // Issuing a bulk copy costs the issuing thread a few hundred cycles, so the copies of a
+                    // round are spread over the first lane of each warp: part 0 arms the stage's barrier and
+                    // fetches s_j, part 1 fetches y_j (the transaction count may complete in any order).
+                    auto issue_part = [&](int t, int part) {
                         const int sg = t % TP_RING_STAGES;
                         const int j = row_of(t);
-                        tp_mbar_expect_tx(&s_bar[sg], 2 * row_bytes);
-                        tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs, lm_s + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
-                        tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs + S.xs, lm_y + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
+                        if (part == 0) {
+                            tp_mbar_expect_tx(&s_bar[sg], 2 * row_bytes);
+                            tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs, lm_s + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
+                        } else {
+                            tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs + S.xs, lm_y + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
+                        }
                     };
-                    if (tid == 0) {
-                        atomicAdd(S.node_count + 1, (unsigned long long)total * (unsigned long long)n);
-                        // the ring region was last written through the generic proxy and this block's
-                        // new history row has to be visible to the bulk-copy engine
-                        asm volatile("fence.proxy.async;" ::: "memory");
-                        for (int t = 0; t < min(total, TP_RING_STAGES); t++) issue(t);
-                    }
-                    for (int t = 0; t < total; t++) {
+                    // copy q (0..3) of a round that refills the stages of steps t and t + 1
+                    auto issue_round = [&](int t) {
+                        if (lane == 0) {
+                            const int tt = t + (warp >> 1);
+                            if (tt < total) issue_part(tt, warp & 1);
+                        }
+                    };
+                    if (tid == 0) atomicAdd(S.node_count + 1, (unsigned long long)total * (unsigned long long)n);
+                    // the ring region was last written through the generic proxy and the block's new
+                    // history row has to be visible to the bulk-copy engine
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    for (int t = 0; t < min(total, TP_RING_STAGES); t += 2) issue_round(t);
+                    // Two history rows per reduction round. For rows A (first) and B (second) of a loop
+                    //   loop 1:  a = s_A.q, b = s_B.q, c = s_B.y_A;  alpha_A = rho_A a,
+                    //            alpha_B = rho_B (b - alpha_A c);    q -= alpha_A y_A + alpha_B y_B
+                    //   loop 2:  a = y_A.r, b = y_B.r, c = y_B.s_A;  k_A = alpha_A - rho_A a,
+                    //            k_B = alpha_B - rho_B (b + k_A c);  r += k_A s_A + k_B s_B
+                    // which is the recursion of lbfgs.hpp:691-710 with s_B.(q - alpha_A y_A) expanded, so
+                    // that the three dot products share one block reduction (one barrier per two rows).
+                    auto load_row = [&](int t, double* cs, double* cy) {
                         const int sg = t % TP_RING_STAGES;
-                        const int j = row_of(t);
                         tp_mbar_wait(&s_bar[sg], (uint32_t)((t / TP_RING_STAGES) & 1));
                         const double* rs_ = ring + (size_t)sg * 2 * S.xs;
                         const double* ry_ = rs_ + S.xs;
-                        double cs[TP_EPT], cy[TP_EPT];
 #pragma unroll
                         for (int e = 0; e < TP_EPT; e++) {
                             const int i = tid + e * TP_CAND_THREADS;
                             cs[e] = i < n ? rs_[i] : 0.0;
                             cy[e] = i < n ? ry_[i] : 0.0;
                         }
+                    };
+                    for (int t = 0; t < total;) {
                         if (t == st.bound) {
                             // between the loops: d *= ys / yy (lbfgs.hpp:701)
                             const double sc = ys / yy;
 #pragma unroll
                             for (int e = 0; e < TP_EPT; e++) rd[e] *= sc;
                         }
-                        double a1[1] = {0.0};
-                        if (t < st.bound) {
+                        const bool first = t < st.bound;
+                        const bool pair = t + 1 < (first ? st.bound : total);
+                        const int jA = row_of(t);
+                        double sA[TP_EPT], yA[TP_EPT];
+                        load_row(t, sA, yA);
+                        if (pair) {
+                            const int jB = row_of(t + 1);
+                            double sB[TP_EPT], yB[TP_EPT];
+                            load_row(t + 1, sB, yB);
+                            double d3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-                            for (int e = 0; e < TP_EPT; e++) a1[0] += cs[e] * rd[e];
+                            for (int e = 0; e < TP_EPT; e++) {
+                                const double uA = first ? sA[e] : yA[e], uB = first ? sB[e] : yB[e];
+                                const double vA = first ? yA[e] : sA[e];
+                                d3[0] += uA * rd[e];
+                                d3[1] += uB * rd[e];
+                                d3[2] += uB * vA;
+                            }
+                            tp_block_sum<3>(d3, red, flip);   // one barrier: every thread has read both stages
+                            issue_round(t + TP_RING_STAGES);
+                            if (first) {
+                                const double alA = d3[0] * s_ys[jA];
+                                const double alB = (d3[1] - alA * d3[2]) * s_ys[jB];
+                                if (tid == 0) {
+                                    s_alpha[jA] = alA;
+                                    s_alpha[jB] = alB;
+                                }
+#pragma unroll
+                                for (int e = 0; e < TP_EPT; e++) {
+                                    rd[e] += (-alA) * yA[e];
+                                    rd[e] += (-alB) * yB[e];
+                                }
+                            } else {
+                                const double kA = s_alpha[jA] - d3[0] * s_ys[jA];
+                                const double kB = s_alpha[jB] - (d3[1] + kA * d3[2]) * s_ys[jB];
+#pragma unroll
+                                for (int e = 0; e < TP_EPT; e++) {
+                                    rd[e] += kA * sA[e];
+                                    rd[e] += kB * sB[e];
+                                }
+                            }
+                            t += 2;
                         } else {
+                            double a1[1] = {0.0};
 #pragma unroll
-                            for (int e = 0; e < TP_EPT; e++) a1[0] += cy[e] * rd[e];
-                        }
-                        tp_block_sum<1>(a1, red, flip);      // one barrier: every thread has read stage sg
-                        if (tid == 0 && t + TP_RING_STAGES < total) issue(t + TP_RING_STAGES);
-                        if (t < st.bound) {
-                            const double al = a1[0] * s_ys[j];
-                            if (tid == 0) s_alpha[j] = al;
+                            for (int e = 0; e < TP_EPT; e++) a1[0] += (first ? sA[e] : yA[e]) * rd[e];
+                            tp_block_sum<1>(a1, red, flip);
+                            if (lane == 0 && warp < 2 && t + TP_RING_STAGES < total) issue_part(t + TP_RING_STAGES, warp);
+                            if (first) {
+                                const double al = a1[0] * s_ys[jA];
+                                if (tid == 0) s_alpha[jA] = al;
 #pragma unroll
-                            for (int e = 0; e < TP_EPT; e++) rd[e] += (-al) * cy[e];
-                        } else {
-                            const double a = s_alpha[j] - a1[0] * s_ys[j];
+                                for (int e = 0; e < TP_EPT; e++) rd[e] += (-al) * yA[e];
+                            } else {
+                                const double k = s_alpha[jA] - a1[0] * s_ys[jA];
 #pragma unroll
-                            for (int e = 0; e < TP_EPT; e++) rd[e] += a * cs[e];
+                                for (int e = 0; e < TP_EPT; e++) rd[e] += k * sA[e];
+                            }
+                            t += 1;
                         }
                     }
                     if (total == 0) {
