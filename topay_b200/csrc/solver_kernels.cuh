@@ -501,26 +501,32 @@ k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams 
             tp_chain_slot(sl, b0, b1, T, K, 2 * K, wx + end_x, wy + end_y, gth, gar, gdt);
         }
     }
+    // Every lane gets the piece sums (butterfly); the read-modify-writes of the piece's outputs are
+    // spread over the lanes so that no lane chains more than two dependent global round trips:
+    // element e of the 54-entry gdC block goes to lane e % Kpad, together with the end-node part.
+    double ath[6], aar[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        const double a = tp_seg_sum(gth[k], Kpad), b = tp_seg_sum(gar[k], Kpad);
-        if (pvalid && jn == 0) {
-            double* row = S.gdC + (prow * 6 + k) * 9;
-            row[0] += a;
-            row[1] += b;
-        }
+        ath[k] = tp_seg_sum(gth[k], Kpad);
+        aar[k] = tp_seg_sum(gar[k], Kpad);
     }
     gdt = tp_seg_sum(gdt, Kpad);
-    if (pvalid && jn == 0) S.gdT[prow] += gdt;
-    // fold the end-node contributions into the piece
-    __syncwarp();
-    if (S.end_tasks && pvalid) {
+    if (pvalid) {
         const double* ge = S.gdC_end + prow * 54;
-        for (int e = jn; e < 54; e += Kpad) S.gdC[prow * 54 + e] += ge[e];
-        if (jn == 0) {
-            S.gdT[prow] += S.gdT_end[prow];
-            for (int t = 0; t < TOPAY_NTERMS; t++) S.terms[prow * TOPAY_NTERMS + t] += S.terms_end[prow * TOPAY_NTERMS + t];
+        for (int e = jn; e < 54; e += Kpad) {
+            const int k = e / 9, d = e % 9;
+            double add = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 6; kk++)
+                if (kk == k) add = d == 0 ? ath[kk] : (d == 1 ? aar[kk] : 0.0);
+            if (S.end_tasks) add += ge[e];
+            if (d < 2 || S.end_tasks) S.gdC[prow * 54 + e] += add;
         }
+        const int lt = Kpad > TOPAY_NTERMS ? TOPAY_NTERMS : Kpad - 1;   // the lane that owns gdT
+        if (jn == lt) S.gdT[prow] += S.end_tasks ? gdt + S.gdT_end[prow] : gdt;
+        if (S.end_tasks)
+            for (int t = jn; t < TOPAY_NTERMS; t += Kpad)
+                S.terms[prow * TOPAY_NTERMS + t] += S.terms_end[prow * TOPAY_NTERMS + t];
     }
 }
 
