@@ -351,6 +351,11 @@ int topay_select_shortest(const int32_t* success, const double* duration, int n)
  * instances, planner.cpp:59-66). The field is borrowed, read-only. */
 int topay_solver_create(const topay_opt_params* opt, const topay_robot_params* robot,
                         topay_field* field, int max_cand, int max_pieces, topay_solver** out);
+/* The same solver reading the ROG-Map ring instead of the dense field: GridMap's use_rog
+ * branches of getDisWithGradI2d / getDisWithGradI3d / getDistance2d / getDistance3d
+ * (grid_map.h:256-267, 307-322, 364-392, 443-461). */
+int topay_solver_create_rog(const topay_opt_params* opt, const topay_robot_params* robot,
+                            topay_rogfield* rog, int max_cand, int max_pieces, topay_solver** out);
 void topay_solver_destroy(topay_solver* s);
 
 /* The fixed data of each candidate's NLP, i.e. what optimizeTraj derives before it

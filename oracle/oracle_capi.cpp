@@ -15,10 +15,12 @@
 using namespace oracle;
 
 static bool g_exact_chain = false;  // debug: see TrajOpt::exact_chain
+static const RogEsdf* g_rog = nullptr;   // when set, the solve / gate read the ROG ring instead of `field`
 
 extern "C" {
 
 void oracle_set_exact_chain(int on) { g_exact_chain = on != 0; }
+void oracle_use_rog(void* rog_handle) { g_rog = (const RogEsdf*)rog_handle; }
 
 void oracle_robot_params_default(topay_robot_params* out) { robot_defaults(out); }
 void oracle_opt_params_default(topay_opt_params* out) { opt_defaults(out); }
@@ -225,6 +227,7 @@ void oracle_eval(const topay_opt_params* opt, const topay_robot_params* rp, void
     t.opt = *opt;
     t.rp = *rp;
     t.grid = (Field*)field;
+    t.rog = g_rog;
     t.exact_chain = g_exact_chain;
     t.set_problem(N, head, tail, sxy, exy, inner_xy, lambda, rho);
     const int n = topay_num_vars(N);
@@ -249,6 +252,7 @@ void oracle_penalty_only(const topay_opt_params* opt, const topay_robot_params* 
     t.opt = *opt;
     t.rp = *rp;
     t.grid = (Field*)field;
+    t.rog = g_rog;
     t.exact_chain = g_exact_chain;
     double head[27] = {0}, tail[27] = {0};
     t.set_problem(N, head, tail, sxy, exy, inner_xy, lambda, rho);
@@ -282,6 +286,7 @@ int oracle_solve(const topay_opt_params* opt, const topay_robot_params* rp, void
     t.opt = *opt;
     t.rp = *rp;
     t.grid = (Field*)field;
+    t.rog = g_rog;
     std::vector<double> tr;
     if (trace_out) t.trace = &tr;
     Vec x;
@@ -454,7 +459,7 @@ void oracle_check_feasible(void* field, const topay_robot_params* rp, const topa
                            topay_feasibility* out) {
     for (int i = 0; i < b->n_traj; i++) {
         MomaTrajO t = make_traj(b, i);
-        Feasibility F = check_feasible(t, *rp, *(Field*)field);
+        Feasibility F = check_feasible(t, *rp, (Field*)field, g_rog);
         out->feasible[i] = F.feasible;
         if (out->feasible_print) out->feasible_print[i] = F.feasible_print;
         if (out->n_samples) out->n_samples[i] = F.n_samples;

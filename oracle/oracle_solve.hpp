@@ -28,6 +28,7 @@
 #include "../include/topay_b200.h"
 #include "oracle_field.hpp"
 #include "oracle_robot.hpp"
+#include "oracle_rog.hpp"
 
 namespace oracle {
 
@@ -495,6 +496,7 @@ struct TrajOpt {
     topay_opt_params opt;
     topay_robot_params rp;
     const Field* grid = nullptr;
+    const RogEsdf* rog = nullptr;   // set => GridMap's use_rog branches (grid_map.h:364-392, 443-461)
 
     // data (moma_traj_opt.h:626-639)
     int piece_num = 0;
@@ -1183,7 +1185,15 @@ struct TrajOpt {
                     // chassis collision (:1304-1332)
                     double sdf_value;
                     double grad_sdf[2];
-                    grid->dis_with_grad_2d(CurrentXY, sdf_value, grad_sdf);
+                    if (rog) {   // getValueGrad2d, no inflation (inflate = critical = false)
+                        const double p3[3] = {CurrentXY[0], CurrentXY[1], 0.0};
+                        double g3[3];
+                        rog->value_grad_2d(p3, false, sdf_value, g3);
+                        grad_sdf[0] = g3[0];
+                        grad_sdf[1] = g3[1];
+                    } else {
+                        grid->dis_with_grad_2d(CurrentXY, sdf_value, grad_sdf);
+                    }
                     violaPos = rp.chassis_colli_radius * 1.05 - sdf_value;
                     if (violaPos > 0) {
                         smoothL1Penalty(violaPos, violaPosPena, violaPosPenaD);
@@ -1269,7 +1279,8 @@ struct TrajOpt {
                     const double cost_scale = 10.0;
                     for (int cidx = 0; cidx < ncp; cidx++) {
                         double grad_pc[3];
-                        grid->dis_with_grad_3d(colli_pts[cidx], sdf_value, grad_pc);
+                        if (rog) rog->value_grad(colli_pts[cidx], sdf_value, grad_pc);   // evaluateEDT + evaluateFirstGrad
+                        else grid->dis_with_grad_3d(colli_pts[cidx], sdf_value, grad_pc);
                         violaPos = colli_pts[cidx][3] * cost_scale * 1.1 - sdf_value * cost_scale;
                         double g2p[3] = {0, 0, 0};
                         if (violaPos > 0) {

@@ -25,6 +25,7 @@
 
 #include "oracle_field.hpp"
 #include "oracle_robot.hpp"
+#include "oracle_rog.hpp"
 
 namespace oracle {
 
@@ -163,7 +164,8 @@ struct Feasibility {
 
 // moma_traj_opt.h:948-1045 (checkFeasible) and :1047-1210 (printConstraintsSituations: the same
 // scan; the manipulator-clearance test does not clear its verdict, :1199).
-inline Feasibility check_feasible(const MomaTrajO& traj, const topay_robot_params& rp, const Field& grid) {
+inline Feasibility check_feasible(const MomaTrajO& traj, const topay_robot_params& rp, const Field* grid,
+                                  const RogEsdf* rog = nullptr) {
     Feasibility F;
     const double res = 0.01;
     double zero[10] = {0};
@@ -187,13 +189,20 @@ inline Feasibility check_feasible(const MomaTrajO& traj, const topay_robot_param
             if (std::fabs(acc[i + 2]) > std::fabs(F.max_d2q[i])) F.max_d2q[i] = acc[i + 2];
         }
         double d = 0.0;
-        grid.distance2d(state, d);
+        if (rog) {   // GridMap::getDistance2d, use_rog branch (grid_map.h:256-267)
+            const double p3[3] = {state[0], state[1], 0.0};
+            double g3[3];
+            rog->value_grad_2d(p3, false, d, g3);
+        } else {
+            grid->distance2d(state, d);
+        }
         if (d < F.min_dist) F.min_dist = d;
         double pts[TOPAY_NSPHERE + 4][4];
         const int n = get_colli_pts(rp, state, pts);
         for (int i = 0; i < n; i++) {
             double dd = 0.0;
-            grid.distance3d(pts[i], dd);
+            if (rog) dd = rog->evaluate_edt(pts[i]);   // getDistance3d, use_rog branch (grid_map.h:307-322)
+            else grid->distance3d(pts[i], dd);
             if (dd < F.min_dist_mani[i]) F.min_dist_mani[i] = dd;
         }
     }

@@ -50,6 +50,11 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def use_rog(rog_field):
+    """Route the solve / evaluation / gate of the oracle to a RogField (None = back to the dense Field)."""
+    lib().oracle_use_rog(rog_field.h if rog_field is not None else None)
+
+
 def robot_defaults():
     rp = RobotParams()
     lib().oracle_robot_params_default(C.byref(rp))
@@ -241,7 +246,7 @@ def eval_one(opt, rp, field: Field, stage, N, head, tail, sxy, exy, inner_xy, la
     cost = C.c_double()
     grad, terms = np.zeros(n), np.zeros(NTERMS)
     coeff, fxy = np.zeros((6 * N, 9)), np.zeros(2)
-    lib().oracle_eval(C.byref(opt), C.byref(rp), field.h, stage, N, _p(head), _p(tail), _p(sxy), _p(exy),
+    lib().oracle_eval(C.byref(opt), C.byref(rp), field.h if field is not None else None, stage, N, _p(head), _p(tail), _p(sxy), _p(exy),
                       _p(inner_xy), _p(lam), _p(rho), _p(x), C.byref(cost), _p(grad), _p(terms), _p(coeff), _p(fxy))
     return cost.value, grad, terms, coeff, fxy
 
@@ -385,7 +390,7 @@ def traj_sample(trajs, t):
 def check_feasible(field, rp, trajs):
     tb, keep = pack_trajs(trajs)
     f, arrs = alloc_feasibility(len(trajs))
-    lib().oracle_check_feasible(field.h, C.byref(rp), C.byref(tb), C.byref(f))
+    lib().oracle_check_feasible(field.h if field is not None else None, C.byref(rp), C.byref(tb), C.byref(f))
     return arrs
 
 

@@ -141,3 +141,56 @@ def test_full_size_ring_properties():
     d2 = dev.getCriticalDistance((q + 0.5) * res)
     sq2 = ((q[:, None, :2] - obs[None, :, :2]) ** 2).sum(-1).min(1)
     assert np.array_equal(d2[sq2 > 0], (res * np.sqrt(sq2))[sq2 > 0])
+
+
+def test_solver_on_the_rog_field_matches_the_oracle(oracle):
+    """GridMap's use_rog branches inside the solve (grid_map.h:364-392, 443-461): one cost / gradient
+    evaluation per stage within 1e-9 of the oracle reading the same ring, then a batched solve whose
+    success gate (solver-resident) agrees with the oracle's gate on the same trajectories."""
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    from topay_b200.rog import ESDFMap
+    desc = tp.rog_desc(half_prob_map_size_i=(100, 100, 18), prob_resolution=0.1, esdf_resolution=0.1,
+                       local_update_box=(19.0, 19.0, 3.0), map_sliding_en=False)
+    dev, orc = ESDFMap(desc), oracle.RogField(desc)
+    pts, _ = scenes.cuboids_scene(42)
+    pts = pts[(np.abs(pts[:, 0]) < 9.4) & (np.abs(pts[:, 1]) < 9.4)]
+    # one counter increment per occupied cell
+    cells = np.unique(np.floor(pts.astype(np.float64) / 0.1).astype(np.int64), axis=0)
+    centres = (cells + 0.5) * 0.1
+    dev.updateGridCounter(centres, UNK, OCC)
+    orc.update_counters(centres, np.full(len(centres), UNK), np.full(len(centres), OCC))
+    dev.updateESDF3D((0.0, 0.0, 0.0))
+    orc.update_esdf((0.0, 0.0, 0.0))
+    assert np.array_equal(dev.getBuffer(0), orc.download(0))
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    n = 4
+    paths, bv, ba = scenes.short_candidates(n, 77, span=6.0)
+    solver = tp.MomaTrajOpt(dev, max_cand=n, max_pieces=16, opt_param=opt, robot=rp)
+    assert solver.use_rog
+    oracle.use_rog(orc)
+    try:
+        prep = [tp.prepare_candidate(opt, rp, paths[c], bv[c], ba[c], 16) for c in range(n)]
+        for stage in (1, 2):
+            args = dict(piece_num=[p["piece_num"] for p in prep], head_pva=np.stack([p["head_pva"] for p in prep]),
+                        tail_pva=np.stack([p["tail_pva"] for p in prep]), start_xy=np.stack([p["start_xy"] for p in prep]),
+                        end_xy=np.stack([p["end_xy"] for p in prep]), init_inner_xy=[p["init_inner_xy"] for p in prep],
+                        x=[p["x0"] for p in prep])
+            got = solver.evaluate(stage, **args)
+            for c in range(n):
+                p = prep[c]
+                cost, grad, _, _, _ = oracle.eval_one(opt, rp, None, stage, p["piece_num"], p["head_pva"], p["tail_pva"],
+                                                      p["start_xy"], p["end_xy"], p["init_inner_xy"], None, None, p["x0"])
+                nv = tp.num_vars(p["piece_num"])
+                assert abs(got["cost"][c] - cost) <= 1e-9 * abs(cost)
+                assert np.abs(got["grad"][c, :nv] - grad[:nv]).max() <= 1e-9 * np.abs(grad).max()
+        res = solver.optimizeTrajBatch(paths, bv, ba)
+        assert res["status"].sum() >= 1
+        arrs, best = solver.checkFeasibleBatch()
+        trajs = [solver.getTraj(c)._tuple() for c in range(n)]
+        exp = oracle.check_feasible(None, rp, trajs)
+        assert np.array_equal(arrs["feasible"], exp["feasible"]) and np.array_equal(arrs["n_samples"], exp["n_samples"])
+        assert np.allclose(arrs["min_dist"], exp["min_dist"], rtol=1e-10, atol=1e-12)
+        assert np.allclose(arrs["min_dist_mani"], exp["min_dist_mani"], rtol=1e-10, atol=1e-12)
+    finally:
+        oracle.use_rog(None)

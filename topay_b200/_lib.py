@@ -86,6 +86,8 @@ PROTOTYPES = {
     "topay_solver_check_feasible": (C.c_int, [C.c_void_p, C.POINTER(Feasibility), _ip]),
     "topay_solver_create": (C.c_int, [C.POINTER(OptParams), C.POINTER(RobotParams), C.c_void_p, C.c_int, C.c_int,
                                       C.POINTER(C.c_void_p)]),
+    "topay_solver_create_rog": (C.c_int, [C.POINTER(OptParams), C.POINTER(RobotParams), C.c_void_p, C.c_int, C.c_int,
+                                          C.POINTER(C.c_void_p)]),
     "topay_solver_destroy": (None, [C.c_void_p]),
     "topay_solver_eval": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ProblemBatch), _dp, C.c_int, _dp, _dp, _dp, _dp,
                                     _dp]),

@@ -14,6 +14,9 @@ int tp_require_device(int device);
 int tp_field_device(const topay_field* f);
 bool tp_field_ready(const topay_field* f);
 void tp_field_grid(const topay_field* f, TpGrid* out);
+int tp_rogfield_device(const topay_rogfield* f);
+bool tp_rogfield_ready(const topay_rogfield* f);
+void tp_rogfield_grid(const topay_rogfield* f, TpGrid* out);   // kind = 1
 
 // Scratch of the separable exact EDT (field.cu), shared by the dense and the ROG-ring field.
 struct TpEdtScratch {

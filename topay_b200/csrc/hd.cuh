@@ -23,7 +23,20 @@
 // Everything the kernels need that is constant for the life of a solver/field:
 // robot constants (moma_param.h:36-143), optimiser weights (optimizer.yaml via
 // moma_traj_opt.h:845-941) and the dense grid geometry (grid_map.cpp:33-54).
+// View of the ROG-Map ring buffers (rog_map::ESDFMap, src/rog_map/include/rog_map/esdf_map.h:119-123);
+// the lookups are in rog_query.cuh.
+struct TpRog {
+    double res, res_inv;
+    int half[3], size[3];
+    const double* dist3;    // distance_buffer,       x*Sy*Sz + y*Sz + z
+    const double* crit;     // distance_buffer_2d,    x*Sy + y
+    const double* flat;     // distance_buffer_flat,  x*Sy + y
+};
+
 struct TpGrid {
+    int32_t kind;           // 0: dense GridMap buffers below; 1: `rog` (GridMap's use_rog branches)
+    int32_t pad_;
+    TpRog rog;
     double resolution, resolution_inv;
     double origin[3];
     double min_boundary[3], max_boundary[3];

@@ -7,7 +7,7 @@
 // 1200-1829) and calFirstStagePenalGrad (:957-1198). Node index j runs 0..2K inside a
 // piece; even j are penalty nodes, odd j are Simpson midpoints.
 #pragma once
-#include "field_query.cuh"
+#include "rog_query.cuh"
 #include "hd.cuh"
 #include "robot.cuh"
 
@@ -182,7 +182,7 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
     // chassis vs the flat 2-D field (:1304-1332)
     {
         double sdf, gs[2];
-        tp_query2d(g, g.esdf2d, xy, sdf, gs);
+        tp_field_query2d_flat(g, xy, sdf, gs);
         const double v = rp.chassis_colli_radius * 1.05 - sdf;
         if (v > 0) {
             double f, df;
@@ -212,7 +212,7 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
     for (int ci = 0; ci < P.n_sphere; ci++) {
         const double pc[3] = {pts.at(ci, 0), pts.at(ci, 1), pts.at(ci, 2)};
         double sdf, gp[3];
-        tp_query3d(g, pc, sdf, gp);
+        tp_field_query3d(g, pc, sdf, gp);
         const double v = P.sphere_r[ci] * cost_scale * 1.1 - sdf * cost_scale;
         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
         if (v > 0) {

@@ -15,14 +15,6 @@
 #define TP_ADD_RN(a, b) ((a) + (b))
 #endif
 
-struct TpRog {
-    double res, res_inv;
-    int half[3], size[3];
-    const double* dist3;    // distance_buffer,       x*Sy*Sz + y*Sz + z
-    const double* crit;     // distance_buffer_2d,    x*Sy + y
-    const double* flat;     // distance_buffer_flat,  x*Sy + y
-};
-
 // posToGlobalIndex (sliding_map.cpp:175-184)
 TP_HD int tp_rog_cell(const TpRog& r, double p) { return (int)floor(p * r.res_inv); }
 // globalIndexToPos (sliding_map.cpp:195-203)
@@ -152,4 +144,41 @@ TP_HD bool tp_rog_line_free2d(const TpRog& r, const double* s, const double* e, 
         if (TP_LDG(r.flat + tp_rog_hash2(r, cx, cy)) < threshold) return false;
     }
     return true;
+}
+
+// ---- GridMap's queries with the use_rog switch (src/map/include/map/grid_map.h), as the solver and the
+// feasibility check call them: getDisWithGradI2d(pos, d, g) with the default flags (:364-392 ->
+// getValueGrad2d, no inflation), getDisWithGradI3d (:443-461 -> evaluateEDT + evaluateFirstGrad),
+// getDistance2d (:256-267) and getDistance3d (:307-322). No in-map test on the ROG side.
+TP_HD void tp_field_query2d_flat(const TpGrid& g, const double* xy, double& d, double* grad) {
+    if (g.kind == 1) {
+        const double p[3] = {xy[0], xy[1], 0.0};
+        double g3[3];
+        tp_rog_value_grad2d(g.rog, g.rog.flat, p, d, g3);
+        grad[0] = g3[0];
+        grad[1] = g3[1];
+    } else {
+        tp_query2d(g, g.esdf2d, xy, d, grad);
+    }
+}
+TP_HD void tp_field_query3d(const TpGrid& g, const double* p, double& d, double* grad) {
+    if (g.kind == 1) tp_rog_value_grad(g.rog, p, d, grad);
+    else tp_query3d(g, p, d, grad);
+}
+TP_HD double tp_field_distance2d(const TpGrid& g, const double* xy) {
+    if (g.kind == 1) {
+        const double p[3] = {xy[0], xy[1], 0.0};
+        double d;
+        tp_rog_value_grad2d(g.rog, g.rog.flat, p, d, nullptr);
+        return d;
+    }
+    return tp_distance2d(g, xy);
+}
+TP_HD double tp_field_distance3d(const TpGrid& g, const double* p) {
+    if (g.kind == 1) {
+        double d;
+        tp_rog_value_grad(g.rog, p, d, nullptr);
+        return d;
+    }
+    return tp_distance3d(g, p);
 }

@@ -40,6 +40,7 @@ struct topay_rogfield {
     int32_t *tmp_pos, *tmp_neg, *sqp, *sqn;
     cudaEvent_t ev0, ev1, ev2;
     float ms_total, ms_3d;
+    bool updated;               // updateESDF3D ran at least once
 };
 
 namespace {
@@ -279,8 +280,16 @@ int reset_counters(topay_rogfield* f) {   // esdf_map.cpp:72-76
 
 }  // namespace
 
-void tp_rogfield_view(const topay_rogfield* f, TpRog* out) { *out = rog_view(f); }
 int tp_rogfield_device(const topay_rogfield* f) { return f->device; }
+bool tp_rogfield_ready(const topay_rogfield* f) { return f->updated; }
+void tp_rogfield_grid(const topay_rogfield* f, TpGrid* out) {
+    memset(out, 0, sizeof(*out));
+    out->kind = 1;
+    out->rog = rog_view(f);
+    out->resolution = f->res;
+    out->resolution_inv = f->res_inv;
+    out->ready = f->updated ? 1 : 0;
+}
 
 extern "C" int topay_rogfield_create(const topay_rog_desc* d, int device, topay_rogfield** out) {
     if (!d || !out || d->prob_resolution <= 0.0 || d->esdf_resolution < d->prob_resolution || d->unk_thresh < 0.0 ||
@@ -479,6 +488,7 @@ extern "C" int topay_rogfield_update_esdf(topay_rogfield* f, const double cur_od
         if (B.idl[i] != 0) wrapped = true;
     }
     f->ms_total = f->ms_3d = 0.f;
+    f->updated = true;
     if (B.b[0] <= 0 || B.b[1] <= 0 || B.b[2] <= 0) return TOPAY_OK;
     const size_t nb3 = (size_t)B.b[0] * B.b[1] * B.b[2], nb2 = (size_t)B.b[0] * B.b[1];
     const unsigned g3 = (unsigned)std::min<size_t>((nb3 + 255) / 256, 148 * 32);

@@ -16,7 +16,8 @@
 struct topay_solver {
     TpSolverDev dev;
     TpParams params;
-    topay_field* field;
+    topay_field* field;          // dense GridMap field, or
+    topay_rogfield* rog;         // the ROG-Map ring (GridMap's use_rog branches); exactly one is set
     int device;
     cudaStream_t stream;
     int n_cand;          // candidates of the uploaded batch
@@ -44,6 +45,12 @@ struct topay_solver {
 };
 
 namespace {
+
+void solver_grid(const topay_solver* s, TpGrid* G) {
+    if (s->rog) tp_rogfield_grid(s->rog, G);
+    else tp_field_grid(s->field, G);
+}
+bool solver_field_ready(const topay_solver* s) { return s->rog ? tp_rogfield_ready(s->rog) : tp_field_ready(s->field); }
 
 template <typename T>
 int dev_alloc(topay_solver* s, T** p, size_t count) {
@@ -81,7 +88,7 @@ void launch_eval(topay_solver* s, bool timed, int tick_in_batch) {
     const size_t sm_int = (size_t)TP_WARPS_PER_BLOCK * D.ppw * 3 * (2 * D.K + 1) * sizeof(double);
     const size_t sm_pen = penalty_smem();
     TpGrid G;
-    tp_field_grid(s->field, &G);
+    solver_grid(s, &G);
     if (timed) cudaEventRecord(s->ev[5 * tick_in_batch], s->stream);
     k_integrate<<<g1, blk, sm_int, s->stream>>>(D);
     if (timed) cudaEventRecord(s->ev[5 * tick_in_batch + 1], s->stream);
@@ -105,9 +112,24 @@ void launch_cand(topay_solver* s, int mode, int slot) {
 
 }  // namespace
 
+static int solver_create(const topay_opt_params* opt, const topay_robot_params* robot, topay_field* field,
+                         topay_rogfield* rog, int max_cand, int max_pieces, topay_solver** out);
+
 extern "C" int topay_solver_create(const topay_opt_params* opt, const topay_robot_params* robot,
                                    topay_field* field, int max_cand, int max_pieces, topay_solver** out) {
-    if (!opt || !robot || !field || !out || max_cand < 1 || max_pieces < 1) return TOPAY_ERR_INVALID_ARG;
+    if (!field) return TOPAY_ERR_INVALID_ARG;
+    return solver_create(opt, robot, field, nullptr, max_cand, max_pieces, out);
+}
+
+extern "C" int topay_solver_create_rog(const topay_opt_params* opt, const topay_robot_params* robot,
+                                       topay_rogfield* rog, int max_cand, int max_pieces, topay_solver** out) {
+    if (!rog) return TOPAY_ERR_INVALID_ARG;
+    return solver_create(opt, robot, nullptr, rog, max_cand, max_pieces, out);
+}
+
+static int solver_create(const topay_opt_params* opt, const topay_robot_params* robot, topay_field* field,
+                         topay_rogfield* rog, int max_cand, int max_pieces, topay_solver** out) {
+    if (!opt || !robot || !out || max_cand < 1 || max_pieces < 1) return TOPAY_ERR_INVALID_ARG;
     if (opt->int_K < 1 || opt->int_K > TP_MAX_K) {
         tp_set_error("int_K must be in [1, 32]");
         return TOPAY_ERR_TOO_LARGE;
@@ -122,11 +144,13 @@ extern "C" int topay_solver_create(const topay_opt_params* opt, const topay_robo
         tp_set_error("max_pieces above 64 or lbfgs mem_size above 256 is not supported");
         return TOPAY_ERR_TOO_LARGE;
     }
-    int rc = tp_require_device(tp_field_device(field));
+    const int dev = rog ? tp_rogfield_device(rog) : tp_field_device(field);
+    int rc = tp_require_device(dev);
     if (rc != TOPAY_OK) return rc;
     topay_solver* s = new topay_solver();
     s->field = field;
-    s->device = tp_field_device(field);
+    s->rog = rog;
+    s->device = dev;
     s->n_cand = 0;
     s->max_N = 0;
     s->slots = 16;
@@ -295,7 +319,7 @@ extern "C" int topay_solver_eval(topay_solver* s, int stage, const topay_problem
                                  int x_stride, double* cost, double* grad, double* term_costs, double* coeff_out,
                                  double* final_xy_out) {
     if (!s || !prob || !x || !cost || !grad || (stage != 1 && stage != 2)) return TOPAY_ERR_INVALID_ARG;
-    if (!tp_field_ready(s->field)) {
+    if (!solver_field_ready(s)) {
         tp_set_error("field not built: call topay_field_rebuild first");
         return TOPAY_ERR_NOT_READY;
     }
@@ -359,7 +383,7 @@ extern "C" int topay_solver_upload(topay_solver* s, int n_cand, const int32_t* p
 
 extern "C" int topay_solver_run(topay_solver* s) {
     if (!s || s->n_cand < 1) return TOPAY_ERR_INVALID_ARG;
-    if (!tp_field_ready(s->field)) {
+    if (!solver_field_ready(s)) {
         tp_set_error("field not built: call topay_field_rebuild first");
         return TOPAY_ERR_NOT_READY;
     }
@@ -549,7 +573,7 @@ extern "C" int topay_solver_check_feasible(topay_solver* s, topay_feasibility* o
     k_solver_traj_view<<<(n + 127) / 128, 128, 0, s->stream>>>(D.st, D.start_xy, D.head_pva, n, s->d_pn, s->d_start);
     TpTrajView V{n, NP, s->d_pn, D.T, D.coeff, s->d_start};
     TpGrid G;
-    tp_field_grid(s->field, &G);
+    solver_grid(s, &G);
     std::vector<int32_t> fp;
     int32_t* keep_fp = out->feasible_print;
     if (!keep_fp) {   // the gate below needs it

@@ -21,7 +21,7 @@
 #include <vector>
 
 #include "common_host.h"
-#include "field_query.cuh"
+#include "rog_query.cuh"
 #include "robot.cuh"
 #include "traj.cuh"
 #include "traj_host.h"
@@ -180,7 +180,7 @@ k_feasible(TpTrajView V, const __grid_constant__ TpParams P, TpGrid g, const TpT
             maxabs_take(mx[11 + q], vel[2 + q], k);
             maxabs_take(mx[18 + q], acc[2 + q], k);
         }
-        const double d2 = tp_distance2d(g, state);
+        const double d2 = tp_field_distance2d(g, state);
         if (d2 < mn[0]) mn[0] = d2;
         TpFK fk;
         TpSphereStoreLocal pts;
@@ -189,7 +189,7 @@ k_feasible(TpTrajView V, const __grid_constant__ TpParams P, TpGrid g, const TpT
         for (int a = 0; a < TOPAY_NSPHERE; a++) {
             if (a < P.n_sphere) {
                 const double pa[3] = {pts.at(a, 0), pts.at(a, 1), pts.at(a, 2)};
-                const double d3 = tp_distance3d(g, pa);
+                const double d3 = tp_field_distance3d(g, pa);
                 if (d3 < mn[1 + a]) mn[1 + a] = d3;
             }
         }

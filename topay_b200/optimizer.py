@@ -102,8 +102,12 @@ class MomaTrajOpt:
         self.moma_param = robot if robot is not None else robot_params_default()
         self.max_cand, self.max_pieces = max_cand, max_pieces
         self.h = C.c_void_p()
-        _lib.check(self._l.topay_solver_create(C.byref(self.opt_param), C.byref(self.moma_param), grid_map.h,
-                                               max_cand, max_pieces, C.byref(self.h)), "topay_solver_create")
+        # GridMap::use_rog (grid_map.h:90): a rog.ESDFMap routes every field lookup of the solve and of the gate
+        # to the ROG-Map ring
+        self.use_rog = not isinstance(grid_map, GridMap)
+        create = self._l.topay_solver_create_rog if self.use_rog else self._l.topay_solver_create
+        _lib.check(create(C.byref(self.opt_param), C.byref(self.moma_param), grid_map.h, max_cand, max_pieces,
+                          C.byref(self.h)), "topay_solver_create")
         self.traj_cost = 0.0
         self._last = None
 
@@ -200,6 +204,8 @@ class MomaTrajOpt:
         returns the verdict(s). The accumulated metrics of the last call are in self.constraints."""
         single = isinstance(trajs, MomaTraj)
         lst = [trajs] if single else list(trajs)
+        if self.use_rog:
+            raise NotImplementedError("on a ROG field use checkFeasibleBatch() (the solver-resident gate)")
         tb, keep = pack_trajs([t._tuple() for t in lst])
         f, arrs = alloc_feasibility(len(lst))
         _lib.check(self._l.topay_traj_check_feasible(self.grid_map.h, C.byref(self.moma_param), C.byref(tb),
