@@ -31,7 +31,7 @@ N_CAND, N_PIECES, INT_K = 256, 64, 32
 NODE_BYTES = 800          # algorithmic ESDF bytes per penalty node, SURVEY.md §8(d)
 NODE_FLOP = 4.0e3         # algorithmic fp64 flop per penalty node, SURVEY.md §8(d)
 MID_FLOP = 0.15e3         # ... per Simpson midpoint node
-K_CAND_DRAM_BYTES = None  # dram bytes of one k_cand launch from the ncu capture (profiles/), filled per round
+K_CAND_DRAM_BYTES = 719.6e6  # dram__bytes_read+write of one mid-solve k_cand launch at 256 candidates (profiles/r01_summary.md)
 
 
 def workload_params(tp):
