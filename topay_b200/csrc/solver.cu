@@ -29,6 +29,8 @@ struct topay_solver {
     int slots;
     std::vector<cudaEvent_t> ev;  // event pool for the penalty kernel timing
     cudaEvent_t ev_begin, ev_end;
+    cudaEvent_t ev_batch;   // blocking-sync event: the host thread sleeps while a batch of ticks runs
+                            // (P plans in flight x N ranks would otherwise spin on as many cores)
     topay_solver_stats stats;
     size_t smem_cand;
     // initial state kept on the host for repeated runs
@@ -222,6 +224,7 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     for (auto& e : s->ev) cudaEventCreate(&e);
     cudaEventCreate(&s->ev_begin);
     cudaEventCreate(&s->ev_end);
+    cudaEventCreateWithFlags(&s->ev_batch, cudaEventBlockingSync | cudaEventDisableTiming);
     // LU band + one right-hand-side matrix, or the two-loop's TMA ring + its two 256-entry tables
     s->smem_cand = std::max((size_t)6 * NP * (TP_BAND + 9), (size_t)TP_RING_STAGES * 2 * D.xs + 512) * sizeof(double);
     if (s->smem_cand > 227 * 1024) {
@@ -260,6 +263,7 @@ extern "C" void topay_solver_destroy(topay_solver* s) {
     for (auto& e : s->ev) cudaEventDestroy(e);
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);
     if (s->ev_end) cudaEventDestroy(s->ev_end);
+    if (s->ev_batch) cudaEventDestroy(s->ev_batch);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -443,7 +447,8 @@ extern "C" int topay_solver_run(topay_solver* s) {
             cudaMemcpyAsync(s->h_active, D.n_active, s->slots * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
         }
         ticks += s->slots;
-        TP_CUDA_OK(cudaStreamSynchronize(q), {});
+        cudaEventRecord(s->ev_batch, q);
+        TP_CUDA_OK(cudaEventSynchronize(s->ev_batch), {});
         if (getenv("TOPAY_TICK_LOG")) {   // dev: wall time of each 16-tick batch vs candidates still active
             static thread_local double t_prev = 0.0;
             timespec ts;
