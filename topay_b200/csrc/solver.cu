@@ -13,6 +13,16 @@
 #include "solver_kernels.cuh"
 #include "traj_host.h"
 
+#include <atomic>
+
+// solves in flight in this process (plans driven by concurrent host threads)
+static std::atomic<int> g_solves_running{0};
+struct TpRunningGuard {
+    int concurrent;
+    TpRunningGuard() : concurrent(++g_solves_running) {}
+    ~TpRunningGuard() { --g_solves_running; }
+};
+
 struct topay_solver {
     TpSolverDev dev;
     TpParams params;
@@ -29,6 +39,8 @@ struct topay_solver {
     int slots;
     std::vector<cudaEvent_t> ev;  // event pool for the penalty kernel timing
     cudaEvent_t ev_begin, ev_end;
+    bool spin_sync;         // TOPAY_SPIN_SYNC=1: always spin on the stream (lowest latency, one busy core per plan);
+                            // default: spin while at most two solves run in this process, sleep beyond that
     cudaEvent_t ev_batch;   // blocking-sync event: the host thread sleeps while a batch of ticks runs
                             // (P plans in flight x N ranks would otherwise spin on as many cores)
     topay_solver_stats stats;
@@ -160,6 +172,7 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     s->graph_exec = nullptr;
     s->graph_n_cand = s->graph_max_N = -1;
     s->checker = nullptr;
+    s->spin_sync = getenv("TOPAY_SPIN_SYNC") && atoi(getenv("TOPAY_SPIN_SYNC")) != 0;
     s->d_pn = nullptr;
     s->d_start = nullptr;
     memset(&s->stats, 0, sizeof(s->stats));
@@ -225,8 +238,12 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     cudaEventCreate(&s->ev_begin);
     cudaEventCreate(&s->ev_end);
     cudaEventCreateWithFlags(&s->ev_batch, cudaEventBlockingSync | cudaEventDisableTiming);
-    // LU band + one right-hand-side matrix, or the two-loop's TMA ring + its two 256-entry tables
-    s->smem_cand = std::max((size_t)6 * NP * (TP_BAND + 9), (size_t)TP_RING_STAGES * 2 * D.xs + 512) * sizeof(double);
+    // LU band + one right-hand-side matrix, or the two-loop's TMA ring + its two 256-entry tables + one
+    // vector of scratch (single-warp variant)
+    // at least six full-width stages; small solvers still get 64 KB so that short rows ride a deep ring
+    s->smem_cand = std::max(std::max((size_t)6 * NP * (TP_BAND + 9), (size_t)6 * 2 * D.xs + 512 + D.xs) * sizeof(double),
+                            (size_t)64 * 1024);
+    D.smem_doubles = (int32_t)(s->smem_cand / sizeof(double));
     if (s->smem_cand > 227 * 1024) {
         tp_set_error("max_pieces too large for the per-candidate shared-memory working set");
         topay_solver_destroy(s);
@@ -394,6 +411,7 @@ extern "C" int topay_solver_run(topay_solver* s) {
     cudaSetDevice(s->device);
     TpSolverDev& D = s->dev;
     cudaStream_t q = s->stream;
+    TpRunningGuard running;
     memset(&s->stats, 0, sizeof(s->stats));
     // reset to the uploaded initial state so that repeated runs do identical work
     TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state.data(), s->n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
@@ -447,8 +465,12 @@ extern "C" int topay_solver_run(topay_solver* s) {
             cudaMemcpyAsync(s->h_active, D.n_active, s->slots * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
         }
         ticks += s->slots;
-        cudaEventRecord(s->ev_batch, q);
-        TP_CUDA_OK(cudaEventSynchronize(s->ev_batch), {});
+        if (s->spin_sync || g_solves_running.load(std::memory_order_relaxed) <= 2) {
+            TP_CUDA_OK(cudaStreamSynchronize(q), {});
+        } else {
+            cudaEventRecord(s->ev_batch, q);
+            TP_CUDA_OK(cudaEventSynchronize(s->ev_batch), {});
+        }
         if (getenv("TOPAY_TICK_LOG")) {   // dev: wall time of each 16-tick batch vs candidates still active
             static thread_local double t_prev = 0.0;
             timespec ts;

@@ -11,6 +11,7 @@
 //               the Simpson-prefix Jacobians                                         (a6 tail, :1812-1822)
 // Nothing returns to the host between ticks; finished candidates are masked.
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "hd.cuh"
@@ -44,6 +45,7 @@ struct TpCandState {
 // All device pointers of a solver; strides are fixed by (max_cand, max_pieces, K).
 struct TpSolverDev {
     int32_t max_cand, max_pieces, K, Kpad, ppw, xs, mem;   // xs = stride of x-like vectors
+    int32_t smem_doubles;     // dynamic shared memory of k_cand, in doubles
     int32_t end_tasks;        // 1 when K == Kpad: node j = 2K is handled by separate end-node warps
     TpCandState* st;
     // problem data
@@ -560,7 +562,7 @@ __device__ __forceinline__ double tp_rcp(double x) {
 }
 
 // ---- TMA bulk copies (cp.async.bulk) of L-BFGS history rows into a shared-memory ring ----
-#define TP_RING_STAGES 6
+#define TP_RING_MAX 32    // most stages of the two-loop's TMA ring (as many as the row size allows)
 __device__ __forceinline__ uint32_t tp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tp_mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tp_smem_u32(bar)), "r"(count));
@@ -853,14 +855,14 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
     double* lu = sm;
     double* cf = lu + (size_t)6 * S.max_pieces * TP_BAND;
     double* wk = cf;
-    double* s_alpha = sm + (size_t)TP_RING_STAGES * 2 * S.xs;
+    double* s_alpha = sm + S.smem_doubles - (512 + S.xs);   // tables + scratch at the end of the region
     double* s_ys = s_alpha + 256;
     __shared__ double red[2 * 4 * TP_CAND_WARPS];
     __shared__ double s_small[4 * 64 + 2 * TOPAY_NTERMS];   // T, totals (x,y), scratch
-    __shared__ uint64_t s_bar[TP_RING_STAGES];
+    __shared__ uint64_t s_bar[TP_RING_MAX];
     if (tid == 0) {
 #pragma unroll
-        for (int q = 0; q < TP_RING_STAGES; q++) tp_mbar_init(&s_bar[q], 1);
+        for (int q = 0; q < TP_RING_MAX; q++) tp_mbar_init(&s_bar[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     int flip = 0;
@@ -1280,9 +1282,14 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     // two-loop recursion (lbfgs.hpp:691-710). The 2*bound history rows it walks —
                     // newest to oldest, then oldest to newest — are streamed by TMA bulk copies
                     // into a ring of shared-memory stages (the LU / coefficient region is free
-                    // during this phase), TP_RING_STAGES rows of (s_j, y_j) ahead of their use.
+                    // during this phase), `nst` rows of (s_j, y_j) ahead of their use. Only the n live
+                    // elements of a row are copied, so small problems get a deep ring (up to 32 rows in
+                    // flight) and their short rounds do not wait on the copy latency.
                     const int total = 2 * st.bound;
-                    const uint32_t row_bytes = (uint32_t)(S.xs * sizeof(double));
+                    const int rowd = (n + 1) & ~1;                       // 16-byte multiple
+                    const uint32_t row_bytes = (uint32_t)(rowd * sizeof(double));
+                    const int ring_doubles = S.smem_doubles - (512 + S.xs);
+                    const int nst = max(2, min(TP_RING_MAX, ring_doubles / (2 * rowd)) & ~1);   // even: rounds take two
                     double* ring = sm;
                     const uint64_t pol = tp_policy_evict_first();
                     // row of step t: (end-1-t) mod m in the first loop, (end-bound+u) mod m in the second;
@@ -1296,114 +1303,159 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     // Issuing a bulk copy costs the issuing thread a few hundred cycles, so the copies of a
                     // round are spread over the first lane of each warp: part 0 arms the stage's barrier and
                     // fetches s_j, part 1 fetches y_j (the transaction count may complete in any order).
-                    auto issue_part = [&](int t, int part) {
-                        const int sg = t % TP_RING_STAGES;
+                    auto issue_part = [&](int t, int sg, int part) {
                         const int j = row_of(t);
+                        double* dst = ring + (size_t)sg * 2 * rowd;
                         if (part == 0) {
                             tp_mbar_expect_tx(&s_bar[sg], 2 * row_bytes);
-                            tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs, lm_s + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
+                            tp_bulk_g2s(dst, lm_s + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
                         } else {
-                            tp_bulk_g2s(ring + (size_t)sg * 2 * S.xs + S.xs, lm_y + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
+                            tp_bulk_g2s(dst + rowd, lm_y + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
                         }
                     };
-                    // copy q (0..3) of a round that refills the stages of steps t and t + 1
-                    auto issue_round = [&](int t) {
-                        if (lane == 0) {
-                            const int tt = t + (warp >> 1);
-                            if (tt < total) issue_part(tt, warp & 1);
-                        }
-                    };
-                    if (tid == 0) atomicAdd(S.node_count + 1, (unsigned long long)total * (unsigned long long)n);
-                    // the ring region was last written through the generic proxy and the block's new
-                    // history row has to be visible to the bulk-copy engine
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    for (int t = 0; t < min(total, TP_RING_STAGES); t += 2) issue_round(t);
+                    // Small problems (n <= 160, i.e. up to 16 pieces) run the whole recursion on warp 0
+                    // with the vector held 5 elements per lane: no block barrier, no shared-memory
+                    // partial sums — the 512 rounds of a full history are pure latency at that size.
+                    const bool solo = n <= TP_EPT * 32;
+                    double* scratch = s_ys + 256;     // n doubles, behind the ring and the two tables
                     // Two history rows per reduction round. For rows A (first) and B (second) of a loop
                     //   loop 1:  a = s_A.q, b = s_B.q, c = s_B.y_A;  alpha_A = rho_A a,
                     //            alpha_B = rho_B (b - alpha_A c);    q -= alpha_A y_A + alpha_B y_B
                     //   loop 2:  a = y_A.r, b = y_B.r, c = y_B.s_A;  k_A = alpha_A - rho_A a,
                     //            k_B = alpha_B - rho_B (b + k_A c);  r += k_A s_A + k_B s_B
                     // which is the recursion of lbfgs.hpp:691-710 with s_B.(q - alpha_A y_A) expanded, so
-                    // that the three dot products share one block reduction (one barrier per two rows).
-                    auto load_row = [&](int t, double* cs, double* cy) {
-                        const int sg = t % TP_RING_STAGES;
-                        tp_mbar_wait(&s_bar[sg], (uint32_t)((t / TP_RING_STAGES) & 1));
-                        const double* rs_ = ring + (size_t)sg * 2 * S.xs;
-                        const double* ry_ = rs_ + S.xs;
+                    // that the three dot products share one reduction (one barrier per two rows).
+                    auto two_loop = [&](auto solo_tag, double* q) {
+                        constexpr bool SOLO = decltype(solo_tag)::value;
+                        constexpr int STRIDE = SOLO ? 32 : TP_CAND_THREADS;
+                        const int me = SOLO ? lane : tid;
+                        // the four copies of a round (steps t, t + 1; s and y) go to four different threads
+                        // step t lives in stage t mod nst, lap parity (t / nst) & 1: tracked incrementally
+                        int sg = 0, ph = 0;
+                        // refill the stages of steps (t, t + 1) that were just read — stages sg0, sg0 + 1 —
+                        // with steps t + nst, t + nst + 1; the four copies go to four different threads
+                        auto issue_round = [&](int t, int sg0, int steps) {
+                            const int who = SOLO ? lane : (lane == 0 ? warp : -1);
+                            if (who >= 0 && who < 2 * steps) {
+                                const int tt = t + (who >> 1);
+                                if (tt < total) issue_part(tt, sg0 + (who >> 1), who & 1);
+                            }
+                        };
+                        auto load_row = [&](double* cs, double* cy) {
+                            tp_mbar_wait(&s_bar[sg], (uint32_t)ph);
+                            const double* rs_ = ring + (size_t)sg * 2 * rowd;
+                            const double* ry_ = rs_ + rowd;
 #pragma unroll
-                        for (int e = 0; e < TP_EPT; e++) {
-                            const int i = tid + e * TP_CAND_THREADS;
-                            cs[e] = i < n ? rs_[i] : 0.0;
-                            cy[e] = i < n ? ry_[i] : 0.0;
-                        }
-                    };
-                    for (int t = 0; t < total;) {
-                        if (t == st.bound) {
-                            // between the loops: d *= ys / yy (lbfgs.hpp:701)
-                            const double sc = ys / yy;
+                            for (int e = 0; e < TP_EPT; e++) {
+                                const int i = me + e * STRIDE;
+                                cs[e] = i < n ? rs_[i] : 0.0;
+                                cy[e] = i < n ? ry_[i] : 0.0;
+                            }
+                            if (++sg == nst) {
+                                sg = 0;
+                                ph ^= 1;
+                            }
+                        };
+                        auto reduce3 = [&](double* d3) {
+                            if (SOLO) {
 #pragma unroll
-                            for (int e = 0; e < TP_EPT; e++) rd[e] *= sc;
-                        }
-                        const bool first = t < st.bound;
-                        const bool pair = t + 1 < (first ? st.bound : total);
-                        const int jA = row_of(t);
-                        double sA[TP_EPT], yA[TP_EPT];
-                        load_row(t, sA, yA);
-                        if (pair) {
-                            const int jB = row_of(t + 1);
-                            double sB[TP_EPT], yB[TP_EPT];
-                            load_row(t + 1, sB, yB);
+                                for (int k = 0; k < 3; k++) d3[k] = tp_warp_sum(d3[k]);
+                                __syncwarp();             // every lane has read both stages
+                            } else {
+                                tp_block_sum<3>(d3, red, flip);   // one barrier: every thread has read both stages
+                            }
+                        };
+                        for (int t = 0; t < min(total, nst); t += 2) issue_round(t, t, 2);
+                        for (int t = 0; t < total;) {
+                            if (t == st.bound) {
+                                // between the loops: d *= ys / yy (lbfgs.hpp:701)
+                                const double sc = ys / yy;
+#pragma unroll
+                                for (int e = 0; e < TP_EPT; e++) q[e] *= sc;
+                            }
+                            const bool first = t < st.bound;
+                            const bool pair = t + 1 < (first ? st.bound : total);
+                            const int jA = row_of(t);
+                            const int jB = pair ? row_of(t + 1) : jA;
+                            double sA[TP_EPT], yA[TP_EPT], sB[TP_EPT], yB[TP_EPT];
+                            const int sg0 = sg;            // nst is even and pairs start on even steps of a loop;
+                            load_row(sA, yA);              // a stage pair never straddles the ring's end unless
+                            if (pair) {                    // a loop has odd length, which the refill handles per step
+                                load_row(sB, yB);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < TP_EPT; e++) sB[e] = yB[e] = 0.0;
+                            }
                             double d3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
                             for (int e = 0; e < TP_EPT; e++) {
                                 const double uA = first ? sA[e] : yA[e], uB = first ? sB[e] : yB[e];
                                 const double vA = first ? yA[e] : sA[e];
-                                d3[0] += uA * rd[e];
-                                d3[1] += uB * rd[e];
+                                d3[0] += uA * q[e];
+                                d3[1] += uB * q[e];
                                 d3[2] += uB * vA;
                             }
-                            tp_block_sum<3>(d3, red, flip);   // one barrier: every thread has read both stages
-                            issue_round(t + TP_RING_STAGES);
+                            reduce3(d3);
+                            // refill exactly the stages just read (the second one may have wrapped to stage 0)
+                            if (pair && sg0 + 1 == nst) {
+                                issue_round(t + nst, sg0, 1);
+                                issue_round(t + nst + 1, 0, 1);
+                            } else {
+                                issue_round(t + nst, sg0, pair ? 2 : 1);
+                            }
                             if (first) {
                                 const double alA = d3[0] * s_ys[jA];
-                                const double alB = (d3[1] - alA * d3[2]) * s_ys[jB];
-                                if (tid == 0) {
+                                const double alB = pair ? (d3[1] - alA * d3[2]) * s_ys[jB] : 0.0;
+                                if (me == 0) {
                                     s_alpha[jA] = alA;
-                                    s_alpha[jB] = alB;
+                                    if (pair) s_alpha[jB] = alB;
                                 }
 #pragma unroll
                                 for (int e = 0; e < TP_EPT; e++) {
-                                    rd[e] += (-alA) * yA[e];
-                                    rd[e] += (-alB) * yB[e];
+                                    q[e] += (-alA) * yA[e];
+                                    if (pair) q[e] += (-alB) * yB[e];
                                 }
                             } else {
                                 const double kA = s_alpha[jA] - d3[0] * s_ys[jA];
-                                const double kB = s_alpha[jB] - (d3[1] + kA * d3[2]) * s_ys[jB];
+                                const double kB = pair ? s_alpha[jB] - (d3[1] + kA * d3[2]) * s_ys[jB] : 0.0;
 #pragma unroll
                                 for (int e = 0; e < TP_EPT; e++) {
-                                    rd[e] += kA * sA[e];
-                                    rd[e] += kB * sB[e];
+                                    q[e] += kA * sA[e];
+                                    if (pair) q[e] += kB * sB[e];
                                 }
                             }
-                            t += 2;
-                        } else {
-                            double a1[1] = {0.0};
-#pragma unroll
-                            for (int e = 0; e < TP_EPT; e++) a1[0] += (first ? sA[e] : yA[e]) * rd[e];
-                            tp_block_sum<1>(a1, red, flip);
-                            if (lane == 0 && warp < 2 && t + TP_RING_STAGES < total) issue_part(t + TP_RING_STAGES, warp);
-                            if (first) {
-                                const double al = a1[0] * s_ys[jA];
-                                if (tid == 0) s_alpha[jA] = al;
-#pragma unroll
-                                for (int e = 0; e < TP_EPT; e++) rd[e] += (-al) * yA[e];
-                            } else {
-                                const double k = s_alpha[jA] - a1[0] * s_ys[jA];
-#pragma unroll
-                                for (int e = 0; e < TP_EPT; e++) rd[e] += k * sA[e];
-                            }
-                            t += 1;
+                            if (SOLO) __syncwarp();       // alpha table writes visible to the warp
+                            t += pair ? 2 : 1;
                         }
+                    };
+                    if (tid == 0) atomicAdd(S.node_count + 1, (unsigned long long)total * (unsigned long long)n);
+                    // the ring region was last written through the generic proxy and the block's new
+                    // history row has to be visible to the bulk-copy engine
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    if (solo) {
+#pragma unroll
+                        for (int e = 0; e < TP_EPT; e++) {
+                            const int i = tid + e * TP_CAND_THREADS;
+                            if (i < n) scratch[i] = rd[e];
+                        }
+                        __syncthreads();
+                        if (warp == 0) {
+                            double q[TP_EPT];
+#pragma unroll
+                            for (int e = 0; e < TP_EPT; e++) q[e] = lane + 32 * e < n ? scratch[lane + 32 * e] : 0.0;
+                            two_loop(std::true_type{}, q);
+#pragma unroll
+                            for (int e = 0; e < TP_EPT; e++)
+                                if (lane + 32 * e < n) scratch[lane + 32 * e] = q[e];
+                        }
+                        __syncthreads();
+#pragma unroll
+                        for (int e = 0; e < TP_EPT; e++) {
+                            const int i = tid + e * TP_CAND_THREADS;
+                            if (i < n) rd[e] = scratch[i];
+                        }
+                    } else {
+                        two_loop(std::false_type{}, rd);
                     }
                     if (total == 0) {
                         const double sc = ys / yy;
