@@ -78,6 +78,30 @@ def test_compute_fails_loudly_without_a_device():
     assert e.value.code == _lib.ERR_NO_DEVICE
     h = C.c_void_p()
     assert _lib.lib().topay_field_create(C.byref(tp.grid_desc()), 0, C.byref(h)) == _lib.ERR_NO_DEVICE
+    # the ROG ring and the trajectory post-processing refuse as well
+    with pytest.raises(_lib.TopayError) as e:
+        tp.ESDFMap(tp.rog_desc(half_prob_map_size_i=(4, 4, 2)))
+    assert e.value.code == _lib.ERR_NO_DEVICE
+    import numpy as np
+    from topay_b200.optimizer import MomaTraj
+    with pytest.raises(_lib.TopayError) as e:
+        MomaTraj(np.ones(1), np.zeros((6, 9)), np.zeros(3)).getState(0.5)
+    assert e.value.code == _lib.ERR_NO_DEVICE
+
+
+def test_select_shortest_is_host_only():
+    """topay_select_shortest (planner.cpp:999-1010) needs no device: first success, strictly shorter replaces."""
+    import numpy as np
+    from topay_b200 import _lib
+    l = _lib.lib()
+
+    def pick(ok, dur):
+        a = np.ascontiguousarray(ok, dtype=np.int32)
+        d = np.ascontiguousarray(dur, dtype=np.float64)
+        return l.topay_select_shortest(a.ctypes.data_as(C.POINTER(C.c_int32)), d.ctypes.data_as(C.POINTER(C.c_double)), len(a))
+    assert pick([0, 1, 1, 1], [1.0, 5.0, 3.0, 3.0]) == 2
+    assert pick([0, 0], [1.0, 2.0]) == -1
+    assert pick([1, 0, 1], [2.0, 1.0, 2.0]) == 0
 
 
 def test_product_package_never_imports_the_oracle():

@@ -194,3 +194,29 @@ def test_solver_on_the_rog_field_matches_the_oracle(oracle):
         assert np.allclose(arrs["min_dist_mani"], exp["min_dist_mani"], rtol=1e-10, atol=1e-12)
     finally:
         oracle.use_rog(None)
+
+
+def test_rog_error_paths():
+    import ctypes as C
+    import topay_b200 as tp
+    from topay_b200 import _lib
+    from topay_b200.rog import ESDFMap
+    with pytest.raises(_lib.TopayError) as e:       # counter resolution finer than the probability map (counter_map.cpp:48)
+        ESDFMap(tp.rog_desc(prob_resolution=0.1, esdf_resolution=0.05))
+    assert e.value.code == _lib.ERR_INVALID_ARG
+    with pytest.raises(_lib.TopayError):            # unk_thresh outside [0, 1] (counter_map.cpp:54)
+        ESDFMap(tp.rog_desc(half_prob_map_size_i=(4, 4, 2), unk_thresh=1.5))
+    dev = ESDFMap(tp.rog_desc(half_prob_map_size_i=(8, 8, 4), prob_resolution=0.1, esdf_resolution=0.1))
+    with pytest.raises(_lib.TopayError):
+        dev._query(9, np.zeros((1, 3)))
+    # a solver on a ring that was never updated refuses to run
+    solver = tp.MomaTrajOpt(dev, max_cand=1, max_pieces=8)
+    from topay_b200 import scenes
+    paths, bv, ba = scenes.short_candidates(1, 3)
+    with pytest.raises(_lib.TopayError) as e:
+        solver.optimizeTrajBatch(paths, bv, ba)
+    assert e.value.code == _lib.ERR_NOT_READY
+    # empty update box (odometry far outside the local map): nothing changes, no error
+    before = dev.getBuffer(0)
+    dev.updateESDF3D((500.0, 0.0, 0.0))
+    assert np.array_equal(before, dev.getBuffer(0))

@@ -110,3 +110,37 @@ def test_limit_cases_and_signed_extremes(solved, small_scene, oracle):
     _assert_same(solver.constraints, exp)
     assert exp["feasible"][1] == 0 and exp["n_samples"][4] == 1 and exp["n_samples"][2] > 11000
     assert np.allclose(exp["max_q"][3], -exp["max_q"][0])
+
+
+def test_traj_error_paths(solved):
+    import ctypes as C
+    import topay_b200 as tp
+    from topay_b200 import _lib
+    from topay_b200._structs import alloc_feasibility, pack_trajs
+    from topay_b200.optimizer import MomaTraj
+    base = solved["trajs"][0]
+    # a field that was never rebuilt
+    gm = tp.GridMap(tp.grid_desc(map_size=(4.0, 4.0, 1.0)))
+    solver = tp.MomaTrajOpt(gm, max_cand=1, max_pieces=8)
+    with pytest.raises(_lib.TopayError) as e:
+        solver.checkFeasible(base)
+    assert e.value.code == _lib.ERR_NOT_READY
+    # piece_num outside 1..max_pieces
+    tb, keep = pack_trajs([base._tuple()])
+    keep[0][0] = 0
+    f, arrs = alloc_feasibility(1)
+    rc = _lib.lib().topay_traj_check_feasible(solved["gm"].h, C.byref(tp.robot_params_default()), C.byref(tb), C.byref(f))
+    assert rc == _lib.ERR_INVALID_ARG
+    # a trajectory longer than the sample clock table (1310 s)
+    N = len(base.durations)
+    slow = MomaTraj(base.durations * 1e3, base.coeff, base.start_se2)
+    with pytest.raises(_lib.TopayError) as e:
+        solved["solver"].checkFeasible(slow)
+    assert e.value.code == _lib.ERR_TOO_LARGE
+    # pose table larger than the caller's buffer
+    tb, keep = pack_trajs([base._tuple()])
+    out = np.zeros((1, 2, 4))
+    ln = np.zeros(1, dtype=np.int32)
+    rc = _lib.lib().topay_traj_car_seq(0, C.byref(tb), 2, out.ctypes.data_as(C.POINTER(C.c_double)),
+                                       ln.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == _lib.ERR_TOO_LARGE and ln[0] > 2
