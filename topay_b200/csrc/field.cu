@@ -588,8 +588,14 @@ int tp_signed_edt(const TpEdtScratch& f_, const int8_t* src, int A, int B, int C
             return (size_t)n_line * rs * 4 + (size_t)tz * n_line * 4 + ((((size_t)n_line * rs + 1) & ~(size_t)1) * 2) +
                    (size_t)tz * 4 + 16;
         };
+        // Shared-memory cap per block (KB) of the two strided passes. The int16 pass is bound by
+        // shared-memory latency: narrow tiles (4 columns x the whole line, <= 40 KB) put five blocks on an
+        // SM instead of one and cut it from 1.62 to 0.55 ms at 800x800x80; the int32 pass is issue bound
+        // and does not care. TOPAY_EDT_CAP16 / TOPAY_EDT_CAP32 override (dev).
+        static const size_t edt_smem_cap16 = getenv("TOPAY_EDT_CAP16") ? (size_t)atoi(getenv("TOPAY_EDT_CAP16")) : 40;
+        static const size_t edt_smem_cap32 = getenv("TOPAY_EDT_CAP32") ? (size_t)atoi(getenv("TOPAY_EDT_CAP32")) : 104;
         int TZ = 16;
-        while (TZ > 1 && smem_of(TZ) > (in16 ? 140 : 104) * 1024) TZ >>= 1;
+        while (TZ > 1 && smem_of(TZ) > (in16 ? edt_smem_cap16 : edt_smem_cap32) * 1024) TZ >>= 1;
         // small grids (the 2-D maps): narrower tiles so that the blocks cover all SMs
         while (TZ > 2 && (long long)n_outer * ((n_inner + TZ - 1) / TZ) < 296) TZ >>= 1;
         const size_t smem = smem_of(TZ);
