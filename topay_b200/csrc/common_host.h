@@ -18,6 +18,17 @@ int tp_rogfield_device(const topay_rogfield* f);
 bool tp_rogfield_ready(const topay_rogfield* f);
 void tp_rogfield_grid(const topay_rogfield* f, TpGrid* out);   // kind = 1
 
+// Optional sink of the EDT's last pass: instead of a dense esdf array the two distances go straight into
+// the ROG ring buffers through the per-axis wrap rule (rogfield.cu; esdf_map.cpp:154-320).
+struct TpRogSink {
+    int enabled, dims3;          // dims3: box is [A][B][C] (x, y, z); else [B][C] (x, y)
+    int lo[3], idl[3], mem_end[3], size[3];
+    int B, C;                    // box extents of the two inner axes
+    int fuse;                    // apply the sign combine on the spot (no wrap on any axis)
+    double* dist;                // res * sqrt(positive transform)  (distance_buffer / 2-D map)
+    double* neg;                 // res * sqrt(negative transform)  (tmp_buffer1_ / neg_buffer)
+};
+
 // Scratch of the separable exact EDT (field.cu), shared by the dense and the ROG-ring field.
 struct TpEdtScratch {
     cudaStream_t stream;
@@ -25,6 +36,7 @@ struct TpEdtScratch {
     int32_t *tmp_pos, *tmp_neg;   // pass-2 output, A*B*C (3-D only)
     bool keep_sq;                 // also store the integer squared distances
     double res;
+    TpRogSink sink;               // enabled = 0 for the dense field
 };
 int tp_signed_edt(const TpEdtScratch& s, const int8_t* src, int A, int B, int C, double* esdf, int32_t* sqp,
                   int32_t* sqn);

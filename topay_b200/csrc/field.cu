@@ -284,7 +284,8 @@ __device__ __forceinline__ int tp_line_min(const int* __restrict__ col, int stri
 
 __device__ __forceinline__ void tp_edt_store(bool FINAL, int bp, int bn, size_t idx, double res,
                                              int32_t* __restrict__ out_pos, int32_t* __restrict__ out_neg,
-                                             double* __restrict__ esdf) {
+                                             double* __restrict__ esdf, const TpRogSink& rs, int c_line, int c_outer,
+                                             int c_inner) {
     if (bp >= TP_INF32) bp = FINAL ? INT32_MAX : TP_INF32;
     if (bn >= TP_INF32) bn = FINAL ? INT32_MAX : TP_INF32;
     if (FINAL) {
@@ -293,6 +294,29 @@ __device__ __forceinline__ void tp_edt_store(bool FINAL, int bp, int bn, size_t 
         const double vn = bn == INT32_MAX ? DBL_MAX : (double)bn;
         const double dp = __dmul_rn(res, __dsqrt_rn(vp));
         const double dn = __dmul_rn(res, __dsqrt_rn(vn));
+        if (rs.enabled) {
+            // ROG ring: box coordinates -> ring memory, q > mem_end ? q + id_l - S : q + id_l per axis
+            size_t m;
+            if (rs.dims3) {
+                // last 3-D pass: line axis = x, outer = y, inner = z
+                const int qx = c_line + rs.lo[0], qy = c_outer + rs.lo[1], qz = c_inner + rs.lo[2];
+                const int mx = qx > rs.mem_end[0] ? qx + rs.idl[0] - rs.size[0] : qx + rs.idl[0];
+                const int my = qy > rs.mem_end[1] ? qy + rs.idl[1] - rs.size[1] : qy + rs.idl[1];
+                const int mz = qz > rs.mem_end[2] ? qz + rs.idl[2] - rs.size[2] : qz + rs.idl[2];
+                m = ((size_t)mx * rs.size[1] + my) * rs.size[2] + mz;
+            } else {
+                // last 2-D pass: line axis = x, inner = y
+                const int qx = c_line + rs.lo[0], qy = c_inner + rs.lo[1];
+                const int mx = qx > rs.mem_end[0] ? qx + rs.idl[0] - rs.size[0] : qx + rs.idl[0];
+                const int my = qy > rs.mem_end[1] ? qy + rs.idl[1] - rs.size[1] : qy + rs.idl[1];
+                m = (size_t)mx * rs.size[1] + my;
+            }
+            double d = dp;
+            if (rs.fuse && dn > 0.0) d = __dadd_rn(d, __dadd_rn(-dn, res));
+            rs.dist[m] = d;
+            rs.neg[m] = dn;
+            return;
+        }
         double d = dp;
         if (dn > 0.0) d = __dadd_rn(d, __dadd_rn(-dn, res));
         if (esdf) esdf[idx] = d;
@@ -315,7 +339,8 @@ __device__ __forceinline__ void tp_edt_store(bool FINAL, int bp, int bn, size_t 
 template <bool FINAL>
 __global__ void k_edt_strided16(const short2* __restrict__ in16, int32_t* __restrict__ out_pos,
                                 int32_t* __restrict__ out_neg, double* __restrict__ esdf, int n_line,
-                                size_t line_stride, size_t outer_stride, int n_inner, int tiles, double res) {
+                                size_t line_stride, size_t outer_stride, int n_inner, int tiles, double res,
+                                const __grid_constant__ TpRogSink sink) {
     extern __shared__ int sm_i[];
     const int TZ = blockDim.x, TY = blockDim.y, RS = TZ + 1;
     short2* s_in = reinterpret_cast<short2*>(sm_i);
@@ -394,7 +419,7 @@ __global__ void k_edt_strided16(const short2* __restrict__ in16, int32_t* __rest
                 if (l + d < n_line) bn = __viaddmin_s32(dd, at(l + d), bn);
             }
         }
-        tp_edt_store(FINAL, bp, bn, base + (size_t)l * line_stride, res, out_pos, out_neg, esdf);
+        tp_edt_store(FINAL, bp, bn, base + (size_t)l * line_stride, res, out_pos, out_neg, esdf, sink, l, outer, c);
     }
 }
 
@@ -404,7 +429,7 @@ template <bool FINAL>
 __global__ void k_edt_strided32(const int32_t* __restrict__ in_pos, const int32_t* __restrict__ in_neg,
                                 int32_t* __restrict__ out_pos, int32_t* __restrict__ out_neg,
                                 double* __restrict__ esdf, int n_line, size_t line_stride, size_t outer_stride,
-                                int n_inner, int tiles, double res) {
+                                int n_inner, int tiles, double res, const __grid_constant__ TpRogSink sink) {
     extern __shared__ int sm_i[];
     const int TZ = blockDim.x, TY = blockDim.y;
     int* s_pos = sm_i;
@@ -428,7 +453,7 @@ __global__ void k_edt_strided32(const int32_t* __restrict__ in_pos, const int32_
     for (int l = threadIdx.y; l < n_line; l += TY) {
         const int bp = tp_line_min(s_pos + threadIdx.x, TZ, n_line, l);
         const int bn = tp_line_min(s_neg + threadIdx.x, TZ, n_line, l);
-        tp_edt_store(FINAL, bp, bn, base + (size_t)l * line_stride, res, out_pos, out_neg, esdf);
+        tp_edt_store(FINAL, bp, bn, base + (size_t)l * line_stride, res, out_pos, out_neg, esdf, sink, l, outer, c);
     }
 }
 
@@ -558,7 +583,7 @@ int fmalloc(T** p, size_t count) {
 // One signed transform over a [A][B][C] array (C contiguous): pass 1 along C, pass 2 along B
 // and, when A > 1, pass 3 along A. The last pass writes `esdf` (+ the integer grids).
 int signed_edt(topay_field* f, const int8_t* src, int A, int B, int C, double* esdf, int32_t* sqp, int32_t* sqn) {
-    TpEdtScratch sc{f->stream, f->packed, f->tmp_pos, f->tmp_neg, f->keep_sq, f->desc.resolution};
+    TpEdtScratch sc{f->stream, f->packed, f->tmp_pos, f->tmp_neg, f->keep_sq, f->desc.resolution, TpRogSink{}};
     return tp_signed_edt(sc, src, A, B, C, esdf, sqp, sqn);
 }
 
@@ -614,15 +639,15 @@ int tp_signed_edt(const TpEdtScratch& f_, const int8_t* src, int A, int B, int C
         if (in16 && fin) {
             TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), {});
             k_edt_strided16<true><<<blocks, blk, smem, q>>>(f->packed, op, on, esdf, n_line, line_stride, outer_stride,
-                                                           n_inner, tiles, res);
+                                                           n_inner, tiles, res, f->sink);
         } else if (in16) {
             TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), {});
             k_edt_strided16<false><<<blocks, blk, smem, q>>>(f->packed, op, on, esdf, n_line, line_stride, outer_stride,
-                                                            n_inner, tiles, res);
+                                                            n_inner, tiles, res, f->sink);
         } else {
             TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), {});
             k_edt_strided32<true><<<blocks, blk, smem, q>>>(f->tmp_pos, f->tmp_neg, op, on, esdf, n_line, line_stride,
-                                                           outer_stride, n_inner, tiles, res);
+                                                           outer_stride, n_inner, tiles, res, f->sink);
         }
         return TOPAY_OK;
     };

@@ -37,7 +37,7 @@ struct topay_rogfield {
     double *dist3, *neg3, *crit, *flat, *neg2;
     int8_t *box_occ, *col_occ;          // dense box occupancy; [2][bx*by] column occupancy (critical, flat)
     short2* packed;
-    int32_t *tmp_pos, *tmp_neg, *sqp, *sqn;
+    int32_t *tmp_pos, *tmp_neg;
     cudaEvent_t ev0, ev1, ev2;
     float ms_total, ms_3d;
     bool updated;               // updateESDF3D ran at least once
@@ -84,29 +84,6 @@ __global__ void k_rog_columns(const int8_t* __restrict__ box, RogBox B, int nz_f
     flat[i] = (int8_t)any_f;
 }
 
-__device__ __forceinline__ double rog_metric(int sq, double res) {
-    return __dmul_rn(res, __dsqrt_rn(sq == INT32_MAX ? DBL_MAX : (double)sq));
-}
-
-// dense box -> ring: distance_buffer = res*sqrt(pos), tmp_buffer1_ = res*sqrt(neg). With no wrap
-// on any axis the image is the memory box itself and the combine is applied on the spot.
-__global__ void k_rog_scatter3(const int32_t* __restrict__ sqp, const int32_t* __restrict__ sqn, RogBox B,
-                               double res, int fuse, double* __restrict__ dist3, double* __restrict__ neg3) {
-    const size_t n = (size_t)B.b[0] * B.b[1] * B.b[2];
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int z = (int)(i % B.b[2]);
-        const size_t t = i / B.b[2];
-        const int y = (int)(t % B.b[1]), x = (int)(t / B.b[1]);
-        const size_t m = ((size_t)rog_wrap(B, x + B.lo[0], 0) * B.size[1] + rog_wrap(B, y + B.lo[1], 1)) * B.size[2] +
-                         rog_wrap(B, z + B.lo[2], 2);
-        double dp = rog_metric(sqp[i], res);
-        const double dn = rog_metric(sqn[i], res);
-        if (fuse && dn > 0.0) dp = __dadd_rn(dp, __dadd_rn(-dn, res));
-        dist3[m] = dp;
-        neg3[m] = dn;
-    }
-}
-
 // esdf_map.cpp:305-315 over the un-wrapped box
 __global__ void k_rog_combine3(RogBox B, double res, double* __restrict__ dist3, const double* __restrict__ neg3) {
     const size_t n = (size_t)B.b[0] * B.b[1] * B.b[2];
@@ -118,17 +95,6 @@ __global__ void k_rog_combine3(RogBox B, double res, double* __restrict__ dist3,
         const double dn = neg3[m];
         if (dn > 0.0) dist3[m] = __dadd_rn(dist3[m], __dadd_rn(-dn, res));
     }
-}
-
-__global__ void k_rog_scatter2(const int32_t* __restrict__ sqp, const int32_t* __restrict__ sqn, RogBox B,
-                               double res, double* __restrict__ out, double* __restrict__ neg) {
-    const size_t n = (size_t)B.b[0] * B.b[1];
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int y = (int)(i % B.b[1]), x = (int)(i / B.b[1]);
-    const size_t m = (size_t)rog_wrap(B, x + B.lo[0], 0) * B.size[1] + rog_wrap(B, y + B.lo[1], 1);
-    out[m] = rog_metric(sqp[i], res);
-    neg[m] = rog_metric(sqn[i], res);
 }
 
 // esdf_map.cpp:391-398 / :491-498: x and y both walk [lo_x, hi_x], un-wrapped; y clipped to the row
@@ -347,8 +313,6 @@ extern "C" int topay_rogfield_create(const topay_rog_desc* d, int device, topay_
     RA(f->packed, f->n3);
     RA(f->tmp_pos, f->n3);
     RA(f->tmp_neg, f->n3);
-    RA(f->sqp, f->n3);
-    RA(f->sqn, f->n3);
 #undef RA
     cudaMemsetAsync(f->dist3, 0, f->n3 * 8, f->stream);
     cudaMemsetAsync(f->neg3, 0, f->n3 * 8, f->stream);
@@ -372,7 +336,7 @@ extern "C" void topay_rogfield_destroy(topay_rogfield* f) {
     cudaSetDevice(f->device);
     if (f->stream) cudaStreamSynchronize(f->stream);
     void* ptrs[] = {f->occ_cnt, f->unk_cnt, f->dist3, f->neg3, f->crit, f->flat, f->neg2, f->box_occ,
-                    f->col_occ, f->packed, f->tmp_pos, f->tmp_neg, f->sqp, f->sqn};
+                    f->col_occ, f->packed, f->tmp_pos, f->tmp_neg};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (f->ev0) cudaEventDestroy(f->ev0);
@@ -492,12 +456,26 @@ extern "C" int topay_rogfield_update_esdf(topay_rogfield* f, const double cur_od
     if (B.b[0] <= 0 || B.b[1] <= 0 || B.b[2] <= 0) return TOPAY_OK;
     const size_t nb3 = (size_t)B.b[0] * B.b[1] * B.b[2], nb2 = (size_t)B.b[0] * B.b[1];
     const unsigned g3 = (unsigned)std::min<size_t>((nb3 + 255) / 256, 148 * 32);
-    TpEdtScratch sc{q, f->packed, f->tmp_pos, f->tmp_neg, true, f->res};
+    // the EDT's last pass writes res*sqrt of both transforms straight into the ring (TpRogSink)
+    TpEdtScratch sc{q, f->packed, f->tmp_pos, f->tmp_neg, false, f->res, TpRogSink{}};
+    TpRogSink& sk = sc.sink;
+    sk.enabled = 1;
+    for (int i = 0; i < 3; i++) {
+        sk.lo[i] = B.lo[i];
+        sk.idl[i] = B.idl[i];
+        sk.mem_end[i] = B.mem_end[i];
+        sk.size[i] = B.size[i];
+    }
     int rc;
     cudaEventRecord(f->ev0, q);
     k_rog_gather<<<g3, 256, 0, q>>>(f->occ_cnt, B, f->box_occ);
-    if ((rc = tp_signed_edt(sc, f->box_occ, B.b[0], B.b[1], B.b[2], nullptr, f->sqp, f->sqn)) != TOPAY_OK) return rc;
-    k_rog_scatter3<<<g3, 256, 0, q>>>(f->sqp, f->sqn, B, f->res, wrapped ? 0 : 1, f->dist3, f->neg3);
+    sk.dims3 = 1;
+    sk.B = B.b[1];
+    sk.C = B.b[2];
+    sk.fuse = wrapped ? 0 : 1;     // no wrap: the image is the memory box, combine on the spot
+    sk.dist = f->dist3;
+    sk.neg = f->neg3;
+    if ((rc = tp_signed_edt(sc, f->box_occ, B.b[0], B.b[1], B.b[2], nullptr, nullptr, nullptr)) != TOPAY_OK) return rc;
     if (wrapped) k_rog_combine3<<<g3, 256, 0, q>>>(B, f->res, f->dist3, f->neg3);
     cudaEventRecord(f->ev1, q);
     // 2-D maps: flat covers box z up to the ring coordinate of z = 0.155 m (esdf_map.cpp:413-421)
@@ -506,14 +484,18 @@ extern "C" int topay_rogfield_update_esdf(topay_rogfield* f, const double cur_od
     const int nz_flat = std::max(0, z_hi - B.lo[2] + 1);
     const unsigned g2 = (unsigned)((nb2 + 255) / 256);
     k_rog_columns<<<g2, 256, 0, q>>>(f->box_occ, B, nz_flat, f->col_occ, f->col_occ + nb2);
+    sk.dims3 = 0;
+    sk.B = B.b[0];
+    sk.C = B.b[1];
+    sk.fuse = 0;                   // the 2-D combine walks its own (quirky) index range
+    sk.neg = f->neg2;
     for (int which = 0; which < 2; which++) {
-        double* out = which == 0 ? f->crit : f->flat;
-        if ((rc = tp_signed_edt(sc, f->col_occ + which * nb2, 1, B.b[0], B.b[1], nullptr, f->sqp, f->sqn)) != TOPAY_OK)
-            return rc;
+        sk.dist = which == 0 ? f->crit : f->flat;
         cudaMemsetAsync(f->neg2, 0, f->n2 * 8, q);
-        k_rog_scatter2<<<g2, 256, 0, q>>>(f->sqp, f->sqn, B, f->res, out, f->neg2);
+        if ((rc = tp_signed_edt(sc, f->col_occ + which * nb2, 1, B.b[0], B.b[1], nullptr, nullptr, nullptr)) != TOPAY_OK)
+            return rc;
         const size_t nc = (size_t)B.b[0] * B.b[0];
-        k_rog_combine2<<<(unsigned)((nc + 255) / 256), 256, 0, q>>>(B, f->res, out, f->neg2);
+        k_rog_combine2<<<(unsigned)((nc + 255) / 256), 256, 0, q>>>(B, f->res, sk.dist, f->neg2);
     }
     cudaEventRecord(f->ev2, q);
     TP_CUDA_OK(cudaStreamSynchronize(q), {});
