@@ -1,9 +1,7 @@
 #!/bin/bash
-# per-kernel durations of one 800x800x80 rebuild + full capture of the two strided passes
+# full capture of the int32 strided pass of one 800x800x80 rebuild
 mkdir -p gpurun_out
 export KEEP_SQ=0
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/field_launches.csv \
-    python scripts/field_probe.py > gpurun_out/field_launches.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_edt_strided -s 10 -c 2 -f -o gpurun_out/prof_edt \
-    python scripts/field_probe.py > gpurun_out/prof_edt.log 2>&1
-ls -la gpurun_out | grep -E "field|edt"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_edt_strided32 -s 2 -c 1 -f -o gpurun_out/prof_edt32 \
+    python scripts/field_probe.py > gpurun_out/prof_edt32.log 2>&1
+ls -la gpurun_out | grep -E "edt32"

@@ -241,42 +241,60 @@ k_edt_contig(const int8_t* __restrict__ src, short2* __restrict__ out, int64_t n
 }
 
 // Exact 1-D squared-distance envelope  min_v (l - v)^2 + f(v)  of one line staged in shared memory
-// (stride = tile width), by outward search with the d*d >= best cut-off: a candidate at distance d
-// cannot improve once d^2 >= best. Two-sided steps are unrolled by four with one cut-off test per
-// group; add+min is a single DPX instruction (__viaddmin_s32).
-__device__ __forceinline__ int tp_line_min(const int* __restrict__ col, int stride, int n, int l) {
+// (stride = tile width): a candidate at distance d cannot improve once d^2 >= best; add+min is a
+// single DPX instruction (__viaddmin_s32).
+// Two-level search: `seg` holds the minimum of every group of TP_SEG
+// consecutive cells of the line. A group whose lower bound (its minimum + the squared distance to its
+// nearest cell) cannot beat `best` is skipped whole, and a side is finished once that distance alone
+// reaches `best`. In open space (distances of tens of cells) this visits a dozen group minima instead
+// of a hundred cells; the result is the exact minimum either way.
+#define TP_SEG 8
+__device__ __forceinline__ int tp_line_min_seg(const int* __restrict__ col, const int* __restrict__ seg, int stride,
+                                               int n, int l) {
     int best = col[(size_t)l * stride];
-    const int dlim = min(l, n - 1 - l);
-    int d = 1;
-    for (; d + 3 <= dlim; d += 4) {
-        int dd = d * d;
-        if (dd >= best) return best;
-        const int* lo = col + (size_t)(l - d) * stride;
-        const int* hi = col + (size_t)(l + d) * stride;
+    const int s0 = l / TP_SEG, nseg = (n + TP_SEG - 1) / TP_SEG;
+    {   // own group
+        const int q0 = s0 * TP_SEG, q1 = min(q0 + TP_SEG, n);
+        for (int q = q0; q < q1; q++) {
+            const int d = q - l;
+            best = __viaddmin_s32(d * d, col[(size_t)q * stride], best);
+        }
+    }
+    bool go_l = s0 > 0, go_r = s0 + 1 < nseg;
+    for (int k = 1; go_l || go_r; k++) {
+        if (go_l) {
+            const int sg = s0 - k;
+            const int dn = l - (sg * TP_SEG + TP_SEG - 1);      // distance to the group's nearest cell
+            if (dn * dn >= best) {
+                go_l = false;
+            } else {
+                if (seg[(size_t)sg * stride] + dn * dn < best) {
+                    const int* c = col + (size_t)(sg * TP_SEG) * stride;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            best = __viaddmin_s32(dd, lo[-k * stride], best);
-            best = __viaddmin_s32(dd, hi[k * stride], best);
-            dd += 2 * (d + k) + 1;
+                    for (int r = 0; r < TP_SEG; r++) {
+                        const int d = dn + (TP_SEG - 1 - r);
+                        best = __viaddmin_s32(d * d, c[(size_t)r * stride], best);
+                    }
+                }
+                go_l = sg > 0;
+            }
         }
-    }
-    for (; d <= dlim; d++) {
-        const int dd = d * d;
-        if (dd >= best) return best;
-        best = __viaddmin_s32(dd, col[(size_t)(l - d) * stride], best);
-        best = __viaddmin_s32(dd, col[(size_t)(l + d) * stride], best);
-    }
-    if (l > n - 1 - l) {
-        for (; d <= l; d++) {
-            const int dd = d * d;
-            if (dd >= best) return best;
-            best = __viaddmin_s32(dd, col[(size_t)(l - d) * stride], best);
-        }
-    } else {
-        for (; d <= n - 1 - l; d++) {
-            const int dd = d * d;
-            if (dd >= best) return best;
-            best = __viaddmin_s32(dd, col[(size_t)(l + d) * stride], best);
+        if (go_r) {
+            const int sg = s0 + k;
+            const int q0 = sg * TP_SEG;
+            const int dn = q0 - l;
+            if (dn * dn >= best) {
+                go_r = false;
+            } else {
+                if (seg[(size_t)sg * stride] + dn * dn < best) {
+                    const int q1 = min(q0 + TP_SEG, n);
+                    for (int q = q0; q < q1; q++) {
+                        const int d = q - l;
+                        best = __viaddmin_s32(d * d, col[(size_t)q * stride], best);
+                    }
+                }
+                go_r = sg + 1 < nseg;
+            }
         }
     }
     return best;
@@ -432,8 +450,11 @@ __global__ void k_edt_strided32(const int32_t* __restrict__ in_pos, const int32_
                                 int n_inner, int tiles, double res, const __grid_constant__ TpRogSink sink) {
     extern __shared__ int sm_i[];
     const int TZ = blockDim.x, TY = blockDim.y;
+    const int nseg = (n_line + TP_SEG - 1) / TP_SEG;
     int* s_pos = sm_i;
     int* s_neg = sm_i + (size_t)n_line * TZ;
+    int* g_pos = s_neg + (size_t)n_line * TZ;      // group minima
+    int* g_neg = g_pos + (size_t)nseg * TZ;
     const int outer = blockIdx.x / tiles, tile = blockIdx.x % tiles;
     const int c = tile * TZ + threadIdx.x;
     const bool cvalid = c < n_inner;
@@ -449,10 +470,21 @@ __global__ void k_edt_strided32(const int32_t* __restrict__ in_pos, const int32_
         s_neg[(size_t)l * TZ + threadIdx.x] = q;
     }
     __syncthreads();
+    for (int sgi = threadIdx.y; sgi < nseg; sgi += TY) {
+        int mp = TP_INF32, mn = TP_INF32;
+        const int q1 = min(sgi * TP_SEG + TP_SEG, n_line);
+        for (int q = sgi * TP_SEG; q < q1; q++) {
+            mp = min(mp, s_pos[(size_t)q * TZ + threadIdx.x]);
+            mn = min(mn, s_neg[(size_t)q * TZ + threadIdx.x]);
+        }
+        g_pos[(size_t)sgi * TZ + threadIdx.x] = mp;
+        g_neg[(size_t)sgi * TZ + threadIdx.x] = mn;
+    }
+    __syncthreads();
     if (!cvalid) return;
     for (int l = threadIdx.y; l < n_line; l += TY) {
-        const int bp = tp_line_min(s_pos + threadIdx.x, TZ, n_line, l);
-        const int bn = tp_line_min(s_neg + threadIdx.x, TZ, n_line, l);
+        const int bp = tp_line_min_seg(s_pos + threadIdx.x, g_pos + threadIdx.x, TZ, n_line, l);
+        const int bn = tp_line_min_seg(s_neg + threadIdx.x, g_neg + threadIdx.x, TZ, n_line, l);
         tp_edt_store(FINAL, bp, bn, base + (size_t)l * line_stride, res, out_pos, out_neg, esdf, sink, l, outer, c);
     }
 }
@@ -608,7 +640,7 @@ int tp_signed_edt(const TpEdtScratch& f_, const int8_t* src, int A, int B, int C
     auto strided = [&](bool in16, bool fin, int n_line, size_t line_stride, int n_outer, size_t outer_stride,
                        int n_inner) -> int {
         auto smem_of = [&](int tz) -> size_t {
-            if (!in16) return (size_t)n_line * tz * 8;
+            if (!in16) return ((size_t)n_line + (n_line + TP_SEG - 1) / TP_SEG) * tz * 8;
             const size_t rs = tz + 1;
             return (size_t)n_line * rs * 4 + (size_t)tz * n_line * 4 + ((((size_t)n_line * rs + 1) & ~(size_t)1) * 2) +
                    (size_t)tz * 4 + 16;
@@ -618,7 +650,7 @@ int tp_signed_edt(const TpEdtScratch& f_, const int8_t* src, int A, int B, int C
         // SM instead of one and cut it from 1.62 to 0.55 ms at 800x800x80; the int32 pass is issue bound
         // and does not care. TOPAY_EDT_CAP16 / TOPAY_EDT_CAP32 override (dev).
         static const size_t edt_smem_cap16 = getenv("TOPAY_EDT_CAP16") ? (size_t)atoi(getenv("TOPAY_EDT_CAP16")) : 40;
-        static const size_t edt_smem_cap32 = getenv("TOPAY_EDT_CAP32") ? (size_t)atoi(getenv("TOPAY_EDT_CAP32")) : 104;
+        static const size_t edt_smem_cap32 = getenv("TOPAY_EDT_CAP32") ? (size_t)atoi(getenv("TOPAY_EDT_CAP32")) : 72;
         int TZ = 16;
         while (TZ > 1 && smem_of(TZ) > (in16 ? edt_smem_cap16 : edt_smem_cap32) * 1024) TZ >>= 1;
         // small grids (the 2-D maps): narrower tiles so that the blocks cover all SMs
