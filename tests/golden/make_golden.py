@@ -86,11 +86,27 @@ def solve_fixture():
     rp, opt = O.robot_defaults(), O.opt_defaults()
     paths, bv, ba = scenes.short_candidates(4, 7)
     out = {"n": len(paths)}
+    def shape_metrics(r, p):
+        """length of the base path (pose table, moma_traj_opt.h:38-68) and the clearances checkFeasible
+        accumulates (moma_traj_opt.h:993-1006): chassis (flat 2-D map) and the tightest arm sphere margin."""
+        tr = (r["T"], r["coeff"], p[0, :3])
+        seq = O.traj_car_seq([tr])[0]
+        end = O.traj_sample([tr], [[float(np.sum(r["T"]))]])[0][0, 0]
+        xy = np.concatenate([seq[:, :2], end[None, :2]])
+        length = float(np.linalg.norm(np.diff(xy, axis=0), axis=1).sum())
+        fz = O.check_feasible(f, rp, [tr])
+        radii = np.zeros((12, 4))
+        import ctypes
+        n = O.lib().oracle_colli_pts(ctypes.byref(rp), O._p(np.zeros(10)), O._p(radii))
+        arm = float((fz["min_dist_mani"][0, :n] - radii[:n, 3]).min())
+        return length, float(fz["min_dist"][0]), arm
+
     for c, p in enumerate(paths):
         r = O.solve_one(opt, rp, f, p, bv[c], ba[c], trace=True)
         # sensitivity band of the reference algorithm itself: the same solve with the interior waypoints
         # perturbed by +-1e-15 relative (see DESIGN.md "final-trajectory tolerance")
         costs, durs = [r["cost"]], [r["duration"]]
+        shp = [shape_metrics(r, p)]
         for eps in (1e-15, -1e-15, 2e-15, -2e-15):
             q = p.copy()
             q[1:-1, :2] *= (1 + eps)
@@ -98,16 +114,23 @@ def solve_fixture():
             if rr["status"] == 1:
                 costs.append(rr["cost"])
                 durs.append(rr["duration"])
+                shp.append(shape_metrics(rr, q))
+        shp = np.array(shp)
         out.update({f"s{c}_path": p, f"s{c}_status": r["status"], f"s{c}_cost": r["cost"],
                     f"s{c}_duration": r["duration"], f"s{c}_piece_num": r["piece_num"],
                     f"s{c}_trace": r["trace"][:40], f"s{c}_cost_band": np.array([min(costs), max(costs)]),
-                    f"s{c}_duration_band": np.array([min(durs), max(durs)])})
+                    f"s{c}_duration_band": np.array([min(durs), max(durs)]),
+                    f"s{c}_length_band": np.array([shp[:, 0].min(), shp[:, 0].max()]),
+                    f"s{c}_clear_base_band": np.array([shp[:, 1].min(), shp[:, 1].max()]),
+                    f"s{c}_clear_arm_band": np.array([shp[:, 2].min(), shp[:, 2].max()])})
     np.savez_compressed(os.path.join(HERE, "solve_cases.npz"), **out)
 
 
 if __name__ == "__main__":
-    field_fixture()
-    eval_fixture()
+    import sys
+    if "solve" not in sys.argv[1:]:
+        field_fixture()
+        eval_fixture()
     solve_fixture()
     for fn in sorted(os.listdir(HERE)):
         print(fn, os.path.getsize(os.path.join(HERE, fn)))

@@ -220,6 +220,21 @@ def test_solve_trace_and_band(gpu_scene, small_scene, oracle):
         assert lo - 3 * w <= res["duration"][c] <= hi + 3 * w
         assert np.linalg.norm(res["final_xy_err"][c]) < opt.alm_tolerance
         assert abs(res["T"][c, :res["piece_num"][c]].sum() - res["duration"][c]) < 1e-9
+        # length of the base path and clearances (north-star: "cost, length and clearance"), all computed on
+        # the device from the device's own trajectory, against the same kind of band
+        tr = solver.getTraj(c)
+        seq = tr.car_seq
+        xy = np.concatenate([seq[:, :2], tr.getState(tr.getTotalDuration())[None, :2]])
+        length = np.linalg.norm(np.diff(xy, axis=0), axis=1).sum()
+        solver.checkFeasible(tr)
+        radii = np.array([rp.colli_point_radius[i] for i in range(16) if rp.colli_points[i] != 0.0])
+        clear_base = solver.constraints["min_dist"][0]
+        clear_arm = (solver.constraints["min_dist_mani"][0, :len(radii)] - radii).min()
+        for val, key, floor in ((length, "length", 0.02 * length), (clear_base, "clear_base", 0.05),
+                                (clear_arm, "clear_arm", 0.05)):
+            lo, hi = z[f"s{c}_{key}_band"]
+            w = max(hi - lo, floor)
+            assert lo - 3 * w <= val <= hi + 3 * w, (c, key, val, lo, hi)
     ok = np.nonzero(res["status"] == 1)[0]
     assert res["best_by_duration"] == ok[np.argmin(res["duration"][ok])]
     assert res["best_by_cost"] == ok[np.argmin(res["cost"][ok])]
