@@ -514,11 +514,11 @@ def main():
                                                 "node against 800 algorithmic bytes"}},
         "clocks": clocks,
     }
-    if not args.no_extras:
+    if not args.no_extras and world == 1:     # single-GPU diagnostics; the scaling runs stay short
         line["latency"] = latency_probe(tp, scenes, gm)
         line["field"] = field_probe(tp, scenes, local, peak)
         line["subpaths"] = subpath_probe(tp, scenes, local, peak, solver, gm, rp, not args.no_cpu_baseline)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only
         cores = os.cpu_count() or 1
         v, m, secs, ok, lat50 = cpu_baseline(opt, rp, pts, paths, bv, ba, cores, desc)
         line["cpu_baseline"] = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port",
