@@ -111,3 +111,11 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in txt and "liboracle" not in txt and "oracle/" not in txt, f
+
+
+def test_cpp_shims_compile_against_the_header():
+    """shim/topay_shim.hpp (GridMap / MomaTrajOpt / MomaTraj / rog_map::ESDFMap look-alikes) and the example
+    call site of INTEGRATION.md §3 compile with the host compiler alone."""
+    import subprocess
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "shim"), os.path.join(ROOT, "shim", "example_worker.cpp")])
