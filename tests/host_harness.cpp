@@ -11,6 +11,8 @@
 #include "../topay_b200/csrc/field_query.cuh"
 #include "../topay_b200/csrc/node.cuh"
 #include "../topay_b200/csrc/robot.cuh"
+#include "../topay_b200/csrc/rog_query.cuh"
+#include "../topay_b200/csrc/traj.cuh"
 
 extern "C" {
 
@@ -212,4 +214,81 @@ void hh_penalty_eval(const TpParams* Pp, const TpGrid* Gp, int stage, int N, con
     }
 }
 
+// ---- ROG-Map ring lookups (rog_query.cuh)
+void hh_make_rog_grid(double res, const int* half, const int* size, const double* dist3, const double* crit,
+                      const double* flat, TpGrid* g) {
+    std::memset(g, 0, sizeof(*g));
+    g->kind = 1;
+    g->rog.res = res;
+    g->rog.res_inv = 1.0 / res;
+    for (int i = 0; i < 3; i++) {
+        g->rog.half[i] = half[i];
+        g->rog.size[i] = size[i];
+    }
+    g->rog.dist3 = dist3;
+    g->rog.crit = crit;
+    g->rog.flat = flat;
+    g->resolution = res;
+    g->resolution_inv = 1.0 / res;
+    g->ready = 1;
+}
+void hh_rog_query(const TpGrid* g, int kind, const double* pos, int64_t n, double* dist, double* grad) {
+    const TpRog& r = g->rog;
+    for (int64_t i = 0; i < n; i++) {
+        const double* p = pos + 3 * i;
+        double gg[3] = {0, 0, 0};
+        switch (kind) {
+            case TOPAY_ROG_Q_EDT: tp_rog_value_grad(r, p, dist[i], gg); break;
+            case TOPAY_ROG_Q_FLAT: tp_rog_value_grad2d(r, r.flat, p, dist[i], gg); break;
+            case TOPAY_ROG_Q_CRITICAL: tp_rog_value_grad2d(r, r.crit, p, dist[i], gg); break;
+            case TOPAY_ROG_Q_CELL: dist[i] = tp_rog_cell3(r, p); break;
+            case TOPAY_ROG_Q_CELL_FLAT: dist[i] = tp_rog_cell2(r, r.flat, p); break;
+            default: dist[i] = tp_rog_cell2(r, r.crit, p); break;
+        }
+        for (int k = 0; k < 3; k++) grad[3 * i + k] = gg[k];
+    }
+}
+void hh_rog_line_free(const TpGrid* g, const double* s, const double* e, int64_t n, double thr, int8_t* out) {
+    for (int64_t i = 0; i < n; i++) {
+        const long cap = labs((long)floor(e[2 * i] / g->rog.res) - (long)floor(s[2 * i] / g->rog.res)) +
+                         labs((long)floor(e[2 * i + 1] / g->rog.res) - (long)floor(s[2 * i + 1] / g->rog.res)) + 1;
+        out[i] = tp_rog_line_free2d(g->rog, s + 2 * i, e + 2 * i, thr, (int)cap) ? 1 : 0;
+    }
+}
+// the field-kind dispatch the solver and the gate use
+void hh_field_dispatch(const TpGrid* g, const double* pos, int64_t n, double* d2, double* g2, double* d3, double* g3,
+                       double* v2, double* v3) {
+    for (int64_t i = 0; i < n; i++) {
+        tp_field_query2d_flat(*g, pos + 3 * i, d2[i], g2 + 2 * i);
+        tp_field_query3d(*g, pos + 3 * i, d3[i], g3 + 3 * i);
+        v2[i] = tp_field_distance2d(*g, pos + 3 * i);
+        v3[i] = tp_field_distance3d(*g, pos + 3 * i);
+    }
+}
+// ---- dense-field predicates and coarse lookups (field_query.cuh)
+void hh_field_misc(const TpGrid* g, const double* p2, const double* q2, const double* p3, const int32_t* idx, int64_t n,
+                   double thr, int critical, int8_t* c2, int8_t* c3, int8_t* line, double* coarse_d, double* coarse_i) {
+    for (int64_t i = 0; i < n; i++) {
+        c2[i] = tp_is_collision2d(*g, p2 + 2 * i, thr);
+        c3[i] = tp_is_collision3d(*g, p3 + 3 * i, thr);
+        line[i] = tp_line_collision_grid2d(*g, p2 + 2 * i, q2 + 2 * i, thr);
+        int id[2];
+        tp_pos_to_index2(*g, p2 + 2 * i, id);
+        coarse_d[i] = tp_dist_coarse2i(*g, id[0], id[1], critical != 0);
+        coarse_i[i] = tp_dist_coarse2i(*g, idx[2 * i], idx[2 * i + 1], critical != 0);
+    }
+}
+// ---- trajectory evaluation (traj.cuh): states at m times given the pose table
+void hh_traj_sample(int N, const double* T, const double* coeff, const double* car_seq, int n_seq, const double* t, int m,
+                    double* state, double* dstate, double* pva) {
+    TpPoly p{N, T, coeff};
+    const double total = tp_poly_total(p);
+    for (int j = 0; j < m; j++) {
+        tp_traj_state(p, car_seq, n_seq, total, t[j], state + 10 * j);
+        tp_traj_dstate(p, total, t[j], dstate + 10 * j);
+        tp_poly_pos(p, t[j], 0, 9, pva + 27 * j);
+        tp_poly_vel(p, t[j], 0, 9, pva + 27 * j + 9);
+        tp_poly_acc(p, t[j], 0, 9, pva + 27 * j + 18);
+    }
+}
 }  // extern "C"

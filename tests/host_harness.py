@@ -64,3 +64,59 @@ class Harness:
         gdC, gdT, terms, fxy = np.zeros((6 * N, 9)), np.zeros(N), np.zeros(13), np.zeros(2)
         self.l.hh_penalty_eval(self.P, self.G, stage, N, *[_p(v) for v in a], _p(gdC), _p(gdT), _p(terms), _p(fxy))
         return gdC, gdT, terms, fxy
+
+
+class RogHarness:
+    """rog_query.cuh on the CPU over the buffers of an oracle RogField."""
+
+    def __init__(self, orog):
+        self.l = lib()
+        self.bufs = [np.ascontiguousarray(orog.download(w)) for w in (0, 2, 3)]     # dist3, critical, flat
+        half = np.array(orog.half, dtype=np.int32)
+        size = np.array(orog.size, dtype=np.int32)
+        self.G = C.create_string_buffer(self.l.hh_grid_size())
+        self.l.hh_make_rog_grid(C.c_double(orog.resolution), _p(half, C.c_int32), _p(size, C.c_int32),
+                                *[_p(b) for b in self.bufs], self.G)
+
+    def query(self, kind, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        d, g = np.empty(len(pos)), np.zeros((len(pos), 3))
+        self.l.hh_rog_query(self.G, kind, _p(pos), C.c_int64(len(pos)), _p(d), _p(g))
+        return d, g
+
+    def line_free(self, s, e, thr):
+        s, e = np.ascontiguousarray(s, dtype=np.float64), np.ascontiguousarray(e, dtype=np.float64)
+        out = np.empty(len(s), dtype=np.int8)
+        self.l.hh_rog_line_free(self.G, _p(s), _p(e), C.c_int64(len(s)), C.c_double(thr), _p(out, C.c_int8))
+        return out
+
+    def dispatch(self, pos):
+        return field_dispatch(self.l, self.G, pos)
+
+
+def field_dispatch(l, G, pos):
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    n = len(pos)
+    d2, g2, d3, g3, v2, v3 = np.empty(n), np.empty((n, 2)), np.empty(n), np.empty((n, 3)), np.empty(n), np.empty(n)
+    l.hh_field_dispatch(G, _p(pos), C.c_int64(n), _p(d2), _p(g2), _p(d3), _p(g3), _p(v2), _p(v3))
+    return d2, g2, d3, g3, v2, v3
+
+
+def field_misc(h: Harness, p2, q2, p3, idx, thr, critical):
+    p2, q2, p3 = (np.ascontiguousarray(a, dtype=np.float64) for a in (p2, q2, p3))
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    n = len(p2)
+    c2, c3, line = (np.empty(n, dtype=np.int8) for _ in range(3))
+    cd, ci = np.empty(n), np.empty(n)
+    h.l.hh_field_misc(h.G, _p(p2), _p(q2), _p(p3), _p(idx, C.c_int32), C.c_int64(n), C.c_double(thr), int(critical),
+                      _p(c2, C.c_int8), _p(c3, C.c_int8), _p(line, C.c_int8), _p(cd), _p(ci))
+    return c2.astype(bool), c3.astype(bool), line.astype(bool), cd, ci
+
+
+def traj_sample(T, coeff, car_seq, t):
+    l = lib()
+    T, coeff, car_seq, t = (np.ascontiguousarray(a, dtype=np.float64) for a in (T, coeff, car_seq, t))
+    m = len(t)
+    st, ds, pva = np.empty((m, 10)), np.empty((m, 10)), np.empty((m, 27))
+    l.hh_traj_sample(len(T), _p(T), _p(coeff), _p(car_seq), len(car_seq), _p(t), m, _p(st), _p(ds), _p(pva))
+    return st, ds, pva

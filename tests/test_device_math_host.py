@@ -62,3 +62,70 @@ def test_penalty_dataflow(oracle, small_scene, K):
             assert np.abs(gdT - gdT1).max() <= 1e-12 * np.abs(gdT).max()
             assert np.abs(tm - tm1).max() <= 1e-12 * np.abs(tm).max()
             assert np.abs(fx0 - fx1).max() < 1e-13
+
+
+def test_rog_lookups_bit_exact(oracle):
+    """rog_query.cuh (ring hash, six query kinds, isLineFree2d walk, the solver's field-kind dispatch) on the
+    CPU against the oracle's ROG field: same buffers, bit-identical answers, wrapped positions included."""
+    from topay_b200._structs import rog_desc
+    desc = rog_desc(half_prob_map_size_i=(30, 22, 9), prob_resolution=0.1, esdf_resolution=0.1,
+                    local_update_box=(5.0, 3.0, 1.5), map_sliding_en=True)
+    orc = oracle.RogField(desc)
+    rng = np.random.default_rng(4)
+    odom = (0.43, -0.31, 0.12)
+    orc.slide(odom)
+    hits = np.array(odom) + rng.uniform(-1, 1, (500, 3)) * np.array([2.8, 2.0, 0.8])
+    orc.update_counters(hits, np.full(500, 1), np.full(500, 3))
+    orc.update_esdf(odom)
+    H = HH.RogHarness(orc)
+    pos = np.concatenate([np.array(odom) + rng.uniform(-1, 1, (4000, 3)) * np.array([2.0, 1.3, 0.6]),
+                          rng.uniform(-40, 40, (500, 3))])
+    for kind in range(6):
+        d0, g0 = orc.query(kind, pos)
+        d1, g1 = H.query(kind, pos)
+        assert np.array_equal(d0, d1), kind
+        if kind < 3:
+            assert np.array_equal(g0, g1), kind
+    s = (np.array(odom) + rng.uniform(-1, 1, (3000, 3)) * np.array([2.0, 1.3, 0.0]))[:, :2]
+    e = (np.array(odom) + rng.uniform(-1, 1, (3000, 3)) * np.array([2.0, 1.3, 0.0]))[:, :2]
+    for thr in (0.0, 0.15, 0.4):
+        assert np.array_equal(H.line_free(s, e, thr), orc.is_line_free2d(s, e, thr)), thr
+    # the dispatch GridMap's use_rog branches go through (grid_map.h:256-267, 307-322, 364-392, 443-461)
+    d2, g2, d3, g3, v2, v3 = H.dispatch(pos)
+    p0 = pos.copy()
+    p0[:, 2] = 0.0
+    e2, eg2 = orc.query(1, p0)
+    e3, eg3 = orc.query(0, pos)
+    assert np.array_equal(d2, e2) and np.array_equal(g2, eg2[:, :2]) and np.array_equal(v2, e2)
+    assert np.array_equal(d3, e3) and np.array_equal(g3, eg3) and np.array_equal(v3, e3)
+
+
+def test_field_predicates_bit_exact(oracle, small_scene, harness):
+    f = small_scene["field"]
+    rng = np.random.default_rng(8)
+    n = 5000
+    p2, q2 = rng.uniform(-10.3, 10.3, (n, 2)), rng.uniform(-10.3, 10.3, (n, 2))
+    p3 = np.concatenate([rng.uniform(-10.3, 10.3, (n, 2)), rng.uniform(-0.2, 1.8, (n, 1))], axis=1)
+    idx = rng.integers(-5, 206, (n, 2))
+    for thr, crit in ((0.0, False), (0.3, True)):
+        c2, c3, line, cd, ci = HH.field_misc(harness, p2, q2, p3, idx, thr, crit)
+        assert np.array_equal(c2, f.is_collision(p2, thr)) and np.array_equal(c3, f.is_collision(p3, thr))
+        assert np.array_equal(line, f.line_collision2d(p2, q2, thr))
+        assert np.array_equal(cd, f.dist_coarse2d(p2, crit)) and np.array_equal(ci, f.dist_coarse2i(idx, crit))
+
+
+def test_traj_evaluation_bit_exact(oracle):
+    """traj.cuh (locatePieceIdx, Piece::getPos/getVel/getAcc, MomaTraj::getState/getDState) on the CPU against
+    the oracle, fed with the oracle's pose table."""
+    rng = np.random.default_rng(12)
+    N = 5
+    T = rng.uniform(0.6, 1.8, N)
+    coeff = rng.normal(size=(6 * N, 9)) * (0.5 ** np.tile(np.arange(6), N))[:, None]
+    tr = (T, coeff, np.array([0.3, -0.2, 0.7]))
+    seq = oracle.traj_car_seq([tr])[0]
+    t = np.concatenate([np.linspace(-0.3, T.sum() + 0.3, 301), np.cumsum(T), [0.0, T.sum()]])
+    st, ds, pva = HH.traj_sample(T, coeff, seq, t)
+    est, eds = oracle.traj_sample([tr], t[None])
+    assert np.array_equal(ds, eds[0])
+    # the state adds one Simpson step with sin/cos: same libm on both sides here
+    assert np.abs(st - est[0]).max() <= 1e-15 * max(1.0, np.abs(est[0]).max())
