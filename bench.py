@@ -145,7 +145,7 @@ def cpu_baseline(opt, rp, pts, paths, bv, ba, cores, desc):
     return m / dt, m, dt, sum(r["status"] for r in res), float(np.median(lat))
 
 
-def latency_probe(tp, scenes, gm, n_plans=120):
+def latency_probe(tp, scenes, gm, n_plans=200):
     """Second headline metric: p50 single-plan latency, upload candidates -> best trajectory on the
     host, at the reference's default scale (BASELINE configs[0]/[1]: <= 8 candidates per plan,
     int_K = 12, sample_interval 1.5 s -> 3-10 pieces), one plan at a time through the public API."""
