@@ -7,6 +7,7 @@
 // are templates over "anything with size() and operator[] / operator()(r, c)". With Eigen present,
 // Eigen::VectorXd / Eigen::MatrixXd / Eigen::Vector3d satisfy these directly.
 #pragma once
+#include <cmath>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -92,6 +93,7 @@ public:
         topay_field_dims(f_, dims);
         for (int i = 0; i < 3; i++) voxel_num[i] = dims[i];
         resolution = res; resolution_inv = 1.0 / res;
+        map_origin[0] = -map_size_x / 2.0; map_origin[1] = -map_size_y / 2.0; map_origin[2] = 0.0;   // grid_map.cpp:41-47
     }
     ~GridMap() { topay_field_destroy(f_); }
 
@@ -186,6 +188,26 @@ public:
         topay_check(topay_field_download(f_, TOPAY_MAP2D_FLAT, b.data()), "topay_field_download");
         return b;
     }
+    // index helpers, pure host arithmetic (grid_map.h:727-885, dense branch)
+    template <class V3, class V3i> void posToIndex3d(const V3& pos, V3i& id) const {
+        for (int i = 0; i < 3; i++) id[i] = (int)std::floor((pos[i] - map_origin[i]) * resolution_inv);
+    }
+    template <class V2, class V2i> void posToIndex2d(const V2& pos, V2i& id) const {
+        for (int i = 0; i < 2; i++) id[i] = (int)std::floor((pos[i] - map_origin[i]) * resolution_inv);
+    }
+    template <class V3i, class V3> void indexToPos3d(const V3i& id, V3& pos) const {
+        for (int i = 0; i < 3; i++) pos[i] = (id[i] + 0.5) * resolution + map_origin[i];
+    }
+    template <class V2i, class V2> void indexToPos2d(const V2i& id, V2& pos) const {
+        for (int i = 0; i < 2; i++) pos[i] = (id[i] + 0.5) * resolution + map_origin[i];
+    }
+    template <class V3i> void boundIndex3d(V3i& id) const {
+        for (int i = 0; i < 3; i++) id[i] = id[i] < 0 ? 0 : (id[i] > voxel_num[i] - 1 ? voxel_num[i] - 1 : id[i]);
+    }
+    template <class V2i> void boundIndex2d(V2i& id) const {
+        for (int i = 0; i < 2; i++) id[i] = id[i] < 0 ? 0 : (id[i] > voxel_num[i] - 1 ? voxel_num[i] - 1 : id[i]);
+    }
+    double map_origin[3] = {0, 0, 0};
     topay_field* handle() const { return f_; }
 
 private:

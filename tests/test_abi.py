@@ -119,3 +119,26 @@ def test_cpp_shims_compile_against_the_header():
     import subprocess
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
                            "-I", os.path.join(ROOT, "shim"), os.path.join(ROOT, "shim", "example_worker.cpp")])
+
+
+def test_gridmap_index_helpers_match_the_oracle_grid(oracle):
+    """posToIndex / indexToPos / boundIndex / isInMap (grid_map.h:727-885) are host arithmetic: no device."""
+    import numpy as np
+    import topay_b200 as tp
+    g = tp.GridMap.__new__(tp.GridMap)           # geometry only, no device object
+    g.desc, g.voxel_num = tp.grid_desc(), (200, 200, 16)
+    rng = np.random.default_rng(0)
+    p = rng.uniform([-10.4, -10.4, -0.2], [10.4, 10.4, 1.8], (2000, 3))
+    idx = g.posToIndex3d(p)
+    assert np.array_equal(idx, np.floor((p - np.array([-10.0, -10.0, 0.0])) * (1.0 / 0.1)).astype(np.int64))
+    inside = g.isInMap3d(p)
+    c = g.indexToPos3d(idx[inside])
+    assert np.all(np.abs(c - p[inside]) <= 0.05 + 1e-12)
+    assert np.array_equal(g.posToIndex2d(p[:, :2]), idx[:, :2])
+    b = g.boundIndex3d(idx)
+    assert b.min() >= 0 and np.all(b.max(axis=0) <= np.array([199, 199, 15]))
+    # the nearest-cell lookups of the oracle use the same indices
+    f = oracle.Field(tp.grid_desc())
+    f.rebuild()
+    assert np.array_equal(g.isInMap2d(p[:, :2]), f.distance2d(p[:, :2]) != 1e10)     # 1e10 <=> outside (grid_map.h:269-273)
+    assert np.array_equal(g.isInMap3d(p), f.distance3d(p) != 1e10)

@@ -148,6 +148,45 @@ class GridMap:
                    "dist_coarse2i")
         return out
 
+    # ---- index helpers (pure host arithmetic, grid_map.h:727-885) ---------------
+    @property
+    def map_origin(self):
+        ms = np.array(self.desc.map_size[:])
+        return np.array([-ms[0] / 2.0, -ms[1] / 2.0, 0.0])        # grid_map.cpp:41-47
+
+    def posToIndex3d(self, pos):
+        pos = np.asarray(pos, dtype=np.float64)
+        return np.floor((pos - self.map_origin) * (1.0 / self.desc.resolution)).astype(np.int64)
+
+    def posToIndex2d(self, pos):
+        pos = np.asarray(pos, dtype=np.float64)
+        return np.floor((pos - self.map_origin[:2]) * (1.0 / self.desc.resolution)).astype(np.int64)
+
+    def indexToPos3d(self, idx):
+        return (np.asarray(idx, dtype=np.float64) + 0.5) * self.desc.resolution + self.map_origin
+
+    def indexToPos2d(self, idx):
+        return (np.asarray(idx, dtype=np.float64) + 0.5) * self.desc.resolution + self.map_origin[:2]
+
+    def boundIndex3d(self, idx):
+        return np.clip(np.asarray(idx), 0, np.array(self.voxel_num) - 1)
+
+    def boundIndex2d(self, idx):
+        return np.clip(np.asarray(idx), 0, np.array(self.voxel_num[:2]) - 1)
+
+    def isInMap3d(self, pos):
+        """Position form (1e-4 margin, grid_map.h:818-833)."""
+        pos = np.asarray(pos, dtype=np.float64)
+        ms = np.array(self.desc.map_size[:])
+        lo = self.map_origin + 1e-4
+        hi = np.array([ms[0] / 2.0, ms[1] / 2.0, ms[2]]) - 1e-4
+        return np.all((pos >= lo) & (pos <= hi), axis=-1)
+
+    def isInMap2d(self, pos):
+        pos = np.asarray(pos, dtype=np.float64)
+        ms = np.array(self.desc.map_size[:2])
+        return np.all((pos >= -ms / 2.0 + 1e-4) & (pos <= ms / 2.0 - 1e-4), axis=-1)
+
     # ---- buffers ------------------------------------------------------------
     def _shape(self, which):
         return self.voxel_num if which == MAP3D else self.voxel_num[:2]
