@@ -32,7 +32,11 @@ struct topay_solver {
     cudaStream_t stream;
     int n_cand;          // candidates of the uploaded batch
     int max_N;           // largest piece count in the batch
-    std::vector<TpCandState> h_state;
+    // pinned host staging (one cudaMallocHost block sized for max_cand): initial per-candidate state and x,
+    // and the packed problem data on their way to the device
+    char* h_pin;
+    TpCandState* h_state;
+    double *p_head, *p_tail, *p_sxy, *p_exy, *p_ixy;
     std::vector<void*> allocs;
     int32_t* h_active;   // pinned
     unsigned long long* h_nodes;  // pinned
@@ -46,7 +50,8 @@ struct topay_solver {
     topay_solver_stats stats;
     size_t smem_cand;
     // initial state kept on the host for repeated runs
-    std::vector<double> h_x0;
+    double* h_x0;
+    size_t h_x0_count;
     // one batch of `slots` ticks as a CUDA graph (launch-bound small plans); rebuilt when the
     // launch geometry or a captured pointer changes
     bool timed;                 // per-launch CUDA events around k_penalty (plain launches, no graph)
@@ -231,6 +236,21 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     ALLOC(D.n_active, (size_t)s->slots);
     ALLOC(D.node_count, 2);
 #undef ALLOC
+    {
+        const size_t C_ = (size_t)max_cand;
+        const size_t b_state = ((C_ * sizeof(TpCandState) + 15) / 16) * 16;
+        const size_t n_dbl = C_ * D.xs + C_ * (27 + 27 + 2 + 2) + C_ * NP * 2;
+        TP_CUDA_OK(cudaMallocHost(&s->h_pin, b_state + n_dbl * sizeof(double)), { topay_solver_destroy(s); });
+        s->h_state = reinterpret_cast<TpCandState*>(s->h_pin);
+        double* dp = reinterpret_cast<double*>(s->h_pin + b_state);
+        s->h_x0 = dp;            dp += C_ * D.xs;
+        s->p_head = dp;          dp += C_ * 27;
+        s->p_tail = dp;          dp += C_ * 27;
+        s->p_sxy = dp;           dp += C_ * 2;
+        s->p_exy = dp;           dp += C_ * 2;
+        s->p_ixy = dp;
+        s->h_x0_count = 0;
+    }
     TP_CUDA_OK(cudaMallocHost(&s->h_active, s->slots * sizeof(int32_t)), { topay_solver_destroy(s); });
     TP_CUDA_OK(cudaMallocHost(&s->h_nodes, 2 * sizeof(unsigned long long)), { topay_solver_destroy(s); });
     s->ev.resize(5 * s->slots);
@@ -275,6 +295,7 @@ extern "C" void topay_solver_destroy(topay_solver* s) {
     for (void* p : s->allocs) cudaFree(p);
     if (s->dev.trace) cudaFree(s->dev.trace);
     if (s->dev.trace_len) cudaFree(s->dev.trace_len);
+    if (s->h_pin) cudaFreeHost(s->h_pin);
     if (s->h_active) cudaFreeHost(s->h_active);
     if (s->h_nodes) cudaFreeHost(s->h_nodes);
     for (auto& e : s->ev) cudaEventDestroy(e);
@@ -306,8 +327,9 @@ static int upload_problem(topay_solver* s, int n_cand, const int32_t* piece_num,
     cudaSetDevice(s->device);
     s->n_cand = n_cand;
     s->max_N = maxN;
-    s->h_state.assign(n_cand, TpCandState());
-    std::vector<double> xs((size_t)n_cand * D.xs, 0.0);
+    double* xs = s->h_x0;
+    memset(xs, 0, (size_t)n_cand * D.xs * sizeof(double));
+    s->h_x0_count = (size_t)n_cand * D.xs;
     for (int c = 0; c < n_cand; c++) {
         TpCandState& st = s->h_state[c];
         memset(&st, 0, sizeof(st));
@@ -322,16 +344,21 @@ static int upload_problem(topay_solver* s, int n_cand, const int32_t* piece_num,
         st.rho[1] = rho ? rho[2 * c + 1] : s->params.opt.alm_init_rho[1];
         memcpy(&xs[(size_t)c * D.xs], x + (size_t)c * x_stride, st.n * sizeof(double));
     }
-    s->h_x0 = xs;
+    // the packed problem goes through the pinned staging block
+    memcpy(s->p_head, head, (size_t)n_cand * 27 * 8);
+    memcpy(s->p_tail, tail, (size_t)n_cand * 27 * 8);
+    memcpy(s->p_sxy, sxy, (size_t)n_cand * 2 * 8);
+    memcpy(s->p_exy, exy, (size_t)n_cand * 2 * 8);
+    memcpy(s->p_ixy, inner_xy, (size_t)n_cand * D.max_pieces * 2 * 8);
     cudaStream_t q = s->stream;
-    TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state.data(), n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
-    TP_CUDA_OK(cudaMemcpyAsync(D.head_pva, head, (size_t)n_cand * 27 * 8, cudaMemcpyHostToDevice, q), {});
-    TP_CUDA_OK(cudaMemcpyAsync(D.tail_pva, tail, (size_t)n_cand * 27 * 8, cudaMemcpyHostToDevice, q), {});
-    TP_CUDA_OK(cudaMemcpyAsync(D.start_xy, sxy, (size_t)n_cand * 2 * 8, cudaMemcpyHostToDevice, q), {});
-    TP_CUDA_OK(cudaMemcpyAsync(D.end_xy, exy, (size_t)n_cand * 2 * 8, cudaMemcpyHostToDevice, q), {});
-    TP_CUDA_OK(cudaMemcpyAsync(D.init_inner_xy, inner_xy, (size_t)n_cand * D.max_pieces * 2 * 8,
+    TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state, n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.head_pva, s->p_head, (size_t)n_cand * 27 * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.tail_pva, s->p_tail, (size_t)n_cand * 27 * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.start_xy, s->p_sxy, (size_t)n_cand * 2 * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.end_xy, s->p_exy, (size_t)n_cand * 2 * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.init_inner_xy, s->p_ixy, (size_t)n_cand * D.max_pieces * 2 * 8,
                                cudaMemcpyHostToDevice, q), {});
-    TP_CUDA_OK(cudaMemcpyAsync(D.x, xs.data(), xs.size() * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.x, xs, s->h_x0_count * 8, cudaMemcpyHostToDevice, q), {});
     TP_CUDA_OK(cudaStreamSynchronize(q), {});
     return TOPAY_OK;
 }
@@ -365,7 +392,7 @@ extern "C" int topay_solver_eval(topay_solver* s, int stage, const topay_problem
     if (coeff_out)
         TP_CUDA_OK(cudaMemcpy(coeff_out, D.coeff, (size_t)n * 6 * D.max_pieces * 9 * 8, cudaMemcpyDeviceToHost), {});
     if (final_xy_out) {
-        TP_CUDA_OK(cudaMemcpy(s->h_state.data(), D.st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), {});
+        TP_CUDA_OK(cudaMemcpy(s->h_state, D.st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), {});
         for (int c = 0; c < n; c++) {
             final_xy_out[2 * c] = s->h_state[c].final_xy[0];
             final_xy_out[2 * c + 1] = s->h_state[c].final_xy[1];
@@ -414,8 +441,8 @@ extern "C" int topay_solver_run(topay_solver* s) {
     TpRunningGuard running;
     memset(&s->stats, 0, sizeof(s->stats));
     // reset to the uploaded initial state so that repeated runs do identical work
-    TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state.data(), s->n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
-    TP_CUDA_OK(cudaMemcpyAsync(D.x, s->h_x0.data(), s->h_x0.size() * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state, s->n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.x, s->h_x0, s->h_x0_count * 8, cudaMemcpyHostToDevice, q), {});
     cudaMemsetAsync(D.node_count, 0, 2 * sizeof(unsigned long long), q);
     if (D.trace) cudaMemsetAsync(D.trace_len, 0, (size_t)D.max_cand * sizeof(int32_t), q);
     cudaEventRecord(s->ev_begin, q);
