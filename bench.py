@@ -504,6 +504,12 @@ def main():
                                     "launches with CUDA events around every kernel launch; averages include the "
                                     "plan's low-activity tail",
                      "share_of_step": rst["ms_cand"] / max(rst["ms_total"], 1e-9),
+                     "full_activity": {"ticks": rst["full_ticks"],
+                                       "achieved": rst["full_hist_bytes"] / max(rst["full_ms_cand"], 1e-9) / 1e6,
+                                       "frac": rst["full_hist_bytes"] / max(rst["full_ms_cand"], 1e-9) / 1e6 / peak,
+                                       "avg_launch_ms": rst["full_ms_cand"] / max(rst["full_ticks"], 1),
+                                       "note": "same figures over the tick batches in which all candidates "
+                                               "were still solving"},
                      "kernel_shares": {k: v / k_sum for k, v in k_ms.items()}},
         "roofline_k_penalty": {"bound": "hbm", "kernel": "k_penalty", "achieved": achieved, "peak": peak,
                                "unit": "GB/s", "frac": achieved / peak, "traffic": 19.9e6,

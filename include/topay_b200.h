@@ -449,6 +449,12 @@ typedef struct topay_solver_stats {
     float   pad_;
     int64_t hist_bytes;        /* algorithmic bytes of L-BFGS history the two-loop recursions walked:
                                 * 2 loops x bound rows x (s_j, y_j) x n x 8 B, summed over candidates */
+    /* timed mode only: the same k_cand figures restricted to the tick batches in which every
+     * candidate was still solving (full activity) */
+    int64_t full_ticks;
+    int64_t full_hist_bytes;
+    float   full_ms_cand;
+    float   pad2_;
 } topay_solver_stats;
 int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out);
 /* The worker's success gate on the device, straight from the solver's result buffers

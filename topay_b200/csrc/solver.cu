@@ -448,7 +448,9 @@ extern "C" int topay_solver_run(topay_solver* s) {
     cudaEventRecord(s->ev_begin, q);
     cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), q);
     launch_cand(s, TP_MODE_GEN, 0);
-    double ms_eval = 0.0, ms_k[3] = {0.0, 0.0, 0.0};
+    double ms_eval = 0.0, ms_k[3] = {0.0, 0.0, 0.0}, full_ms_cand = 0.0;
+    unsigned long long hist_prev = 0, full_hist = 0;
+    long long full_ticks = 0;
     // hard cap on ticks: every candidate does at most this many evaluations
     const long long max_ticks =
         (long long)(s->params.opt.alm_max_rounds + 1) * ((long long)s->params.opt.s2_lbfgs.max_iterations + 2) *
@@ -490,6 +492,7 @@ extern "C" int topay_solver_run(topay_solver* s) {
                 cudaEventRecord(s->ev[5 * t + 4], q);
             }
             cudaMemcpyAsync(s->h_active, D.n_active, s->slots * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
+            cudaMemcpyAsync(s->h_nodes, D.node_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q);
         }
         ticks += s->slots;
         if (s->spin_sync || g_solves_running.load(std::memory_order_relaxed) <= 2) {
@@ -506,7 +509,11 @@ extern "C" int topay_solver_run(topay_solver* s) {
             if (ticks > s->slots) fprintf(stderr, "TICKLOG %lld %d %.1f\n", ticks, s->h_active[s->slots - 1], (now - t_prev) * 1e6 / s->slots);
             t_prev = now;
         }
-        if (!use_graph)
+        if (!use_graph) {
+            // batches in which every candidate was still solving: the full-activity figures
+            const bool full = s->h_active[s->slots - 1] == s->n_cand;
+            const unsigned long long hist_now = s->h_nodes[1];
+            double cand_batch = 0.0;
             for (int t = 0; t < s->slots; t++) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, s->ev[5 * t + 1], s->ev[5 * t + 2]);
@@ -517,7 +524,15 @@ extern "C" int topay_solver_run(topay_solver* s) {
                 ms_k[1] += ms;
                 cudaEventElapsedTime(&ms, s->ev[5 * t + 3], s->ev[5 * t + 4]);
                 ms_k[2] += ms;
+                cand_batch += ms;
             }
+            if (full) {
+                full_ms_cand += cand_batch;
+                full_hist += hist_now - hist_prev;
+                full_ticks += s->slots;
+            }
+            hist_prev = hist_now;
+        }
         done = s->h_active[s->slots - 1] == 0;
     }
     cudaEventRecord(s->ev_end, q);
@@ -531,7 +546,10 @@ extern "C" int topay_solver_run(topay_solver* s) {
     s->stats.ms_cand = (float)ms_k[2];
     s->stats.ticks = ticks;
     s->stats.eval_nodes = (int64_t)s->h_nodes[0];
-    s->stats.hist_bytes = (int64_t)s->h_nodes[1] * 16;   // one s_j and one y_j element per row element
+    s->stats.hist_bytes = (int64_t)s->h_nodes[1] * 16;
+    s->stats.full_ticks = full_ticks;
+    s->stats.full_hist_bytes = (int64_t)full_hist * 16;
+    s->stats.full_ms_cand = (float)full_ms_cand;   // one s_j and one y_j element per row element
     return TOPAY_OK;
 }
 
