@@ -315,3 +315,19 @@ def test_front_end_predicates_and_coarse_lookups(gpu_scene, small_scene):
         assert np.array_equal(gpu_scene.getDistCoarse2d(p2, crit), of.dist_coarse2d(p2, crit))
         idx = rng.integers(-5, 206, (5000, 2))
         assert np.array_equal(gpu_scene.getDistCoarse2i(idx, crit), of.dist_coarse2i(idx, crit))
+
+
+def test_solvers_of_different_capacity_coexist(gpu_scene):
+    """Kernel attributes (dynamic shared memory) are per kernel, not per solver: a small solver created after a
+    large one must not break the large one, and results do not depend on what else was created."""
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    paths, bv, ba = scenes.short_candidates(2, 7)
+    big = tp.MomaTrajOpt(gpu_scene, max_cand=2, max_pieces=64)
+    a = big.optimizeTrajBatch(paths, bv, ba)
+    small = tp.MomaTrajOpt(gpu_scene, max_cand=2, max_pieces=16)
+    b = small.optimizeTrajBatch(paths, bv, ba)
+    c = big.optimizeTrajBatch(paths, bv, ba)
+    for r in (b, c):
+        assert np.array_equal(a["evals"], r["evals"]) and np.array_equal(a["cost"], r["cost"])
+        assert np.array_equal(a["T"][:, :16], r["T"][:, :16])

@@ -269,11 +269,23 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
         topay_solver_destroy(s);
         return TOPAY_ERR_TOO_LARGE;
     }
-    TP_CUDA_OK(cudaFuncSetAttribute(k_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_cand),
-               { topay_solver_destroy(s); });
+    // the attribute belongs to the kernel, not to this solver: solvers of different capacities coexist
+    // (bench: 64-piece plans and 16-piece latency plans), so it only ever grows
+    {
+        static std::atomic<size_t> attr_set{0};
+        size_t cur = attr_set.load();
+        while (cur < s->smem_cand && !attr_set.compare_exchange_weak(cur, s->smem_cand)) {}
+        TP_CUDA_OK(cudaFuncSetAttribute(k_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_set.load()),
+                   { topay_solver_destroy(s); });
+    }
     const size_t sm_int = (size_t)TP_WARPS_PER_BLOCK * D.ppw * 3 * (2 * D.K + 1) * sizeof(double);
-    TP_CUDA_OK(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_int),
-               { topay_solver_destroy(s); });
+    {
+        static std::atomic<size_t> attr_int{0};
+        size_t cur = attr_int.load();
+        while (cur < sm_int && !attr_int.compare_exchange_weak(cur, sm_int)) {}
+        TP_CUDA_OK(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_int.load()),
+                   { topay_solver_destroy(s); });
+    }
     {
         const int smp = (int)penalty_smem();
         TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp), { topay_solver_destroy(s); });

@@ -865,6 +865,10 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         for (int q = 0; q < TP_RING_MAX; q++) tp_mbar_init(&s_bar[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+#ifdef TP_DEBUG_ZERO_SMEM
+    for (int e = tid; e < S.smem_doubles; e += TP_CAND_THREADS) sm[e] = TP_DEBUG_ZERO_SMEM;
+    __syncthreads();
+#endif
     int flip = 0;
     double* x = S.x + (size_t)cand * S.xs;
     double* g = S.g + (size_t)cand * S.xs;
@@ -1304,6 +1308,9 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     // round are spread over the first lane of each warp: part 0 arms the stage's barrier and
                     // fetches s_j, part 1 fetches y_j (the transaction count may complete in any order).
                     auto issue_part = [&](int t, int sg, int part) {
+#ifdef TP_DEBUG_NO_TMA
+                        return;
+#endif
                         const int j = row_of(t);
                         double* dst = ring + (size_t)sg * 2 * rowd;
                         if (part == 0) {
@@ -1341,10 +1348,15 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                                 if (tt < total) issue_part(tt, sg0 + (who >> 1), who & 1);
                             }
                         };
-                        auto load_row = [&](double* cs, double* cy) {
+                        auto load_row = [&](int jrow, double* cs, double* cy) {
+#ifdef TP_DEBUG_NO_TMA
+                            const double* rs_ = lm_s + (size_t)jrow * S.xs;     // debug: plain loads, no ring
+                            const double* ry_ = lm_y + (size_t)jrow * S.xs;
+#else
                             tp_mbar_wait(&s_bar[sg], (uint32_t)ph);
                             const double* rs_ = ring + (size_t)sg * 2 * rowd;
                             const double* ry_ = rs_ + rowd;
+#endif
 #pragma unroll
                             for (int e = 0; e < TP_EPT; e++) {
                                 const int i = me + e * STRIDE;
@@ -1379,9 +1391,9 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                             const int jB = pair ? row_of(t + 1) : jA;
                             double sA[TP_EPT], yA[TP_EPT], sB[TP_EPT], yB[TP_EPT];
                             const int sg0 = sg;            // nst is even and pairs start on even steps of a loop;
-                            load_row(sA, yA);              // a stage pair never straddles the ring's end unless
+                            load_row(jA, sA, yA);          // a stage pair never straddles the ring's end unless
                             if (pair) {                    // a loop has odd length, which the refill handles per step
-                                load_row(sB, yB);
+                                load_row(jB, sB, yB);
                             } else {
 #pragma unroll
                                 for (int e = 0; e < TP_EPT; e++) sB[e] = yB[e] = 0.0;
