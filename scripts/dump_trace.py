@@ -1,0 +1,15 @@
+import os, sys
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
+import numpy as np
+import topay_b200 as tp
+from topay_b200 import scenes
+pts, _ = scenes.cuboids_scene(42)
+gm = tp.GridMap(tp.grid_desc()); gm.regenerateMap(pts)
+paths, bv, ba = scenes.short_candidates(4, 7)
+solver = tp.MomaTrajOpt(gm, max_cand=4, max_pieces=16)
+solver.set_trace(4000)
+r = solver.optimizeTrajBatch(paths, bv, ba)
+out = {f"t{c}": solver.trace(c) for c in range(4)}
+out["evals"] = r["evals"]
+np.savez(os.path.join(R, "gpurun_out", sys.argv[1]), **out)
+print(sys.argv[1], r["evals"])

@@ -142,3 +142,19 @@ def test_gridmap_index_helpers_match_the_oracle_grid(oracle):
     f.rebuild()
     assert np.array_equal(g.isInMap2d(p[:, :2]), f.distance2d(p[:, :2]) != 1e10)     # 1e10 <=> outside (grid_map.h:269-273)
     assert np.array_equal(g.isInMap3d(p), f.distance3d(p) != 1e10)
+
+
+def test_plain_c_caller_links_and_runs(tmp_path):
+    """examples/c_abi_demo.c: the header is C99-clean and the library is callable without C++ or Python; on a
+    box without a GPU the compute entry points refuse (no CPU path), the host-only ones answer."""
+    import subprocess
+    from topay_b200 import _lib
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-ltopay_b200",
+                           f"-Wl,-rpath,{libdir}", "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "select_shortest -> 2" in out.stdout
+    assert ("no CUDA device" in out.stdout) or ("status 1" in out.stdout)
