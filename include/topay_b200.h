@@ -476,6 +476,9 @@ int topay_solver_download_trace(topay_solver* s, int cand, double* out /*cap x 4
 /* Developer profiling: accumulated SM clock cycles of the per-candidate kernel's phases
  * (candidate 0) since the last call; enable != 0 switches the counters on. out16 may be NULL. */
 int topay_solver_phase_clocks(topay_solver* s, int enable, long long* out16);
+/* Developer aid: raw copy of an intermediate device array of the last topay_solver_eval (bit-level A/B
+ * runs). which: 0 gnode, 1 gsum, 2 gdC, 3 gdT, 4 tot, 5 Ixy, 6 g. Returns the doubles written or a status. */
+int64_t topay_solver_debug_download(topay_solver* s, int which, double* out, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,11 @@ for stage in (1, 2):
                          [q["tail_pva"] for q in prep], [q["start_xy"] for q in prep], [q["end_xy"] for q in prep],
                          [q["init_inner_xy"] for q in prep], xs, alm_lambda=np.zeros((4, 2)), alm_rho=np.full((4, 2), 1e4))
     dump[f"g{stage}"] = ev["grad"]
+    import ctypes as C
+    for which, name in enumerate(("gnode", "gsum", "gdC", "gdT", "tot", "Ixy", "gdev", "dbg")):
+        buf = np.zeros(4 * 16 * 13 * 2 * 30)
+        n = solver._l.topay_solver_debug_download(solver.h, which, buf.ctypes.data_as(C.POINTER(C.c_double)), len(buf))
+        dump[f"{name}{stage}"] = buf[:n].copy()
     dump["pn"] = np.array([q["piece_num"] for q in prep])
     for c in range(4):
         print(stage, c, ev["cost"][c].hex(), hashlib.md5(ev["grad"][c].tobytes()).hexdigest()[:10],

@@ -100,6 +100,7 @@ PROTOTYPES = {
     "topay_solver_download": (C.c_int, [C.c_void_p, C.POINTER(ResultBatch), _ip, _ip]),
     "topay_solver_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "topay_solver_download_trace": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int, _ip]),
+    "topay_solver_debug_download": (C.c_int64, [C.c_void_p, C.c_int, _dp, C.c_int64]),
     "topay_solver_phase_clocks": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]),
     "topay_solver_set_timed": (C.c_int, [C.c_void_p, C.c_int]),
     "topay_solver_last_stats": (C.c_int, [C.c_void_p, C.POINTER(SolverStats)]),

@@ -681,6 +681,32 @@ extern "C" int topay_solver_check_feasible(topay_solver* s, topay_feasibility* o
     return rc;
 }
 
+// Developer aid: raw copy of one of the evaluation's intermediate device arrays after topay_solver_eval
+// (bit-level A/B runs). which: 0 gnode, 1 gsum, 2 gdC, 3 gdT, 4 tot, 5 Ixy, 6 g. Returns the number of
+// doubles written (<= cap) or a negative status.
+extern "C" int64_t topay_solver_debug_download(topay_solver* s, int which, double* out, int64_t cap) {
+    if (!s || !out) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(s->device);
+    const TpSolverDev& D = s->dev;
+    const size_t C_ = (size_t)D.max_cand, NP = (size_t)D.max_pieces, K = (size_t)D.K;
+    const double* src = nullptr;
+    size_t n = 0;
+    switch (which) {
+        case 0: src = D.gnode; n = C_ * NP * (K + 1) * 2; break;
+        case 1: src = D.gsum; n = C_ * NP * 2; break;
+        case 2: src = D.gdC; n = C_ * 6 * NP * 9; break;
+        case 3: src = D.gdT; n = C_ * NP; break;
+        case 4: src = D.tot; n = C_ * NP * 2; break;
+        case 5: src = D.Ixy; n = C_ * NP * K * 2; break;
+        case 6: src = D.g; n = C_ * (size_t)D.xs; break;
+        case 7: src = D.gdC_end; n = C_ * NP * 54; break;
+        default: return TOPAY_ERR_INVALID_ARG;
+    }
+    if ((int64_t)n > cap) n = (size_t)cap;
+    TP_CUDA_OK(cudaMemcpy(out, src, n * sizeof(double), cudaMemcpyDeviceToHost), {});
+    return (int64_t)n;
+}
+
 // Dev profiling: accumulated clock64() deltas of k_cand's phases for candidate 0 (16 slots).
 extern "C" int topay_solver_phase_clocks(topay_solver* s, int enable, long long* out16) {
     if (!s) return TOPAY_ERR_INVALID_ARG;

@@ -225,6 +225,10 @@ k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParam
 
     if (task >= n_groups) {
         // ---- end-node task: lane = piece, node j = 2K (only when K == KPAD) ----
+        // With K < KPAD node 2K lives in the piece's own segment; the spare warp that rounds the grid up
+        // to whole blocks must not evaluate it a second time (it would race with the segment's lane on
+        // gnode[K] with a differently rounded prefix position).
+        if (!S.end_tasks) return;
         const int piece = (task - n_groups) * 32 + lane;
         if (piece >= N) return;
         const double T = S.T[(size_t)cand * S.max_pieces + piece];
@@ -312,6 +316,18 @@ k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParam
         for (int k = 0; k < 6; k++) b0[k] = b1[k] = b2[k] = 0.0;
     }
     const size_t prow = (size_t)cand * S.max_pieces + piece;
+#ifdef TP_DEBUG_NODE
+    // dev: inputs / outputs of node K of every piece into the (otherwise unused when K < Kpad) gdC_end rows
+    if (active && STAGE == 2 && !S.end_tasks && jn == K) {
+        double* dbg = S.gdC_end + prow * 54;
+        double sdf, gs[2];
+        tp_field_query2d_flat(G, xy, sdf, gs);
+        dbg[0] = xy[0]; dbg[1] = xy[1]; dbg[2] = sdf; dbg[3] = gs[0]; dbg[4] = gs[1];
+        dbg[5] = o.gx; dbg[6] = o.gy; dbg[7] = T; dbg[8] = c[0]; dbg[9] = c[53];
+        dbg[10] = o.G0[0]; dbg[11] = o.G0[1]; dbg[12] = o.gdT; dbg[13] = o.terms[TOPAY_TERM_CHASSIS_COLLI];
+        dbg[14] = o.terms[TOPAY_TERM_MANI_COLLI]; dbg[15] = o.G0[2]; dbg[16] = o.G0[5];
+    }
+#endif
     // per-node xy adjoint, kept for the suffix sums of k_chain, and its sum over the piece
     if (STAGE == 2) {
         if (active) {
