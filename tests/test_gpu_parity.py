@@ -331,3 +331,23 @@ def test_solvers_of_different_capacity_coexist(gpu_scene):
     for r in (b, c):
         assert np.array_equal(a["evals"], r["evals"]) and np.array_equal(a["cost"], r["cost"])
         assert np.array_equal(a["T"][:, :16], r["T"][:, :16])
+
+
+def test_spare_warp_does_not_reevaluate_the_end_node(gpu_scene):
+    """K < K-hat: node 2K belongs to the piece's own segment. The warp that rounds k_penalty's grid up to whole
+    blocks used to run as an end-node task and write gnode[K] a second time (a race with last-bit effects);
+    its footprint was the end-node scratch, which must now stay untouched."""
+    import ctypes as C
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()      # int_K = 12 -> K-hat = 16, two pieces per warp
+    paths, bv, ba = scenes.short_candidates(4, 7)
+    solver = tp.MomaTrajOpt(gpu_scene, max_cand=4, max_pieces=16, opt_param=opt, robot=rp)
+    prep = [tp.prepare_candidate(opt, rp, p, bv[0], ba[0], 16) for p in paths]
+    assert any(((q["piece_num"] + 1) // 2) % 2 == 1 for q in prep)    # an odd number of piece groups occurs
+    solver.evaluate(2, [q["piece_num"] for q in prep], [q["head_pva"] for q in prep], [q["tail_pva"] for q in prep],
+                    [q["start_xy"] for q in prep], [q["end_xy"] for q in prep], [q["init_inner_xy"] for q in prep],
+                    [q["x0"] for q in prep], alm_lambda=np.zeros((4, 2)), alm_rho=np.full((4, 2), 1e4))
+    buf = np.full(4 * 16 * 54, np.nan)
+    n = solver._l.topay_solver_debug_download(solver.h, 7, buf.ctypes.data_as(C.POINTER(C.c_double)), len(buf))
+    assert n == len(buf) and np.all(buf == 0.0)
