@@ -1,0 +1,5 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY: plain-struct stand-in for the ROS message.
+#pragma once
+#include <vector>
+#include "geometry_msgs/PoseStamped.h"
+namespace nav_msgs { struct Path { std_msgs::Header header; std::vector<geometry_msgs::PoseStamped> poses; }; }

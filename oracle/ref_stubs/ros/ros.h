@@ -16,31 +16,51 @@ struct Duration {
     explicit Duration(double v) : s(v) {}
     double toSec() const { return s; }
 };
+// test knobs (see oracle/ref_driver_full.cpp): a frozen clock and a per-thread budget of ros::ok() calls
+inline bool& stub_clock_frozen() {
+    static bool frozen = false;
+    return frozen;
+}
+inline int& stub_ok_budget() {
+    static thread_local int budget = -1;   // < 0: unlimited
+    return budget;
+}
 struct Time {
     double s = 0.0;
     static Time now() {
         Time t;
-        t.s = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        if (!stub_clock_frozen())
+            t.s = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
         return t;
     }
     double toSec() const { return s; }
     Duration operator-(const Time& o) const { return Duration(s - o.s); }
 };
-inline bool ok() { return true; }
+inline bool ok() {
+    int& b = stub_ok_budget();
+    if (b < 0) return true;
+    if (b == 0) return false;
+    b--;
+    return true;
+}
+inline void spinOnce() {}
 
 // parameter table: name -> list of doubles (scalars are one-element lists)
 inline std::map<std::string, std::vector<double>>& stub_params() {
     static std::map<std::string, std::vector<double>> t;
     return t;
 }
-template <class M>
 struct Publisher {
-    void publish(const M&) const {}
-};
-struct AnyPublisher {
     template <class M> void publish(const M&) const {}
     int getNumSubscribers() const { return 0; }
 };
+struct Subscriber {};
+struct Timer {};
+struct TimerEvent {};
+inline std::map<std::string, std::string>& stub_string_params() {
+    static std::map<std::string, std::string> t;
+    return t;
+}
 class NodeHandle {
 public:
     NodeHandle() {}
@@ -59,7 +79,12 @@ public:
         out.assign(it->second.begin(), it->second.end());
         return true;
     }
-    bool getParam(const std::string&, std::string&) const { return false; }
+    bool getParam(const std::string& name, std::string& out) const {
+        auto it = stub_string_params().find(name);
+        if (it == stub_string_params().end()) return false;
+        out = it->second;
+        return true;
+    }
     template <class T>
     bool param(const std::string& name, T& out, const T& dflt) const {
         if (getParam(name, out)) return true;
@@ -67,7 +92,11 @@ public:
         return false;
     }
     template <class M>
-    AnyPublisher advertise(const std::string&, int, bool = false) { return AnyPublisher(); }
+    Publisher advertise(const std::string&, int, bool = false) { return Publisher(); }
+    template <class... A>
+    Subscriber subscribe(const std::string&, int, A&&...) { return Subscriber(); }
+    template <class... A>
+    Timer createTimer(Duration, A&&...) { return Timer(); }
 };
 }  // namespace ros
 

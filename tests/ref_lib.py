@@ -99,3 +99,124 @@ def robot_constants():
     lib().ref_robot_constants(_p(cl), _p(cp), _p(cr), _p(lm, C.c_int), _p(lim), _p(jp), _p(rt), _p(rR), _p(cm, C.c_int))
     return dict(colli_length=cl, colli_points=cp, colli_radius=cr, link_map=lm, limits=lim, joint_pos_max=jp,
                 relative_t=rt, relative_R=rR.reshape(3, 3), collision_matrix=cm.reshape(12, 12))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's GridMap and MomaTrajOpt themselves (oracle/ref_driver_full.cpp)
+class RefSolveOut(C.Structure):
+    _fields_ = [("status", C.c_int32), ("piece_num", C.c_int32), ("cost", C.c_double), ("duration", C.c_double),
+                ("final_xy_err", C.c_double * 2)]
+
+
+class GridMap:
+    """nmoma_planner::GridMap (src/map), `use_rog: false`."""
+
+    def __init__(self, desc):
+        l = lib()
+        l.ref_grid_create.restype = C.c_void_p
+        self.desc = desc
+        self.h = C.c_void_p(l.ref_grid_create(C.byref(desc)))
+        d = (C.c_int32 * 3)()
+        l.ref_grid_dims(self.h, d)
+        self.dims = tuple(d)
+
+    def set_cloud(self, xyz, clear=1):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        lib().ref_grid_set_cloud(self.h, _p(xyz, C.c_float), C.c_int64(len(xyz)), clear)
+
+    def load_map(self, occ2d, occ3d):
+        occ2d, occ3d = np.ascontiguousarray(occ2d, dtype=np.int8), np.ascontiguousarray(occ3d, dtype=np.int8)
+        lib().ref_grid_load_map(self.h, _p(occ2d, C.c_int8), _p(occ3d, C.c_int8))
+
+    def download(self, which):
+        nx, ny, nz = self.dims
+        out = np.zeros((nx, ny, nz) if which == 3 else (nx, ny))
+        lib().ref_grid_download(self.h, which, _p(out))
+        return out
+
+    def download_occupancy(self, which):
+        nx, ny, nz = self.dims
+        out = np.zeros((nx, ny, nz) if which == 3 else (nx, ny), dtype=np.int8)
+        lib().ref_grid_download_occupancy(self.h, which, _p(out, C.c_int8))
+        return out
+
+    def query3d(self, pos):
+        pos = _f64(pos)
+        d, g = np.zeros(len(pos)), np.zeros((len(pos), 3))
+        lib().ref_grid_query3d(self.h, _p(pos), C.c_int64(len(pos)), _p(d), _p(g))
+        return d, g
+
+    def query2d(self, pos, which=0):
+        pos = _f64(pos)
+        d, g = np.zeros(len(pos)), np.zeros((len(pos), 2))
+        lib().ref_grid_query2d(self.h, _p(pos), C.c_int64(len(pos)), which, _p(d), _p(g))
+        return d, g
+
+    def distance3d(self, pos):
+        pos = _f64(pos)
+        d = np.zeros(len(pos))
+        lib().ref_grid_distance3d(self.h, _p(pos), C.c_int64(len(pos)), _p(d))
+        return d
+
+    def distance2d(self, pos):
+        pos = _f64(pos)
+        d = np.zeros(len(pos))
+        lib().ref_grid_distance2d(self.h, _p(pos), C.c_int64(len(pos)), _p(d))
+        return d
+
+    def whole_body_collision(self, states):
+        states = _f64(states)
+        out = np.zeros(len(states), dtype=np.int8)
+        lib().ref_grid_whole_body_collision(self.h, _p(states), C.c_int64(len(states)), _p(out, C.c_int8))
+        return out.astype(bool)
+
+
+class MomaTrajOpt:
+    """nmoma_planner::MomaTrajOpt (src/planner), parameters taken from a topay_opt_params."""
+
+    def __init__(self, grid: GridMap, opt):
+        l = lib()
+        l.ref_opt_create.restype = C.c_void_p
+        self.grid, self.opt = grid, opt
+        self.h = C.c_void_p(l.ref_opt_create(grid.h, C.byref(opt)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_opt_destroy(self.h)
+            self.h = None
+
+    def eval_one(self, stage, N, head, tail, sxy, exy, inner_xy, lam, rho, x):
+        from topay_b200._structs import NTERMS, num_vars
+        head, tail, sxy, exy, inner_xy, x, lam, rho = map(_f64, (head, tail, sxy, exy, inner_xy, x, lam, rho))
+        n = num_vars(N)
+        cost = C.c_double()
+        grad, terms, coeff, fxy = np.zeros(n), np.zeros(NTERMS), np.zeros((6 * N, 9)), np.zeros(2)
+        lib().ref_opt_eval(self.h, stage, N, _p(head), _p(tail), _p(sxy), _p(exy), _p(inner_xy), _p(lam), _p(rho),
+                           _p(x), C.byref(cost), _p(grad), _p(terms), _p(coeff), _p(fxy))
+        return cost.value, grad, terms, coeff, fxy
+
+    def solve_one(self, init_path, bvel, bacc, alm_max_rounds=20, wall_clock=False, max_pieces=64):
+        init_path, bvel, bacc = _f64(init_path), _f64(bvel), _f64(bacc)
+        out = RefSolveOut()
+        T, coeff = np.zeros(max_pieces), np.zeros((6 * max_pieces, 9))
+        lib().ref_opt_solve(self.h, _p(init_path), init_path.shape[0], _p(bvel), _p(bacc), alm_max_rounds,
+                            int(wall_clock), C.byref(out), _p(T), _p(coeff))
+        N = out.piece_num
+        return dict(status=out.status, piece_num=N, cost=out.cost, duration=out.duration,
+                    final_xy_err=np.array(out.final_xy_err[:]), T=T[:N].copy(), coeff=coeff[:6 * N].copy())
+
+    def gate(self):
+        a, b, d = C.c_int32(), C.c_int32(), C.c_double()
+        lib().ref_opt_gate(self.h, C.byref(a), C.byref(b), C.byref(d))
+        return bool(a.value), bool(b.value), d.value
+
+
+def solve_batch(grid: GridMap, opt, paths, bvel, bacc, n_threads, alm_max_rounds=20, wall_clock=False):
+    n = len(paths)
+    plen = np.array([p.shape[0] for p in paths], dtype=np.int32)
+    flat = _f64(np.concatenate(paths, axis=0))
+    bvel, bacc = _f64(bvel), _f64(bacc)
+    outs = (RefSolveOut * n)()
+    lib().ref_solve_batch(grid.h, C.byref(opt), n, _p(plen, C.c_int32), _p(flat), _p(bvel), _p(bacc), alm_max_rounds,
+                          int(wall_clock), n_threads, outs)
+    return [dict(status=o.status, piece_num=o.piece_num, cost=o.cost, duration=o.duration) for o in outs]

@@ -124,3 +124,112 @@ def test_lbfgs_bit_exact(oracle, case):
         assert r_ref == -997 or len(trace) == 7   # LBFGSERR_MAXIMUMITERATION
     if case == "ls_fail":
         assert r_ref == -1009 and len(trace) > 5   # LBFGSERR_MAXIMUMLINESEARCH after some accepted iterations
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's whole optimizer and map (moma_traj_opt.cpp, grid_map.cpp) against the oracle
+@pytest.fixture(scope="module")
+def ref_scene(oracle, small_scene):
+    g = R.GridMap(small_scene["desc"])
+    g.set_cloud(small_scene["points"])
+    return g
+
+
+def test_gridmap_buffers_bit_exact(oracle, small_scene, ref_scene):
+    """a20, a21, a22: cloudCallback rasterisation + updateESDF (grid_map.cpp:543-578, 89-521): occupancy and all four
+    signed ESDF buffers (flat, inflated, critical, 3-D) of the default 200 x 200 x 16 scene."""
+    of = small_scene["field"]
+    for which in (0, 2, 3):
+        assert np.array_equal(ref_scene.download_occupancy(which), of.download_occupancy(which)), which
+    for which in range(4):
+        assert np.array_equal(ref_scene.download(which), of.download(which)), which
+
+
+@pytest.mark.parametrize("size,res", [((3.1, 2.3, 0.9), 0.1), ((1.0, 1.0, 0.5), 0.25), ((6.0, 4.0, 1.2), 0.2)])
+def test_gridmap_ragged_grids_bit_exact(oracle, size, res):
+    """a20/a21 on small ragged grids incl. the accumulate-critical quirk (grid_map.cpp:719-722) over two scenes."""
+    from topay_b200._structs import grid_desc
+    d = grid_desc(map_size=size, resolution=res)
+    g, of = R.GridMap(d), oracle.Field(d)
+    rng = np.random.default_rng(int(size[0] * 10))
+    for scene in range(2):
+        pts = (rng.uniform(-0.5, 0.5, (60, 3)) * np.array(size) + np.array([0, 0, size[2] / 2])).astype(np.float32)
+        g.set_cloud(pts, clear=1)
+        of.clear(False)
+        of.rasterize(pts)
+        of.rebuild()
+        for which in range(4):
+            assert np.array_equal(g.download(which), of.download(which)), (scene, which)
+
+
+def test_gridmap_queries_bit_exact(oracle, small_scene, ref_scene):
+    """a17, a18, a19: getDisWithGradI2d/3d, getDistance2d/3d, isWholeBodyCollision (grid_map.h:256-725), incl.
+    positions outside the map and on its border."""
+    of = small_scene["field"]
+    rng = np.random.default_rng(0)
+    q = np.concatenate([rng.uniform(-10.5, 10.5, (20000, 2)), rng.uniform(-0.2, 1.8, (20000, 1))], axis=1)
+    q[:50, 0] = 10.0 - 1e-4 * np.arange(50) / 25
+    for a, b in zip(ref_scene.query3d(q), of.query3d(q)):
+        assert np.array_equal(a, b)
+    for which in range(3):
+        for a, b in zip(ref_scene.query2d(q[:, :2], which), of.query2d(q[:, :2], which)):
+            assert np.array_equal(a, b), which
+    assert np.array_equal(ref_scene.distance3d(q), of.distance3d(q))
+    assert np.array_equal(ref_scene.distance2d(q[:, :2]), of.distance2d(q[:, :2]))
+    rp = oracle.robot_defaults()
+    st = np.concatenate([rng.uniform(-9, 9, (3000, 2)), rng.uniform(-np.pi, np.pi, (3000, 1)), rng.uniform(-2, 2, (3000, 7))], axis=1)
+    assert np.array_equal(ref_scene.whole_body_collision(st), of.whole_body_collision(rp, st))
+
+
+@pytest.mark.parametrize("int_K,pieces", [(12, 0), (5, 0), (32, 64)])
+def test_cost_callbacks_bit_exact(oracle, small_scene, ref_scene, int_K, pieces):
+    """a2, a6, a7, a12: first/secondStageCostCallback (moma_traj_opt.cpp:817-955) = generate + jerk + the penalty loops
+    (:957-1829) + calGradCTtoQT + the C2 maps: cost, gradient and coefficients IDENTICAL; stage 2 also the 13 per-term
+    costs and final_xy_error. (Stage 1 never resets the reference's debug terms, so they are not compared there.)"""
+    from topay_b200 import scenes
+    of = small_scene["field"]
+    opt, rp = oracle.opt_defaults(), oracle.robot_defaults()
+    opt.int_K = int_K
+    if pieces:
+        opt.min_piece_num, opt.sample_interval = pieces, 1e9
+        paths, bv, ba = scenes.synthetic_batch(2, 1234)
+    else:
+        paths, bv, ba = scenes.short_candidates(4, 7)
+    ro = R.MomaTrajOpt(ref_scene, opt)
+    rng = np.random.default_rng(3)
+    for c, p in enumerate(paths):
+        q = oracle.prepare_candidate(opt, rp, p, bv[c], ba[c], 64)
+        N = q["piece_num"]
+        for x in (q["x0"], q["x0"] + 0.05 * rng.normal(size=len(q["x0"]))):
+            for stage in (1, 2):
+                lam, rho = np.array([0.3, -0.2]), np.array([1e4, 3e4])
+                args = (stage, N, q["head_pva"], q["tail_pva"], q["start_xy"], q["end_xy"], q["init_inner_xy"][:N], lam, rho, x)
+                f_r, g_r, t_r, c_r, e_r = ro.eval_one(*args)
+                f_o, g_o, t_o, c_o, e_o = oracle.eval_one(opt, rp, of, *args)
+                assert f_r == f_o and np.array_equal(g_r, g_o) and np.array_equal(c_r, c_o), (c, stage)
+                if stage == 2:
+                    assert np.array_equal(t_r, t_o) and np.array_equal(e_r, e_o)
+
+
+def test_optimize_traj_bit_exact(oracle, small_scene, ref_scene):
+    """a1, a13-a16 + N1: MomaTrajOpt::optimizeTraj (moma_traj_opt.cpp:142-498) end to end — pre-processing, stage 1,
+    the ALM loop — then getTraj / checkFeasible / printConstraintsSituations: same status, and the final cost,
+    durations and all 6N x 9 coefficients IDENTICAL to the oracle's; same gate verdicts. The reference's 1.0 s wall
+    clock is frozen and ros::ok() carries the deterministic round cap (oracle/ref_driver_full.cpp)."""
+    from topay_b200 import scenes
+    of = small_scene["field"]
+    opt, rp = oracle.opt_defaults(), oracle.robot_defaults()
+    paths, bv, ba = scenes.short_candidates(4, 7)
+    ro = R.MomaTrajOpt(ref_scene, opt)
+    for c, p in enumerate(paths):
+        a = ro.solve_one(p, bv[c], ba[c], alm_max_rounds=opt.alm_max_rounds)
+        b = oracle.solve_one(opt, rp, of, p, bv[c], ba[c], max_pieces=16)
+        assert a["status"] == b["status"] and a["piece_num"] == b["piece_num"]
+        assert a["cost"] == b["cost"] and np.array_equal(a["T"], b["T"]) and np.array_equal(a["coeff"], b["coeff"])
+        assert np.array_equal(a["final_xy_err"], b["final_xy_err"])
+        chk, prt, dur = ro.gate()
+        N = b["piece_num"]
+        start = np.array([p[0][0], p[0][1], p[0][2]])
+        g = oracle.check_feasible(of, rp, [(b["T"], b["coeff"], start)])
+        assert bool(g["feasible"][0]) == chk and bool(g["feasible_print"][0]) == prt
+        assert abs(g["total_duration"][0] - dur) <= 1e-12 * dur if "total_duration" in g else True
