@@ -65,6 +65,8 @@ class NodeHandle {
 public:
     NodeHandle() {}
     explicit NodeHandle(const std::string&) {}
+    std::string getNamespace() const { return ""; }
+    bool hasParam(const std::string& name) const { return stub_params().count(name) || stub_string_params().count(name); }
     template <class T>
     bool getParam(const std::string& name, T& out) const {
         auto it = stub_params().find(name);

@@ -220,3 +220,71 @@ def solve_batch(grid: GridMap, opt, paths, bvel, bacc, n_threads, alm_max_rounds
     lib().ref_solve_batch(grid.h, C.byref(opt), n, _p(plen, C.c_int32), _p(flat), _p(bvel), _p(bacc), alm_max_rounds,
                           int(wall_clock), n_threads, outs)
     return [dict(status=o.status, piece_num=o.piece_num, cost=o.cost, duration=o.duration) for o in outs]
+
+
+class RogESDFMap:
+    """rog_map::ESDFMap itself (oracle/ref_driver_rog.cpp); same surface as oracle_lib.RogField."""
+
+    def __init__(self, desc):
+        l = lib()
+        l.ref_rog_create.restype = C.c_void_p
+        self.h = C.c_void_p(l.ref_rog_create(C.byref(desc)))
+        g = self._geometry()
+        self.half, self.size, self.half_box, self.resolution = g[0], g[1], g[3], g[4]
+
+    def _geometry(self):
+        half, size, org, hb = ((C.c_int32 * 3)() for _ in range(4))
+        res = C.c_double()
+        lib().ref_rog_geometry(self.h, half, size, C.byref(res), org, hb)
+        return tuple(half), tuple(size), tuple(org), tuple(hb), res.value
+
+    @property
+    def origin_i(self):
+        return self._geometry()[2]
+
+    def slide(self, odom):
+        o = _f64(odom)
+        lib().ref_rog_slide(self.h, _p(o))
+
+    def update_counters(self, pos, from_type, to_type):
+        pos = _f64(pos)
+        a = np.ascontiguousarray(from_type, dtype=np.uint8)
+        b = np.ascontiguousarray(to_type, dtype=np.uint8)
+        lib().ref_rog_update_counters(self.h, _p(pos), _p(a, C.c_uint8), _p(b, C.c_uint8), C.c_int64(pos.shape[0]))
+
+    def set_occupied_cnt(self, cnt):
+        cnt = np.ascontiguousarray(cnt, dtype=np.int16)
+        lib().ref_rog_set_occupied_cnt(self.h, _p(cnt, C.c_int16))
+
+    def download_counters(self):
+        a, b = np.empty(self.size, dtype=np.int16), np.empty(self.size, dtype=np.int16)
+        lib().ref_rog_download_counters(self.h, _p(a, C.c_int16), _p(b, C.c_int16))
+        return a, b
+
+    def update_esdf(self, odom):
+        o = _f64(odom)
+        lib().ref_rog_update_esdf(self.h, _p(o))
+
+    def query(self, kind, pos):
+        pos = _f64(pos)
+        n = pos.shape[0]
+        d, g = np.empty(n), np.zeros((n, 3))
+        lib().ref_rog_query(self.h, kind, _p(pos), C.c_int64(n), _p(d), _p(g))
+        return d, g
+
+    def evaluate_edt(self, pos):
+        pos = _f64(pos)
+        d = np.empty(pos.shape[0])
+        lib().ref_rog_evaluate_edt(self.h, _p(pos), C.c_int64(pos.shape[0]), _p(d), None)
+        return d
+
+    def is_line_free2d(self, start, end, threshold=0.0):
+        s, e = _f64(start), _f64(end)
+        out = np.empty(s.shape[0], dtype=np.int8)
+        lib().ref_rog_is_line_free2d(self.h, _p(s), _p(e), C.c_int64(s.shape[0]), C.c_double(threshold), _p(out, C.c_int8))
+        return out
+
+    def download(self, which):
+        out = np.empty(self.size if which < 2 else self.size[:2])
+        lib().ref_rog_download(self.h, which, _p(out))
+        return out

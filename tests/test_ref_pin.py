@@ -233,3 +233,45 @@ def test_optimize_traj_bit_exact(oracle, small_scene, ref_scene):
         g = oracle.check_feasible(of, rp, [(b["T"], b["coeff"], start)])
         assert bool(g["feasible"][0]) == chk and bool(g["feasible_print"][0]) == prt
         assert abs(g["total_duration"][0] - dur) <= 1e-12 * dur if "total_duration" in g else True
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's ROG-Map ESDF layer (esdf_map.cpp, counter_map.cpp, sliding_map.cpp, raycaster.cpp)
+@pytest.mark.parametrize("half,box", [((26, 26, 9), (4.0, 4.0, 1.5)), ((12, 12, 5), (9.0, 9.0, 9.0))])
+def test_rog_esdf_layer_bit_exact(oracle, half, box):
+    """a23, a24, N3 (ESDF side): mapSliding, updateGridCounter, updateESDF3D with the ring-wrapped fillESDF, the six
+    lookups and evaluateEDT over a sequence of slides that wraps every axis, clipped and full update boxes, cells
+    seen free again — counters, the four persistent buffers (distance_buffer, tmp_buffer1_, critical, flat) and every
+    query IDENTICAL to the reference's own classes. (Square rings: on non-square rings the reference's 2-D combine
+    walks y over the x bounds, esdf_map.cpp:398-405, i.e. out of the row — the oracle clips it, a stated deviation.)"""
+    from topay_b200._structs import rog_desc
+    d = rog_desc(half_prob_map_size_i=half, prob_resolution=0.1, esdf_resolution=0.1, local_update_box=box,
+                 map_sliding_en=True)
+    ref, orc = R.RogESDFMap(d), oracle.RogField(d)
+    assert (ref.size, ref.half, ref.half_box, ref.resolution) == (orc.size, orc.half, orc.half_box, orc.resolution)
+    rng = np.random.default_rng(half[0])
+    ext = np.array(half) * 0.1 * 0.8
+    for step, odom in enumerate([(0.0, 0.0, 0.0), (0.43, -0.31, 0.12), (0.9, -0.7, 0.2), (-0.3, 0.4, -0.1), (2.5, 1.9, 0.5)]):
+        for m in (ref, orc):
+            m.slide(odom)
+        assert ref.origin_i == orc.origin_i
+        hits = rng.uniform(-1, 1, (300, 3)) * ext + np.array(odom)
+        for m in (ref, orc):
+            m.update_counters(hits, np.full(300, 1), np.full(300, 3))      # UNKNOWN -> OCCUPIED
+            if step == 2:
+                m.update_counters(hits[:100], np.full(100, 3), np.full(100, 4))   # OCCUPIED -> KNOWN_FREE
+        for a, b in zip(ref.download_counters(), orc.download_counters()):
+            assert np.array_equal(a, b)
+        for m in (ref, orc):
+            m.update_esdf(odom)
+        for which in range(4):
+            assert np.array_equal(ref.download(which), orc.download(which)), (step, which)
+        q = rng.uniform(-1, 1, (2000, 3)) * ext + np.array(odom)
+        for kind in range(6):
+            for a, b in zip(ref.query(kind, q), orc.query(kind, q)):
+                assert np.array_equal(a, b), (step, kind)
+        assert np.array_equal(ref.evaluate_edt(q), orc.evaluate_edt(q))
+        # isLineFree2d (esdf_map.cpp:122-152) on short rays
+        s2 = rng.uniform(-1, 1, (200, 2)) * ext[:2] * 0.8 + np.array(odom[:2])
+        e2 = s2 + rng.uniform(-0.6, 0.6, (200, 2))
+        assert np.array_equal(ref.is_line_free2d(s2, e2, 0.05), orc.is_line_free2d(s2, e2, 0.05))
