@@ -31,7 +31,6 @@ N_CAND, N_PIECES, INT_K = 256, 64, 32
 NODE_BYTES = 800          # algorithmic ESDF bytes per penalty node, SURVEY.md §8(d)
 NODE_FLOP = 4.0e3         # algorithmic fp64 flop per penalty node, SURVEY.md §8(d)
 MID_FLOP = 0.15e3         # ... per Simpson midpoint node
-K_CAND_DRAM_BYTES = 719.6e6  # dram__bytes_read+write of one mid-solve k_cand launch at 256 candidates (profiles/r01_summary.md)
 
 
 def workload_params(tp):
@@ -349,13 +348,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="topay_b200", choices=["topay_b200", "reference"])
-    ap.add_argument("--candidates", type=int, default=N_CAND, help="candidates per GPU (dev only; bench = 256)")
+    ap.add_argument("--candidates", type=int, default=N_CAND, help="candidates per plan (dev only; bench = 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (dev only)")
     ap.add_argument("--no-extras", action="store_true", help="skip the latency and field sub-benchmarks")
-    ap.add_argument("--plans", type=int, default=8,
-                    help="plans (256-candidate batches) in flight per GPU, each on its own stream")
+    ap.add_argument("--slots", type=int, default=1024,
+                    help="candidates in flight on the device (continuous batching: a finished candidate's slot is "
+                         "refilled from the queue of waiting plans on the device)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -371,160 +371,154 @@ def main():
     pts, _ = scenes.cuboids_scene(42)
     gm = tp.GridMap(desc, device=local)
     gm.regenerateMap(pts)
-    P = max(1, min(args.plans, args.steps))
-    # P independent plans in flight per GPU: each has its own solver (device state + stream) and is
-    # driven by its own host thread; the K timed steps are dealt round-robin to the P slots.
-    # Weak scaling = identical work per GPU: every rank solves the same P plans, rotated by its rank so the
-    # ranks are not in lock-step. (With per-rank random scenarios the chaotic iteration counts make the
-    # per-rank work differ by ~5 %, which measures the draw, not the scaling: 94.5 % at 4 GPUs.)
-    batches = [scenes.synthetic_batch(n_cand, 1234 + 1000 * ((p + rank) % P)) for p in range(P)]
-    paths, bv, ba = batches[0]
-    solvers = [tp.MomaTrajOpt(gm, max_cand=n_cand, max_pieces=N_PIECES, opt_param=opt, robot=rp) for _ in range(P)]
-    # throughput region: every slot replays its ticks as CUDA graphs. The roofline of the dominant
-    # kernel is measured right after it, live, with CUDA events around every k_penalty launch of one
-    # plan running alone (under 8-way concurrency a launch's duration says nothing about the kernel).
+    K, W = max(args.steps, 1), max(args.warmup, 0)
+    # One step = one plan of 256 candidates. Every rank owns DISTINCT plans (seeded by rank and step): candidates
+    # and plans are independent, so they shard with no data-path collective (weak scaling: K plans per GPU). The
+    # K plans of a rank are queued on its device and stream through a fixed pool of candidate slots.
+    plans = [scenes.synthetic_batch(n_cand, 1234 + 1000 * (rank * K + p)) for p in range(K)]
+    paths, bv, ba = plans[0]
+    n_slots = max(1, min(args.slots, K * n_cand))
+    solver = tp.MomaTrajOpt(gm, max_cand=K * n_cand, max_pieces=N_PIECES, opt_param=opt, robot=rp, n_slots=n_slots)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
-    import threading
 
-    def run_steps(n_steps, fn):
-        """n_steps calls of fn(slot), dealt to P threads; returns when all are done."""
-        errs = []
+    def cat(pl):
+        return ([q for p in pl for q in p[0]], np.concatenate([p[1] for p in pl]), np.concatenate([p[2] for p in pl]))
 
-        def work(slot):
-            try:
-                for _ in range(slot, n_steps, P):
-                    fn(slot)
-            except Exception as e:      # surface worker failures in the main thread
-                errs.append(e)
-        th = [threading.Thread(target=work, args=(p,)) for p in range(P)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        if errs:
-            raise errs[0]
-
-    # ---- resident arm: candidates pre-processed and uploaded once, K timed device solves
-    for p in range(P):
-        solvers[p].upload(*batches[p])
-    acc = {"launches": 0, "ticks": 0, "evals_launch": 0, "nodes": 0, "ms_eval": 0.0, "ms_dev": 0.0}
-    lock = threading.Lock()
-
-    def resident_step(slot):
-        solvers[slot].run()
-        st = solvers[slot].stats()
-        with lock:
-            acc["launches"] += st["kernel_launches"]
-            acc["ticks"] += st["ticks"]
-            acc["ms_dev"] += st["ms_total"]
-
-    run_steps(max(args.warmup, 0), lambda slot: solvers[slot].run())
+    # ---- warm-up: W plans through the pool (graphs instantiated, clocks up)
+    if W > 0:
+        solver.upload(*cat([plans[i % K] for i in range(W)]))
+        solver.run()
+    # ---- resident arm: the K plans pre-processed and uploaded once, one timed device solve of all of them
+    solver.upload(*cat(plans))
     torch.cuda.synchronize()
     barrier_max(dist, local, 0.0)
     sampler = ClockSampler(local) if rank == 0 else None
     flush.zero_()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    run_steps(args.steps, resident_step)
+    solver.run()
     torch.cuda.synchronize()
     dt = barrier_max(dist, local, time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
-    res = solvers[0].download()
+    st_run = solver.stats()
+    res = solver.download()
     n_ok = int(res["status"].sum())
-    launches, ticks, ms_dev = acc["launches"], acc["ticks"], acc["ms_dev"]
+    evals_total = int(res["evals"].sum())
 
-    # ---- roofline pass: one plan alone, plain launches, CUDA events around every kernel launch
-    solvers[0].set_timed(True)
-    flush.zero_()
-    solvers[0].run()
-    rst = solvers[0].stats()
-    solvers[0].set_timed(False)
-    evals_launch, nodes, ms_eval = rst["eval_launches"], rst["eval_nodes"], rst["ms_eval"]
-
-    # ---- end-to-end arm: host buffers in, host results out, through the public API every step
+    # ---- end-to-end arm: host buffers in, host results out, through the public API (pre-processing, H2D of the
+    # problems, the solve, D2H of every candidate's result and the per-plan winners inside the timed region)
     barrier_max(dist, local, 0.0)
     flush.zero_()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    run_steps(args.steps, lambda slot: solvers[slot].optimizeTrajBatch(*batches[slot]))
+    r_e2e = solver.optimizeTrajPlans(plans)
     torch.cuda.synchronize()
     dt_e2e = barrier_max(dist, local, time.perf_counter() - t0)
-    solver = solvers[0]
+    h2d, d2h = solver.h2d_bytes, solver.d2h_bytes
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    total = n_cand * world
-    value = total * args.steps / dt
+
+    # ---- roofline pass (rank 0, after the timed regions): the same pool on 4 plans with plain launches and CUDA
+    # events around every kernel launch -> live per-kernel device time, averaged over the launches of the pass
+    kr = min(K, 4)
+    solver.upload(*cat(plans[:kr]))
+    solver.set_timed(True)
+    flush.zero_()
+    solver.run()
+    rst = solver.stats()
+    solver.set_timed(False)
+    # one plan alone (256 candidates, no refill): the tail-bound figure
+    solver.upload(*plans[0])
+    solver.run()
+    t0 = time.perf_counter()
+    solver.run()
+    dt_single = time.perf_counter() - t0
+    st_single = solver.stats()
+
+    total = n_cand * K * world
+    value = total / dt
     peak, peak_src = measured_peaks()
-    # Live device time per kernel over the roofline pass. The dominant one is k_cand (adjoint solves,
-    # L-BFGS two-loop, banded LU): its algorithmic traffic is the L-BFGS history the two-loop
-    # recursions walk, 2 loops x bound rows x (s_j, y_j) x n x 8 B, counted on the device.
     ticks_r = max(rst["ticks"], 1)
-    k_ms = {"k_cand": rst["ms_cand"], "k_penalty": rst["ms_eval"], "k_chain": rst["ms_chain"],
-            "k_integrate": rst["ms_integrate"]}
+    k_ms = {"k_penalty": rst["ms_eval"], "k_cand<lbfgs>": rst["ms_lbfgs"], "k_cand<generate>": rst["ms_gen"],
+            "k_cand<adjoint>": rst["ms_adj"], "k_chain": rst["ms_chain"], "k_integrate": rst["ms_integrate"]}
     k_sum = max(sum(k_ms.values()), 1e-9)
-    cand_ms = max(rst["ms_cand"] / ticks_r, 1e-9)
-    cand_bytes = rst["hist_bytes"] / ticks_r
-    cand_achieved = cand_bytes / (cand_ms * 1e-3) / 1e9
-    # second kernel: k_penalty (ESDF gathers + FK + penalties, one lane per sample node)
-    pen_ms = ms_eval / max(evals_launch, 1)
-    nodes_per_launch = nodes / max(evals_launch, 1)
-    alg_bytes = nodes_per_launch * NODE_BYTES
-    pen_ms = max(pen_ms, 1e-9)
-    achieved = alg_bytes / (pen_ms * 1e-3) / 1e9
-    mids_per_launch = nodes_per_launch * INT_K / (INT_K + 1)
-    flop = nodes_per_launch * NODE_FLOP + mids_per_launch * MID_FLOP
+    shares = {k: v / k_sum for k, v in k_ms.items()}
+    live_avg = rst["slot_ticks"] / ticks_r
+    # k_cand<lbfgs>: algorithmic bytes = the L-BFGS history the two-loop recursions walk, counted on the device
+    lb_ms = max(rst["ms_lbfgs"] / ticks_r, 1e-9)
+    lb_bytes = rst["hist_bytes"] / ticks_r
+    lb_achieved = lb_bytes / (lb_ms * 1e-3) / 1e9
+    # k_penalty: 800 B of ESDF taps and 4.0 kflop per penalty node
+    pen_ms = max(rst["ms_eval"] / ticks_r, 1e-9)
+    nodes_per_launch = rst["eval_nodes"] / ticks_r
+    pen_bytes = nodes_per_launch * NODE_BYTES
+    pen_achieved = pen_bytes / (pen_ms * 1e-3) / 1e9
+    flop = nodes_per_launch * NODE_FLOP + nodes_per_launch * INT_K / (INT_K + 1) * MID_FLOP
+    roof_pen = {"bound": "hbm", "kernel": "k_penalty", "achieved": pen_achieved, "peak": peak, "unit": "GB/s",
+                "frac": pen_achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": pen_ms, "nodes_per_launch": nodes_per_launch,
+                "algorithmic_bytes_per_launch": pen_bytes,
+                "algorithmic_bytes": "800 B of ESDF taps per penalty node (12 x 3-D + 1 x 2-D lookups, SURVEY §8d) x the "
+                                     "nodes of the live candidates of a launch; the 5 MB field is L2-resident, so the "
+                                     "kernel is FP64-issue bound, not HBM bound (see fp64)",
+                "share_of_step": shares["k_penalty"],
+                "fp64": {"achieved_tflops": flop / (pen_ms * 1e-3) / 1e12, "nominal_peak_tflops": 40.0,
+                         "note": "4.0 kflop per penalty node + 0.15 kflop per midpoint (SURVEY §8d); MEASURED_PEAKS.json "
+                                 "has no FP64 figure, 40 TFLOP/s is the nominal B200 FP64 rate"}}
+    roof_lb = {"bound": "hbm", "kernel": "k_cand<lbfgs>", "achieved": lb_achieved, "peak": peak, "unit": "GB/s",
+               "frac": lb_achieved / peak, "traffic": None, "peak_source": peak_src, "avg_launch_ms": lb_ms,
+               "algorithmic_bytes_per_launch": lb_bytes,
+               "algorithmic_bytes": "L-BFGS history walked by the two-loop recursions: 2 loops x bound rows x (s_j, y_j) "
+                                    "x n x 8 B per accepted iteration (5.2 MB at m = 256, n = 632), counted on the device; "
+                                    "candidates in a line-search trial stream nothing",
+               "share_of_step": shares["k_cand<lbfgs>"]}
+    dominant = max(shares, key=shares.get)
+    roofline = dict(roof_pen if dominant == "k_penalty" else roof_lb)
+    roofline["kernel_shares"] = shares
+    roofline["measured_on"] = (f"{kr} plans ({kr * n_cand} candidates) through the same {n_slots}-slot pool right after the "
+                               f"timed regions, plain launches with CUDA events around every kernel launch; averages over "
+                               f"all {rst['ticks']} ticks of the pass ({live_avg:.0f} live candidates per launch on average)")
     line = {
         "metric": "optimized trajectories/sec at 256 candidates", "value": value, "unit": "trajectories/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"synthetic {n_cand}-candidate batch per GPU, {N_PIECES} pieces x int_K {INT_K}, "
                                f"cuboids scene 200x200x16 @0.1 m (BASELINE configs[2])",
                    "candidates_per_gpu": n_cand, "pieces": N_PIECES, "int_K": INT_K, "variables": 10 * N_PIECES - 8,
-                   "plans_in_flight": P,
-                   "l2": "working set larger than L2: the L-BFGS history alone is 665 MB per plan in flight "
-                         "(126 MB L2); a 512 MiB buffer is rewritten before the timed region",
-                   "successes_last_step": n_ok},
-        "e2e": {"value": total * args.steps / dt_e2e, "unit": "trajectories/s",
-                "h2d_bytes_per_step": solver.h2d_bytes, "d2h_bytes_per_step": solver.d2h_bytes},
-        "gpu_launches": int(launches),
-        "device_ms_per_step": ms_dev / args.steps, "ticks_per_step": ticks / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "k_cand", "achieved": cand_achieved, "peak": peak, "unit": "GB/s",
-                     "frac": cand_achieved / peak, "traffic": K_CAND_DRAM_BYTES, "peak_source": peak_src,
-                     "traffic_source": "ncu --set full, dram__bytes_read+write of one mid-solve launch at 256 "
-                                       "candidates (profiles/r01_summary.md)",
-                     "avg_launch_ms": cand_ms, "algorithmic_bytes_per_launch": cand_bytes,
-                     "algorithmic_bytes": "L-BFGS history walked by the two-loop recursions: 2 loops x bound "
-                                          "rows x (s_j, y_j) x n x 8 B per accepted iteration (5.2 MB at m = 256, "
-                                          "n = 632), counted on the device; launches without an accepted "
-                                          "iteration (line-search trials) stream nothing",
-                     "measured_on": "one 256-candidate plan running alone right after the timed region, plain "
-                                    "launches with CUDA events around every kernel launch; averages include the "
-                                    "plan's low-activity tail",
-                     "share_of_step": rst["ms_cand"] / max(rst["ms_total"], 1e-9),
-                     "full_activity": {"ticks": rst["full_ticks"],
-                                       "achieved": rst["full_hist_bytes"] / max(rst["full_ms_cand"], 1e-9) / 1e6,
-                                       "frac": rst["full_hist_bytes"] / max(rst["full_ms_cand"], 1e-9) / 1e6 / peak,
-                                       "avg_launch_ms": rst["full_ms_cand"] / max(rst["full_ticks"], 1),
-                                       "note": "same figures over the tick batches in which all candidates "
-                                               "were still solving"},
-                     "kernel_shares": {k: v / k_sum for k, v in k_ms.items()}},
-        "roofline_k_penalty": {"bound": "hbm", "kernel": "k_penalty", "achieved": achieved, "peak": peak,
-                               "unit": "GB/s", "frac": achieved / peak, "traffic": 19.9e6,
-                               "traffic_source": "ncu --set full at 256 candidates: the 5 MB field is served from "
-                                                 "L1/L2", "avg_launch_ms": pen_ms,
-                               "nodes_per_launch": nodes_per_launch,
-                               "share_of_step": ms_eval / max(rst["ms_total"], 1e-9),
-                               "fp64": {"achieved_tflops": flop / (pen_ms * 1e-3) / 1e12, "nominal_peak_tflops": 40.0,
-                                        "note": "FP64-pipe/latency bound, not HBM bound: 4.0 kflop per penalty "
-                                                "node against 800 algorithmic bytes"}},
+                   "scheduling": f"continuous batching: the K plans of a rank ({K} x {n_cand} candidates, distinct per "
+                                 f"rank and step) are queued on the device and stream through {n_slots} candidate slots; "
+                                 f"a finished candidate's slot takes the next waiting candidate inside the kernel",
+                   "slots": n_slots,
+                   "l2": "working set larger than L2: the L-BFGS history is 2.6 MB per slot (2.7 GB at 1024 slots, "
+                         "126 MB L2); a 512 MiB buffer is rewritten before each timed region",
+                   "successes": n_ok},
+        "e2e": {"value": total / dt_e2e, "unit": "trajectories/s", "h2d_bytes_per_step": h2d // K,
+                "d2h_bytes_per_step": d2h // K,
+                "api": "MomaTrajOpt.optimizeTrajPlans(plans): host waypoints -> pre-processing -> pinned H2D -> device "
+                       "solve -> D2H of every candidate's status / cost / durations / coefficients + per-plan winners"},
+        "gpu_launches": int(st_run["kernel_launches"]),
+        "device_ms_per_step": st_run["ms_total"] / K, "ticks": int(st_run["ticks"]),
+        "slot_utilisation": evals_total / max(st_run["slot_ticks"], 1),
+        "evals_per_candidate": evals_total / max(n_cand * K, 1),
+        "us_per_evaluation": 1e3 * st_run["ms_total"] / max(evals_total, 1),
+        "single_plan": {"value": n_cand / dt_single, "unit": "trajectories/s", "ms": dt_single * 1e3,
+                        "ticks": int(st_single["ticks"]),
+                        "note": "one 256-candidate plan alone on the device (no other plan to refill from): bound by "
+                                "its slowest candidate"},
+        "roofline": roofline,
+        "roofline_k_penalty": roof_pen,
+        "roofline_k_lbfgs": roof_lb,
         "clocks": clocks,
     }
     if not args.no_extras and world == 1:     # single-GPU diagnostics; the scaling runs stay short
         line["latency"] = latency_probe(tp, scenes, gm)
         line["field"] = field_probe(tp, scenes, local, peak)
+        solver.upload(*plans[0])
+        solver.run()
+        solver.download()
         line["subpaths"] = subpath_probe(tp, scenes, local, peak, solver, gm, rp, not args.no_cpu_baseline)
     if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only
         cores = os.cpu_count() or 1

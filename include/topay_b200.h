@@ -68,7 +68,10 @@ enum {
     TOPAY_LBFGSERR_MAXIMUMITERATION = -1008,
     TOPAY_LBFGSERR_WIDTHTOOSMALL = -1007,
     TOPAY_LBFGSERR_INVALIDPARAMETERS = -1006,
-    TOPAY_LBFGSERR_INCREASEGRADIENT = -1005
+    TOPAY_LBFGSERR_INCREASEGRADIENT = -1005,
+    /* not a reference code: the device solve stopped this candidate at its hard cap on evaluations
+     * (topay_solver_run); the candidate comes back with status 0 */
+    TOPAY_LBFGSERR_TICK_CAP = -2000
 };
 
 /* ------------------------------------------------------------------ params */
@@ -356,6 +359,16 @@ int topay_solver_create(const topay_opt_params* opt, const topay_robot_params* r
  * (grid_map.h:256-267, 307-322, 364-392, 443-461). */
 int topay_solver_create_rog(const topay_opt_params* opt, const topay_robot_params* robot,
                             topay_rogfield* rog, int max_cand, int max_pieces, topay_solver** out);
+/* Continuous batching: an upload may hold up to max_cand candidates (several plans back to back) while only
+ * n_slots of them are in flight on the device; the moment a candidate reaches a terminal state its slot takes
+ * the next waiting one, on the device, so every tick runs over live candidates only. This is the worker pool
+ * of planner.cpp:921-952 (a fixed number of workers, each taking the next candidate when it is done) with the
+ * queue on the GPU. topay_solver_create(max_cand) == topay_solver_create_pool(max_cand, n_slots = max_cand).
+ * Device memory: n_slots x 2 x mem_size x (10 max_pieces - 8) x 8 B of L-BFGS history (2.6 MB per slot at
+ * 64 pieces) + 30 KB of results per stored candidate. */
+int topay_solver_create_pool(const topay_opt_params* opt, const topay_robot_params* robot,
+                             topay_field* field, int max_cand, int n_slots, int max_pieces,
+                             topay_solver** out);
 void topay_solver_destroy(topay_solver* s);
 
 /* The fixed data of each candidate's NLP, i.e. what optimizeTraj derives before it
@@ -455,6 +468,11 @@ typedef struct topay_solver_stats {
     int64_t full_hist_bytes;
     float   full_ms_cand;
     float   pad2_;
+    int64_t slot_ticks;        /* live slots summed over the ticks: the evaluations the launches were sized for;
+                                * evals_total / slot_ticks = slot utilisation */
+    float   ms_adj, ms_lbfgs, ms_gen;   /* timed mode only: the three per-candidate launches that make up ms_cand;
+                                         * full_ms_cand is the L-BFGS launch alone */
+    float   pad3_;
 } topay_solver_stats;
 int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out);
 /* The worker's success gate on the device, straight from the solver's result buffers
@@ -479,6 +497,16 @@ int topay_solver_phase_clocks(topay_solver* s, int enable, long long* out16);
 /* Developer aid: raw copy of an intermediate device array of the last topay_solver_eval (bit-level A/B
  * runs). which: 0 gnode, 1 gsum, 2 gdC, 3 gdT, 4 tot, 5 Ixy, 6 g. Returns the doubles written or a status. */
 int64_t topay_solver_debug_download(topay_solver* s, int which, double* out, int64_t cap);
+
+/* Parity hook for the L-BFGS direction update (lbfgs.hpp:657-710): loads a history into the first slot and runs
+ * ONE launch of the L-BFGS kernel in which the line search is accepted, the pair (s, y) = (x - xp, g - gp) enters
+ * the ring at slot `end`, and the two-loop recursion over min(bound + 1, m) pairs produces the next search
+ * direction d_out[n_vars]. S_rows / Y_rows are [m][n_vars] (row j = pair j of the ring, m = the stage-2 mem_size),
+ * ys is [m]; bound pairs are valid, the newest at (end - 1) mod m. Every y_j . s_j must be positive. */
+int topay_solver_debug_direction(topay_solver* s, int n_vars, int bound, int end, const double* S_rows,
+                                 const double* Y_rows, const double* ys, const double* x, const double* xp,
+                                 const double* g, const double* gp, double* d_out, int32_t* bound_out,
+                                 int32_t* end_out);
 
 #ifdef __cplusplus
 }

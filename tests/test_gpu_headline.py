@@ -1,0 +1,201 @@
+"""GPU parity at the HEADLINE configuration (BASELINE configs[2]: 64 pieces x int_K 32) and of the pieces of the
+device solve the short reference-scale tests cannot reach: the full-history L-BFGS two-loop, the slot pool, and the
+BASELINE-size field. The oracle is bit-identical to the reference's own code (tests/test_ref_pin.py)."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu_scene(small_scene):
+    import topay_b200 as tp
+    gm = tp.GridMap(small_scene["desc"], device=0)
+    gm.regenerateMap(small_scene["points"])
+    yield gm
+    gm.close()
+
+
+def _two_loop(S, Y, ys, g, end, bound, m, ys_new, yy_new):
+    """lbfgs.hpp:691-710 verbatim: d = -g, first loop newest -> oldest, scale by ys/yy, second loop back."""
+    d = -g.copy()
+    alpha = np.zeros(m)
+    j = end
+    for _ in range(bound):
+        j = (j + m - 1) % m
+        alpha[j] = S[j].dot(d) / ys[j]
+        d += (-alpha[j]) * Y[j]
+    d *= ys_new / yy_new
+    for _ in range(bound):
+        beta = Y[j].dot(d) / ys[j]
+        d += (alpha[j] - beta) * S[j]
+        j = (j + 1) % m
+    return d
+
+
+@pytest.mark.parametrize("n", [52, 160, 161, 632])
+@pytest.mark.parametrize("bound0,end0", [(0, 0), (0, 200), (6, 6), (6, 2), (254, 254), (255, 255), (256, 0), (256, 131),
+                                         (256, 255)])
+def test_lbfgs_direction_full_history(gpu_scene, n, bound0, end0):
+    """a13: the device's paired, TMA-streamed two-loop (one launch of k_cand<L-BFGS> through
+    topay_solver_debug_direction) against the reference recursion on the same (S, Y, g): histories of 1, 7, 255 and
+    256 pairs, ring positions that wrap, the single-warp (n <= 160) and block-wide (n >= 161) variants, odd and even
+    loop lengths. <= 1e-9 relative to |d|."""
+    import topay_b200 as tp
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    m = opt.s2_lbfgs.mem_size
+    assert m == 256
+    solver = tp.MomaTrajOpt(gpu_scene, max_cand=1, max_pieces=64, opt_param=opt, robot=rp)
+    rng = np.random.default_rng(n * 1000 + bound0 * 3 + end0)
+    S = rng.normal(size=(m, n)) * np.exp(rng.normal(size=(m, 1)))          # rows of very different scale
+    A = np.exp(rng.normal(size=n))                                         # SPD diagonal "Hessian"
+    Y = S * A + 0.05 * rng.normal(size=(m, n)) * np.abs(S).mean(axis=1, keepdims=True)
+    ys = np.einsum("ij,ij->i", S, Y)
+    assert (ys > 0).all()
+    xp, gp = rng.normal(size=n), rng.normal(size=n)
+    s_new = 0.3 * rng.normal(size=n)
+    x, g = xp + s_new, gp + s_new * A + 0.01 * rng.normal(size=n)
+    d = np.zeros(n)
+    b_out, e_out = C.c_int32(), C.c_int32()
+    dp = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
+    rc = solver._l.topay_solver_debug_direction(solver.h, n, bound0, end0, dp(S), dp(Y), dp(ys), dp(x), dp(xp), dp(g), dp(gp),
+                                                dp(d), C.byref(b_out), C.byref(e_out))
+    assert rc == 0
+    # the reference's update (lbfgs.hpp:657-689): the new pair goes to row end0, then bound and end advance
+    S2, Y2, ys2 = S.copy(), Y.copy(), ys.copy()
+    S2[end0], Y2[end0] = x - xp, g - gp
+    ys_new, yy_new = Y2[end0].dot(S2[end0]), Y2[end0].dot(Y2[end0])
+    ys2[end0] = ys_new
+    bound, end = min(bound0 + 1, m), (end0 + 1) % m
+    assert (b_out.value, e_out.value) == (bound, end)
+    exp = _two_loop(S2, Y2, ys2, g, end, bound, m, ys_new, yy_new)
+    assert np.abs(d - exp).max() <= 1e-9 * np.abs(exp).max(), (np.abs(d - exp).max(), np.abs(exp).max())
+    solver.close()
+
+
+def test_pool_results_do_not_depend_on_the_slot_count(gpu_scene):
+    """Continuous batching: 32 candidates through 32, 8 and 3 slots — the queue hands candidates to whichever slot
+    frees first, yet every candidate's result is bit-identical (a candidate's arithmetic never depends on its slot or
+    on its neighbours), all slots stay busy, and the per-plan winners of optimizeTrajPlans equal the flat solve's."""
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    paths, bv, ba = scenes.short_candidates(32, 11)
+    res = {}
+    for ns in (32, 8, 3):
+        s = tp.MomaTrajOpt(gpu_scene, max_cand=32, max_pieces=16, opt_param=opt, robot=rp, n_slots=ns)
+        res[ns] = s.optimizeTrajBatch(paths, bv, ba)
+        st = s.stats()
+        assert res[ns]["evals"].sum() <= st["slot_ticks"] <= res[ns]["evals"].sum() + 32 * 16 * 2
+        if ns == 3:
+            assert res[ns]["evals"].sum() / st["slot_ticks"] > 0.97          # slots never idle while work waits
+            plans = [(paths[i:i + 8], bv[i:i + 8], ba[i:i + 8]) for i in range(0, 32, 8)]
+            rp_ = s.optimizeTrajPlans(plans)
+            for i in range(4):
+                sub = {k: res[32][k][8 * i:8 * i + 8] for k in ("status", "duration", "cost")}
+                ok = np.flatnonzero(sub["status"] == 1)
+                assert rp_["plan_best_by_duration"][i] == (ok[np.argmin(sub["duration"][ok])] if len(ok) else -1)
+            assert np.array_equal(rp_["cost"], res[32]["cost"])
+        s.close()
+    for ns in (8, 3):
+        for k in ("status", "lbfgs_code", "evals", "iters", "alm_rounds", "cost", "T", "coeff", "x", "final_xy_err"):
+            assert np.array_equal(res[32][k], res[ns][k]), (ns, k)
+
+
+def test_headline_config_solve_against_the_oracle(gpu_scene, small_scene, oracle):
+    """The headline workload itself: the first 4 candidates of scenes.synthetic_batch(256, 1234) at 64 pieces x
+    int_K 32, solved on the device and by the oracle (= the reference, bit for bit). The solve is chaotic — the
+    oracle with its interior waypoints perturbed by 1e-15 relative already lands elsewhere — so the stated tolerance
+    is: same success status; ALM rounds within 1; the first 15 accepted L-BFGS iterations replay the oracle's
+    (same k, same line-search count, f within 1e-9); final cost, duration, base-path length inside the oracle's own
+    perturbation band widened 3x (at least +-9 %); clearances within 0.15 m; BOTH gate verdicts (checkFeasible and
+    printConstraintsSituations, planner.cpp:877-880) equal to the oracle's on its own trajectory."""
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    n = 4
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    opt.int_K, opt.min_piece_num, opt.sample_interval = 32, 64, 1e9
+    paths, bv, ba = scenes.synthetic_batch(256, 1234)
+    paths, bv, ba = paths[:n], bv[:n], ba[:n]
+    of = small_scene["field"]
+    solver = tp.MomaTrajOpt(gpu_scene, max_cand=n, max_pieces=64, opt_param=opt, robot=rp)
+    solver.set_trace(20000)
+    res = solver.optimizeTrajBatch(paths, bv, ba)
+    gate, _ = solver.checkFeasibleBatch()
+    gate = {k: v.copy() for k, v in gate.items()}
+    exact, pert = [None] * n, [None] * n
+
+    def work(c):
+        exact[c] = oracle.solve_one(opt, rp, of, paths[c], bv[c], ba[c], max_pieces=64, trace=True)
+        pp = paths[c].copy()
+        pp[1:-1] *= (1 + 1e-15)
+        pert[c] = oracle.solve_one(opt, rp, of, pp, bv[c], ba[c], max_pieces=64)
+
+    th = [threading.Thread(target=work, args=(c,)) for c in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    radii = np.array([rp.colli_point_radius[i] for i in range(16) if rp.colli_points[i] != 0.0])
+
+    def metrics(T, coeff, start):
+        g = oracle.check_feasible(of, rp, [(T, coeff, start)])
+        seq = oracle.traj_car_seq([(T, coeff, start)])[0]
+        length = np.linalg.norm(np.diff(seq[:, :2], axis=0), axis=1).sum()
+        return g, length
+
+    for c in range(n):
+        o, p = exact[c], pert[c]
+        assert res["status"][c] == o["status"] == 1 and res["piece_num"][c] == o["piece_num"] == 64
+        assert abs(int(res["alm_rounds"][c]) - o["alm_rounds"]) <= 1
+        tg, tc = solver.trace(c), o["trace"]
+        m = 15
+        assert np.array_equal(tg[:m, 2:], tc[:m, 2:])
+        assert np.abs(tg[:m, 0] - tc[:m, 0]).max() <= 1e-9 * np.abs(tc[:m, 0]).max()
+        start = paths[c][0, :3]
+        go, len_o = metrics(o["T"], o["coeff"], start)
+        gp_, len_p = metrics(p["T"], p["coeff"], start)
+        N = 64
+        gd, len_d = metrics(res["T"][c, :N], res["coeff"][c, :6 * N], start)
+        for name, dev, a, b in (("cost", res["cost"][c], o["cost"], p["cost"]),
+                                ("duration", res["duration"][c], o["duration"], p["duration"]),
+                                ("length", len_d, len_o, len_p)):
+            lo, hi = min(a, b), max(a, b)
+            w = max(hi - lo, 0.03 * hi)
+            assert lo - 3 * w <= dev <= hi + 3 * w, (c, name, dev, a, b)
+        assert np.linalg.norm(res["final_xy_err"][c]) < opt.alm_tolerance
+        # clearances of the device trajectory (device gate) against the oracle's on its trajectory
+        assert abs(gate["min_dist"][c] - go["min_dist"][0]) <= 0.15
+        arm_d = (gate["min_dist_mani"][c, :len(radii)] - radii).min()
+        arm_o = (go["min_dist_mani"][0, :len(radii)] - radii).min()
+        assert abs(arm_d - arm_o) <= 0.15
+        # both verdicts of the success gate: device gate on the device trajectory == oracle gate on the same
+        # trajectory (exact), and == the oracle's verdict on its own trajectory
+        assert gate["feasible"][c] == gd["feasible"][0] and gate["feasible_print"][c] == gd["feasible_print"][0]
+        assert gate["feasible"][c] == go["feasible"][0] and gate["feasible_print"][c] == go["feasible_print"][0]
+    solver.close()
+
+
+@pytest.mark.parametrize("dims", [(800, 800, 80), (803, 803, 83)])
+def test_baseline_size_field_bit_exact(oracle, dims):
+    """a20/a21 at BASELINE configs[3] size: the whole 800 x 800 x 80 grid (and the odd-sized 803 x 803 x 83 one)
+    against the oracle — the integer squared-distance grids of both signs, all four signed ESDF buffers, bit for bit."""
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    size = tuple((d - 0.5) * 0.05 for d in dims)       # GridMap::init takes ceil(size / resolution)
+    desc = tp.grid_desc(map_size=size, resolution=0.05)
+    gm = tp.GridMap(desc)
+    assert gm.voxel_num == dims
+    pts, _ = scenes.cuboids_scene(7, size_x=40.0, size_y=40.0, scale=2.0)
+    gm.regenerateMap(pts)
+    of = oracle.Field(desc)
+    of.rasterize(pts)
+    of.rebuild()
+    assert np.array_equal(gm.getOccBuffer3d(), of.download_occupancy(3))
+    for which in (3, 0, 1, 2):
+        assert np.array_equal(gm._download(which), of.download(which)), which
+    sqp, sqn = gm.getSqDist(3)
+    osp, osn = of.download_sqdist(3)
+    assert np.array_equal(sqp, osp) and np.array_equal(sqn, osn)
+    gm.close()

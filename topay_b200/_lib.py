@@ -88,6 +88,8 @@ PROTOTYPES = {
                                       C.POINTER(C.c_void_p)]),
     "topay_solver_create_rog": (C.c_int, [C.POINTER(OptParams), C.POINTER(RobotParams), C.c_void_p, C.c_int, C.c_int,
                                           C.POINTER(C.c_void_p)]),
+    "topay_solver_create_pool": (C.c_int, [C.POINTER(OptParams), C.POINTER(RobotParams), C.c_void_p, C.c_int, C.c_int,
+                                           C.c_int, C.POINTER(C.c_void_p)]),
     "topay_solver_destroy": (None, [C.c_void_p]),
     "topay_solver_eval": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ProblemBatch), _dp, C.c_int, _dp, _dp, _dp, _dp,
                                     _dp]),
@@ -101,6 +103,8 @@ PROTOTYPES = {
     "topay_solver_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "topay_solver_download_trace": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int, _ip]),
     "topay_solver_debug_download": (C.c_int64, [C.c_void_p, C.c_int, _dp, C.c_int64]),
+    "topay_solver_debug_direction": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
+                                               _dp, _ip, _ip]),
     "topay_solver_phase_clocks": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]),
     "topay_solver_set_timed": (C.c_int, [C.c_void_p, C.c_int]),
     "topay_solver_last_stats": (C.c_int, [C.c_void_p, C.POINTER(SolverStats)]),

@@ -156,7 +156,9 @@ class SolverStats(C.Structure):
                 ("ms_total", C.c_float), ("ms_eval", C.c_float), ("eval_launches", C.c_int64),
                 ("eval_nodes", C.c_int64), ("ms_integrate", C.c_float), ("ms_chain", C.c_float), ("ms_cand", C.c_float),
                 ("pad_", C.c_float), ("hist_bytes", C.c_int64), ("full_ticks", C.c_int64),
-                ("full_hist_bytes", C.c_int64), ("full_ms_cand", C.c_float), ("pad2_", C.c_float)]
+                ("full_hist_bytes", C.c_int64), ("full_ms_cand", C.c_float), ("pad2_", C.c_float),
+                ("slot_ticks", C.c_int64), ("ms_adj", C.c_float), ("ms_lbfgs", C.c_float), ("ms_gen", C.c_float),
+                ("pad3_", C.c_float)]
 
 
 def num_vars(piece_num):

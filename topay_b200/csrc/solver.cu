@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <ctime>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -23,6 +24,8 @@ struct TpRunningGuard {
     ~TpRunningGuard() { --g_solves_running; }
 };
 
+#define TP_EV 7   // CUDA events per tick in timed mode: start, after integrate / penalty / chain / adjoint / L-BFGS / generate
+
 struct topay_solver {
     TpSolverDev dev;
     TpParams params;
@@ -38,9 +41,10 @@ struct topay_solver {
     TpCandState* h_state;
     double *p_head, *p_tail, *p_sxy, *p_exy, *p_ixy;
     std::vector<void*> allocs;
-    int32_t* h_active;   // pinned
+    int32_t* h_active;   // pinned: [0] live slots after the batch, [1..3] queue state
     unsigned long long* h_nodes;  // pinned
-    int slots;
+    int slots;           // ticks per batch (TP_TICKS)
+    int n_slots_used;    // slots seeded by the last run (min(n_slots, n_cand))
     std::vector<cudaEvent_t> ev;  // event pool for the penalty kernel timing
     cudaEvent_t ev_begin, ev_end;
     bool spin_sync;         // TOPAY_SPIN_SYNC=1: always spin on the stream (lowest latency, one busy core per plan);
@@ -48,15 +52,17 @@ struct topay_solver {
     cudaEvent_t ev_batch;   // blocking-sync event: the host thread sleeps while a batch of ticks runs
                             // (P plans in flight x N ranks would otherwise spin on as many cores)
     topay_solver_stats stats;
-    size_t smem_cand;
+    size_t smem_cand;    // dynamic shared memory of the adjoint / generate launches (banded system)
+    size_t smem_lbfgs;   // ... of the L-BFGS launch (TMA ring + tables)
     // initial state kept on the host for repeated runs
     double* h_x0;
     size_t h_x0_count;
     // one batch of `slots` ticks as a CUDA graph (launch-bound small plans); rebuilt when the
     // launch geometry or a captured pointer changes
     bool timed;                 // per-launch CUDA events around k_penalty (plain launches, no graph)
-    cudaGraphExec_t graph_exec;
-    int graph_n_cand, graph_max_N;
+    // one CUDA graph per launch-grid bucket (live slots rounded up), rebuilt when max_N or a captured pointer changes
+    std::map<int, cudaGraphExec_t> graphs;
+    int graph_max_N;
     // success gate (topay_solver_check_feasible): built on first use
     TpTrajChecker* checker;
     int32_t* d_pn;
@@ -96,59 +102,89 @@ size_t penalty_smem() {
     return (size_t)(72 * TP_PEN_WARPS * 32 + TP_PEN_WARPS * 8 * 54) * sizeof(double);
 }
 
-void launch_eval(topay_solver* s, bool timed, int tick_in_batch) {
+// grid.y / grid.x of a tick: the live-slot count rounded up to a bucket (1..8, then 12, 16, 24, 32, 48, ...),
+// so that a handful of graphs covers a run; blocks beyond the live count exit at once
+int grid_bucket(int n) {
+    if (n <= 8) return n < 1 ? 1 : n;
+    for (int p = 8;; p *= 2) {
+        if (n <= p) return p;
+        if (n <= p + p / 2) return p + p / 2;
+    }
+}
+
+void launch_eval(topay_solver* s, bool timed, int tick, int ny) {
     const TpSolverDev& D = s->dev;
     const int groups = (s->max_N + D.ppw - 1) / D.ppw;
     const int end_warps = D.end_tasks ? (s->max_N + 31) / 32 : 0;
     dim3 blk(TP_WARPS_PER_BLOCK * 32);
-    dim3 g1((groups + TP_WARPS_PER_BLOCK - 1) / TP_WARPS_PER_BLOCK, s->n_cand);
+    dim3 g1((groups + TP_WARPS_PER_BLOCK - 1) / TP_WARPS_PER_BLOCK, ny);
     dim3 blk2(TP_PEN_WARPS * 32);
-    dim3 g2((groups + end_warps + TP_PEN_WARPS - 1) / TP_PEN_WARPS, s->n_cand);
+    dim3 g2((groups + end_warps + TP_PEN_WARPS - 1) / TP_PEN_WARPS, ny);
     const size_t sm_int = (size_t)TP_WARPS_PER_BLOCK * D.ppw * 3 * (2 * D.K + 1) * sizeof(double);
     const size_t sm_pen = penalty_smem();
     TpGrid G;
     solver_grid(s, &G);
-    if (timed) cudaEventRecord(s->ev[5 * tick_in_batch], s->stream);
-    k_integrate<<<g1, blk, sm_int, s->stream>>>(D);
-    if (timed) cudaEventRecord(s->ev[5 * tick_in_batch + 1], s->stream);
+    const int te = tick % TP_TICKS;
+    if (timed) cudaEventRecord(s->ev[TP_EV * te], s->stream);
+    k_integrate<<<g1, blk, sm_int, s->stream>>>(D, tick);
+    if (timed) cudaEventRecord(s->ev[TP_EV * te + 1], s->stream);
     switch (D.Kpad) {
-        case 4: k_penalty<4><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
-        case 8: k_penalty<8><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
-        case 16: k_penalty<16><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
-        default: k_penalty<32><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups); break;
+        case 4: k_penalty<4><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+        case 8: k_penalty<8><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+        case 16: k_penalty<16><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+        default: k_penalty<32><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
     }
-    if (timed) cudaEventRecord(s->ev[5 * tick_in_batch + 2], s->stream);
-    k_chain<<<g1, blk, 0, s->stream>>>(D, s->params);
-    if (timed) cudaEventRecord(s->ev[5 * tick_in_batch + 3], s->stream);
+    if (timed) cudaEventRecord(s->ev[TP_EV * te + 2], s->stream);
+    k_chain<<<g1, blk, 0, s->stream>>>(D, s->params, tick);
+    if (timed) cudaEventRecord(s->ev[TP_EV * te + 3], s->stream);
     s->stats.kernel_launches += 3;
     s->stats.eval_launches += 1;
 }
 
-void launch_cand(topay_solver* s, int mode, int slot) {
-    k_cand<<<s->n_cand, TP_CAND_THREADS, s->smem_cand, s->stream>>>(s->dev, s->params, mode, slot);
+void launch_cand(topay_solver* s, int mode, int tick_in, int tick_out, int nx) {
+    const int sd = (int)(s->smem_cand / sizeof(double)), sl = (int)(s->smem_lbfgs / sizeof(double));
+    if (mode == TP_MODE_GEN)
+        k_cand<TP_MODE_GEN><<<nx, TP_CAND_THREADS, s->smem_cand, s->stream>>>(s->dev, s->params, sd, tick_in, tick_out);
+    else if (mode == TP_MODE_ADJ)
+        k_cand<TP_MODE_ADJ><<<nx, TP_CAND_THREADS, s->smem_cand, s->stream>>>(s->dev, s->params, sd, tick_in, tick_out);
+    else
+        k_cand<TP_MODE_ADVANCE><<<nx, TP_CAND_THREADS, s->smem_lbfgs, s->stream>>>(s->dev, s->params, sl, tick_in, tick_out);
     s->stats.kernel_launches += 1;
+}
+
+void drop_graphs(topay_solver* s) {
+    for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second);
+    s->graphs.clear();
 }
 
 }  // namespace
 
 static int solver_create(const topay_opt_params* opt, const topay_robot_params* robot, topay_field* field,
-                         topay_rogfield* rog, int max_cand, int max_pieces, topay_solver** out);
+                         topay_rogfield* rog, int max_cand, int n_slots, int max_pieces, topay_solver** out);
 
 extern "C" int topay_solver_create(const topay_opt_params* opt, const topay_robot_params* robot,
                                    topay_field* field, int max_cand, int max_pieces, topay_solver** out) {
     if (!field) return TOPAY_ERR_INVALID_ARG;
-    return solver_create(opt, robot, field, nullptr, max_cand, max_pieces, out);
+    return solver_create(opt, robot, field, nullptr, max_cand, max_cand, max_pieces, out);
 }
 
 extern "C" int topay_solver_create_rog(const topay_opt_params* opt, const topay_robot_params* robot,
                                        topay_rogfield* rog, int max_cand, int max_pieces, topay_solver** out) {
     if (!rog) return TOPAY_ERR_INVALID_ARG;
-    return solver_create(opt, robot, nullptr, rog, max_cand, max_pieces, out);
+    return solver_create(opt, robot, nullptr, rog, max_cand, max_cand, max_pieces, out);
+}
+
+extern "C" int topay_solver_create_pool(const topay_opt_params* opt, const topay_robot_params* robot,
+                                        topay_field* field, int max_cand, int n_slots, int max_pieces,
+                                        topay_solver** out) {
+    if (!field) return TOPAY_ERR_INVALID_ARG;
+    return solver_create(opt, robot, field, nullptr, max_cand, n_slots, max_pieces, out);
 }
 
 static int solver_create(const topay_opt_params* opt, const topay_robot_params* robot, topay_field* field,
-                         topay_rogfield* rog, int max_cand, int max_pieces, topay_solver** out) {
-    if (!opt || !robot || !out || max_cand < 1 || max_pieces < 1) return TOPAY_ERR_INVALID_ARG;
+                         topay_rogfield* rog, int max_cand, int n_slots, int max_pieces, topay_solver** out) {
+    if (!opt || !robot || !out || max_cand < 1 || max_pieces < 1 || n_slots < 1) return TOPAY_ERR_INVALID_ARG;
+    if (n_slots > max_cand) n_slots = max_cand;
     if (opt->int_K < 1 || opt->int_K > TP_MAX_K) {
         tp_set_error("int_K must be in [1, 32]");
         return TOPAY_ERR_TOO_LARGE;
@@ -172,10 +208,10 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     s->device = dev;
     s->n_cand = 0;
     s->max_N = 0;
-    s->slots = 16;
+    s->slots = TP_TICKS;
+    s->n_slots_used = 0;
     s->timed = false;
-    s->graph_exec = nullptr;
-    s->graph_n_cand = s->graph_max_N = -1;
+    s->graph_max_N = -1;
     s->checker = nullptr;
     s->spin_sync = getenv("TOPAY_SPIN_SYNC") && atoi(getenv("TOPAY_SPIN_SYNC")) != 0;
     s->d_pn = nullptr;
@@ -190,6 +226,7 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     TpSolverDev& D = s->dev;
     memset(&D, 0, sizeof(D));
     D.max_cand = max_cand;
+    D.n_slots = n_slots;
     D.max_pieces = max_pieces;
     D.K = opt->int_K;
     D.Kpad = kpad_of(D.K);
@@ -197,18 +234,31 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     D.end_tasks = D.K == D.Kpad ? 1 : 0;
     D.xs = (topay_num_vars(max_pieces) + 3) & ~3;
     D.mem = std::max(1, std::max(opt->s1_lbfgs.mem_size, opt->s2_lbfgs.mem_size));
-    const size_t C = max_cand, NP = max_pieces, K = D.K;
+    const size_t G = max_cand, C = n_slots, NP = max_pieces, K = D.K;
 #define ALLOC(ptr, count)                                    \
     if ((rc = dev_alloc(s, &(ptr), (count))) != TOPAY_OK) {  \
         topay_solver_destroy(s);                             \
         return rc;                                           \
     }
+    // store
+    ALLOC(D.head_pva, G * 27);
+    ALLOC(D.tail_pva, G * 27);
+    ALLOC(D.start_xy, G * 2);
+    ALLOC(D.end_xy, G * 2);
+    ALLOC(D.init_inner_xy, G * NP * 2);
+    ALLOC(D.x0, G * D.xs);
+    ALLOC(D.st0, G);
+    ALLOC(D.res_st, G);
+    ALLOC(D.res_T, G * NP);
+    ALLOC(D.res_coeff, G * 6 * NP * 9);
+    ALLOC(D.res_x, G * D.xs);
+    // scheduling
+    ALLOC(D.slot_gid, C);
+    ALLOC(D.list, (size_t)(TP_TICKS + 1) * C);
+    ALLOC(D.count, (size_t)TP_TICKS + 1);
+    ALLOC(D.queue, 4);
+    // slots
     ALLOC(D.st, C);
-    ALLOC(D.head_pva, C * 27);
-    ALLOC(D.tail_pva, C * 27);
-    ALLOC(D.start_xy, C * 2);
-    ALLOC(D.end_xy, C * 2);
-    ALLOC(D.init_inner_xy, C * NP * 2);
     ALLOC(D.x, C * D.xs);
     ALLOC(D.g, C * D.xs);
     ALLOC(D.xp, C * D.xs);
@@ -233,27 +283,25 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     ALLOC(D.terms_end, C * NP * TOPAY_NTERMS);
     ALLOC(D.f, C);
     ALLOC(D.term_out, C * TOPAY_NTERMS);
-    ALLOC(D.n_active, (size_t)s->slots);
     ALLOC(D.node_count, 2);
 #undef ALLOC
     {
-        const size_t C_ = (size_t)max_cand;
-        const size_t b_state = ((C_ * sizeof(TpCandState) + 15) / 16) * 16;
-        const size_t n_dbl = C_ * D.xs + C_ * (27 + 27 + 2 + 2) + C_ * NP * 2;
+        const size_t b_state = ((G * sizeof(TpCandState) + 15) / 16) * 16;
+        const size_t n_dbl = G * D.xs + G * (27 + 27 + 2 + 2) + G * NP * 2;
         TP_CUDA_OK(cudaMallocHost(&s->h_pin, b_state + n_dbl * sizeof(double)), { topay_solver_destroy(s); });
         s->h_state = reinterpret_cast<TpCandState*>(s->h_pin);
         double* dp = reinterpret_cast<double*>(s->h_pin + b_state);
-        s->h_x0 = dp;            dp += C_ * D.xs;
-        s->p_head = dp;          dp += C_ * 27;
-        s->p_tail = dp;          dp += C_ * 27;
-        s->p_sxy = dp;           dp += C_ * 2;
-        s->p_exy = dp;           dp += C_ * 2;
+        s->h_x0 = dp;            dp += G * D.xs;
+        s->p_head = dp;          dp += G * 27;
+        s->p_tail = dp;          dp += G * 27;
+        s->p_sxy = dp;           dp += G * 2;
+        s->p_exy = dp;           dp += G * 2;
         s->p_ixy = dp;
         s->h_x0_count = 0;
     }
-    TP_CUDA_OK(cudaMallocHost(&s->h_active, s->slots * sizeof(int32_t)), { topay_solver_destroy(s); });
+    TP_CUDA_OK(cudaMallocHost(&s->h_active, 8 * sizeof(int32_t)), { topay_solver_destroy(s); });
     TP_CUDA_OK(cudaMallocHost(&s->h_nodes, 2 * sizeof(unsigned long long)), { topay_solver_destroy(s); });
-    s->ev.resize(5 * s->slots);
+    s->ev.resize(TP_EV * s->slots);
     for (auto& e : s->ev) cudaEventCreate(&e);
     cudaEventCreate(&s->ev_begin);
     cudaEventCreate(&s->ev_end);
@@ -264,6 +312,15 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     s->smem_cand = std::max(std::max((size_t)6 * NP * (TP_BAND + 9), (size_t)6 * 2 * D.xs + 512 + D.xs) * sizeof(double),
                             (size_t)64 * 1024);
     D.smem_doubles = (int32_t)(s->smem_cand / sizeof(double));
+    // L-BFGS launch: four full-width stages of (s_j, y_j) + the alpha / 1/ys tables + one vector of scratch; short rows
+    // (small plans run the recursion on one warp) still get up to 64 KB so that they ride a deep ring
+    {
+        const size_t rowd = (size_t)((topay_num_vars(max_pieces) + 1) & ~1);
+        const size_t tail = (size_t)512 + D.xs;
+        const size_t four = (4 * 2 * rowd + tail) * sizeof(double);
+        const size_t deep = std::min((size_t)64 * 1024, (TP_RING_MAX * 2 * rowd + tail) * sizeof(double));
+        s->smem_lbfgs = std::max(four, deep);
+    }
     if (s->smem_cand > 227 * 1024) {
         tp_set_error("max_pieces too large for the per-candidate shared-memory working set");
         topay_solver_destroy(s);
@@ -272,10 +329,16 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     // the attribute belongs to the kernel, not to this solver: solvers of different capacities coexist
     // (bench: 64-piece plans and 16-piece latency plans), so it only ever grows
     {
-        static std::atomic<size_t> attr_set{0};
+        static std::atomic<size_t> attr_set{0}, attr_lb{0};
         size_t cur = attr_set.load();
         while (cur < s->smem_cand && !attr_set.compare_exchange_weak(cur, s->smem_cand)) {}
-        TP_CUDA_OK(cudaFuncSetAttribute(k_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_set.load()),
+        cur = attr_lb.load();
+        while (cur < s->smem_lbfgs && !attr_lb.compare_exchange_weak(cur, s->smem_lbfgs)) {}
+        TP_CUDA_OK(cudaFuncSetAttribute(k_cand<TP_MODE_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_set.load()),
+                   { topay_solver_destroy(s); });
+        TP_CUDA_OK(cudaFuncSetAttribute(k_cand<TP_MODE_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_set.load()),
+                   { topay_solver_destroy(s); });
+        TP_CUDA_OK(cudaFuncSetAttribute(k_cand<TP_MODE_ADVANCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_lb.load()),
                    { topay_solver_destroy(s); });
     }
     const size_t sm_int = (size_t)TP_WARPS_PER_BLOCK * D.ppw * 3 * (2 * D.K + 1) * sizeof(double);
@@ -302,11 +365,12 @@ extern "C" void topay_solver_destroy(topay_solver* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    drop_graphs(s);
     delete s->checker;
     for (void* p : s->allocs) cudaFree(p);
     if (s->dev.trace) cudaFree(s->dev.trace);
     if (s->dev.trace_len) cudaFree(s->dev.trace_len);
+    if (s->dev.prof) cudaFree(s->dev.prof);
     if (s->h_pin) cudaFreeHost(s->h_pin);
     if (s->h_active) cudaFreeHost(s->h_active);
     if (s->h_nodes) cudaFreeHost(s->h_nodes);
@@ -318,7 +382,7 @@ extern "C" void topay_solver_destroy(topay_solver* s) {
     delete s;
 }
 
-// Uploads problem data + x and (re)initialises the per-candidate state.
+// Uploads problem data + x of n_cand candidates into the store and their initial per-candidate state.
 static int upload_problem(topay_solver* s, int n_cand, const int32_t* piece_num, const double* head,
                           const double* tail, const double* sxy, const double* exy, const double* inner_xy,
                           const double* x, int x_stride, const int32_t* s1_past, int phase, const double* lambda,
@@ -363,16 +427,25 @@ static int upload_problem(topay_solver* s, int n_cand, const int32_t* piece_num,
     memcpy(s->p_exy, exy, (size_t)n_cand * 2 * 8);
     memcpy(s->p_ixy, inner_xy, (size_t)n_cand * D.max_pieces * 2 * 8);
     cudaStream_t q = s->stream;
-    TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state, n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.st0, s->h_state, n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
     TP_CUDA_OK(cudaMemcpyAsync(D.head_pva, s->p_head, (size_t)n_cand * 27 * 8, cudaMemcpyHostToDevice, q), {});
     TP_CUDA_OK(cudaMemcpyAsync(D.tail_pva, s->p_tail, (size_t)n_cand * 27 * 8, cudaMemcpyHostToDevice, q), {});
     TP_CUDA_OK(cudaMemcpyAsync(D.start_xy, s->p_sxy, (size_t)n_cand * 2 * 8, cudaMemcpyHostToDevice, q), {});
     TP_CUDA_OK(cudaMemcpyAsync(D.end_xy, s->p_exy, (size_t)n_cand * 2 * 8, cudaMemcpyHostToDevice, q), {});
     TP_CUDA_OK(cudaMemcpyAsync(D.init_inner_xy, s->p_ixy, (size_t)n_cand * D.max_pieces * 2 * 8,
                                cudaMemcpyHostToDevice, q), {});
-    TP_CUDA_OK(cudaMemcpyAsync(D.x, xs, s->h_x0_count * 8, cudaMemcpyHostToDevice, q), {});
+    TP_CUDA_OK(cudaMemcpyAsync(D.x0, xs, s->h_x0_count * 8, cudaMemcpyHostToDevice, q), {});
     TP_CUDA_OK(cudaStreamSynchronize(q), {});
     return TOPAY_OK;
+}
+
+// Seeds the slots with the first candidates of the store; the live list is list TP_TICKS.
+static int seed_slots(topay_solver* s) {
+    const TpSolverDev& D = s->dev;
+    const int n0 = std::min(D.n_slots, s->n_cand);
+    s->n_slots_used = n0;
+    k_slot_init<<<n0, 128, 0, s->stream>>>(D, n0, s->n_cand);
+    return n0;
 }
 
 extern "C" int topay_solver_eval(topay_solver* s, int stage, const topay_problem_batch* prob, const double* x,
@@ -383,18 +456,23 @@ extern "C" int topay_solver_eval(topay_solver* s, int stage, const topay_problem
         tp_set_error("field not built: call topay_field_rebuild first");
         return TOPAY_ERR_NOT_READY;
     }
+    if (prob->n_cand > s->dev.n_slots) {
+        tp_set_error("topay_solver_eval evaluates at most n_slots candidates at a time");
+        return TOPAY_ERR_TOO_LARGE;
+    }
     int rc = upload_problem(s, prob->n_cand, prob->piece_num, prob->head_pva, prob->tail_pva, prob->start_xy,
                             prob->end_xy, prob->init_inner_xy, x, x_stride, nullptr, stage, prob->alm_lambda,
                             prob->alm_rho);
     if (rc != TOPAY_OK) return rc;
     const TpSolverDev& D = s->dev;
     const int n = prob->n_cand;
-    cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), s->stream);
-    launch_cand(s, TP_MODE_GEN, 0);
-    launch_eval(s, false, 0);
-    launch_cand(s, TP_MODE_ADJ, 1);
+    seed_slots(s);   // slot i <- candidate i
+    launch_cand(s, TP_MODE_GEN, TP_TICKS, -1, n);
+    launch_eval(s, false, TP_TICKS, n);
+    launch_cand(s, TP_MODE_ADJ, TP_TICKS, -1, n);
     TP_CUDA_OK(cudaStreamSynchronize(s->stream), {});
     TP_CUDA_OK(cudaGetLastError(), {});
+    s->n_cand = 0;   // the uploaded problem carried the evaluation's phase / multipliers: not a solvable upload
     std::vector<double> g((size_t)n * D.xs);
     TP_CUDA_OK(cudaMemcpy(cost, D.f, n * 8, cudaMemcpyDeviceToHost), {});
     TP_CUDA_OK(cudaMemcpy(g.data(), D.g, g.size() * 8, cudaMemcpyDeviceToHost), {});
@@ -404,10 +482,11 @@ extern "C" int topay_solver_eval(topay_solver* s, int stage, const topay_problem
     if (coeff_out)
         TP_CUDA_OK(cudaMemcpy(coeff_out, D.coeff, (size_t)n * 6 * D.max_pieces * 9 * 8, cudaMemcpyDeviceToHost), {});
     if (final_xy_out) {
-        TP_CUDA_OK(cudaMemcpy(s->h_state, D.st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), {});
+        std::vector<TpCandState> st(n);
+        TP_CUDA_OK(cudaMemcpy(st.data(), D.st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), {});
         for (int c = 0; c < n; c++) {
-            final_xy_out[2 * c] = s->h_state[c].final_xy[0];
-            final_xy_out[2 * c + 1] = s->h_state[c].final_xy[1];
+            final_xy_out[2 * c] = st[c].final_xy[0];
+            final_xy_out[2 * c + 1] = st[c].final_xy[1];
         }
     }
     return TOPAY_OK;
@@ -441,6 +520,49 @@ extern "C" int topay_solver_upload(topay_solver* s, int n_cand, const int32_t* p
                           x.data(), xstride, past.data(), 1, nullptr, nullptr);
 }
 
+// One batch of TP_TICKS ticks over at most `ny` live slots: roll the list, then per tick the three evaluation
+// kernels and k_cand; the live count after the batch and the queue state return through pinned memory.
+static void enqueue_batch(topay_solver* s, int ny, bool timed) {
+    const TpSolverDev& D = s->dev;
+    cudaStream_t q = s->stream;
+    k_list_roll<<<1, 1024, 0, q>>>(D);
+    for (int t = 0; t < TP_TICKS; t++) {
+        launch_eval(s, timed, t, ny);
+        launch_cand(s, TP_MODE_ADJ, t, -1, ny);
+        if (timed) cudaEventRecord(s->ev[TP_EV * t + 4], q);
+        launch_cand(s, TP_MODE_ADVANCE, t, -1, ny);
+        if (timed) cudaEventRecord(s->ev[TP_EV * t + 5], q);
+        launch_cand(s, TP_MODE_GEN, t, t + 1, ny);
+        if (timed) cudaEventRecord(s->ev[TP_EV * t + 6], q);
+    }
+    cudaMemcpyAsync(s->h_active, D.count + TP_TICKS, sizeof(int32_t), cudaMemcpyDeviceToHost, q);
+    cudaMemcpyAsync(s->h_active + 1, D.queue, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
+    s->stats.kernel_launches += 1;
+}
+
+// Marks every candidate that is still live (or was never started) as stopped by the tick cap.
+__global__ void k_mark_tick_cap(const __grid_constant__ TpSolverDev S, int n_store) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S.count[TP_TICKS]) {
+        const int slot = S.list[(size_t)TP_TICKS * S.n_slots + i];
+        TpCandState st = S.st[slot];
+        if (st.phase != 0) {
+            st.phase = 0;
+            st.status = 0;
+            st.last_code = TOPAY_LBFGSERR_TICK_CAP;
+            S.st[slot] = st;
+            S.res_st[S.slot_gid[slot]] = st;
+        }
+    }
+    if (i >= S.queue[0] && i < n_store) {   // never handed to a slot
+        TpCandState st = S.st0[i];
+        st.phase = 0;
+        st.status = 0;
+        st.last_code = TOPAY_LBFGSERR_TICK_CAP;
+        S.res_st[i] = st;
+    }
+}
+
 extern "C" int topay_solver_run(topay_solver* s) {
     if (!s || s->n_cand < 1) return TOPAY_ERR_INVALID_ARG;
     if (!solver_field_ready(s)) {
@@ -452,100 +574,101 @@ extern "C" int topay_solver_run(topay_solver* s) {
     cudaStream_t q = s->stream;
     TpRunningGuard running;
     memset(&s->stats, 0, sizeof(s->stats));
-    // reset to the uploaded initial state so that repeated runs do identical work
-    TP_CUDA_OK(cudaMemcpyAsync(D.st, s->h_state, s->n_cand * sizeof(TpCandState), cudaMemcpyHostToDevice, q), {});
-    TP_CUDA_OK(cudaMemcpyAsync(D.x, s->h_x0, s->h_x0_count * 8, cudaMemcpyHostToDevice, q), {});
     cudaMemsetAsync(D.node_count, 0, 2 * sizeof(unsigned long long), q);
     if (D.trace) cudaMemsetAsync(D.trace_len, 0, (size_t)D.max_cand * sizeof(int32_t), q);
     cudaEventRecord(s->ev_begin, q);
-    cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), q);
-    launch_cand(s, TP_MODE_GEN, 0);
-    double ms_eval = 0.0, ms_k[3] = {0.0, 0.0, 0.0}, full_ms_cand = 0.0;
+    // the store holds the uploaded initial state, so repeated runs do identical work
+    int live = seed_slots(s);
+    launch_cand(s, TP_MODE_GEN, TP_TICKS, -1, live);
+    s->stats.kernel_launches += 1;
+    double ms_eval = 0.0, ms_k[3] = {0.0, 0.0, 0.0}, ms_c[3] = {0.0, 0.0, 0.0}, full_ms_cand = 0.0;
     unsigned long long hist_prev = 0, full_hist = 0;
     long long full_ticks = 0;
-    // hard cap on ticks: every candidate does at most this many evaluations
-    const long long max_ticks =
-        (long long)(s->params.opt.alm_max_rounds + 1) * ((long long)s->params.opt.s2_lbfgs.max_iterations + 2) *
-        (s->params.opt.s2_lbfgs.max_linesearch + 1);
+    // Hard cap on ticks: no candidate does more evaluations than this (max_iterations == 0 means unbounded in
+    // lbfgs.hpp; the cap then only guards against a runaway loop), times the number of refills of a slot.
+    const topay_opt_params& op = s->params.opt;
+    auto evals_of = [](const topay_lbfgs_params& lp) -> double {
+        const double it = lp.max_iterations > 0 ? lp.max_iterations + 2.0 : 1e7;
+        return it * (lp.max_linesearch + 1.0);
+    };
+    const double per_cand = evals_of(op.s1_lbfgs) + (op.alm_max_rounds + 1.0) * evals_of(op.s2_lbfgs);
+    const double waves = std::ceil((double)s->n_cand / std::max(1, s->n_slots_used));
+    const long long max_ticks = (long long)std::min(per_cand * waves, 4e15);
     long long ticks = 0;
+    long long slot_ticks = 0;      // live slots summed over the batches (upper bound of the evaluations done)
     bool done = false;
     const bool use_graph = !s->timed;
-    if (use_graph && (!s->graph_exec || s->graph_n_cand != s->n_cand || s->graph_max_N != s->max_N)) {
-        if (s->graph_exec) {
-            cudaGraphExecDestroy(s->graph_exec);
-            s->graph_exec = nullptr;
-        }
-        cudaGraph_t g = nullptr;
-        const topay_solver_stats keep = s->stats;
-        TP_CUDA_OK(cudaStreamBeginCapture(q, cudaStreamCaptureModeThreadLocal), {});
-        cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), q);
-        for (int t = 0; t < s->slots; t++) {
-            launch_eval(s, false, t);
-            launch_cand(s, TP_MODE_ADJ | TP_MODE_ADVANCE | TP_MODE_GEN, t);
-        }
-        cudaMemcpyAsync(s->h_active, D.n_active, s->slots * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
-        TP_CUDA_OK(cudaStreamEndCapture(q, &g), {});
-        TP_CUDA_OK(cudaGraphInstantiate(&s->graph_exec, g, 0), { cudaGraphDestroy(g); });
-        cudaGraphDestroy(g);
-        s->graph_n_cand = s->n_cand;
+    if (s->graph_max_N != s->max_N) {
+        drop_graphs(s);
         s->graph_max_N = s->max_N;
-        s->stats = keep;   // the capture pass launched nothing
     }
     while (!done && ticks < max_ticks) {
+        const int ny = grid_bucket(live);
         if (use_graph) {
-            TP_CUDA_OK(cudaGraphLaunch(s->graph_exec, q), {});
-            s->stats.kernel_launches += 4 * s->slots;
-            s->stats.eval_launches += s->slots;
-        } else {
-            cudaMemsetAsync(D.n_active, 0, s->slots * sizeof(int32_t), q);
-            for (int t = 0; t < s->slots; t++) {
-                launch_eval(s, true, t);
-                launch_cand(s, TP_MODE_ADJ | TP_MODE_ADVANCE | TP_MODE_GEN, t);
-                cudaEventRecord(s->ev[5 * t + 4], q);
+            auto it = s->graphs.find(ny);
+            if (it == s->graphs.end()) {
+                cudaGraph_t g = nullptr;
+                cudaGraphExec_t ge = nullptr;
+                const topay_solver_stats keep = s->stats;
+                TP_CUDA_OK(cudaStreamBeginCapture(q, cudaStreamCaptureModeThreadLocal), {});
+                enqueue_batch(s, ny, false);
+                TP_CUDA_OK(cudaStreamEndCapture(q, &g), {});
+                TP_CUDA_OK(cudaGraphInstantiate(&ge, g, 0), { cudaGraphDestroy(g); });
+                cudaGraphDestroy(g);
+                s->stats = keep;   // the capture pass launched nothing
+                it = s->graphs.emplace(ny, ge).first;
             }
-            cudaMemcpyAsync(s->h_active, D.n_active, s->slots * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
+            TP_CUDA_OK(cudaGraphLaunch(it->second, q), {});
+            s->stats.kernel_launches += 6 * TP_TICKS + 1;
+            s->stats.eval_launches += TP_TICKS;
+        } else {
+            enqueue_batch(s, ny, true);
             cudaMemcpyAsync(s->h_nodes, D.node_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q);
         }
-        ticks += s->slots;
+        ticks += TP_TICKS;
+        slot_ticks += (long long)live * TP_TICKS;
         if (s->spin_sync || g_solves_running.load(std::memory_order_relaxed) <= 2) {
             TP_CUDA_OK(cudaStreamSynchronize(q), {});
         } else {
             cudaEventRecord(s->ev_batch, q);
             TP_CUDA_OK(cudaEventSynchronize(s->ev_batch), {});
         }
-        if (getenv("TOPAY_TICK_LOG")) {   // dev: wall time of each 16-tick batch vs candidates still active
-            static thread_local double t_prev = 0.0;
-            timespec ts;
-            clock_gettime(CLOCK_MONOTONIC, &ts);
-            const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
-            if (ticks > s->slots) fprintf(stderr, "TICKLOG %lld %d %.1f\n", ticks, s->h_active[s->slots - 1], (now - t_prev) * 1e6 / s->slots);
-            t_prev = now;
-        }
+        const int live_after = s->h_active[0];
         if (!use_graph) {
-            // batches in which every candidate was still solving: the full-activity figures
-            const bool full = s->h_active[s->slots - 1] == s->n_cand;
+            // batches in which every slot was still solving: the full-activity figures
+            const bool full = live_after == live;
             const unsigned long long hist_now = s->h_nodes[1];
-            double cand_batch = 0.0;
-            for (int t = 0; t < s->slots; t++) {
+            double cand_batch = 0.0, lbfgs_batch = 0.0;
+            for (int t = 0; t < TP_TICKS; t++) {
                 float ms = 0.f;
-                cudaEventElapsedTime(&ms, s->ev[5 * t + 1], s->ev[5 * t + 2]);
+                cudaEventElapsedTime(&ms, s->ev[TP_EV * t + 1], s->ev[TP_EV * t + 2]);
                 ms_eval += ms;
-                cudaEventElapsedTime(&ms, s->ev[5 * t], s->ev[5 * t + 1]);
+                cudaEventElapsedTime(&ms, s->ev[TP_EV * t], s->ev[TP_EV * t + 1]);
                 ms_k[0] += ms;
-                cudaEventElapsedTime(&ms, s->ev[5 * t + 2], s->ev[5 * t + 3]);
+                cudaEventElapsedTime(&ms, s->ev[TP_EV * t + 2], s->ev[TP_EV * t + 3]);
                 ms_k[1] += ms;
-                cudaEventElapsedTime(&ms, s->ev[5 * t + 3], s->ev[5 * t + 4]);
+                cudaEventElapsedTime(&ms, s->ev[TP_EV * t + 3], s->ev[TP_EV * t + 6]);
                 ms_k[2] += ms;
                 cand_batch += ms;
+                for (int k = 0; k < 3; k++) {
+                    cudaEventElapsedTime(&ms, s->ev[TP_EV * t + 3 + k], s->ev[TP_EV * t + 4 + k]);
+                    ms_c[k] += ms;
+                    if (k == 1) lbfgs_batch += ms;
+                }
             }
             if (full) {
-                full_ms_cand += cand_batch;
+                full_ms_cand += lbfgs_batch;
                 full_hist += hist_now - hist_prev;
-                full_ticks += s->slots;
+                full_ticks += TP_TICKS;
             }
             hist_prev = hist_now;
         }
-        done = s->h_active[s->slots - 1] == 0;
+        live = live_after;
+        done = live == 0;
+    }
+    if (!done) {
+        k_mark_tick_cap<<<(std::max(s->n_cand, D.n_slots) + 127) / 128, 128, 0, q>>>(D, s->n_cand);
+        tp_set_error("tick cap reached: unfinished candidates carry TOPAY_LBFGSERR_TICK_CAP");
     }
     cudaEventRecord(s->ev_end, q);
     cudaMemcpyAsync(s->h_nodes, D.node_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q);
@@ -556,7 +679,11 @@ extern "C" int topay_solver_run(topay_solver* s) {
     s->stats.ms_integrate = (float)ms_k[0];
     s->stats.ms_chain = (float)ms_k[1];
     s->stats.ms_cand = (float)ms_k[2];
+    s->stats.ms_adj = (float)ms_c[0];
+    s->stats.ms_lbfgs = (float)ms_c[1];
+    s->stats.ms_gen = (float)ms_c[2];
     s->stats.ticks = ticks;
+    s->stats.slot_ticks = slot_ticks;
     s->stats.eval_nodes = (int64_t)s->h_nodes[0];
     s->stats.hist_bytes = (int64_t)s->h_nodes[1] * 16;
     s->stats.full_ticks = full_ticks;
@@ -572,9 +699,9 @@ extern "C" int topay_solver_download(topay_solver* s, topay_result_batch* out, i
     const TpSolverDev& D = s->dev;
     const int n = s->n_cand, NP = D.max_pieces;
     std::vector<TpCandState> st(n);
-    TP_CUDA_OK(cudaMemcpy(st.data(), D.st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), {});
+    TP_CUDA_OK(cudaMemcpy(st.data(), D.res_st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), {});
     std::vector<double> T((size_t)n * NP);
-    TP_CUDA_OK(cudaMemcpy(T.data(), D.T, T.size() * 8, cudaMemcpyDeviceToHost), {});
+    TP_CUDA_OK(cudaMemcpy(T.data(), D.res_T, T.size() * 8, cudaMemcpyDeviceToHost), {});
     int bd = -1, bc = -1;
     double bdv = 0, bcv = 0;
     int64_t evals = 0;
@@ -608,10 +735,10 @@ extern "C" int topay_solver_download(topay_solver* s, topay_result_batch* out, i
     }
     s->stats.evals_total = evals;
     if (out->T) memcpy(out->T, T.data(), T.size() * 8);
-    if (out->coeff) TP_CUDA_OK(cudaMemcpy(out->coeff, D.coeff, (size_t)n * 6 * NP * 9 * 8, cudaMemcpyDeviceToHost), {});
+    if (out->coeff) TP_CUDA_OK(cudaMemcpy(out->coeff, D.res_coeff, (size_t)n * 6 * NP * 9 * 8, cudaMemcpyDeviceToHost), {});
     if (out->x) {
         std::vector<double> xs((size_t)n * D.xs);
-        TP_CUDA_OK(cudaMemcpy(xs.data(), D.x, xs.size() * 8, cudaMemcpyDeviceToHost), {});
+        TP_CUDA_OK(cudaMemcpy(xs.data(), D.res_x, xs.size() * 8, cudaMemcpyDeviceToHost), {});
         const int xstride = topay_num_vars(NP);
         for (int c = 0; c < n; c++) memcpy(out->x + (size_t)c * xstride, &xs[(size_t)c * D.xs], st[c].n * 8);
     }
@@ -654,8 +781,8 @@ extern "C" int topay_solver_check_feasible(topay_solver* s, topay_feasibility* o
         s->checker = new TpTrajChecker();
         if ((rc = s->checker->init(s->device, s->stream)) != TOPAY_OK) return rc;
     }
-    k_solver_traj_view<<<(n + 127) / 128, 128, 0, s->stream>>>(D.st, D.start_xy, D.head_pva, n, s->d_pn, s->d_start);
-    TpTrajView V{n, NP, s->d_pn, D.T, D.coeff, s->d_start};
+    k_solver_traj_view<<<(n + 127) / 128, 128, 0, s->stream>>>(D.res_st, D.start_xy, D.head_pva, n, s->d_pn, s->d_start);
+    TpTrajView V{n, NP, s->d_pn, D.res_T, D.res_coeff, s->d_start};
     TpGrid G;
     solver_grid(s, &G);
     std::vector<int32_t> fp;
@@ -668,7 +795,7 @@ extern "C" int topay_solver_check_feasible(topay_solver* s, topay_feasibility* o
     if (rc == TOPAY_OK && best_success) {
         // planner.cpp:877-880 + :999-1010: optimizeTraj && printConstraintsSituations, shortest duration
         std::vector<TpCandState> st(n);
-        TP_CUDA_OK(cudaMemcpy(st.data(), D.st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), { out->feasible_print = keep_fp; });
+        TP_CUDA_OK(cudaMemcpy(st.data(), D.res_st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), { out->feasible_print = keep_fp; });
         std::vector<int32_t> ok(n);
         std::vector<double> dur(n);
         for (int c = 0; c < n; c++) {
@@ -688,7 +815,7 @@ extern "C" int64_t topay_solver_debug_download(topay_solver* s, int which, doubl
     if (!s || !out) return TOPAY_ERR_INVALID_ARG;
     cudaSetDevice(s->device);
     const TpSolverDev& D = s->dev;
-    const size_t C_ = (size_t)D.max_cand, NP = (size_t)D.max_pieces, K = (size_t)D.K;
+    const size_t C_ = (size_t)D.n_slots, NP = (size_t)D.max_pieces, K = (size_t)D.K;
     const double* src = nullptr;
     size_t n = 0;
     switch (which) {
@@ -707,12 +834,74 @@ extern "C" int64_t topay_solver_debug_download(topay_solver* s, int which, doubl
     return (int64_t)n;
 }
 
+// Parity hook for the L-BFGS direction update (lbfgs.hpp:657-710). Loads a history into slot 0 and runs ONE launch
+// of the L-BFGS kernel in which the line search is accepted, the pair (s, y) = (x - xp, g - gp) enters the ring at
+// `end`, and the two-loop recursion over min(bound + 1, m) pairs produces the next direction.
+extern "C" int topay_solver_debug_direction(topay_solver* s, int n_vars, int bound, int end, const double* S_rows,
+                                            const double* Y_rows, const double* ys, const double* x, const double* xp,
+                                            const double* g, const double* gp, double* d_out, int32_t* bound_out,
+                                            int32_t* end_out) {
+    if (!s || !S_rows || !Y_rows || !ys || !x || !xp || !g || !gp || !d_out) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(s->device);
+    const TpSolverDev& D = s->dev;
+    const int m = std::min(s->params.opt.s2_lbfgs.mem_size, D.mem);
+    if (n_vars < 1 || n_vars > D.xs || bound < 0 || bound > m || end < 0 || end >= m) return TOPAY_ERR_INVALID_ARG;
+    TpCandState st;
+    memset(&st, 0, sizeof(st));
+    st.phase = 2;
+    st.N = D.max_pieces;
+    st.n = n_vars;
+    st.k = bound + 1;
+    st.end = end;
+    st.bound = bound;
+    st.stp = 1.0;
+    st.finit = st.fx = 1.0;          // |finit - f| = 0: the reference's early accept (lbfgs.hpp:327-330) ends the search
+    st.dgtest = st.dstest = -1.0;
+    for (int i = 0; i < TP_LBFGS_MAX_PAST; i++) st.pf[i] = 1e30;   // the past-delta test does not stop the run
+    st.rho[0] = st.rho[1] = 1.0;
+    cudaStream_t q = s->stream;
+    auto up = [&](double* dst, const double* src, size_t rows, size_t row_len) {
+        std::vector<double> pad(rows * D.xs, 0.0);
+        for (size_t r = 0; r < rows; r++) memcpy(&pad[r * D.xs], src + r * row_len, row_len * sizeof(double));
+        return cudaMemcpy(dst, pad.data(), pad.size() * sizeof(double), cudaMemcpyHostToDevice);
+    };
+    TP_CUDA_OK(up(D.x, x, 1, n_vars), {});
+    TP_CUDA_OK(up(D.xp, xp, 1, n_vars), {});
+    TP_CUDA_OK(up(D.g, g, 1, n_vars), {});
+    TP_CUDA_OK(up(D.gp, gp, 1, n_vars), {});
+    TP_CUDA_OK(up(D.lm_s, S_rows, m, n_vars), {});
+    TP_CUDA_OK(up(D.lm_y, Y_rows, m, n_vars), {});
+    TP_CUDA_OK(cudaMemcpy(D.lm_ys, ys, m * sizeof(double), cudaMemcpyHostToDevice), {});
+    const double f = 1.0;
+    const int32_t zero = 0, one = 1, queue[3] = {1, 1, 0};
+    TP_CUDA_OK(cudaMemcpy(D.f, &f, sizeof(double), cudaMemcpyHostToDevice), {});
+    TP_CUDA_OK(cudaMemcpy(D.st, &st, sizeof(st), cudaMemcpyHostToDevice), {});
+    TP_CUDA_OK(cudaMemcpy(D.slot_gid, &zero, sizeof(int32_t), cudaMemcpyHostToDevice), {});
+    TP_CUDA_OK(cudaMemcpy(D.list + (size_t)TP_TICKS * D.n_slots, &zero, sizeof(int32_t), cudaMemcpyHostToDevice), {});
+    TP_CUDA_OK(cudaMemcpy(D.count + TP_TICKS, &one, sizeof(int32_t), cudaMemcpyHostToDevice), {});
+    TP_CUDA_OK(cudaMemcpy(D.queue, queue, sizeof(queue), cudaMemcpyHostToDevice), {});
+    launch_cand(s, TP_MODE_ADVANCE, TP_TICKS, -1, 1);
+    TP_CUDA_OK(cudaStreamSynchronize(q), {});
+    TP_CUDA_OK(cudaGetLastError(), {});
+    s->n_cand = 0;   // not a solvable upload
+    TP_CUDA_OK(cudaMemcpy(d_out, D.d, n_vars * sizeof(double), cudaMemcpyDeviceToHost), {});
+    TP_CUDA_OK(cudaMemcpy(&st, D.st, sizeof(st), cudaMemcpyDeviceToHost), {});
+    if (st.phase != 2) {
+        tp_set_error("debug_direction: the crafted iteration did not reach the two-loop (ys <= cautious bound or "
+                     "an ascent direction)");
+        return TOPAY_ERR_INVALID_ARG;
+    }
+    if (bound_out) *bound_out = st.bound;
+    if (end_out) *end_out = st.end;
+    return TOPAY_OK;
+}
+
 // Dev profiling: accumulated clock64() deltas of k_cand's phases for candidate 0 (16 slots).
 extern "C" int topay_solver_phase_clocks(topay_solver* s, int enable, long long* out16) {
     if (!s) return TOPAY_ERR_INVALID_ARG;
     cudaSetDevice(s->device);
     TpSolverDev& D = s->dev;
-    s->graph_n_cand = -1;   // captured kernel arguments change
+    drop_graphs(s);   // captured kernel arguments change
     if (enable && !D.prof) {
         TP_CUDA_OK(cudaMalloc(&D.prof, 16 * sizeof(long long)), {});
         cudaMemset(D.prof, 0, 16 * sizeof(long long));
@@ -738,7 +927,7 @@ extern "C" int topay_solver_set_trace(topay_solver* s, int cap) {
     if (!s || cap < 0) return TOPAY_ERR_INVALID_ARG;
     cudaSetDevice(s->device);
     TpSolverDev& D = s->dev;
-    s->graph_n_cand = -1;   // captured kernel arguments change
+    drop_graphs(s);   // captured kernel arguments change
     if (D.trace) {
         cudaFree(D.trace);
         cudaFree(D.trace_len);

@@ -9,7 +9,11 @@
 //               per-piece reduction of gdC / gdT / cost terms                        (a6,a7,a8,a9,a17,a18)
 //   k_chain     sub-warp per piece: suffix sums of the xy adjoints and the contraction with
 //               the Simpson-prefix Jacobians                                         (a6 tail, :1812-1822)
-// Nothing returns to the host between ticks; finished candidates are masked.
+// Nothing returns to the host between ticks. Candidates live in working SLOTS; the problems of an upload
+// (the STORE, indexed by candidate id `gid`) are handed to slots on the device: the moment a slot's candidate
+// reaches a terminal state its results go to the store and the same CTA pops the next waiting candidate
+// (continuous batching — the reference's "first success + grace" worker pool of planner.cpp:921-952 turned
+// into a device-side queue). Every tick runs over the compacted list of live slots only.
 #pragma once
 #include <type_traits>
 #include <cuda_runtime.h>
@@ -42,16 +46,32 @@ struct TpCandState {
     double cost;
 };
 
-// All device pointers of a solver; strides are fixed by (max_cand, max_pieces, K).
+#define TP_TICKS 16   // ticks per batch (one CUDA graph); the live lists form a ring of TP_TICKS + 1 entries
+
+// All device pointers of a solver; strides are fixed by (max_cand, n_slots, max_pieces, K).
+// "[store]" arrays are indexed by candidate id (gid < max_cand), "[slot]" arrays by working slot (< n_slots).
 struct TpSolverDev {
-    int32_t max_cand, max_pieces, K, Kpad, ppw, xs, mem;   // xs = stride of x-like vectors
+    int32_t max_cand, n_slots, max_pieces, K, Kpad, ppw, xs, mem;   // xs = stride of x-like vectors
     int32_t smem_doubles;     // dynamic shared memory of k_cand, in doubles
     int32_t end_tasks;        // 1 when K == Kpad: node j = 2K is handled by separate end-node warps
-    TpCandState* st;
-    // problem data
+    // [store] problem data + initial state, written by the upload
     double *head_pva, *tail_pva, *start_xy, *end_xy, *init_inner_xy;
-    // vectors [max_cand][xs]
+    double *x0;               // [store][xs]
+    TpCandState* st0;         // [store]
+    // [store] results, written by the CTA that finishes the candidate
+    TpCandState* res_st;      // [store]
+    double *res_T;            // [store][max_pieces]
+    double *res_coeff;        // [store][6*max_pieces][9]   coefficients of the last evaluation (what getTraj() returns)
+    double *res_x;            // [store][xs]
+    // scheduling
+    int32_t *slot_gid;        // [slot] candidate in the slot
+    int32_t *list;            // [TP_TICKS + 1][n_slots] live slots before tick t
+    int32_t *count;           // [TP_TICKS + 1]
+    int32_t *queue;           // [0] next gid to hand out, [1] candidates in the store, [2] finished so far
+    TpCandState* st;          // [slot]
+    // vectors [slot][xs]
     double *x, *g, *xp, *gp, *d;
+    // everything below is [slot]-indexed (the comments say max_cand for the slot count)
     // L-BFGS memory: lm_s, lm_y [max_cand][mem][xs]; lm_ys, lm_alpha [max_cand][mem]
     double *lm_s, *lm_y, *lm_ys, *lm_alpha;
     // spline state
@@ -72,12 +92,11 @@ struct TpSolverDev {
     // outputs of an evaluation
     double *f;        // [max_cand]
     double *term_out; // [max_cand][TOPAY_NTERMS]
-    int32_t *n_active; // [slots] candidates still solving after tick `slot` (written by k_cand)
     unsigned long long *node_count; // [0] penalty nodes scheduled for evaluation so far; [1] history rows x n
                                     // walked by the two-loop recursions so far (each row = one s_j and one y_j)
     // optional L-BFGS iterate trace (debug / parity): 4 doubles (f, step, k, ls) per accepted iteration
-    double *trace;        // [max_cand][trace_cap][4] or null
-    int32_t *trace_len;   // [max_cand]
+    double *trace;        // [store][trace_cap][4] or null
+    int32_t *trace_len;   // [store]
     int32_t trace_cap;
     long long *prof;      // optional phase clocks of candidate 0 (dev profiling), [16] or null
 };
@@ -98,13 +117,51 @@ __device__ __forceinline__ double tp_warp_max(double v) {
     return v;
 }
 
+// Live-list lookup shared by the kernels of a tick: entry `li` of list `tick`.
+__device__ __forceinline__ int tp_live_slot(const TpSolverDev& S, int tick, int li) {
+    if (li >= S.count[tick]) return -1;
+    return S.list[(size_t)tick * S.n_slots + li];
+}
+
+// Start of a batch (one CTA): the list the previous batch ended with becomes list 0, the other counters are cleared.
+__global__ void k_list_roll(const __grid_constant__ TpSolverDev S) {
+    const int n = S.count[TP_TICKS];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) S.list[i] = S.list[(size_t)TP_TICKS * S.n_slots + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        S.count[0] = n;
+        for (int t = 1; t <= TP_TICKS; t++) S.count[t] = 0;
+    }
+}
+
+// Hands the first n0 candidates of the store to slots 0..n0-1 and makes them the live list TP_TICKS.
+__global__ void k_slot_init(const __grid_constant__ TpSolverDev S, int n0, int n_store) {
+    const int slot = blockIdx.x;
+    if (slot >= n0) return;
+    const TpCandState st = S.st0[slot];
+    for (int i = threadIdx.x; i < st.n; i += blockDim.x) S.x[(size_t)slot * S.xs + i] = S.x0[(size_t)slot * S.xs + i];
+    if (threadIdx.x == 0) {
+        S.st[slot] = st;
+        S.slot_gid[slot] = slot;
+        S.list[(size_t)TP_TICKS * S.n_slots + slot] = slot;
+        if (slot == 0) {
+            for (int t = 0; t < TP_TICKS; t++) S.count[t] = 0;
+            S.count[TP_TICKS] = n0;
+            S.queue[0] = n0;
+            S.queue[1] = n_store;
+            S.queue[2] = 0;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ k_integrate
 // Simpson interval integrals of one piece (moma_traj_opt.cpp:1282-1291, 1731-1732):
 //   I[k] = coeff v(2k) + 4 coeff v(2k+1) + coeff v(2k+2),  v = s' (cos yaw, sin yaw)
 // and the piece totals (IntegralX.sum(), :1750).
 __global__ void __launch_bounds__(TP_WARPS_PER_BLOCK * 32)
-k_integrate(const __grid_constant__ TpSolverDev S) {
-    const int cand = blockIdx.y;
+k_integrate(const __grid_constant__ TpSolverDev S, int tick) {
+    const int cand = tp_live_slot(S, tick, blockIdx.y);   // slot
+    if (cand < 0) return;
     const TpCandState& cs = S.st[cand];
     if (cs.phase == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -204,16 +261,18 @@ __device__ __forceinline__ void tp_transpose_reduce64(double* v, int jn) {
 template <int KPAD>
 __global__ void __launch_bounds__(TP_PEN_WARPS * 32, TP_PEN_MIN_BLOCKS)
 k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P,
-          const __grid_constant__ TpGrid G, int n_groups) {
-    const int cand = blockIdx.y;
+          const __grid_constant__ TpGrid G, int n_groups, int tick) {
+    const int cand = tp_live_slot(S, tick, blockIdx.y);   // slot
+    if (cand < 0) return;
     const TpCandState& cs = S.st[cand];
     if (cs.phase == 0) return;
+    const int gid = S.slot_gid[cand];
     const int STAGE = cs.phase;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = S.K, N = cs.N;
     constexpr int PPW = 32 / KPAD;
     const int task = blockIdx.x * TP_PEN_WARPS + warp;
-    const double* start_xy = S.start_xy + (size_t)cand * 2;
+    const double* start_xy = S.start_xy + (size_t)gid * 2;
     const double* totc = S.tot + (size_t)cand * S.max_pieces * 2;
     extern __shared__ double sm[];
     // [2 stores][36][block threads] sphere stores, then per-warp coefficient staging
@@ -380,10 +439,12 @@ k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParam
 // Stage 1: weight of every slot of piece p = sum over pieces i > p of 2 w (F_{i+1} - target_i)
 // (`head(i*(2K+1))`, :1175 — piece i itself excluded, reference quirk 1).
 __global__ void __launch_bounds__(TP_WARPS_PER_BLOCK * 32)
-k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P) {
-    const int cand = blockIdx.y;
+k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P, int tick) {
+    const int cand = tp_live_slot(S, tick, blockIdx.y);   // slot
+    if (cand < 0) return;
     const TpCandState& cs = S.st[cand];
     if (cs.phase == 0) return;
+    const int gid = S.slot_gid[cand];
     const int STAGE = cs.phase;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = S.K, Kpad = S.Kpad, N = cs.N;
@@ -406,8 +467,8 @@ k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams 
         __syncwarp();
         if (lane == 0) {
             const double wgt = P.opt.s1_path_pos_weight;
-            const double* tgt = S.init_inner_xy + (size_t)cand * S.max_pieces * 2;
-            double fx = S.start_xy[(size_t)cand * 2], fy = S.start_xy[(size_t)cand * 2 + 1];
+            const double* tgt = S.init_inner_xy + (size_t)gid * S.max_pieces * 2;
+            double fx = S.start_xy[(size_t)gid * 2], fy = S.start_xy[(size_t)gid * 2 + 1];
             for (int i = 0; i < N; i++) {
                 fx += w[2 * i];
                 fy += w[2 * i + 1];
@@ -437,8 +498,8 @@ k_chain(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams 
         }
         tx = tp_seg_sum(tx, Kpad);
         ty = tp_seg_sum(ty, Kpad);
-        const double ex = S.start_xy[(size_t)cand * 2] + tx - S.end_xy[(size_t)cand * 2];
-        const double ey = S.start_xy[(size_t)cand * 2 + 1] + ty - S.end_xy[(size_t)cand * 2 + 1];
+        const double ex = S.start_xy[(size_t)gid * 2] + tx - S.end_xy[(size_t)gid * 2];
+        const double ey = S.start_xy[(size_t)gid * 2 + 1] + ty - S.end_xy[(size_t)gid * 2 + 1];
         wx = cs.rho[0] * (ex + cs.lambda[0] / cs.rho[0]);
         wy = cs.rho[1] * (ey + cs.lambda[1] / cs.rho[1]);
         // adjoints of all later pieces
@@ -852,15 +913,25 @@ __device__ __forceinline__ bool tp_ok_code(int r) {
 
 #define TP_PROF(slot) do { if (S.prof && cand == 0 && tid == 0) S.prof[slot] += clock64() - t_prof; t_prof = clock64(); } while (0)
 
-__global__ void __launch_bounds__(TP_CAND_THREADS, 3)
-k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P, int mode, int slot) {
-    const int cand = blockIdx.x;
+// The three halves are separate launches with their own footprint — the adjoint and generate halves need the
+// whole banded system in shared memory (70 KB at 64 pieces: three CTAs per SM, a 45 / 80 us sequential chain each),
+// the L-BFGS half only its TMA ring (50 KB: four CTAs per SM, 128 registers) — so that the long two-loop streams
+// at a higher occupancy than the banded solves allow. MODE is a compile-time mask of TP_MODE_*; smem_doubles is
+// the launch's dynamic shared memory in doubles.
+template <int MODE>
+__global__ void __launch_bounds__(TP_CAND_THREADS, (MODE == TP_MODE_ADVANCE) ? 4 : 3)
+k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P, int smem_doubles, int tick_in,
+       int tick_out) {
+    constexpr int mode = MODE;
+    const int cand = tp_live_slot(S, tick_in, blockIdx.x);   // slot: every [slot] array below is indexed by it
+    if (cand < 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     TpCandState* gs = S.st + cand;
     if (gs->phase == 0) return;
     TpCandState st = *gs;          // uniform copy per thread
+    int gid = S.slot_gid[cand];    // candidate of the store in this slot
     long long t_prof = clock64();
-    const int N = st.N, n = st.n, n6 = 6 * N;
+    int N = st.N, n = st.n, n6 = 6 * N;
     const int stage = st.phase;
     extern __shared__ __align__(16) double sm[];
     // Dynamic shared memory (70.7 KB at 64 pieces, three CTAs per SM): the banded LU (6N x TP_BAND) and
@@ -871,7 +942,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
     double* lu = sm;
     double* cf = lu + (size_t)6 * S.max_pieces * TP_BAND;
     double* wk = cf;
-    double* s_alpha = sm + S.smem_doubles - (512 + S.xs);   // tables + scratch at the end of the region
+    double* s_alpha = sm + smem_doubles - (512 + S.xs);   // tables + scratch at the end of the region
     double* s_ys = s_alpha + 256;
     __shared__ double red[2 * 4 * TP_CAND_WARPS];
     __shared__ double s_small[4 * 64 + 2 * TOPAY_NTERMS];   // T, totals (x,y), scratch
@@ -882,7 +953,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 #ifdef TP_DEBUG_ZERO_SMEM
-    for (int e = tid; e < S.smem_doubles; e += TP_CAND_THREADS) sm[e] = TP_DEBUG_ZERO_SMEM;
+    for (int e = tid; e < smem_doubles; e += TP_CAND_THREADS) sm[e] = TP_DEBUG_ZERO_SMEM;
     __syncthreads();
 #endif
     int flip = 0;
@@ -899,7 +970,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
     double f_eval = 0.0;
 
     // ================= adjoint half of the evaluation in flight =================
-    if (mode & TP_MODE_ADJ) {
+    if constexpr ((mode & TP_MODE_ADJ) != 0) {
         for (int e = tid; e < n6 * TP_BAND; e += TP_CAND_THREADS) lu[e] = lug[e];
         const double* cfr = cg;   // coefficients of this evaluation, written by the previous launch
         const double* gdCp = S.gdC + (size_t)cand * 6 * S.max_pieces * 9;
@@ -926,9 +997,9 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         TP_PROF(0);
         if (tid == 0) {
             // end point, VecTrajFinalXY order (:1750); stage-1 path cost (:1173-1178)
-            double fx = S.start_xy[cand * 2], fy = S.start_xy[cand * 2 + 1];
+            double fx = S.start_xy[gid * 2], fy = S.start_xy[gid * 2 + 1];
             double cost_path = 0.0, avg = 0.0;
-            const double* tgt = S.init_inner_xy + (size_t)cand * S.max_pieces * 2;
+            const double* tgt = S.init_inner_xy + (size_t)gid * S.max_pieces * 2;
             for (int i = 0; i < N; i++) {
                 fx += sTot[2 * i];
                 fy += sTot[2 * i + 1];
@@ -956,8 +1027,8 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     }
                 }
             }
-            sMisc[0] = fx - S.end_xy[cand * 2];
-            sMisc[1] = fy - S.end_xy[cand * 2 + 1];
+            sMisc[0] = fx - S.end_xy[gid * 2];
+            sMisc[1] = fy - S.end_xy[gid * 2 + 1];
             sMisc[2] = cost_path;
             sMisc[3] = avg;
             sMisc[4] = tsum;
@@ -1103,7 +1174,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
 
     // ================= line search / L-BFGS / ALM state machine =================
     bool need_eval = true;
-    if (mode & TP_MODE_ADVANCE) {
+    if constexpr ((mode & TP_MODE_ADVANCE) != 0) {
         const int m = lp.mem_size < S.mem ? lp.mem_size : S.mem;
         double* lm_s = S.lm_s + (size_t)cand * S.mem * S.xs;
         double* lm_y = S.lm_y + (size_t)cand * S.mem * S.xs;
@@ -1122,7 +1193,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
         }
         int ret = 0;
         enum { A_NONE, A_BEGIN_LS, A_LS_DONE, A_FINISH } action = A_NONE;
-        const double f = f_eval;
+        const double f = (mode & TP_MODE_ADJ) ? f_eval : S.f[cand];   // a separate adjoint launch left it in S.f
         if (st.ls_init) {
             // lbfgs.hpp:522-554
             st.ls_init = 0;
@@ -1221,14 +1292,14 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             const int k = st.k;
             bool fin = false;
             if (S.trace && tid == 0) {   // where the reference calls proc_progress (:585-592)
-                const int tl = S.trace_len[cand];
+                const int tl = S.trace_len[gid];
                 if (tl < S.trace_cap) {
-                    double* tr = S.trace + ((size_t)cand * S.trace_cap + tl) * 4;
+                    double* tr = S.trace + ((size_t)gid * S.trace_cap + tl) * 4;
                     tr[0] = st.fx;
                     tr[1] = st.stp;
                     tr[2] = (double)k;
                     tr[3] = (double)st.ls_count;
-                    S.trace_len[cand] = tl + 1;
+                    S.trace_len[gid] = tl + 1;
                 }
             }
             if (stage == 2 && k > lp.max_iterations) {   // progress callback earlyExit, :1873
@@ -1308,7 +1379,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     const int total = 2 * st.bound;
                     const int rowd = (n + 1) & ~1;                       // 16-byte multiple
                     const uint32_t row_bytes = (uint32_t)(rowd * sizeof(double));
-                    const int ring_doubles = S.smem_doubles - (512 + S.xs);
+                    const int ring_doubles = smem_doubles - (512 + S.xs);
                     const int nst = max(2, min(TP_RING_MAX, ring_doubles / (2 * rowd)) & ~1);   // even: rounds take two
                     double* ring = sm;
                     const uint64_t pol = tp_policy_evict_first();
@@ -1578,24 +1649,60 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             }
             need_eval = st.phase != 0;
         }
-        // write this thread's elements back
+        if (action == A_FINISH && st.phase == 0) {
+            // ---- the candidate is done: results to the store, then the slot takes the next waiting candidate
 #pragma unroll
-        for (int e = 0; e < TP_EPT; e++) {
-            const int i = tid + e * TP_CAND_THREADS;
-            if (i < n) {
-                x[i] = rx[e];
-                g[i] = rg[e];
-                xp[i] = rxp[e];
-                gp[i] = rgp[e];
-                dv[i] = rd[e];
+            for (int e = 0; e < TP_EPT; e++) {
+                const int i = tid + e * TP_CAND_THREADS;
+                if (i < n) S.res_x[(size_t)gid * S.xs + i] = rx[e];
             }
+            for (int i = tid; i < N; i += TP_CAND_THREADS) S.res_T[(size_t)gid * S.max_pieces + i] = Tg[i];
+            {
+                double* rc = S.res_coeff + (size_t)gid * 6 * S.max_pieces * 9;
+                for (int e = tid; e < n6 * 9; e += TP_CAND_THREADS) rc[e] = cg[e];
+            }
+            __shared__ int s_next;
+            if (tid == 0) {
+                S.res_st[gid] = st;
+                atomicAdd(S.queue + 2, 1);
+                const int q = atomicAdd(S.queue, 1);
+                s_next = q < S.queue[1] ? q : -1;
+            }
+            __syncthreads();
+            const int nxt = s_next;
+            if (nxt >= 0) {
+                gid = nxt;
+                st = S.st0[gid];
+                N = st.N;
+                n = st.n;
+                n6 = 6 * N;
+                const double* xn = S.x0 + (size_t)gid * S.xs;
+                for (int i = tid; i < n; i += TP_CAND_THREADS) x[i] = xn[i];
+                if (tid == 0) S.slot_gid[cand] = gid;
+                need_eval = true;
+            }
+            __syncthreads();
+        } else {
+            // write this thread's elements back
+#pragma unroll
+            for (int e = 0; e < TP_EPT; e++) {
+                const int i = tid + e * TP_CAND_THREADS;
+                if (i < n) {
+                    x[i] = rx[e];
+                    g[i] = rg[e];
+                    xp[i] = rxp[e];
+                    gp[i] = rgp[e];
+                    dv[i] = rd[e];
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
         TP_PROF(8);
     }
 
     // ================= generate half of the next evaluation =================
     if ((mode & TP_MODE_GEN) && need_eval) {
+        if (!(mode & TP_MODE_ADVANCE)) gid = S.slot_gid[cand];
         double* sT = s_small;
         for (int i = tid; i < N; i += TP_CAND_THREADS) {
             const double t = tp_expC2(x[i]);
@@ -1603,7 +1710,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
             Tg[i] = t;
         }
         __syncthreads();
-        tp_fill_system(N, sT, S.head_pva + (size_t)cand * 27, S.tail_pva + (size_t)cand * 27, x, P, lu, cf);
+        tp_fill_system(N, sT, S.head_pva + (size_t)gid * 27, S.tail_pva + (size_t)gid * 27, x, P, lu, cf);
         TP_PROF(9);
         if (warp == 0) tp_lu_factor(n6, lu, lane);
         __syncthreads();
@@ -1623,7 +1730,10 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
     if (tid == 0) {
         *gs = st;
         if (st.phase != 0 && (mode & TP_MODE_GEN)) {
-            atomicAdd(S.n_active + slot, 1);
+            if (tick_out >= 0) {
+                const int q = atomicAdd(S.count + tick_out, 1);
+                S.list[(size_t)tick_out * S.n_slots + q] = cand;
+            }
             atomicAdd(S.node_count, (unsigned long long)(N * (S.K + 1)));
         }
     }

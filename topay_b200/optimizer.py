@@ -95,7 +95,10 @@ class MomaTraj:
 
 class MomaTrajOpt:
     def __init__(self, grid_map: GridMap, max_cand=8, max_pieces=16, opt_param: OptParams = None,
-                 robot: RobotParams = None):
+                 robot: RobotParams = None, n_slots=None):
+        """max_cand: candidates one upload may hold (several plans back to back); n_slots: how many of them are in
+        flight on the device at a time (default: all) — finished candidates hand their slot to the next waiting
+        one on the device (topay_solver_create_pool)."""
         self._l = _lib.lib()
         self.grid_map = grid_map
         self.opt_param = opt_param if opt_param is not None else opt_params_default()
@@ -105,9 +108,15 @@ class MomaTrajOpt:
         # GridMap::use_rog (grid_map.h:90): a rog.ESDFMap routes every field lookup of the solve and of the gate
         # to the ROG-Map ring
         self.use_rog = not isinstance(grid_map, GridMap)
-        create = self._l.topay_solver_create_rog if self.use_rog else self._l.topay_solver_create
-        _lib.check(create(C.byref(self.opt_param), C.byref(self.moma_param), grid_map.h, max_cand, max_pieces,
-                          C.byref(self.h)), "topay_solver_create")
+        self.n_slots = max_cand if n_slots is None else min(n_slots, max_cand)
+        if self.use_rog or self.n_slots == max_cand:
+            create = self._l.topay_solver_create_rog if self.use_rog else self._l.topay_solver_create
+            _lib.check(create(C.byref(self.opt_param), C.byref(self.moma_param), grid_map.h, max_cand, max_pieces,
+                              C.byref(self.h)), "topay_solver_create")
+        else:
+            _lib.check(self._l.topay_solver_create_pool(C.byref(self.opt_param), C.byref(self.moma_param), grid_map.h,
+                                                        max_cand, self.n_slots, max_pieces, C.byref(self.h)),
+                       "topay_solver_create_pool")
         self.traj_cost = 0.0
         self._last = None
 
@@ -185,6 +194,32 @@ class MomaTrajOpt:
         self.upload(paths, boundary_vel, boundary_acc)
         self.run()
         return self.download()
+
+    def optimizeTrajPlans(self, plans):
+        """Several plans through one device solve with continuous batching: `plans` is a list of
+        (paths, boundary_vel, boundary_acc); their candidates are queued back to back and flow through the solver's
+        slots (n_slots in flight, the next waiting candidate takes a slot the moment one finishes). Returns the
+        result dict of download() over all candidates plus `plan_offset` (first candidate of each plan) and the
+        per-plan winners `plan_best_by_duration` / `plan_best_by_cost` (index inside the plan, -1 if none)."""
+        paths = [q for p in plans for q in p[0]]
+        bv = np.concatenate([np.asarray(p[1], dtype=np.float64).reshape(len(p[0]), 10, 2) for p in plans])
+        ba = np.concatenate([np.asarray(p[2], dtype=np.float64).reshape(len(p[0]), 10, 2) for p in plans])
+        self.upload(paths, bv, ba)
+        self.run()
+        r = self.download()
+        off = np.cumsum([0] + [len(p[0]) for p in plans])
+        bd, bc = [], []
+        for i in range(len(plans)):
+            ok = np.flatnonzero(r["status"][off[i]:off[i + 1]] == 1)
+            if len(ok) == 0:
+                bd.append(-1)
+                bc.append(-1)
+                continue
+            dur, cost = r["duration"][off[i]:off[i + 1]][ok], r["cost"][off[i]:off[i + 1]][ok]
+            bd.append(int(ok[np.argmin(dur)]))      # argmin takes the first minimum: planner.cpp:999-1010
+            bc.append(int(ok[np.argmin(cost)]))
+        r["plan_offset"], r["plan_best_by_duration"], r["plan_best_by_cost"] = off, np.array(bd), np.array(bc)
+        return r
 
     def optimizeTraj(self, init_path, boundary_vel, boundary_acc):
         """bool MomaTrajOpt::optimizeTraj(init_path, boundary_vel, boundary_acc) (moma_traj_opt.cpp:142)."""
