@@ -41,6 +41,13 @@ def workload_params(tp):
     return opt, rp
 
 
+def base_config(n_cand):
+    """The `config` object both arms print (the device arm's scheduling details go under `details`)."""
+    return {"workload": f"synthetic {n_cand}-candidate batch per GPU, {N_PIECES} pieces x int_K {INT_K}, cuboids scene "
+                        f"200x200x16 @0.1 m (BASELINE configs[2])",
+            "candidates_per_gpu": n_cand, "pieces": N_PIECES, "int_K": INT_K, "variables": 10 * N_PIECES - 8}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -312,7 +319,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     paths, bv, ba = scenes.synthetic_batch(N_CAND, 1234)
     m = min(cores, N_CAND)
-    warm = min(args.warmup, 1)     # a CPU solve needs no clock/cache warm-up beyond one pass
+    warm = min(args.warmup, 1)     # warm-up passes actually run: a CPU solve needs no clock/cache warm-up beyond one
     step_i = 0
 
     def one_step():
@@ -330,12 +337,10 @@ def run_reference(args):
     value = m * args.steps / dt
     line = {
         "impl": "reference", "metric": "optimized trajectories/sec at 256 candidates", "value": value,
-        "unit": "trajectories/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+        "unit": "trajectories/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "warmup_passes_run": warm,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {N_CAND}-candidate batch, {N_PIECES} pieces x int_K {INT_K}, cuboids "
-                               f"scene 200x200x16 @0.1 m (BASELINE configs[2])",
-                   "candidates_per_gpu": N_CAND, "pieces": N_PIECES, "int_K": INT_K},
+        "config": base_config(N_CAND),
         "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port",
                          "sample": f"{m} of the {N_CAND} candidates per step (one per host core, thread per "
                                    f"candidate), a different slice each step"},
@@ -485,16 +490,14 @@ def main():
         "metric": "optimized trajectories/sec at 256 candidates", "value": value, "unit": "trajectories/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {n_cand}-candidate batch per GPU, {N_PIECES} pieces x int_K {INT_K}, "
-                               f"cuboids scene 200x200x16 @0.1 m (BASELINE configs[2])",
-                   "candidates_per_gpu": n_cand, "pieces": N_PIECES, "int_K": INT_K, "variables": 10 * N_PIECES - 8,
-                   "scheduling": f"continuous batching: the K plans of a rank ({K} x {n_cand} candidates, distinct per "
-                                 f"rank and step) are queued on the device and stream through {n_slots} candidate slots; "
-                                 f"a finished candidate's slot takes the next waiting candidate inside the kernel",
-                   "slots": n_slots,
-                   "l2": "working set larger than L2: the L-BFGS history is 2.6 MB per slot (2.7 GB at 1024 slots, "
-                         "126 MB L2); a 512 MiB buffer is rewritten before each timed region",
-                   "successes": n_ok},
+        "config": base_config(n_cand),
+        "details": {"scheduling": f"continuous batching: the K plans of a rank ({K} x {n_cand} candidates, distinct per "
+                                  f"rank and step) are queued on the device and stream through {n_slots} candidate "
+                                  f"slots; a finished candidate's slot takes the next waiting candidate inside the kernel",
+                    "slots": n_slots,
+                    "l2": "working set larger than L2: the L-BFGS history is 2.6 MB per slot (2.7 GB at 1024 slots, "
+                          "126 MB L2); a 512 MiB buffer is rewritten before each timed region",
+                    "successes": n_ok},
         "e2e": {"value": total / dt_e2e, "unit": "trajectories/s", "h2d_bytes_per_step": h2d // K,
                 "d2h_bytes_per_step": d2h // K,
                 "api": "MomaTrajOpt.optimizeTrajPlans(plans): host waypoints -> pre-processing -> pinned H2D -> device "

@@ -12,6 +12,7 @@ ap.add_argument("--plans", type=int, default=8)
 ap.add_argument("--slots", type=int, nargs="+", default=[256, 512, 1024])
 ap.add_argument("--cand", type=int, default=256)
 ap.add_argument("--skip-small", action="store_true")
+ap.add_argument("--no-timed", action="store_true")
 args = ap.parse_args()
 
 pts, _ = scenes.cuboids_scene(42)
@@ -55,6 +56,8 @@ for ns in args.slots:
           f"util {r['evals'].sum()/max(st['slot_ticks'],1):.2f} evals/cand {r['evals'].mean():.0f} ok {int(r['status'].sum())}", flush=True)
     s.close()
 
+if args.no_timed:
+    sys.exit(0)
 # per-kernel device time, plain launches with events (timed mode), the last slot count
 ns = args.slots[-1]
 s = tp.MomaTrajOpt(gm, max_cand=P * C, max_pieces=64, opt_param=opt, robot=rp, n_slots=ns)

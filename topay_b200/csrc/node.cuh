@@ -47,8 +47,7 @@ TP_HD void tp_slot(const double* c, double t, TpSlot& o, double* b0, double* b1,
     tp_rows<0, 2>(c, b0, st);
     tp_rows<0, 2>(c, b1, d1);
     tp_rows<0, 2>(c, b2, d2);
-    o.sy = sin(st[0]);
-    o.cy = cos(st[0]);
+    tp_sincos(st[0], o.sy, o.cy);
     o.dth = d1[0];
     o.ds = d1[1];
     o.d2th = d2[0];
@@ -170,11 +169,14 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
     const double step = T / K;
     const double t = j * (step / 2.0);
     tp_basis(t, b0, b1, b2, b3);
-    double st[9], dst[9], d2st[9], d3st[9];
+    // Only the state and the yaw / arc derivatives are needed before the arm's FK, lookups, pair tests and adjoint;
+    // the joint derivatives are evaluated after them (below), so that 42 doubles do not sit in registers across
+    // the heaviest part of the node.
+    double st[9], dst[2], d2st[2], d3st[2];
     tp_rows<0, 9>(c, b0, st);
-    tp_rows<0, 9>(c, b1, dst);
-    tp_rows<0, 9>(c, b2, d2st);
-    tp_rows<0, 9>(c, b3, d3st);
+    tp_rows<0, 2>(c, b1, dst);
+    tp_rows<0, 2>(c, b2, d2st);
+    tp_rows<0, 2>(c, b3, d3st);
     const double omg = (j == 0 || j == 2 * K) ? 0.5 : 1.0;
     const double real_alpha = 1.0 / K * ((double)j / 2.0);
     tp_node_clear(o);
@@ -299,18 +301,29 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
     o.gy += mu[1];
     o.G0[0] += mu[2];
     o.gdT += mu[2] * dst[0] * real_alpha;
+    // joint derivatives: the basis is evaluated again from an opaque copy of t (the compiler would otherwise keep
+    // the first evaluation alive instead); same operations, same bits
+    double t2 = t;
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+d"(t2));
+#endif
+    tp_basis(t2, b0, b1, b2, b3);
+    double dstq[9], d2stq[9], d3stq[9];
+    tp_rows<2, 9>(c, b1, dstq);
+    tp_rows<2, 9>(c, b2, d2stq);
+    tp_rows<2, 9>(c, b3, d3stq);
     double dsum = 0.0;
 #pragma unroll
     for (int q = 0; q < TOPAY_DOF; q++) {
         o.G0[2 + q] = mu[3 + q];
-        dsum += mu[3 + q] * dst[2 + q];
+        dsum += mu[3 + q] * dstq[2 + q];
     }
     o.gdT += dsum * real_alpha;
     // joint velocity / acceleration limits (:1674-1710)
     const double w_mv = op.s2_mani_vel_weight, w_ma = op.s2_mani_acc_weight;
 #pragma unroll
     for (int q = 0; q < TOPAY_DOF; q++) {
-        const double dq = dst[2 + q], d2q = d2st[2 + q], d3q = d3st[2 + q];
+        const double dq = dstq[2 + q], d2q = d2stq[2 + q], d3q = d3stq[2 + q];
         const double vdq = dq * dq - rp.joint_vel_limit[q] * rp.joint_vel_limit[q];
         const double vd2q = d2q * d2q - rp.joint_acc_limit[q] * rp.joint_acc_limit[q];
         if (vdq > 0) {

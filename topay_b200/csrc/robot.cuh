@@ -17,6 +17,16 @@
 #pragma once
 #include "hd.cuh"
 
+// sin and cos of the same angle with one range reduction (device: sincos(), same results as sin() and cos())
+TP_HD void tp_sincos(double a, double& s, double& c) {
+#if defined(__CUDA_ARCH__)
+    sincos(a, &s, &c);
+#else
+    s = sin(a);
+    c = cos(a);
+#endif
+}
+
 // Per-thread storage of 12 x 3 doubles with a runtime sphere index. Kernels place it in
 // shared memory (element stride = block size, so lanes never conflict); the CPU harness
 // uses a plain array.
@@ -41,7 +51,8 @@ struct TpFK {
 template <class Store>
 TP_HD void tp_fk(const TpParams& P, const double* pos, TpFK& fk, Store& pts) {
     const topay_robot_params& rp = P.robot;
-    const double s = sin(pos[2]), c = cos(pos[2]);
+    double s, c;
+    tp_sincos(pos[2], s, c);
     fk.sy = s;
     fk.cy = c;
     const double* R = rp.relative_R;
@@ -73,7 +84,8 @@ TP_HD void tp_fk(const TpParams& P, const double* pos, TpFK& fk, Store& pts) {
         if (i < TOPAY_DOF) {
 #pragma unroll
             for (int d = 0; d < 3; d++) pcur[d] += z[d] * rp.colli_length[i];
-            const double sq = sin(pos[3 + i]), cq = cos(pos[3 + i]);
+            double sq, cq;
+            tp_sincos(pos[3 + i], sq, cq);
             fk.sq[i] = sq;
             fk.cq[i] = cq;
             if (i % 2 == 0) {  // Rz(q)

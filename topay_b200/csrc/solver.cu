@@ -98,8 +98,8 @@ int kpad_of(int K) {
     return p;
 }
 
-size_t penalty_smem() {
-    return (size_t)(72 * TP_PEN_WARPS * 32 + TP_PEN_WARPS * 8 * 54) * sizeof(double);
+size_t penalty_smem(int kpad) {   // two sphere stores per thread + the coefficient blocks of the warp's 32 / kpad pieces
+    return (size_t)(72 * TP_PEN_WARPS * 32 + TP_PEN_WARPS * (32 / kpad) * 54) * sizeof(double);
 }
 
 // grid.y / grid.x of a tick: the live-slot count rounded up to a bucket (1..8, then 12, 16, 24, 32, 48, ...),
@@ -121,7 +121,7 @@ void launch_eval(topay_solver* s, bool timed, int tick, int ny) {
     dim3 blk2(TP_PEN_WARPS * 32);
     dim3 g2((groups + end_warps + TP_PEN_WARPS - 1) / TP_PEN_WARPS, ny);
     const size_t sm_int = (size_t)TP_WARPS_PER_BLOCK * D.ppw * 3 * (2 * D.K + 1) * sizeof(double);
-    const size_t sm_pen = penalty_smem();
+    const size_t sm_pen = penalty_smem(D.Kpad);
     TpGrid G;
     solver_grid(s, &G);
     const int te = tick % TP_TICKS;
@@ -350,11 +350,10 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
                    { topay_solver_destroy(s); });
     }
     {
-        const int smp = (int)penalty_smem();
-        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp), { topay_solver_destroy(s); });
-        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp), { topay_solver_destroy(s); });
-        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp), { topay_solver_destroy(s); });
-        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp), { topay_solver_destroy(s); });
+        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(4)), { topay_solver_destroy(s); });
+        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(8)), { topay_solver_destroy(s); });
+        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(16)), { topay_solver_destroy(s); });
+        TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(32)), { topay_solver_destroy(s); });
     }
     TP_CUDA_OK(cudaStreamSynchronize(s->stream), { topay_solver_destroy(s); });
     *out = s;

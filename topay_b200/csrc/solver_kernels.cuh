@@ -232,22 +232,36 @@ k_integrate(const __grid_constant__ TpSolverDev S, int tick) {
 // memory too, everything else in registers.
 #define TP_PEN_WARPS 2
 #ifndef TP_PEN_MIN_BLOCKS
-#define TP_PEN_MIN_BLOCKS 5
+#define TP_PEN_MIN_BLOCKS 6   // 12 warps per SM = 3 per scheduler: 168 registers; needs <= 37 KB of shared memory per block
 #endif
 
 // Sum of 64 values per lane over an aligned segment of KPAD lanes with 64/KPAD results per lane
 // ("transpose-reduce": each butterfly step halves the values a lane still carries, so the whole
 // reduction costs ~64 shuffles instead of 64 x log2(KPAD)). On return v[i], i < 64/KPAD, holds
 // the segment sum of element (64/KPAD) * jn + i.
-template <int KPAD>
-__device__ __forceinline__ void tp_transpose_reduce64(double* v, int jn) {
-    int cnt = 64;
+// The 64 inputs come from a generator with a compile-time index, and the first butterfly step consumes them as
+// they are produced: a lane never holds more than 32 partial sums (the 64 products of the penalty kernel used
+// to sit in 128 registers on top of the operands they are made from).
+template <int KPAD, class Gen>
+__device__ __forceinline__ void tp_transpose_reduce64(Gen gen, double* v /*[32]*/, int jn) {
+    {
+        constexpr int m = KPAD >> 1;
+        const bool hi = (jn & m) != 0;
 #pragma unroll
-    for (int m = KPAD >> 1; m > 0; m >>= 1) {
+        for (int i = 0; i < 32; i++) {
+            const double a = gen(i), b = gen(i + 32);
+            const double send = hi ? a : b;
+            const double keep = hi ? b : a;
+            v[i] = keep + tp_shfl_xor(send, m);
+        }
+    }
+    int cnt = 32;
+#pragma unroll
+    for (int m = KPAD >> 2; m > 0; m >>= 1) {
         const bool hi = (jn & m) != 0;
         const int half = cnt >> 1;
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
+        for (int i = 0; i < 16; i++) {
             if (i < half) {
                 const double send = hi ? v[i] : v[i + half];
                 const double keep = hi ? v[i + half] : v[i];
@@ -278,33 +292,91 @@ k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParam
     // [2 stores][36][block threads] sphere stores, then per-warp coefficient staging
     TpSphereStoreStrided pts{sm + threadIdx.x, TP_PEN_WARPS * 32};
     TpSphereStoreStrided pg{sm + 36 * TP_PEN_WARPS * 32 + threadIdx.x, TP_PEN_WARPS * 32};
-    double* s_c = sm + 72 * TP_PEN_WARPS * 32 + warp * (8 * 54);   // up to 8 pieces x 54 per warp
+    double* s_c = sm + 72 * TP_PEN_WARPS * 32 + warp * (PPW * 54);   // PPW pieces x 54 per warp
     double b0[6], b1[6], b2[6];
     TpNodeOut o;
 
-    if (task >= n_groups) {
-        // ---- end-node task: lane = piece, node j = 2K (only when K == KPAD) ----
-        // With K < KPAD node 2K lives in the piece's own segment; the spare warp that rounds the grid up
-        // to whole blocks must not evaluate it a second time (it would race with the segment's lane on
-        // gnode[K] with a differently rounded prefix position).
-        if (!S.end_tasks) return;
-        const int piece = (task - n_groups) * 32 + lane;
-        if (piece >= N) return;
-        const double T = S.T[(size_t)cand * S.max_pieces + piece];
-        const double* c = S.coeff + ((size_t)cand * 6 * S.max_pieces + 6 * piece) * 9;
-        double xy[2] = {start_xy[0], start_xy[1]};
-        if (STAGE == 2) {
-            double ax = 0.0, ay = 0.0;
-            for (int i = 0; i <= piece; i++) {
-                ax += totc[2 * i];
-                ay += totc[2 * i + 1];
-            }
-            xy[0] += ax;
-            xy[1] += ay;
-            tp_node_stage2(P, G, c, T, K, 2 * K, xy, o, b0, b1, b2, pts, pg);
+    // Two kinds of task share ONE inlined copy of the node body (the kernel is instruction-fetch bound when the
+    // ~6000-instruction stage-2 body exists twice): piece tasks (a segment of KPAD lanes per piece, lane = node) and,
+    // when K == KPAD, end-node tasks (lane = piece, node j = 2K).
+    const bool end_task = task >= n_groups;
+    // With K < KPAD node 2K lives in the piece's own segment; the spare warp that rounds the grid up to whole
+    // blocks must not evaluate it a second time (it would race with the segment's lane on gnode[K] with a
+    // differently rounded prefix position).
+    if (end_task && !S.end_tasks) return;
+    const int seg = lane / KPAD, jn = lane % KPAD;
+    const int piece = end_task ? (task - n_groups) * 32 + lane : task * PPW + seg;
+    const bool pvalid = piece < N;
+    const int n_nodes = S.end_tasks ? K : K + 1;   // nodes handled inside a piece task's segment
+    const bool active = pvalid && (end_task || jn < n_nodes);
+    const int jnode = end_task ? 2 * K : 2 * jn;
+    double T = 1.0;
+    const double* c = s_c + seg * 54;
+    if (pvalid) {
+        T = S.T[(size_t)cand * S.max_pieces + piece];
+        const double* cgl = S.coeff + ((size_t)cand * 6 * S.max_pieces + 6 * piece) * 9;
+        if (end_task) {
+            c = cgl;   // every lane has its own piece: straight from global memory
         } else {
-            tp_node_stage1(P, c, T, K, 2 * K, o, b0, b1, b2);
+            double* cs_ = s_c + seg * 54;
+            for (int e = jn; e < 54; e += KPAD) cs_[e] = cgl[e];
         }
+    }
+    __syncwarp();
+    double xy[2] = {0.0, 0.0};
+    if (STAGE == 2) {
+        if (end_task) {
+            // CurrentXY at the end of the piece: start + all intervals up to and including this piece
+            double ax = 0.0, ay = 0.0;
+            if (pvalid)
+                for (int i = 0; i <= piece; i++) {
+                    ax += totc[2 * i];
+                    ay += totc[2 * i + 1];
+                }
+            xy[0] = start_xy[0] + ax;
+            xy[1] = start_xy[1] + ay;
+        } else {
+            // CurrentXY (moma_traj_opt.cpp:1302): start + all earlier intervals
+            double px = 0.0, py = 0.0;
+            if (pvalid)
+                for (int i = jn; i < piece; i += KPAD) {
+                    px += totc[2 * i];
+                    py += totc[2 * i + 1];
+                }
+            px = tp_seg_sum(px, KPAD);
+            py = tp_seg_sum(py, KPAD);
+            // inclusive scan of this piece's intervals; node jn sees intervals 0..jn-1
+            double ix = 0.0, iy = 0.0;
+            if (pvalid && jn < K) {
+                const double* I = S.Ixy + (((size_t)cand * S.max_pieces + piece) * K + jn) * 2;
+                ix = I[0];
+                iy = I[1];
+            }
+#pragma unroll
+            for (int dlt = 1; dlt < KPAD; dlt <<= 1) {
+                const double ux = tp_shfl_up(ix, dlt, KPAD), uy = tp_shfl_up(iy, dlt, KPAD);
+                if (jn >= dlt) {
+                    ix += ux;
+                    iy += uy;
+                }
+            }
+            const double ex = tp_shfl_up(ix, 1, KPAD), ey = tp_shfl_up(iy, 1, KPAD);
+            xy[0] = start_xy[0] + px + (jn > 0 ? ex : 0.0);
+            xy[1] = start_xy[1] + py + (jn > 0 ? ey : 0.0);
+        }
+    }
+    if (active) {
+        if (STAGE == 2)
+            tp_node_stage2(P, G, c, T, K, jnode, xy, o, b0, b1, b2, pts, pg);
+        else
+            tp_node_stage1(P, c, T, K, jnode, o, b0, b1, b2);
+    } else {
+        tp_node_clear(o);
+#pragma unroll
+        for (int k = 0; k < 6; k++) b0[k] = b1[k] = b2[k] = 0.0;
+    }
+    if (end_task) {
+        if (!pvalid) return;
         double* gc = S.gdC_end + ((size_t)cand * S.max_pieces + piece) * 54;
 #pragma unroll
         for (int k = 0; k < 6; k++)
@@ -318,61 +390,6 @@ k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParam
         gn[0] = o.gx;
         gn[1] = o.gy;
         return;
-    }
-
-    // ---- piece task: segment of KPAD lanes per piece ----
-    const int seg = lane / KPAD, jn = lane % KPAD;
-    const int piece = task * PPW + seg;
-    const bool pvalid = piece < N;
-    const int n_nodes = S.end_tasks ? K : K + 1;   // nodes handled inside the segment
-    const bool active = pvalid && jn < n_nodes;
-    double T = 1.0;
-    double* c = s_c + seg * 54;
-    if (pvalid) {
-        T = S.T[(size_t)cand * S.max_pieces + piece];
-        const double* cgl = S.coeff + ((size_t)cand * 6 * S.max_pieces + 6 * piece) * 9;
-        for (int e = jn; e < 54; e += KPAD) c[e] = cgl[e];
-    }
-    __syncwarp();
-    double xy[2] = {0.0, 0.0};
-    if (STAGE == 2) {
-        // CurrentXY (moma_traj_opt.cpp:1302): start + all earlier intervals
-        double px = 0.0, py = 0.0;
-        if (pvalid)
-            for (int i = jn; i < piece; i += KPAD) {
-                px += totc[2 * i];
-                py += totc[2 * i + 1];
-            }
-        px = tp_seg_sum(px, KPAD);
-        py = tp_seg_sum(py, KPAD);
-        // inclusive scan of this piece's intervals; node jn sees intervals 0..jn-1
-        double ix = 0.0, iy = 0.0;
-        if (pvalid && jn < K) {
-            const double* I = S.Ixy + (((size_t)cand * S.max_pieces + piece) * K + jn) * 2;
-            ix = I[0];
-            iy = I[1];
-        }
-#pragma unroll
-        for (int dlt = 1; dlt < KPAD; dlt <<= 1) {
-            const double ux = tp_shfl_up(ix, dlt, KPAD), uy = tp_shfl_up(iy, dlt, KPAD);
-            if (jn >= dlt) {
-                ix += ux;
-                iy += uy;
-            }
-        }
-        const double ex = tp_shfl_up(ix, 1, KPAD), ey = tp_shfl_up(iy, 1, KPAD);
-        xy[0] = start_xy[0] + px + (jn > 0 ? ex : 0.0);
-        xy[1] = start_xy[1] + py + (jn > 0 ? ey : 0.0);
-    }
-    if (active) {
-        if (STAGE == 2)
-            tp_node_stage2(P, G, c, T, K, 2 * jn, xy, o, b0, b1, b2, pts, pg);
-        else
-            tp_node_stage1(P, c, T, K, 2 * jn, o, b0, b1, b2);
-    } else {
-        tp_node_clear(o);
-#pragma unroll
-        for (int k = 0; k < 6; k++) b0[k] = b1[k] = b2[k] = 0.0;
     }
     const size_t prow = (size_t)cand * S.max_pieces + piece;
 #ifdef TP_DEBUG_NODE
@@ -401,15 +418,16 @@ k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParam
         }
     }
     // reduction over the piece of gdC (54), gdT (1) and the 9 per-node cost terms
-    double v[64];
-#pragma unroll
-    for (int k = 0; k < 6; k++)
-#pragma unroll
-        for (int d = 0; d < 9; d++) v[k * 9 + d] = b0[k] * o.G0[d] + b1[k] * o.G1[d] + b2[k] * o.G2[d];
-    v[54] = o.gdT;
-#pragma unroll
-    for (int t = 0; t < 9; t++) v[55 + t] = o.terms[TOPAY_TERM_CHASSIS_COLLI + t];
-    tp_transpose_reduce64<KPAD>(v, jn);
+    double v[32];
+    auto gen = [&](int e) -> double {
+        if (e < 54) {
+            const int k = e / 9, d = e % 9;
+            return b0[k] * o.G0[d] + b1[k] * o.G1[d] + b2[k] * o.G2[d];
+        }
+        if (e == 54) return o.gdT;
+        return o.terms[TOPAY_TERM_CHASSIS_COLLI + (e - 55)];
+    };
+    tp_transpose_reduce64<KPAD>(gen, v, jn);
     if (pvalid) {
         constexpr int PER = 64 / KPAD;
 #pragma unroll
