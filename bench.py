@@ -127,18 +127,71 @@ def barrier_max(dist, local, value):
     return float(t.item())
 
 
+class CpuArm:
+    """The reference's CPU solve of the path on the host cores, thread per candidate like planner.cpp:921-925.
+    kind "reference": oracle/_ref/libtopay_ref.so — the reference's own moma_traj_opt.cpp / grid_map.cpp compiled
+    unmodified (prebuilt in the build container, it travels with the snapshot); kind "port": the oracle's restatement
+    (bit-identical to it, tests/test_ref_pin.py) when that library is absent. Checker / baseline code only."""
+
+    def __init__(self, desc, pts):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        self.O = O
+        self.rp = O.robot_defaults()
+        self.of = O.Field(desc)
+        self.of.rasterize(pts)
+        self.of.rebuild()
+        self.kind, self.R, self.grid = "port", None, None
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libtopay_ref.so")):
+            try:
+                import ref_lib as R
+                self.grid = R.GridMap(desc)
+                self.grid.set_cloud(pts)
+                self.R, self.kind = R, "reference"
+            except Exception as e:   # noqa: BLE001 — fall back to the port, say why
+                print(f"bench: oracle/_ref unusable ({e}); CPU arm = oracle port", file=sys.stderr)
+
+    def solve_batch(self, opt, paths, bv, ba, n_threads, wall_clock=False):
+        """-> list of dicts with at least status. wall_clock: the reference's own 1.0 s ALM cap
+        (moma_traj_opt.cpp:403) on the real clock instead of the deterministic alm_max_rounds."""
+        if self.R is not None:
+            return self.R.solve_batch(self.grid, opt, paths, bv, ba, n_threads, alm_max_rounds=opt.alm_max_rounds,
+                                      wall_clock=wall_clock)
+        return self.O.solve_batch(opt, self.rp, self.of, paths, bv, ba, n_threads=n_threads,
+                                  wall_cap_s=1.0 if wall_clock else 0.0)
+
+    def gate_pass(self, opt, paths, bv, ba, max_pieces):
+        """Both verdicts of the worker's success gate (planner.cpp:877-880) on the CPU solves of these candidates
+        (oracle solve = the reference's, bit for bit; its trajectories are what the gate needs)."""
+        import threading
+        res = [None] * len(paths)
+
+        def work(c):
+            res[c] = self.O.solve_one(opt, self.rp, self.of, paths[c], bv[c], ba[c], max_pieces=max_pieces)
+
+        th = [threading.Thread(target=work, args=(c,)) for c in range(len(paths))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        g = self.O.check_feasible(self.of, self.rp, [(r["T"], r["coeff"], paths[c][0, :3]) for c, r in enumerate(res)])
+        ok = np.array([r["status"] == 1 for r in res])
+        return int((ok & (g["feasible_print"] != 0)).sum()), int(ok.sum())
+
+
 def cpu_baseline(opt, rp, pts, paths, bv, ba, cores, desc):
-    """The oracle (CPU restatement of the reference's algorithm, thread per candidate like
-    planner.cpp:921-925) on a bounded sample: one candidate per host core."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    of = O.Field(desc)
-    of.rasterize(pts)
-    of.rebuild()
+    """The reference's CPU solve on a bounded sample: one candidate per host core."""
+    arm = CpuArm(desc, pts)
+    O = arm.O
     m = min(cores, len(paths))
     t0 = time.perf_counter()
-    res = O.solve_batch(opt, rp, of, paths[:m], bv[:m], ba[:m], n_threads=cores)
+    res = arm.solve_batch(opt, paths[:m], bv[:m], ba[:m], cores)
     dt = time.perf_counter() - t0
+    # the launch-file-equivalent figure: the same sample with the reference's 1.0 s wall-clock ALM cap
+    t0 = time.perf_counter()
+    res_cap = arm.solve_batch(opt, paths[:m], bv[:m], ba[:m], cores, wall_clock=True)
+    dt_cap = time.perf_counter() - t0
+    # success gate of the CPU solves of the first candidates (what the device's pass count is compared with)
+    n_gate = min(m, 8)
+    gate_ok, solved = arm.gate_pass(opt, paths[:n_gate], bv[:n_gate], ba[:n_gate], N_PIECES)
     # single-plan latency of the same algorithm at the reference's default scale (8 candidates on 8 threads,
     # planner.cpp:921-925), same plans as latency_probe
     from topay_b200 import scenes
@@ -146,9 +199,19 @@ def cpu_baseline(opt, rp, pts, paths, bv, ba, cores, desc):
     for plan in range(8):
         p8, bv8, ba8 = scenes.short_candidates(8, 5005 + plan)
         t1 = time.perf_counter()
-        O.solve_batch(o2, rp, of, p8, bv8, ba8, n_threads=min(8, cores))
+        arm.solve_batch(o2, p8, bv8, ba8, min(8, cores))
         lat.append((time.perf_counter() - t1) * 1e3)
-    return m / dt, m, dt, sum(r["status"] for r in res), float(np.median(lat))
+    return {"value": m / dt, "unit": "trajectories/s", "cores": cores, "kind": arm.kind,
+            "sample": f"{m} of the {len(paths)} candidates, one per host core (thread per candidate), {dt:.1f} s, "
+                      f"{sum(r['status'] for r in res)} succeeded",
+            "with_1s_alm_cap": {"value": m / dt_cap, "seconds": dt_cap, "succeeded": int(sum(r["status"] for r in res_cap)),
+                                "note": "same sample under the reference's own 1.0 s wall-clock ALM cap "
+                                        "(moma_traj_opt.cpp:403) instead of the deterministic alm_max_rounds"},
+            "success_gate": {"candidates": n_gate, "solved": solved, "passed": gate_ok,
+                             "note": "optimizeTraj && printConstraintsSituations (planner.cpp:877-880) on the CPU "
+                                     "solves of the first candidates of the plan"},
+            "latency_p50_ms": float(np.median(lat)),
+            "latency_sample": "8 plans of 8 candidates on 8 threads, reference scale"}
 
 
 def latency_probe(tp, scenes, gm, n_plans=200):
@@ -299,23 +362,19 @@ def subpath_probe(tp, scenes, device, hbm_peak, solver, gm, rp, with_cpu):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm for the path on the host cores. The
-    reference's sources cannot be compiled here (they need Eigen + ROS, absent), so this is the
-    oracle port (kind = "port"); rank 0 alone runs it."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores — oracle/_ref (the
+    reference's optimizer and map compiled unmodified) when that library is present, else the oracle port; rank 0
+    alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import topay_b200._structs as S  # structs only; no GPU library needed on this arm
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
     from topay_b200 import scenes
-    opt, rp = O.opt_defaults(), O.robot_defaults()
-    opt.int_K, opt.min_piece_num, opt.sample_interval = INT_K, N_PIECES, 1e9
     desc = S.grid_desc()
     pts, _ = scenes.cuboids_scene(42)
-    of = O.Field(desc)
-    of.rasterize(pts)
-    of.rebuild()
+    arm = CpuArm(desc, pts)
+    opt = arm.O.opt_defaults()
+    opt.int_K, opt.min_piece_num, opt.sample_interval = INT_K, N_PIECES, 1e9
     cores = os.cpu_count() or 1
     paths, bv, ba = scenes.synthetic_batch(N_CAND, 1234)
     m = min(cores, N_CAND)
@@ -326,7 +385,7 @@ def run_reference(args):
         nonlocal step_i
         lo = (step_i * m) % (N_CAND - m + 1)     # a different slice of the batch every step
         step_i += 1
-        return O.solve_batch(opt, rp, of, paths[lo:lo + m], bv[lo:lo + m], ba[lo:lo + m], n_threads=cores)
+        return arm.solve_batch(opt, paths[lo:lo + m], bv[lo:lo + m], ba[lo:lo + m], cores)
 
     for _ in range(warm):
         one_step()
@@ -341,7 +400,7 @@ def run_reference(args):
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": base_config(N_CAND),
-        "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": arm.kind,
                          "sample": f"{m} of the {N_CAND} candidates per step (one per host core, thread per "
                                    f"candidate), a different slice each step"},
         "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -525,12 +584,7 @@ def main():
         line["subpaths"] = subpath_probe(tp, scenes, local, peak, solver, gm, rp, not args.no_cpu_baseline)
     if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only
         cores = os.cpu_count() or 1
-        v, m, secs, ok, lat50 = cpu_baseline(opt, rp, pts, paths, bv, ba, cores, desc)
-        line["cpu_baseline"] = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                                "sample": f"{m} of the {n_cand} candidates, one per host core (thread per "
-                                          f"candidate), {secs:.1f} s, {ok} succeeded",
-                                "latency_p50_ms": lat50,
-                                "latency_sample": "8 plans of 8 candidates on 8 threads, reference scale"}
+        line["cpu_baseline"] = cpu_baseline(opt, rp, pts, paths, bv, ba, cores, desc)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

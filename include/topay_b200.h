@@ -480,6 +480,18 @@ int topay_solver_last_stats(topay_solver* s, topay_solver_stats* out);
  * the shortest-duration candidate among those with status && feasible_print (the gate the
  * planner applies), -1 if none. */
 int topay_solver_check_feasible(topay_solver* s, topay_feasibility* out, int32_t* best_success);
+/* The planner's pick among the candidates of the last run, ON THE DEVICE (planner.cpp:999-1010: the first success,
+ * replaced only by a strictly shorter duration; the same rule on the cost): the upload is read as n_plans plans,
+ * plan i = candidates plan_offset[i] .. plan_offset[i+1]-1 (plan_offset has n_plans + 1 entries). A candidate
+ * counts when optimizeTraj succeeded and, with use_gate != 0, printConstraintsSituations passed
+ * (planner.cpp:877-880; topay_solver_check_feasible must have run on this solve). Writes, per plan, the index
+ * INSIDE the plan of the winner by duration / by cost (-1: none); either output may be NULL. Two ints per plan
+ * cross the bus. */
+int topay_solver_select(topay_solver* s, int n_plans, const int32_t* plan_offset, int use_gate,
+                        int32_t* best_by_duration, int32_t* best_by_cost);
+/* Results of ONE candidate of the last run (e.g. the winner): `out`'s arrays have length 1 (T: max_pieces,
+ * coeff: 6 max_pieces x 9, x: topay_num_vars(max_pieces)). 28 KB at 64 pieces instead of the whole batch. */
+int topay_solver_download_candidate(topay_solver* s, int cand, topay_result_batch* out);
 /* timed != 0: every k_penalty launch is bracketed by CUDA events (stats.ms_eval) and the ticks are
  * plain launches; timed == 0 (default): a batch of 16 ticks is replayed as one CUDA graph, which
  * removes the per-launch host cost that dominates small plans; stats.ms_eval is then 0. */

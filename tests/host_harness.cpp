@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../topay_b200/csrc/hd.cuh"
+#include "../topay_b200/csrc/edt_line.cuh"
 #include "../topay_b200/csrc/field_query.cuh"
 #include "../topay_b200/csrc/node.cuh"
 #include "../topay_b200/csrc/robot.cuh"
@@ -291,4 +292,45 @@ void hh_traj_sample(int N, const double* T, const double* coeff, const double* c
         tp_poly_acc(p, t[j], 0, 9, pva + 27 * j + 18);
     }
 }
+// ---- one line of the strided EDT passes (edt_line.cuh) in k_edt_line's schedule, serially: skip distances of the
+// "no source" runs, chunk boundaries against the whole line, chunk insides by halving. Sign-packed line in, positive
+// and negative transform out.
+void hh_edt_line(const int32_t* f_in, int n, int CH, int32_t* out_pos, int32_t* out_neg) {
+    std::vector<int> f(f_in, f_in + n), arg(n);
+    {
+        int nextc = n, lastc = -1;
+        for (int v = n - 1; v >= 0; v--) {
+            if (f[v] < TP_INF32) nextc = v;
+            else f[v] = tp_skip_make(0, nextc - v);
+        }
+        for (int v = 0; v < n; v++) {
+            if (f[v] < TP_INF32) lastc = v;
+            else f[v] |= (v - lastc) << TP_SKIP_BITS;
+        }
+    }
+    auto emit = [&](int q, int bp) {
+        out_pos[q] = bp >= TP_INF32 ? TP_INF32 : bp;
+        out_neg[q] = tp_neg_search<1>(f.data(), n, q);
+    };
+    const int nb = tp_edt_boundaries(n, CH);
+    for (int b = 0; b < nb; b++) {
+        const int q = tp_edt_boundary(b, n, CH);
+        int a;
+        const int bp = tp_dc_query<1>(f.data(), q, 0, n - 1, a);
+        arg[q] = a;
+        emit(q, bp);
+    }
+    for (int ch = 0; ch < nb - 1; ch++) {
+        const int lo = tp_edt_boundary(ch, n, CH), hi = tp_edt_boundary(ch + 1, n, CH);
+        for (int h = tp_dc_top(hi - lo) >> 1; h >= 1; h >>= 1)
+            for (int q = lo + h; q < hi; q += 2 * h) {
+                const int qr = q + h < hi ? q + h : hi;
+                int a;
+                const int bp = tp_dc_query<1>(f.data(), q, arg[q - h], arg[qr], a);
+                arg[q] = a;
+                emit(q, bp);
+            }
+    }
+}
+int hh_sq16(int v) { return tp_sq16(v); }
 }  // extern "C"

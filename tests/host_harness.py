@@ -120,3 +120,13 @@ def traj_sample(T, coeff, car_seq, t):
     st, ds, pva = np.empty((m, 10)), np.empty((m, 10)), np.empty((m, 27))
     l.hh_traj_sample(len(T), _p(T), _p(coeff), _p(car_seq), len(car_seq), _p(t), m, _p(st), _p(ds), _p(pva))
     return st, ds, pva
+
+
+def edt_line(f, chunk=32):
+    """One line through the strided EDT pass's schedule (edt_line.cuh): sign-packed int32 in, (pos, neg) out."""
+    l = lib()
+    f = np.ascontiguousarray(f, dtype=np.int32)
+    n = len(f)
+    pos, neg = np.full(n, -1, dtype=np.int32), np.full(n, -1, dtype=np.int32)
+    l.hh_edt_line(_p(f, C.c_int32), n, int(chunk), _p(pos, C.c_int32), _p(neg, C.c_int32))
+    return pos, neg

@@ -129,3 +129,36 @@ def test_traj_evaluation_bit_exact(oracle):
     assert np.array_equal(ds, eds[0])
     # the state adds one Simpson step with sin/cos: same libm on both sides here
     assert np.abs(st - est[0]).max() <= 1e-15 * max(1.0, np.abs(est[0]).max())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 16, 17, 32, 33, 34, 64, 65, 80, 83, 200, 513, 800, 803])
+def test_edt_line_divide_and_conquer(n):
+    """a20: the per-line arithmetic of the strided EDT passes (edt_line.cuh) in the kernel's schedule (skip distances, chunk boundaries, halving inside the chunks) against the
+    brute-force minimum  min_v (q - v)^2 + f(v)  of both transforms: dense, sparse, single-source, all-source and
+    source-free lines, first-pass (squared int16) and second-pass (arbitrary squared distances) value ranges."""
+    import host_harness as hh
+    INF = 1 << 29
+    rng = np.random.default_rng(n)
+    q = np.arange(n)
+    d2 = (q[:, None] - q[None, :]) ** 2
+    cases = []
+    for density in (0.0, 0.003, 0.02, 0.3, 0.9, 1.0):
+        occ = rng.random(n) < density
+        # second-pass style input: occupied cells are sources of the positive transform (0) and carry their
+        # negative value; free cells carry a positive value (or INF)
+        pos = np.where(occ, 0, np.where(rng.random(n) < 0.5, rng.integers(1, 90, n) ** 2 + rng.integers(0, 50, n), INF))
+        neg = np.where(occ, np.where(rng.random(n) < 0.9, rng.integers(1, 6, n) ** 2, INF), 0)
+        cases.append((pos, neg))
+    one = np.full(n, INF)
+    one[n // 3] = 7
+    cases.append((one, np.zeros(n, dtype=np.int64)))
+    for pos, neg in cases:
+        packed = np.where(neg > 0, -neg, pos).astype(np.int32)
+        assert not (packed == 0).any() or n >= 1
+        packed[packed == 0] = INF          # a free cell with no finite value
+        fp, fn = np.maximum(packed, 0).astype(np.int64), np.maximum(-packed.astype(np.int64), 0)
+        exp_p, exp_n = (d2 + fp[None, :]).min(axis=1), (d2 + fn[None, :]).min(axis=1)
+        for chunk in (4, 8, 32):
+            got_p, got_n = hh.edt_line(packed, chunk)
+            assert np.array_equal(got_p, np.minimum(exp_p, INF)) and np.array_equal(got_n, exp_n), chunk
+    assert hh.lib().hh_sq16(-16383) == -INF and hh.lib().hh_sq16(16383) == INF and hh.lib().hh_sq16(-5) == -25

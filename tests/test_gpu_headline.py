@@ -199,3 +199,62 @@ def test_baseline_size_field_bit_exact(oracle, dims):
     osp, osn = of.download_sqdist(3)
     assert np.array_equal(sqp, osp) and np.array_equal(sqn, osn)
     gm.close()
+
+
+def test_device_side_selection_and_winner_download(gpu_scene, small_scene, oracle):
+    """planner.cpp:999-1010 on the device (topay_solver_select): per-plan winners by duration and by cost equal the
+    host rule applied to the full download (first success, replaced only by a strictly shorter duration), with and
+    without the success gate; the single-candidate download equals the batch download's row; planWinners returns
+    exactly those candidates while only the winners cross the bus."""
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    plans = [scenes.short_candidates(8, 40 + i) for i in range(5)]
+    plans[2] = (plans[2][0][:3], plans[2][1][:3], plans[2][2][:3])          # a ragged plan
+    s = tp.MomaTrajOpt(gpu_scene, max_cand=40, max_pieces=16, opt_param=opt, robot=rp, n_slots=16)
+    r = s.optimizeTrajPlans(plans)
+    off = r["plan_offset"].astype(np.int32)
+    gate, _ = s.checkFeasibleBatch()
+    gate = {k: v.copy() for k, v in gate.items()}
+
+    def host_pick(ok, val):
+        best = -1
+        for c in range(len(ok)):
+            if ok[c] and (best < 0 or val[c] < val[best]):
+                best = c
+        return best
+
+    for use_gate in (False, True):
+        bd, bc = s.select(off, use_gate)
+        for i in range(len(plans)):
+            sl = slice(off[i], off[i + 1])
+            ok = r["status"][sl] == 1
+            if use_gate:
+                ok = ok & (gate["feasible_print"][sl] != 0)
+            assert bd[i] == host_pick(ok, r["duration"][sl]) and bc[i] == host_pick(ok, r["cost"][sl]), (use_gate, i)
+        if not use_gate:
+            assert np.array_equal(bd, r["plan_best_by_duration"]) and np.array_equal(bc, r["plan_best_by_cost"])
+    one = s.download_candidate(int(off[1]) + 2)
+    for k in ("status", "lbfgs_code", "piece_num", "iters", "evals", "alm_rounds", "cost", "duration", "T", "coeff",
+              "final_xy_err", "x"):
+        assert np.array_equal(one[k], r[k][off[1] + 2]), k
+    # ties go to the lowest index: the same plan twice in one upload picks its first copy
+    twice = [(plans[0][0] + plans[0][0], np.concatenate([plans[0][1]] * 2), np.concatenate([plans[0][2]] * 2))]
+    r2 = s.optimizeTrajPlans(twice)
+    bd2, bc2 = s.select()
+    assert 0 <= bd2[0] < 8 and 0 <= bc2[0] < 8 and np.array_equal(r2["cost"][:8], r2["cost"][8:])
+    # the whole worker flow with only the winners on the bus
+    bd_gate, _ = None, None
+    w = s.planWinners(plans, use_gate=True)
+    r3 = s.optimizeTrajPlans(plans)
+    g3, _ = s.checkFeasibleBatch()
+    for i, wi in enumerate(w):
+        sl = slice(off[i], off[i + 1])
+        exp = host_pick((r3["status"][sl] == 1) & (g3["feasible_print"][sl] != 0), r3["duration"][sl])
+        assert (wi is None) == (exp < 0)
+        if wi is not None:
+            assert wi["index"] == exp and np.array_equal(wi["coeff"], r3["coeff"][off[i] + exp])
+    s.upload(*[np.concatenate(x) if not isinstance(x[0], list) else sum(x, []) for x in
+               ([p[0] for p in plans], [p[1] for p in plans], [p[2] for p in plans])])
+    assert s.d2h_bytes >= 0
+    s.close()

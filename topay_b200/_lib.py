@@ -84,6 +84,8 @@ PROTOTYPES = {
     "topay_traj_sample": (C.c_int, [C.c_int, C.POINTER(TrajBatch), _dp, C.c_int, _dp, _dp]),
     "topay_select_shortest": (C.c_int, [_ip, _dp, C.c_int]),
     "topay_solver_check_feasible": (C.c_int, [C.c_void_p, C.POINTER(Feasibility), _ip]),
+    "topay_solver_select": (C.c_int, [C.c_void_p, C.c_int, _ip, C.c_int, _ip, _ip]),
+    "topay_solver_download_candidate": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ResultBatch)]),
     "topay_solver_create": (C.c_int, [C.POINTER(OptParams), C.POINTER(RobotParams), C.c_void_p, C.c_int, C.c_int,
                                       C.POINTER(C.c_void_p)]),
     "topay_solver_create_rog": (C.c_int, [C.POINTER(OptParams), C.POINTER(RobotParams), C.c_void_p, C.c_int, C.c_int,

@@ -143,11 +143,14 @@ def pack_trajs(trajs):
     return tb, keep
 
 
-def alloc_feasibility(n):
-    """(Feasibility, dict of numpy arrays it points to)."""
-    arrs = {name: np.zeros((n,) + shape, dtype=t) for name, t, shape in FEAS_FIELDS}
+def alloc_feasibility(n, verdicts_only=False):
+    """(Feasibility, dict of numpy arrays it points to). verdicts_only: just the two verdicts, every metric
+    pointer NULL (the library skips what it is not asked for)."""
+    want = [(name, t, shape) for name, t, shape in FEAS_FIELDS
+            if not verdicts_only or name in ("feasible", "feasible_print")]
+    arrs = {name: np.zeros((n,) + shape, dtype=t) for name, t, shape in want}
     f = Feasibility(*[arrs[name].ctypes.data_as(C.POINTER(C.c_int32 if t is np.int32 else C.c_double))
-                      for name, t, _ in FEAS_FIELDS])
+                      if name in arrs else None for name, t, _ in FEAS_FIELDS])
     return f, arrs
 
 

@@ -32,8 +32,8 @@ struct TpRogSink {
 // Scratch of the separable exact EDT (field.cu), shared by the dense and the ROG-ring field.
 struct TpEdtScratch {
     cudaStream_t stream;
-    short2* packed;               // pass-1 output, A*B*C
-    int32_t *tmp_pos, *tmp_neg;   // pass-2 output, A*B*C (3-D only)
+    int16_t* packed16;            // pass-1 output (sign-packed 1-D distances), A*B*C
+    int32_t* packed32;            // pass-2 output (sign-packed squared distances), A*B*C (3-D only)
     bool keep_sq;                 // also store the integer squared distances
     double res;
     TpRogSink sink;               // enabled = 0 for the dense field

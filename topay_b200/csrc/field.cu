@@ -13,11 +13,13 @@
 // contraction) so the fp64 grids are bit-identical too.
 //
 // Layout (as the reference): 3-D x*Ny*Nz + y*Nz + z, 2-D x*Ny + y.
-// Pass 1 runs along the contiguous axis from the binary occupancy (two sweeps per line in
-// shared memory, positive and negative transform together, output packed int16 pairs);
-// passes 2/3 run along a strided axis on tiles of 16 contiguous cells x the whole line
-// staged in shared memory, every global access a 64-128 B contiguous segment.
+// Pass 1 runs along the contiguous axis from the binary occupancy (warp scans, positive and
+// negative transform together, one sign-packed int16 per cell); passes 2/3 run along a strided
+// axis on tiles of 16 contiguous cells x the whole line staged in shared memory, each line
+// answered by a divide and conquer over its queries (edt_line.cuh); every global access is a
+// 64-128 B contiguous segment and a voxel moves 1 + 2 | 2 + 4 | 4 + 8 = 21 B through the passes.
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cstdio>
 #include <cstring>
@@ -25,11 +27,9 @@
 #include <vector>
 
 #include "common_host.h"
+#include "edt_line.cuh"
 #include "field_query.cuh"
 #include "robot.cuh"
-
-#define TP_INF16 16383
-#define TP_INF32 (1 << 29)
 
 static thread_local std::string g_last_error;
 void tp_set_error(const std::string& msg) { g_last_error = msg; }
@@ -68,8 +68,8 @@ struct topay_field {
     size_t n2, n3;
     int8_t *occ3d, *occ2d, *occ2d_crit, *src2d;
     double *esdf3d, *esdf2d, *esdf2d_inflate, *esdf2d_crit;
-    short2* packed;         // pass-1 output (3-D sized)
-    int32_t *tmp_pos, *tmp_neg;   // pass-2 output (3-D sized)
+    int16_t* packed16;      // pass-1 output, sign-packed 1-D distances (3-D sized)
+    int32_t* packed32;      // pass-2 output, sign-packed squared distances (3-D sized)
     int32_t *sq_pos[4], *sq_neg[4];
     bool keep_sq;
     bool ready;
@@ -107,8 +107,8 @@ __global__ void k_threshold(const double* __restrict__ esdf, double thr, int8_t*
 }
 
 // Pass 1, along the contiguous axis: 1-D distance to the nearest source (pos) and to the nearest
-// non-source (neg) cell of each line, as int16 (TP_INF16 = none on this line). One warp per line,
-// four consecutive cells per lane (one 4-byte load, one 16-byte store when C % 4 == 0): the index of
+// non-source (neg) cell of each line, sign-packed into one int16 (edt_line.cuh; TP_INF16 = none on this line). One warp
+// per line, four consecutive cells per lane (one 4-byte load, one 8-byte store when C % 4 == 0): the index of
 // the last source at or before a cell is a running max inside the lane, a warp max-scan across
 // lanes and a carry across the 128-cell chunks; the next source at or after it is the mirror image.
 // Lines of up to 128 cells (the z axis of the 3-D grid) take a single chunk, everything in
@@ -141,12 +141,12 @@ __device__ __forceinline__ int tp_scan_min_excl_rev(int v, int lane) {
 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-k_edt_contig(const int8_t* __restrict__ src, short2* __restrict__ out, int64_t n_lines, int C) {
+k_edt_contig(const int8_t* __restrict__ src, int16_t* __restrict__ out, int64_t n_lines, int C) {
     const int lane = threadIdx.x & 31;
     const int64_t line = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (line >= n_lines) return;
     const int8_t* in = src + line * C;
-    short2* o = out + line * C;
+    int16_t* o = out + line * C;
     const int nchunk = (C + 127) >> 7;
     auto load4 = [&](int c0, bool occ[4]) {
         if (VEC) {
@@ -185,10 +185,10 @@ k_edt_contig(const int8_t* __restrict__ src, short2* __restrict__ out, int64_t n
         }
         carry_p = max(carry_p, __shfl_sync(0xffffffffu, max(lp, ep), 31));
         carry_n = max(carry_n, __shfl_sync(0xffffffffu, max(ln, en), 31));
-        if (nchunk > 1) {
+        if (nchunk > 1) {   // the forward result of the transform the cell is not a source of, sign-packed
 #pragma unroll
             for (int k = 0; k < 4; k++)
-                if (c0 + k < C) o[c0 + k] = make_short2((short)fp[k], (short)fn[k]);
+                if (c0 + k < C) o[c0 + k] = (int16_t)(occ[k] ? -fn[k] : fp[k]);
         }
     }
     // backward: next source / next free cell at or after each cell, min with the forward result
@@ -209,7 +209,7 @@ k_edt_contig(const int8_t* __restrict__ src, short2* __restrict__ out, int64_t n
         }
         const int ep = min(tp_scan_min_excl_rev(np_, lane), carry_p);
         const int en = min(tp_scan_min_excl_rev(nn_, lane), carry_n);
-        short2 res[4];
+        int16_t res[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int c = c0 + k;
@@ -218,86 +218,27 @@ k_edt_contig(const int8_t* __restrict__ src, short2* __restrict__ out, int64_t n
             int bn = b >= TP_POS_BIG ? TP_INF16 : min(b - c, TP_INF16);
             if (nchunk > 1) {
                 if (c < C) {
-                    const short2 f = o[c];
-                    bp = min(bp, (int)f.x);
-                    bn = min(bn, (int)f.y);
+                    const int f = o[c];
+                    if (occ[k]) bn = min(bn, -f);
+                    else bp = min(bp, f);
                 }
             } else {
                 bp = min(bp, fp[k]);
                 bn = min(bn, fn[k]);
             }
-            res[k] = make_short2((short)bp, (short)bn);
+            res[k] = (int16_t)(occ[k] ? -bn : bp);   // sign-packed (edt_line.cuh)
         }
         carry_p = min(carry_p, __shfl_sync(0xffffffffu, min(np_, ep), 0));
         carry_n = min(carry_n, __shfl_sync(0xffffffffu, min(nn_, en), 0));
         if (VEC) {
-            if (c0 < C) *reinterpret_cast<uint4*>(o + c0) = *reinterpret_cast<const uint4*>(res);
+            if (c0 < C) *reinterpret_cast<uint2*>(o + c0) = make_uint2((uint16_t)res[0] | ((uint32_t)(uint16_t)res[1] << 16),
+                                                                       (uint16_t)res[2] | ((uint32_t)(uint16_t)res[3] << 16));
         } else {
 #pragma unroll
             for (int k = 0; k < 4; k++)
                 if (c0 + k < C) o[c0 + k] = res[k];
         }
     }
-}
-
-// Exact 1-D squared-distance envelope  min_v (l - v)^2 + f(v)  of one line staged in shared memory
-// (stride = tile width): a candidate at distance d cannot improve once d^2 >= best; add+min is a
-// single DPX instruction (__viaddmin_s32).
-// Two-level search: `seg` holds the minimum of every group of TP_SEG
-// consecutive cells of the line. A group whose lower bound (its minimum + the squared distance to its
-// nearest cell) cannot beat `best` is skipped whole, and a side is finished once that distance alone
-// reaches `best`. In open space (distances of tens of cells) this visits a dozen group minima instead
-// of a hundred cells; the result is the exact minimum either way.
-#define TP_SEG 8
-__device__ __forceinline__ int tp_line_min_seg(const int* __restrict__ col, const int* __restrict__ seg, int stride,
-                                               int n, int l) {
-    int best = col[(size_t)l * stride];
-    const int s0 = l / TP_SEG, nseg = (n + TP_SEG - 1) / TP_SEG;
-    {   // own group
-        const int q0 = s0 * TP_SEG, q1 = min(q0 + TP_SEG, n);
-        for (int q = q0; q < q1; q++) {
-            const int d = q - l;
-            best = __viaddmin_s32(d * d, col[(size_t)q * stride], best);
-        }
-    }
-    bool go_l = s0 > 0, go_r = s0 + 1 < nseg;
-    for (int k = 1; go_l || go_r; k++) {
-        if (go_l) {
-            const int sg = s0 - k;
-            const int dn = l - (sg * TP_SEG + TP_SEG - 1);      // distance to the group's nearest cell
-            if (dn * dn >= best) {
-                go_l = false;
-            } else {
-                if (seg[(size_t)sg * stride] + dn * dn < best) {
-                    const int* c = col + (size_t)(sg * TP_SEG) * stride;
-#pragma unroll
-                    for (int r = 0; r < TP_SEG; r++) {
-                        const int d = dn + (TP_SEG - 1 - r);
-                        best = __viaddmin_s32(d * d, c[(size_t)r * stride], best);
-                    }
-                }
-                go_l = sg > 0;
-            }
-        }
-        if (go_r) {
-            const int sg = s0 + k;
-            const int q0 = sg * TP_SEG;
-            const int dn = q0 - l;
-            if (dn * dn >= best) {
-                go_r = false;
-            } else {
-                if (seg[(size_t)sg * stride] + dn * dn < best) {
-                    const int q1 = min(q0 + TP_SEG, n);
-                    for (int q = q0; q < q1; q++) {
-                        const int d = q - l;
-                        best = __viaddmin_s32(d * d, col[(size_t)q * stride], best);
-                    }
-                }
-                go_r = sg + 1 < nseg;
-            }
-        }
-    }
-    return best;
 }
 
 __device__ __forceinline__ void tp_edt_store(bool FINAL, int bp, int bn, size_t idx, double res,
@@ -311,7 +252,7 @@ __device__ __forceinline__ void tp_edt_store(bool FINAL, int bp, int bn, size_t 
         const double vp = bp == INT32_MAX ? DBL_MAX : (double)bp;
         const double vn = bn == INT32_MAX ? DBL_MAX : (double)bn;
         const double dp = __dmul_rn(res, __dsqrt_rn(vp));
-        const double dn = __dmul_rn(res, __dsqrt_rn(vn));
+        const double dn = bn > 0 ? __dmul_rn(res, __dsqrt_rn(vn)) : 0.0;   // res * sqrt(0) = +0
         if (rs.enabled) {
             // ROG ring: box coordinates -> ring memory, q > mem_end ? q + id_l - S : q + id_l per axis
             size_t m;
@@ -348,145 +289,120 @@ __device__ __forceinline__ void tp_edt_store(bool FINAL, int bp, int bn, size_t 
     }
 }
 
-// Pass 2 (and the last pass of the 2-D maps): input is pass 1's packed int16 1-D distances.
-// Most entries of the positive transform are "no source on this line" (columns without any
-// obstacle), so each column's finite entries are compacted — (index << 16 | distance), in order —
-// and an output only walks its finite neighbours outwards, nearest first, with the same cut-off.
-// The negative transform (sources = free cells, dense and mostly zero) keeps the dense search.
-// smem: tile [n_line][TZ+1] short2 | compact [TZ][n_line] int32 | rank [n_line][TZ+1] int16 | cnt [TZ]
-template <bool FINAL>
-__global__ void k_edt_strided16(const short2* __restrict__ in16, int32_t* __restrict__ out_pos,
-                                int32_t* __restrict__ out_neg, double* __restrict__ esdf, int n_line,
-                                size_t line_stride, size_t outer_stride, int n_inner, int tiles, double res,
-                                const __grid_constant__ TpRogSink sink) {
-    extern __shared__ int sm_i[];
-    const int TZ = blockDim.x, TY = blockDim.y, RS = TZ + 1;
-    short2* s_in = reinterpret_cast<short2*>(sm_i);
-    int* s_cv = sm_i + (size_t)n_line * RS;
-    short* s_rank = reinterpret_cast<short*>(s_cv + (size_t)TZ * n_line);
-    int* s_cnt = reinterpret_cast<int*>(s_rank + (((size_t)n_line * RS + 1) & ~(size_t)1));
+// Passes 2 and 3 (and the last pass of the 2-D maps), along a strided axis. Block = one outer index x TZ
+// contiguous inner cells; the whole line of the tile is staged in shared memory as sign-packed squared distances
+// (edt_line.cuh), TZ x 2-4 B contiguous per row on the way in, TZ x 4 B (intermediate) or TZ x 8 B (ESDF) on the
+// way out. Thread (x, y): column x of the tile, chunk y (y + TY, ...) of TP_EDT_CHUNK consecutive cells.
+//   1. runs of "no source" cells get their skip distances (two walks over the thread's own chunk, the carries of
+//      the neighbouring chunks through first / last tables);
+//   2. the chunk boundaries are answered against the whole line (window cut-off + skips);
+//   3. every thread answers the inside of its chunk by halving between known minimisers — no barrier, the
+//      minimisers (int16) of a chunk are private to its thread.
+// The negative transform of each cell is the short outward search; both results leave the block the moment they
+// are known. The 16 threads of a row write 64 / 128 contiguous bytes.
+// IN16: input = pass 1's sign-packed int16 1-D distances, else pass 2's sign-packed int32 squared distances.
+template <bool IN16, bool FINAL, int TZ>
+__global__ void k_edt_line(const void* __restrict__ in_, int32_t* __restrict__ out32, int32_t* __restrict__ out_pos,
+                           int32_t* __restrict__ out_neg, double* __restrict__ esdf, int n_line, size_t line_stride,
+                           size_t outer_stride, int n_inner, int tiles, int CH, double res,
+                           const __grid_constant__ TpRogSink sink) {
+    extern __shared__ __align__(16) int sm_i[];
+    const int TY = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
+    const int nseg = (n_line + CH - 1) / CH, nb = tp_edt_boundaries(n_line, CH);
+    int* s_f = sm_i;                                                        // [n_line][TZ]
+    short* s_arg = reinterpret_cast<short*>(s_f + n_line * TZ);     // [n_line][TZ]
+    short* s_first = s_arg + n_line * TZ;                           // [nseg][TZ]
+    short* s_last = s_first + nseg * TZ;                            // [nseg][TZ]
     const int outer = blockIdx.x / tiles, tile = blockIdx.x % tiles;
-    const int c = tile * TZ + threadIdx.x;
+    const int c = tile * TZ + tx;
     const bool cvalid = c < n_inner;
     const size_t base = (size_t)outer * outer_stride + c;
-    for (int l = threadIdx.y; l < n_line; l += TY) {
-        short2 v = make_short2(TP_INF16, TP_INF16);
-        if (cvalid) v = in16[base + (size_t)l * line_stride];
-        s_in[(size_t)l * RS + threadIdx.x] = v;
-    }
-    __syncthreads();
-    // compaction: one warp per column at a time
-    const int tid = threadIdx.y * TZ + threadIdx.x, nthreads = TZ * TY;
-    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-    for (int col = warp; col < TZ; col += max(nwarps, 1)) {
-        int count = 0;
-        for (int l0 = 0; l0 < n_line; l0 += 32) {
-            const int l = l0 + lane;
-            const int v = l < n_line ? (int)s_in[(size_t)l * RS + col].x : TP_INF16;
-            const bool fin = v < TP_INF16;
-            const unsigned m = __ballot_sync(0xffffffffu, fin);
-            const int before = count + __popc(m & ((1u << lane) - 1u));
-            if (l < n_line) s_rank[(size_t)l * RS + col] = (short)before;
-            if (fin) s_cv[(size_t)col * n_line + before] = (l << 16) | v;
-            count += __popc(m);
-        }
-        if (lane == 0) s_cnt[col] = count;
-    }
-    __syncthreads();
-    if (!cvalid) return;
-    const int cnt = s_cnt[threadIdx.x];
-    const int* cv = s_cv + (size_t)threadIdx.x * n_line;
-    for (int l = threadIdx.y; l < n_line; l += TY) {
-        // positive transform: walk the finite entries outwards from l, the nearer side first
-        int bp = TP_INF32;
-        {
-            const int b0 = s_rank[(size_t)l * RS + threadIdx.x];
-            const bool right_first = b0 < cnt && (b0 == 0 || (cv[b0] >> 16) - l <= l - (cv[b0 - 1] >> 16));
-#pragma unroll
-            for (int side = 0; side < 2; side++) {
-                if ((side == 0) == right_first) {
-                    for (int b = b0; b < cnt; b++) {
-                        const int e = cv[b], d = (e >> 16) - l, v = e & 0xffff;
-                        const int dd = d * d;
-                        if (dd >= bp) break;
-                        bp = min(bp, dd + v * v);
-                    }
-                } else {
-                    for (int a = b0 - 1; a >= 0; a--) {
-                        const int e = cv[a], d = l - (e >> 16), v = e & 0xffff;
-                        const int dd = d * d;
-                        if (dd >= bp) break;
-                        bp = min(bp, dd + v * v);
-                    }
-                }
-            }
-        }
-        // negative transform: dense outward search on the packed tile
-        int bn;
-        {
-            const short2* colp = s_in + threadIdx.x;
-            auto at = [&](int q) {
-                const int v = colp[(size_t)q * RS].y;
-                return v >= TP_INF16 ? TP_INF32 : v * v;
-            };
-            bn = at(l);
-            for (int d = 1; d < n_line; d++) {
-                const int dd = d * d;
-                if (dd >= bn) break;
-                if (l - d >= 0) bn = __viaddmin_s32(dd, at(l - d), bn);
-                if (l + d < n_line) bn = __viaddmin_s32(dd, at(l + d), bn);
-            }
-        }
-        tp_edt_store(FINAL, bp, bn, base + (size_t)l * line_stride, res, out_pos, out_neg, esdf, sink, l, outer, c);
-    }
-}
-
-// Pass 3 (3-D maps): input = pass 2's int32 squared distances of both transforms, dense. Block = one
-// outer index x TZ contiguous inner cells; the whole line is staged in shared memory.
-template <bool FINAL>
-__global__ void k_edt_strided32(const int32_t* __restrict__ in_pos, const int32_t* __restrict__ in_neg,
-                                int32_t* __restrict__ out_pos, int32_t* __restrict__ out_neg,
-                                double* __restrict__ esdf, int n_line, size_t line_stride, size_t outer_stride,
-                                int n_inner, int tiles, double res, const __grid_constant__ TpRogSink sink) {
-    extern __shared__ int sm_i[];
-    const int TZ = blockDim.x, TY = blockDim.y;
-    const int nseg = (n_line + TP_SEG - 1) / TP_SEG;
-    int* s_pos = sm_i;
-    int* s_neg = sm_i + (size_t)n_line * TZ;
-    int* g_pos = s_neg + (size_t)n_line * TZ;      // group minima
-    int* g_neg = g_pos + (size_t)nseg * TZ;
-    const int outer = blockIdx.x / tiles, tile = blockIdx.x % tiles;
-    const int c = tile * TZ + threadIdx.x;
-    const bool cvalid = c < n_inner;
-    const size_t base = (size_t)outer * outer_stride + c;
-    for (int l = threadIdx.y; l < n_line; l += TY) {
-        int p = TP_INF32, q = TP_INF32;
+    for (int l = ty; l < n_line; l += TY) {
+        int v = TP_INF32;
         if (cvalid) {
             const size_t idx = base + (size_t)l * line_stride;
-            p = in_pos[idx];
-            q = in_neg[idx];
+            v = IN16 ? tp_sq16(static_cast<const int16_t*>(in_)[idx]) : static_cast<const int32_t*>(in_)[idx];
         }
-        s_pos[(size_t)l * TZ + threadIdx.x] = p;
-        s_neg[(size_t)l * TZ + threadIdx.x] = q;
+        s_f[l * TZ + tx] = v;
     }
     __syncthreads();
-    for (int sgi = threadIdx.y; sgi < nseg; sgi += TY) {
-        int mp = TP_INF32, mn = TP_INF32;
-        const int q1 = min(sgi * TP_SEG + TP_SEG, n_line);
-        for (int q = sgi * TP_SEG; q < q1; q++) {
-            mp = min(mp, s_pos[(size_t)q * TZ + threadIdx.x]);
-            mn = min(mn, s_neg[(size_t)q * TZ + threadIdx.x]);
+    int* col = s_f + tx;
+    // 1. skip distances of the "no source" runs
+    uint32_t has_run = 0u;      // bit i: the i-th chunk of this thread holds a "no source" cell
+    if (cvalid) {
+        int it = 0;
+        for (int sg = ty; sg < nseg; sg += TY, it++) {
+            const int v0 = sg * CH, v1 = min(v0 + CH, n_line);
+            int first = -1, last = -1, cnt = 0;
+            for (int v = v0; v < v1; v++)
+                if (col[v * TZ] < TP_INF32) {
+                    if (first < 0) first = v;
+                    last = v;
+                    cnt++;
+                }
+            s_first[sg * TZ + tx] = (short)first;
+            s_last[sg * TZ + tx] = (short)last;
+            if (cnt != v1 - v0 || it >= 32) has_run |= 1u << (it & 31);
         }
-        g_pos[(size_t)sgi * TZ + threadIdx.x] = mp;
-        g_neg[(size_t)sgi * TZ + threadIdx.x] = mn;
     }
     __syncthreads();
-    if (!cvalid) return;
-    for (int l = threadIdx.y; l < n_line; l += TY) {
-        const int bp = tp_line_min_seg(s_pos + threadIdx.x, g_pos + threadIdx.x, TZ, n_line, l);
-        const int bn = tp_line_min_seg(s_neg + threadIdx.x, g_neg + threadIdx.x, TZ, n_line, l);
-        tp_edt_store(FINAL, bp, bn, base + (size_t)l * line_stride, res, out_pos, out_neg, esdf, sink, l, outer, c);
+    if (cvalid && has_run != 0u) {
+        int it = 0;
+        for (int sg = ty; sg < nseg; sg += TY, it++) {
+            if (!((has_run >> (it & 31)) & 1u)) continue;
+            const int v0 = sg * CH, v1 = min(v0 + CH, n_line);
+            int lastc = -1, nextc = n_line;     // nearest cell with a value before / after the chunk
+            for (int k = sg - 1; k >= 0 && lastc < 0; k--) lastc = s_last[k * TZ + tx];
+            for (int k = sg + 1; k < nseg && nextc >= n_line; k++) {
+                const int fk = s_first[k * TZ + tx];
+                if (fk >= 0) nextc = fk;
+            }
+            for (int v = v1 - 1; v >= v0; v--) {
+                if (col[v * TZ] < TP_INF32) nextc = v;
+                else col[v * TZ] = tp_skip_make(0, nextc - v);
+            }
+            for (int v = v0; v < v1; v++) {
+                const int fv = col[v * TZ];
+                if (fv < TP_INF32) lastc = v;
+                else col[v * TZ] = fv | ((v - lastc) << TP_SKIP_BITS);
+            }
+        }
     }
+    __syncthreads();
+    auto emit = [&](int l, int bp) {
+        const int bn = tp_neg_search<TZ>(col, n_line, l);
+        const size_t idx = base + (size_t)l * line_stride;
+        if (FINAL) {
+            tp_edt_store(true, bp, bn, idx, res, out_pos, out_neg, esdf, sink, l, outer, c);
+        } else {
+            // exactly one of the two is non-zero (the cell is a source of the other transform)
+            out32[idx] = bn > 0 ? -(bn >= TP_INF32 ? TP_INF32 : bn) : (bp >= TP_INF32 ? TP_INF32 : bp);
+        }
+    };
+    // 2. chunk boundaries, each against the whole line
+    if (cvalid)
+        for (int b = ty; b < nb; b += TY) {
+            const int q = tp_edt_boundary(b, n_line, CH);
+            int arg;
+            const int bp = tp_dc_query<TZ>(col, q, 0, n_line - 1, arg);
+            s_arg[q * TZ + tx] = (short)arg;
+            emit(q, bp);
+        }
+    __syncthreads();
+    // 3. the inside of the chunks, one thread per chunk
+    if (cvalid)
+        for (int ch = ty; ch < nb - 1; ch += TY) {
+            const int lo = tp_edt_boundary(ch, n_line, CH), hi = tp_edt_boundary(ch + 1, n_line, CH);
+            for (int h = tp_dc_top(hi - lo) >> 1; h >= 1; h >>= 1)
+                for (int q = lo + h; q < hi; q += 2 * h) {
+                    const int qr = q + h < hi ? q + h : hi;
+                    const int a_lo = s_arg[(q - h) * TZ + tx], a_hi = s_arg[qr * TZ + tx];
+                    int arg;
+                    const int bp = tp_dc_query<TZ>(col, q, a_lo, a_hi, arg);
+                    s_arg[q * TZ + tx] = (short)arg;
+                    emit(q, bp);
+                }
+        }
 }
 
 __global__ void k_query3d(TpGrid g, const double* __restrict__ pos, int64_t n, double* dist, double* grad,
@@ -615,7 +531,7 @@ int fmalloc(T** p, size_t count) {
 // One signed transform over a [A][B][C] array (C contiguous): pass 1 along C, pass 2 along B
 // and, when A > 1, pass 3 along A. The last pass writes `esdf` (+ the integer grids).
 int signed_edt(topay_field* f, const int8_t* src, int A, int B, int C, double* esdf, int32_t* sqp, int32_t* sqn) {
-    TpEdtScratch sc{f->stream, f->packed, f->tmp_pos, f->tmp_neg, f->keep_sq, f->desc.resolution, TpRogSink{}};
+    TpEdtScratch sc{f->stream, f->packed16, f->packed32, f->keep_sq, f->desc.resolution, TpRogSink{}};
     return tp_signed_edt(sc, src, A, B, C, esdf, sqp, sqn);
 }
 
@@ -633,55 +549,62 @@ int tp_signed_edt(const TpEdtScratch& f_, const int8_t* src, int A, int B, int C
         const int wpb = 8;
         const unsigned blocks = (unsigned)((n_lines + wpb - 1) / wpb);
         if (C % 4 == 0)
-            k_edt_contig<true><<<blocks, wpb * 32, 0, q>>>(src, f->packed, n_lines, C);
+            k_edt_contig<true><<<blocks, wpb * 32, 0, q>>>(src, f->packed16, n_lines, C);
         else
-            k_edt_contig<false><<<blocks, wpb * 32, 0, q>>>(src, f->packed, n_lines, C);
+            k_edt_contig<false><<<blocks, wpb * 32, 0, q>>>(src, f->packed16, n_lines, C);
     }
     auto strided = [&](bool in16, bool fin, int n_line, size_t line_stride, int n_outer, size_t outer_stride,
                        int n_inner) -> int {
+        // Chunk length: 32 queries per thread on large grids; small grids (the 2-D maps, the default 200 x 200 x 16
+        // field) take shorter chunks so that the chunk threads of the whole grid still fill the machine.
+        static const int env_ch = getenv("TOPAY_EDT_CH") ? atoi(getenv("TOPAY_EDT_CH")) : 0;
+        int CH = env_ch >= 4 ? env_ch : 32;
+        while (CH > 4 && (long long)n_outer * n_inner * ((n_line + CH - 1) / CH) < 148 * 1024) CH >>= 1;
+        // staged line (int32) + the minimisers (int16) + first / last tables of the chunks (int16)
+        const int nseg = (n_line + CH - 1) / CH, nb = tp_edt_boundaries(n_line, CH);
         auto smem_of = [&](int tz) -> size_t {
-            if (!in16) return ((size_t)n_line + (n_line + TP_SEG - 1) / TP_SEG) * tz * 8;
-            const size_t rs = tz + 1;
-            return (size_t)n_line * rs * 4 + (size_t)tz * n_line * 4 + ((((size_t)n_line * rs + 1) & ~(size_t)1) * 2) +
-                   (size_t)tz * 4 + 16;
+            return (size_t)n_line * tz * 4 + (size_t)n_line * tz * 2 + (size_t)2 * nseg * tz * 2 + 16;
         };
-        // Shared-memory cap per block (KB) of the two strided passes. The int16 pass is bound by
-        // shared-memory latency: narrow tiles (4 columns x the whole line, <= 40 KB) put five blocks on an
-        // SM instead of one and cut it from 1.62 to 0.55 ms at 800x800x80; the int32 pass is issue bound
-        // and does not care. TOPAY_EDT_CAP16 / TOPAY_EDT_CAP32 override (dev).
-        static const size_t edt_smem_cap16 = getenv("TOPAY_EDT_CAP16") ? (size_t)atoi(getenv("TOPAY_EDT_CAP16")) : 40;
-        static const size_t edt_smem_cap32 = getenv("TOPAY_EDT_CAP32") ? (size_t)atoi(getenv("TOPAY_EDT_CAP32")) : 72;
-        int TZ = 16;
-        while (TZ > 1 && smem_of(TZ) > (in16 ? edt_smem_cap16 : edt_smem_cap32) * 1024) TZ >>= 1;
-        // small grids (the 2-D maps): narrower tiles so that the blocks cover all SMs
-        while (TZ > 2 && (long long)n_outer * ((n_inner + TZ - 1) / TZ) < 296) TZ >>= 1;
+        // Tile width: 16 cells (64 B rows in, 128 B rows of ESDF out) while at least two blocks fit an SM;
+        // TOPAY_EDT_TZ / TOPAY_EDT_TY override (dev).
+        static const int env_tz = getenv("TOPAY_EDT_TZ") ? atoi(getenv("TOPAY_EDT_TZ")) : 0;
+        static const int env_ty = getenv("TOPAY_EDT_TY") ? atoi(getenv("TOPAY_EDT_TY")) : 0;
+        int TZ = (env_tz == 4 || env_tz == 8 || env_tz == 16) ? env_tz : 16;
+        while (TZ > 4 && smem_of(TZ) > (size_t)100 * 1024) TZ >>= 1;
+        // small grids: narrower tiles so that the blocks cover all SMs
+        while (env_tz <= 0 && TZ > 4 && (long long)n_outer * ((n_inner + TZ - 1) / TZ) < 296) TZ >>= 1;
         const size_t smem = smem_of(TZ);
         if (smem > 200 * 1024) {
             tp_set_error("grid line too long for the strided-pass staging buffer");
             return TOPAY_ERR_TOO_LARGE;
         }
-        int TY = std::max(1, std::min(512 / TZ, n_line));
-        while ((TZ * TY) % 32 != 0 && TY < 1024 / TZ) TY++;     // whole warps (the compaction uses ballots)
+        int TY = env_ty > 0 ? env_ty : std::max(1, std::min(1024 / TZ, nb));    // one thread per chunk boundary
+        while ((TZ * TY) % 32 != 0 && TY < 1024 / TZ) TY++;     // whole warps
         const int tiles = (n_inner + TZ - 1) / TZ;
         dim3 blk(TZ, TY);
         const unsigned blocks = (unsigned)n_outer * tiles;
-        int32_t* op = fin ? (f->keep_sq ? sqp : nullptr) : f->tmp_pos;
-        int32_t* on = fin ? (f->keep_sq ? sqn : nullptr) : f->tmp_neg;
+        int32_t* op = fin && f->keep_sq ? sqp : nullptr;
+        int32_t* on = fin && f->keep_sq ? sqn : nullptr;
         const double res = f->res;
-        if (in16 && fin) {
-            TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), {});
-            k_edt_strided16<true><<<blocks, blk, smem, q>>>(f->packed, op, on, esdf, n_line, line_stride, outer_stride,
-                                                           n_inner, tiles, res, f->sink);
-        } else if (in16) {
-            TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), {});
-            k_edt_strided16<false><<<blocks, blk, smem, q>>>(f->packed, op, on, esdf, n_line, line_stride, outer_stride,
-                                                            n_inner, tiles, res, f->sink);
-        } else {
-            TP_CUDA_OK(cudaFuncSetAttribute(k_edt_strided32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), {});
-            k_edt_strided32<true><<<blocks, blk, smem, q>>>(f->tmp_pos, f->tmp_neg, op, on, esdf, n_line, line_stride,
-                                                           outer_stride, n_inner, tiles, res, f->sink);
-        }
-        return TOPAY_OK;
+        // the attribute is per kernel and process-wide: it only ever grows (fields of different sizes coexist)
+        static std::atomic<size_t> attr[9];
+        auto launch = [&](auto kern, int slot, const void* in, int32_t* out32) -> int {
+            size_t cur = attr[slot].load();
+            while (cur < smem && !attr[slot].compare_exchange_weak(cur, smem)) {}
+            TP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr[slot].load()), {});
+            kern<<<blocks, blk, smem, q>>>(in, out32, op, on, fin ? esdf : nullptr, n_line, line_stride, outer_stride,
+                                          n_inner, tiles, CH, res, f->sink);
+            return TOPAY_OK;
+        };
+        const int tzi = TZ == 16 ? 0 : (TZ == 8 ? 1 : 2);
+#define TP_EDT_DISPATCH(IN, FIN, SLOT, INP, OUT)                                                        \
+        (tzi == 0 ? launch(k_edt_line<IN, FIN, 16>, (SLOT) * 3 + 0, INP, OUT)                           \
+                  : tzi == 1 ? launch(k_edt_line<IN, FIN, 8>, (SLOT) * 3 + 1, INP, OUT)                 \
+                             : launch(k_edt_line<IN, FIN, 4>, (SLOT) * 3 + 2, INP, OUT))
+        if (in16 && fin) return TP_EDT_DISPATCH(true, true, 0, f->packed16, nullptr);
+        if (in16) return TP_EDT_DISPATCH(true, false, 1, f->packed16, f->packed32);
+        return TP_EDT_DISPATCH(false, true, 2, f->packed32, nullptr);
+#undef TP_EDT_DISPATCH
     };
     int rc;
     if (A == 1) {
@@ -742,9 +665,8 @@ extern "C" int topay_field_create(const topay_grid_desc* desc, int device, topay
     FA(f->esdf2d, f->n2);
     FA(f->esdf2d_inflate, f->n2);
     FA(f->esdf2d_crit, f->n2);
-    FA(f->packed, f->n3);
-    FA(f->tmp_pos, f->n3);
-    FA(f->tmp_neg, f->n3);
+    FA(f->packed16, f->n3);
+    FA(f->packed32, f->n3);
     for (int w = 0; w < 3; w++) {
         FA(f->sq_pos[w], f->n2);
         FA(f->sq_neg[w], f->n2);
@@ -777,7 +699,7 @@ extern "C" void topay_field_destroy(topay_field* f) {
     cudaSetDevice(f->device);
     if (f->stream) cudaStreamSynchronize(f->stream);
     void* ptrs[] = {f->occ3d, f->occ2d, f->occ2d_crit, f->src2d, f->esdf3d, f->esdf2d, f->esdf2d_inflate,
-                    f->esdf2d_crit, f->packed, f->tmp_pos, f->tmp_neg, f->sq_pos[0], f->sq_pos[1], f->sq_pos[2],
+                    f->esdf2d_crit, f->packed16, f->packed32, f->sq_pos[0], f->sq_pos[1], f->sq_pos[2],
                     f->sq_pos[3], f->sq_neg[0], f->sq_neg[1], f->sq_neg[2], f->sq_neg[3]};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -241,32 +241,43 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
         pg.at(ci, 1) = g1;
         pg.at(ci, 2) = g2;
     }
-    // link vs link (:1566-1611)
+    // link vs link (:1566-1611). Penetrating pairs are rare, so the 66 pair distances are evaluated branch-free
+    // first (unrolled by four: the shared-memory loads of a group are issued ahead of its arithmetic), and only the
+    // pairs that do penetrate — kept as a bit mask, walked in the reference's order — enter the penalty and its
+    // gradient.
     for (int ci = 0; ci < P.n_sphere; ci++) {
         const uint32_t mask = P.pair_mask[ci];
         if (mask == 0u) continue;
         const double pi0 = pts.at(ci, 0), pi1 = pts.at(ci, 1), pi2 = pts.at(ci, 2);
         const double ri = P.sphere_r[ci];
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int cj = ci + 1; cj < P.n_sphere; cj++) {
-            if (!((mask >> cj) & 1u)) continue;
+        uint32_t hit = 0u;
+#pragma unroll 4
+        for (int cj = ci + 1; cj < TOPAY_NSPHERE; cj++) {
             const double dx = pi0 - pts.at(cj, 0), dy = pi1 - pts.at(cj, 1), dz = pi2 - pts.at(cj, 2);
             const double rs = ri + P.sphere_r[cj];
             const double dist = rs * rs - (dx * dx + dy * dy + dz * dz);
-            if (dist > 0) {
-                double f, df;
-                tp_smoothL1(P, dist, f, df);
-                const double k = -omg * step * w_sc * df;
-                const double h0 = k * dx * 2.0, h1 = k * dy * 2.0, h2 = k * dz * 2.0;
-                o.gdT += omg * w_sc * (f / K);
-                o.terms[TOPAY_TERM_SELF_COLLI] += omg * step * w_sc * f;
-                a0 += h0;
-                a1 += h1;
-                a2 += h2;
-                pg.at(cj, 0) -= h0;
-                pg.at(cj, 1) -= h1;
-                pg.at(cj, 2) -= h2;
-            }
+            hit |= dist > 0 ? (1u << cj) : 0u;
+        }
+        hit &= mask;          // pair_mask holds bits c2 > ci, c2 < n_sphere only
+        if (hit == 0u) continue;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int cj = ci + 1; cj < P.n_sphere; cj++) {
+            if (!((hit >> cj) & 1u)) continue;
+            const double dx = pi0 - pts.at(cj, 0), dy = pi1 - pts.at(cj, 1), dz = pi2 - pts.at(cj, 2);
+            const double rs = ri + P.sphere_r[cj];
+            const double dist = rs * rs - (dx * dx + dy * dy + dz * dz);
+            double f, df;
+            tp_smoothL1(P, dist, f, df);
+            const double k = -omg * step * w_sc * df;
+            const double h0 = k * dx * 2.0, h1 = k * dy * 2.0, h2 = k * dz * 2.0;
+            o.gdT += omg * w_sc * (f / K);
+            o.terms[TOPAY_TERM_SELF_COLLI] += omg * step * w_sc * f;
+            a0 += h0;
+            a1 += h1;
+            a2 += h2;
+            pg.at(cj, 0) -= h0;
+            pg.at(cj, 1) -= h1;
+            pg.at(cj, 2) -= h2;
         }
         pg.at(ci, 0) += a0;
         pg.at(ci, 1) += a1;

@@ -36,8 +36,8 @@ struct topay_rogfield {
     int16_t *occ_cnt, *unk_cnt;
     double *dist3, *neg3, *crit, *flat, *neg2;
     int8_t *box_occ, *col_occ;          // dense box occupancy; [2][bx*by] column occupancy (critical, flat)
-    short2* packed;
-    int32_t *tmp_pos, *tmp_neg;
+    int16_t* packed16;
+    int32_t* packed32;
     cudaEvent_t ev0, ev1, ev2;
     float ms_total, ms_3d;
     bool updated;               // updateESDF3D ran at least once
@@ -310,9 +310,8 @@ extern "C" int topay_rogfield_create(const topay_rog_desc* d, int device, topay_
     RA(f->neg2, f->n2);
     RA(f->box_occ, f->n3);
     RA(f->col_occ, 2 * f->n2);
-    RA(f->packed, f->n3);
-    RA(f->tmp_pos, f->n3);
-    RA(f->tmp_neg, f->n3);
+    RA(f->packed16, f->n3);
+    RA(f->packed32, f->n3);
 #undef RA
     cudaMemsetAsync(f->dist3, 0, f->n3 * 8, f->stream);
     cudaMemsetAsync(f->neg3, 0, f->n3 * 8, f->stream);
@@ -336,7 +335,7 @@ extern "C" void topay_rogfield_destroy(topay_rogfield* f) {
     cudaSetDevice(f->device);
     if (f->stream) cudaStreamSynchronize(f->stream);
     void* ptrs[] = {f->occ_cnt, f->unk_cnt, f->dist3, f->neg3, f->crit, f->flat, f->neg2, f->box_occ,
-                    f->col_occ, f->packed, f->tmp_pos, f->tmp_neg};
+                    f->col_occ, f->packed16, f->packed32};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (f->ev0) cudaEventDestroy(f->ev0);
@@ -452,12 +451,16 @@ extern "C" int topay_rogfield_update_esdf(topay_rogfield* f, const double cur_od
         if (B.idl[i] != 0) wrapped = true;
     }
     f->ms_total = f->ms_3d = 0.f;
-    f->updated = true;
-    if (B.b[0] <= 0 || B.b[1] <= 0 || B.b[2] <= 0) return TOPAY_OK;
+    if (B.b[0] <= 0 || B.b[1] <= 0 || B.b[2] <= 0) {
+        f->updated = true;
+        return TOPAY_OK;
+    }
+    // the ring counts as built only once this update has completed: a failed update leaves it not ready
+    f->updated = false;
     const size_t nb3 = (size_t)B.b[0] * B.b[1] * B.b[2], nb2 = (size_t)B.b[0] * B.b[1];
     const unsigned g3 = (unsigned)std::min<size_t>((nb3 + 255) / 256, 148 * 32);
     // the EDT's last pass writes res*sqrt of both transforms straight into the ring (TpRogSink)
-    TpEdtScratch sc{q, f->packed, f->tmp_pos, f->tmp_neg, false, f->res, TpRogSink{}};
+    TpEdtScratch sc{q, f->packed16, f->packed32, false, f->res, TpRogSink{}};
     TpRogSink& sk = sc.sink;
     sk.enabled = 1;
     for (int i = 0; i < 3; i++) {
@@ -475,7 +478,10 @@ extern "C" int topay_rogfield_update_esdf(topay_rogfield* f, const double cur_od
     sk.fuse = wrapped ? 0 : 1;     // no wrap: the image is the memory box, combine on the spot
     sk.dist = f->dist3;
     sk.neg = f->neg3;
-    if ((rc = tp_signed_edt(sc, f->box_occ, B.b[0], B.b[1], B.b[2], nullptr, nullptr, nullptr)) != TOPAY_OK) return rc;
+    if ((rc = tp_signed_edt(sc, f->box_occ, B.b[0], B.b[1], B.b[2], nullptr, nullptr, nullptr)) != TOPAY_OK) {
+        cudaStreamSynchronize(q);
+        return rc;
+    }
     if (wrapped) k_rog_combine3<<<g3, 256, 0, q>>>(B, f->res, f->dist3, f->neg3);
     cudaEventRecord(f->ev1, q);
     // 2-D maps: flat covers box z up to the ring coordinate of z = 0.155 m (esdf_map.cpp:413-421)
@@ -492,8 +498,10 @@ extern "C" int topay_rogfield_update_esdf(topay_rogfield* f, const double cur_od
     for (int which = 0; which < 2; which++) {
         sk.dist = which == 0 ? f->crit : f->flat;
         cudaMemsetAsync(f->neg2, 0, f->n2 * 8, q);
-        if ((rc = tp_signed_edt(sc, f->col_occ + which * nb2, 1, B.b[0], B.b[1], nullptr, nullptr, nullptr)) != TOPAY_OK)
+        if ((rc = tp_signed_edt(sc, f->col_occ + which * nb2, 1, B.b[0], B.b[1], nullptr, nullptr, nullptr)) != TOPAY_OK) {
+            cudaStreamSynchronize(q);
             return rc;
+        }
         const size_t nc = (size_t)B.b[0] * B.b[0];
         k_rog_combine2<<<(unsigned)((nc + 255) / 256), 256, 0, q>>>(B, f->res, sk.dist, f->neg2);
     }
@@ -505,6 +513,7 @@ extern "C" int topay_rogfield_update_esdf(topay_rogfield* f, const double cur_od
     cudaEventElapsedTime(&b, f->ev1, f->ev2);
     f->ms_total = a + b;
     f->ms_3d = a;
+    f->updated = true;
     return TOPAY_OK;
 }
 

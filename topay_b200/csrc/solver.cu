@@ -54,6 +54,7 @@ struct topay_solver {
     topay_solver_stats stats;
     size_t smem_cand;    // dynamic shared memory of the adjoint / generate launches (banded system)
     size_t smem_lbfgs;   // ... of the L-BFGS launch (TMA ring + tables)
+    int fuse_max;        // live slots up to which a tick runs k_cand as one fused launch (TOPAY_FUSE_MAX)
     // initial state kept on the host for repeated runs
     double* h_x0;
     size_t h_x0_count;
@@ -143,7 +144,11 @@ void launch_eval(topay_solver* s, bool timed, int tick, int ny) {
 
 void launch_cand(topay_solver* s, int mode, int tick_in, int tick_out, int nx) {
     const int sd = (int)(s->smem_cand / sizeof(double)), sl = (int)(s->smem_lbfgs / sizeof(double));
-    if (mode == TP_MODE_GEN)
+    constexpr int ALL = TP_MODE_ADJ | TP_MODE_ADVANCE | TP_MODE_GEN;
+    if (mode == ALL) {
+        const size_t sm = std::max(s->smem_cand, s->smem_lbfgs);
+        k_cand<ALL><<<nx, TP_CAND_THREADS, sm, s->stream>>>(s->dev, s->params, (int)(sm / sizeof(double)), tick_in, tick_out);
+    } else if (mode == TP_MODE_GEN)
         k_cand<TP_MODE_GEN><<<nx, TP_CAND_THREADS, s->smem_cand, s->stream>>>(s->dev, s->params, sd, tick_in, tick_out);
     else if (mode == TP_MODE_ADJ)
         k_cand<TP_MODE_ADJ><<<nx, TP_CAND_THREADS, s->smem_cand, s->stream>>>(s->dev, s->params, sd, tick_in, tick_out);
@@ -214,6 +219,7 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     s->graph_max_N = -1;
     s->checker = nullptr;
     s->spin_sync = getenv("TOPAY_SPIN_SYNC") && atoi(getenv("TOPAY_SPIN_SYNC")) != 0;
+    s->fuse_max = getenv("TOPAY_FUSE_MAX") ? atoi(getenv("TOPAY_FUSE_MAX")) : 444;   // 3 blocks x 148 SMs
     s->d_pn = nullptr;
     s->d_start = nullptr;
     memset(&s->stats, 0, sizeof(s->stats));
@@ -339,6 +345,10 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
         TP_CUDA_OK(cudaFuncSetAttribute(k_cand<TP_MODE_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_set.load()),
                    { topay_solver_destroy(s); });
         TP_CUDA_OK(cudaFuncSetAttribute(k_cand<TP_MODE_ADVANCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_lb.load()),
+                   { topay_solver_destroy(s); });
+        TP_CUDA_OK(cudaFuncSetAttribute(k_cand<TP_MODE_ADJ | TP_MODE_ADVANCE | TP_MODE_GEN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)std::max(attr_set.load(), attr_lb.load())),
                    { topay_solver_destroy(s); });
     }
     const size_t sm_int = (size_t)TP_WARPS_PER_BLOCK * D.ppw * 3 * (2 * D.K + 1) * sizeof(double);
@@ -525,8 +535,16 @@ static void enqueue_batch(topay_solver* s, int ny, bool timed) {
     const TpSolverDev& D = s->dev;
     cudaStream_t q = s->stream;
     k_list_roll<<<1, 1024, 0, q>>>(D);
+    // Up to one wave of candidate blocks the three halves of k_cand run as ONE launch (the banded system stays in
+    // shared memory from the adjoint solve to the next factorisation, two launch boundaries less on the dependent
+    // chain of a small plan); above that they are separate launches, each at its own occupancy.
+    const bool fused = !timed && ny <= s->fuse_max;
     for (int t = 0; t < TP_TICKS; t++) {
         launch_eval(s, timed, t, ny);
+        if (fused) {
+            launch_cand(s, TP_MODE_ADJ | TP_MODE_ADVANCE | TP_MODE_GEN, t, t + 1, ny);
+            continue;
+        }
         launch_cand(s, TP_MODE_ADJ, t, -1, ny);
         if (timed) cudaEventRecord(s->ev[TP_EV * t + 4], q);
         launch_cand(s, TP_MODE_ADVANCE, t, -1, ny);
@@ -618,7 +636,7 @@ extern "C" int topay_solver_run(topay_solver* s) {
                 it = s->graphs.emplace(ny, ge).first;
             }
             TP_CUDA_OK(cudaGraphLaunch(it->second, q), {});
-            s->stats.kernel_launches += 6 * TP_TICKS + 1;
+            s->stats.kernel_launches += (ny <= s->fuse_max ? 4 : 6) * TP_TICKS + 1;
             s->stats.eval_launches += TP_TICKS;
         } else {
             enqueue_batch(s, ny, true);
@@ -791,20 +809,130 @@ extern "C" int topay_solver_check_feasible(topay_solver* s, topay_feasibility* o
         out->feasible_print = fp.data();
     }
     rc = s->checker->check(V, s->params, G, out);
-    if (rc == TOPAY_OK && best_success) {
-        // planner.cpp:877-880 + :999-1010: optimizeTraj && printConstraintsSituations, shortest duration
-        std::vector<TpCandState> st(n);
-        TP_CUDA_OK(cudaMemcpy(st.data(), D.res_st, n * sizeof(TpCandState), cudaMemcpyDeviceToHost), { out->feasible_print = keep_fp; });
-        std::vector<int32_t> ok(n);
-        std::vector<double> dur(n);
-        for (int c = 0; c < n; c++) {
-            ok[c] = st[c].status == 1 && out->feasible_print[c];
-            dur[c] = s->checker->h_meta[c].total;
-        }
-        *best_success = topay_select_shortest(ok.data(), dur.data(), n);
-    }
+    s->checker->checked_n = rc == TOPAY_OK ? n : 0;
     out->feasible_print = keep_fp;
+    if (rc == TOPAY_OK && best_success) {
+        // planner.cpp:877-880 + :999-1010: optimizeTraj && printConstraintsSituations, shortest duration — on the device
+        const int32_t off[2] = {0, n};
+        rc = topay_solver_select(s, 1, off, 1, best_success, nullptr);
+    }
     return rc;
+}
+
+// Selection on the device (planner.cpp:999-1010: the first success, replaced only by a strictly shorter duration;
+// the same rule on the cost): one block per plan walks its candidates, `ok` = optimizeTraj's status and, when the
+// gate ran, printConstraintsSituations' verdict (planner.cpp:877-880). Durations are summed in piece order like the
+// host loop of topay_solver_download, ties go to the lowest index.
+__global__ void __launch_bounds__(128)
+k_select(const TpCandState* __restrict__ st, const double* __restrict__ T, int max_pieces,
+         const TpFeasOut* __restrict__ feas, const int32_t* __restrict__ plan_off, int32_t* __restrict__ out) {
+    const int plan = blockIdx.x, c0 = plan_off[plan], c1 = plan_off[plan + 1];
+    int bd = INT32_MAX, bc = INT32_MAX;
+    double bdv = 0.0, bcv = 0.0;
+    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+        const bool ok = st[c].status == 1 && (!feas || feas[c].feasible_print != 0);
+        if (!ok) continue;
+        double dur = 0.0;
+        for (int i = 0; i < st[c].N; i++) dur += T[(size_t)c * max_pieces + i];
+        if (bd == INT32_MAX || dur < bdv) {
+            bd = c;
+            bdv = dur;
+        }
+        if (bc == INT32_MAX || st[c].cost < bcv) {
+            bc = c;
+            bcv = st[c].cost;
+        }
+    }
+    __shared__ double s_v[2][128];
+    __shared__ int s_i[2][128];
+    s_v[0][threadIdx.x] = bdv; s_i[0][threadIdx.x] = bd;
+    s_v[1][threadIdx.x] = bcv; s_i[1][threadIdx.x] = bc;
+    __syncthreads();
+    for (int w = 64; w > 0; w >>= 1) {
+        if (threadIdx.x < w)
+            for (int k = 0; k < 2; k++) {
+                const int ia = s_i[k][threadIdx.x], ib = s_i[k][threadIdx.x + w];
+                const double va = s_v[k][threadIdx.x], vb = s_v[k][threadIdx.x + w];
+                // smaller value wins; equal values: the lower index (= the first in the reference's scan)
+                if (ib != INT32_MAX && (ia == INT32_MAX || vb < va || (vb == va && ib < ia))) {
+                    s_i[k][threadIdx.x] = ib;
+                    s_v[k][threadIdx.x] = vb;
+                }
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[2 * plan] = s_i[0][0] == INT32_MAX ? -1 : s_i[0][0] - c0;
+        out[2 * plan + 1] = s_i[1][0] == INT32_MAX ? -1 : s_i[1][0] - c0;
+    }
+}
+
+extern "C" int topay_solver_select(topay_solver* s, int n_plans, const int32_t* plan_offset, int use_gate,
+                                   int32_t* best_by_duration, int32_t* best_by_cost) {
+    if (!s || s->n_cand < 1 || n_plans < 1 || !plan_offset || (!best_by_duration && !best_by_cost))
+        return TOPAY_ERR_INVALID_ARG;
+    for (int i = 0; i < n_plans; i++)
+        if (plan_offset[i] < 0 || plan_offset[i] > plan_offset[i + 1] || plan_offset[i + 1] > s->n_cand)
+            return TOPAY_ERR_INVALID_ARG;
+    if (use_gate && (!s->checker || s->checker->checked_n != s->n_cand)) {
+        tp_set_error("topay_solver_select(use_gate): run topay_solver_check_feasible on this solve first");
+        return TOPAY_ERR_NOT_READY;
+    }
+    cudaSetDevice(s->device);
+    const TpSolverDev& D = s->dev;
+    int32_t* d = nullptr;
+    TP_CUDA_OK(cudaMallocAsync(&d, (size_t)(3 * n_plans + 1) * sizeof(int32_t), s->stream), {});
+    int32_t* d_off = d + 2 * n_plans;
+    TP_CUDA_OK(cudaMemcpyAsync(d_off, plan_offset, (size_t)(n_plans + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream),
+               { cudaFreeAsync(d, s->stream); });
+    k_select<<<n_plans, 128, 0, s->stream>>>(D.res_st, D.res_T, D.max_pieces, use_gate ? s->checker->feas : nullptr, d_off, d);
+    std::vector<int32_t> h((size_t)2 * n_plans);
+    TP_CUDA_OK(cudaMemcpyAsync(h.data(), d, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream),
+               { cudaFreeAsync(d, s->stream); });
+    cudaFreeAsync(d, s->stream);
+    TP_CUDA_OK(cudaStreamSynchronize(s->stream), {});
+    TP_CUDA_OK(cudaGetLastError(), {});
+    for (int i = 0; i < n_plans; i++) {
+        if (best_by_duration) best_by_duration[i] = h[2 * i];
+        if (best_by_cost) best_by_cost[i] = h[2 * i + 1];
+    }
+    return TOPAY_OK;
+}
+
+// Results of ONE candidate of the last run (the winner): the arrays of `out` have length 1 (T: max_pieces,
+// coeff: 6 max_pieces x 9, x: num_vars(max_pieces)).
+extern "C" int topay_solver_download_candidate(topay_solver* s, int cand, topay_result_batch* out) {
+    if (!s || !out || !out->status || cand < 0 || cand >= s->n_cand) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(s->device);
+    const TpSolverDev& D = s->dev;
+    const int NP = D.max_pieces;
+    TpCandState st;
+    TP_CUDA_OK(cudaMemcpyAsync(&st, D.res_st + cand, sizeof(st), cudaMemcpyDeviceToHost, s->stream), {});
+    std::vector<double> T(NP);
+    TP_CUDA_OK(cudaMemcpyAsync(T.data(), D.res_T + (size_t)cand * NP, NP * 8, cudaMemcpyDeviceToHost, s->stream), {});
+    if (out->coeff)
+        TP_CUDA_OK(cudaMemcpyAsync(out->coeff, D.res_coeff + (size_t)cand * 6 * NP * 9, (size_t)6 * NP * 9 * 8,
+                                   cudaMemcpyDeviceToHost, s->stream), {});
+    std::vector<double> xs(out->x ? D.xs : 0);
+    if (out->x) TP_CUDA_OK(cudaMemcpyAsync(xs.data(), D.res_x + (size_t)cand * D.xs, (size_t)D.xs * 8, cudaMemcpyDeviceToHost, s->stream), {});
+    TP_CUDA_OK(cudaStreamSynchronize(s->stream), {});
+    double dur = 0.0;
+    for (int i = 0; i < st.N; i++) dur += T[i];
+    out->status[0] = st.status;
+    if (out->lbfgs_code) out->lbfgs_code[0] = st.last_code;
+    if (out->piece_num) out->piece_num[0] = st.N;
+    if (out->iters) out->iters[0] = st.iters_total;
+    if (out->evals) out->evals[0] = st.evals_total;
+    if (out->alm_rounds) out->alm_rounds[0] = st.alm_round;
+    if (out->cost) out->cost[0] = st.cost;
+    if (out->duration) out->duration[0] = dur;
+    if (out->final_xy_err) {
+        out->final_xy_err[0] = st.final_xy[0];
+        out->final_xy_err[1] = st.final_xy[1];
+    }
+    if (out->T) memcpy(out->T, T.data(), (size_t)NP * 8);
+    if (out->x) memcpy(out->x, xs.data(), (size_t)st.n * 8);
+    return TOPAY_OK;
 }
 
 // Developer aid: raw copy of one of the evaluation's intermediate device arrays after topay_solver_eval

@@ -39,6 +39,7 @@ struct TpTrajChecker {
     int cap_n = 0;
     size_t cap_seq = 0;
     std::vector<TpTrajMeta> h_meta;
+    int checked_n = 0;          // trajectories of the last successful check() (their verdicts are still in `feas`)
 
     TpTrajChecker() = default;
     TpTrajChecker(const TpTrajChecker&) = delete;

@@ -189,6 +189,65 @@ class MomaTrajOpt:
         self._last = r
         return r
 
+    def select(self, plan_offset=None, use_gate=False):
+        """topay_solver_select: the planner's pick (planner.cpp:999-1010) per plan ON THE DEVICE; two ints per plan
+        come back. plan_offset: first candidate of each plan + the total (default: one plan = the whole upload).
+        Returns (best_by_duration, best_by_cost): indices inside each plan, -1 where no candidate qualifies."""
+        off = np.ascontiguousarray([0, self._n] if plan_offset is None else plan_offset, dtype=np.int32)
+        n_plans = len(off) - 1
+        bd, bc = np.full(n_plans, -1, np.int32), np.full(n_plans, -1, np.int32)
+        _lib.check(self._l.topay_solver_select(self.h, n_plans, _p(off, C.c_int32), int(use_gate), _p(bd, C.c_int32),
+                                               _p(bc, C.c_int32)), "topay_solver_select")
+        return bd, bc
+
+    def download_candidate(self, cand):
+        """Results of one candidate of the last run (the winner): 28 KB at 64 pieces instead of the whole batch."""
+        NP = self.max_pieces
+        r = dict(status=np.zeros(1, np.int32), lbfgs_code=np.zeros(1, np.int32), piece_num=np.zeros(1, np.int32),
+                 iters=np.zeros(1, np.int32), evals=np.zeros(1, np.int32), alm_rounds=np.zeros(1, np.int32),
+                 cost=np.zeros(1), duration=np.zeros(1), T=np.zeros((1, NP)), coeff=np.zeros((1, 6 * NP, 9)),
+                 final_xy_err=np.zeros((1, 2)), x=np.zeros((1, num_vars(NP))))
+        rb = ResultBatch(*[_p(r[k], C.c_int32 if r[k].dtype == np.int32 else C.c_double) for k in
+                           ("status", "lbfgs_code", "piece_num", "iters", "evals", "alm_rounds", "cost", "duration",
+                            "T", "coeff", "final_xy_err", "x")])
+        _lib.check(self._l.topay_solver_download_candidate(self.h, int(cand), C.byref(rb)), "download_candidate")
+        out = {k: v[0] for k, v in r.items()}
+        out["index"] = int(cand)
+        out["nbytes"] = int(sum(v.nbytes for v in r.values()))
+        return out
+
+    def planWinners(self, plans, use_gate=True):
+        """The worker loop of planner.cpp:847-1010 for several plans in one device solve: every candidate is optimised
+        (continuous batching), passed through the success gate (optimizeTraj && printConstraintsSituations,
+        :877-880) and the shortest trajectory of each plan is picked (:999-1010) — all on the device; only each
+        plan's winner crosses the bus. Returns a list with one entry per plan: the winner's result dict
+        (download_candidate, `index` inside the plan) or None."""
+        paths = [q for p in plans for q in p[0]]
+        bv = np.concatenate([np.asarray(p[1], dtype=np.float64).reshape(len(p[0]), 10, 2) for p in plans])
+        ba = np.concatenate([np.asarray(p[2], dtype=np.float64).reshape(len(p[0]), 10, 2) for p in plans])
+        self.upload(paths, bv, ba)
+        self.run()
+        self.d2h_bytes = 0
+        if use_gate:
+            f, arrs = alloc_feasibility(self._n, verdicts_only=True)
+            _lib.check(self._l.topay_solver_check_feasible(self.h, C.byref(f), None), "topay_solver_check_feasible")
+            self.constraints = arrs
+            self.d2h_bytes += self._n * 352     # what the gate itself reads back: per-trajectory metrics + sizes
+        off = np.cumsum([0] + [len(p[0]) for p in plans]).astype(np.int32)
+        bd, _ = self.select(off, use_gate)
+        self.d2h_bytes += int(bd.nbytes * 2)
+        out = []
+        for i, w in enumerate(bd):
+            if w < 0:
+                out.append(None)
+                continue
+            r = self.download_candidate(int(off[i] + w))
+            r["index"] = int(w)
+            self.d2h_bytes += r["nbytes"]
+            out.append(r)
+        self._last = None
+        return out
+
     def optimizeTrajBatch(self, paths, boundary_vel, boundary_acc):
         """All candidates of a plan in one device solve; returns the result dict of download()."""
         self.upload(paths, boundary_vel, boundary_acc)
