@@ -279,6 +279,78 @@ def field_probe(tp, scenes, device, hbm_peak):
                     "8 taps x 8 B + 32 B result per point, points resident in HBM"}
 
 
+def sweep_probe(tp, scenes, local, rank, world, dist, per_rank=24, candidates=8, in_flight=8):
+    """BASELINE configs[4] (the scenario sweep, bounded): `per_rank` x world independent table / cuboid scenarios,
+    static round-robin over the ranks (one process per GPU, no data-path collective). Every scenario runs the whole
+    device pipeline the planner drives: rasterise its point cloud -> rebuild the field (4 x 2-D + 3-D ESDF) -> solve
+    its candidates in one batch -> success gate -> shortest feasible trajectory (selected on the device, the winner
+    alone crosses the bus). The per-scenario winners (scenario, index, duration, cost: 32 B each) are then gathered
+    on every rank, over NCCL and over the host (gloo), both timed: north_star uses NCCL only if it measurably wins."""
+    import threading
+    import torch
+    from topay_b200 import shard
+    total = per_rank * world
+    mine = shard.round_robin(total, rank, world)
+    P = max(1, min(in_flight, len(mine)))
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    slots = []
+    for _ in range(P):
+        g = tp.GridMap(tp.grid_desc(), device=local)
+        g.set_keep_sqdist(False)
+        slots.append((g, tp.MomaTrajOpt(g, max_cand=candidates, max_pieces=16, opt_param=opt, robot=rp)))
+    clouds = {s: (scenes.tables_scene(s)[0] if s % 2 == 0 else scenes.cuboids_scene(s)[0]) for s in mine}
+    cands = {s: scenes.short_candidates(candidates, 100000 + s) for s in mine}
+    out, lock = {}, threading.Lock()
+
+    def worker(slot):
+        g, solver = slots[slot]
+        for s in mine[slot::P]:
+            g.regenerateMap(clouds[s])
+            w = solver.planWinners([cands[s]], use_gate=True)[0]
+            with lock:
+                out[s] = (float(w["index"]), float(w["duration"]), float(w["cost"])) if w is not None else (-1.0, 0.0, 0.0)
+
+    for warm in (True, False):        # one untimed pass (graphs, allocations), one timed
+        out.clear()
+        barrier_max(dist, local, 0.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=worker, args=(i,)) for i in range(P)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        torch.cuda.synchronize()
+        dt = barrier_max(dist, local, time.perf_counter() - t0)
+    rows = torch.tensor([[float(s), *out[s]] for s in mine], dtype=torch.float64)
+    gather = {"bytes_per_rank": int(rows.numel() * 8)}
+    n_win = int((rows[:, 1] >= 0).sum())
+    if dist is not None:
+        dev_rows = rows.to(f"cuda:{local}")
+        gl = dist.new_group(backend="gloo")
+        for name, t_in, grp in (("nccl", dev_rows, None), ("host_gloo", rows, gl)):
+            bufs = [torch.empty_like(t_in) for _ in range(world)]
+            ts = []
+            for _ in range(30):
+                if name == "nccl":
+                    torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                dist.all_gather(bufs, t_in, group=grp)
+                if name == "nccl":
+                    torch.cuda.synchronize()
+                ts.append((time.perf_counter() - t0) * 1e6)
+            gather[name + "_us_p50"] = barrier_max(dist, local, float(np.median(ts[5:])))
+            allr = torch.cat([b.cpu() for b in bufs])
+        n_win = int((allr[:, 1] >= 0).sum())
+        gather["faster"] = "nccl" if gather["nccl_us_p50"] < gather["host_gloo_us_p50"] else "host"
+    for g, solver in slots:
+        solver.close()
+        g.close()
+    return {"workload": "scenario sweep (BASELINE configs[4], bounded): rasterise + field rebuild + batched solve + "
+                        "success gate + device-side selection per scenario, round-robin over ranks",
+            "scenarios": total, "scenarios_per_gpu": per_rank, "candidates_per_scenario": candidates, "n_gpus": world,
+            "in_flight_per_gpu": P, "scenarios_per_s": total / dt, "trajectories_per_s": total * candidates / dt,
+            "scenarios_with_a_feasible_winner": n_win, "seconds": dt, "winner_gather": gather}
+
+
 def subpath_probe(tp, scenes, device, hbm_peak, solver, gm, rp, with_cpu):
     """The other rows of SURVEY.md §8 next to the solve, each with the oracle timed beside it on a bounded
     sample (single host thread — these reference routines are serial): ROG-Map ring update (a23), field
@@ -469,16 +541,20 @@ def main():
     n_ok = int(res["status"].sum())
     evals_total = int(res["evals"].sum())
 
-    # ---- end-to-end arm: host buffers in, host results out, through the public API (pre-processing, H2D of the
-    # problems, the solve, D2H of every candidate's result and the per-plan winners inside the timed region)
+    # ---- end-to-end arm: host buffers in, host results out, through the public API — the worker flow of
+    # planner.cpp:847-1010 (pre-processing, H2D of the problems, the solve, the success gate, the per-plan selection
+    # and the D2H of each plan's winning trajectory inside the timed region)
     barrier_max(dist, local, 0.0)
     flush.zero_()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    r_e2e = solver.optimizeTrajPlans(plans)
+    r_e2e = solver.planWinners(plans, use_gate=True)
     torch.cuda.synchronize()
     dt_e2e = barrier_max(dist, local, time.perf_counter() - t0)
     h2d, d2h = solver.h2d_bytes, solver.d2h_bytes
+
+    # ---- BASELINE configs[4], bounded: independent scenarios sharded round-robin over the ranks (all ranks take part)
+    sweep = None if args.no_extras else sweep_probe(tp, scenes, local, rank, world, dist)
 
     if rank != 0:
         if dist is not None:
@@ -559,8 +635,11 @@ def main():
                     "successes": n_ok},
         "e2e": {"value": total / dt_e2e, "unit": "trajectories/s", "h2d_bytes_per_step": h2d // K,
                 "d2h_bytes_per_step": d2h // K,
-                "api": "MomaTrajOpt.optimizeTrajPlans(plans): host waypoints -> pre-processing -> pinned H2D -> device "
-                       "solve -> D2H of every candidate's status / cost / durations / coefficients + per-plan winners"},
+                "plans_with_a_feasible_winner": int(sum(w is not None for w in r_e2e)),
+                "api": "MomaTrajOpt.planWinners(plans): host waypoints -> pre-processing -> pinned H2D -> device solve "
+                       "of every candidate -> success gate (checkFeasible / printConstraintsSituations) and "
+                       "shortest-duration selection per plan on the device -> D2H of the gate's per-trajectory "
+                       "metrics and of each plan's winning trajectory (status, cost, durations, coefficients, x)"},
         "gpu_launches": int(st_run["kernel_launches"]),
         "device_ms_per_step": st_run["ms_total"] / K, "ticks": int(st_run["ticks"]),
         "slot_utilisation": evals_total / max(st_run["slot_ticks"], 1),
@@ -575,6 +654,8 @@ def main():
         "roofline_k_lbfgs": roof_lb,
         "clocks": clocks,
     }
+    if sweep is not None:
+        line["sweep"] = sweep
     if not args.no_extras and world == 1:     # single-GPU diagnostics; the scaling runs stay short
         line["latency"] = latency_probe(tp, scenes, gm)
         line["field"] = field_probe(tp, scenes, local, peak)

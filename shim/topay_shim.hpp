@@ -85,7 +85,7 @@ public:
 
     // GridMap::init (grid_map.cpp:6-87) with the rosparams passed explicitly.
     void init(double map_size_x, double map_size_y, double map_size_z, double res, int device = 0) {
-        topay_grid_desc d;
+        topay_grid_desc d = {};
         d.map_size[0] = map_size_x; d.map_size[1] = map_size_y; d.map_size[2] = map_size_z;
         d.resolution = res; d.chassis_colli_radius = 0.4; d.chassis_height = 0.155;
         topay_check(topay_field_create(&d, device, &f_), "topay_field_create");
@@ -95,6 +95,9 @@ public:
         resolution = res; resolution_inv = 1.0 / res;
         map_origin[0] = -map_size_x / 2.0; map_origin[1] = -map_size_y / 2.0; map_origin[2] = 0.0;   // grid_map.cpp:41-47
     }
+    GridMap() = default;
+    GridMap(const GridMap&) = delete;               // owns the device field
+    GridMap& operator=(const GridMap&) = delete;
     ~GridMap() { topay_field_destroy(f_); }
 
     void loadMap(const std::vector<char>& occ_2d, const std::vector<char>& occ_3d) {      // grid_map.cpp:800
@@ -228,6 +231,8 @@ public:
         topay_opt_params_default(&opt_param);
         topay_robot_params_default(&moma_param);
     }
+    MomaTrajOpt(const MomaTrajOpt&) = delete;       // owns the device solver
+    MomaTrajOpt& operator=(const MomaTrajOpt&) = delete;
     ~MomaTrajOpt() { topay_solver_destroy(s_); }
 
     // void init(ros::NodeHandle&) reads the rosparams into opt_param (moma_traj_opt.h:845-941); here the
@@ -342,13 +347,16 @@ namespace rog_map {
 class ESDFMap {
 public:
     typedef std::shared_ptr<ESDFMap> Ptr;
+    ESDFMap() = default;
+    ESDFMap(const ESDFMap&) = delete;               // owns the device ring
+    ESDFMap& operator=(const ESDFMap&) = delete;
     ~ESDFMap() { topay_rogfield_destroy(f_); }
     // initESDFMap (esdf_map.cpp:28-57); sliding_thresh is the caller's business (prob_map.cpp:292-298)
     template <class V3i, class V3>
     void initESDFMap(const V3i& half_prob_map_size_i, double prob_map_resolution, double temp_counter_map_resolution,
                      const V3& local_update_box, bool map_sliding_en, double /*sliding_thresh*/,
                      const V3& fix_map_origin, double unk_thresh, int device = 0) {
-        topay_rog_desc d;
+        topay_rog_desc d = {};
         for (int i = 0; i < 3; i++) {
             d.half_prob_map_size_i[i] = half_prob_map_size_i[i];
             d.local_update_box[i] = local_update_box[i];

@@ -680,6 +680,17 @@ __device__ __forceinline__ void tp_bulk_g2s(void* dst, const void* src, uint32_t
         "l"(src), "r"(bytes), "r"(tp_smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// 16-byte asynchronous copies (LDGSTS) for the single-warp two-loop of small problems: a history row of a
+// 16-piece candidate is < 1.3 KB, and bulk copies of that size complete one after the other (ncu: ~1300 cycles per
+// round of four copies, the warp idle on the mbarrier) — 32 lanes x 16 B in flight per instruction do not.
+__device__ __forceinline__ void tp_cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tp_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tp_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tp_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#define TP_SOLO_GROUPS 8     // copy groups (rounds) in flight in the single-warp two-loop: 16 ring stages
+
 __device__ __forceinline__ void tp_mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     do {
@@ -922,6 +933,134 @@ __device__ __forceinline__ void tp_band_transpose(int n, double* lu) {
         }
     }
     __syncthreads();
+}
+
+// ---- two-loop recursion of small problems (n <= 160: up to 16 pieces) on ONE warp ----
+// lbfgs.hpp:691-710. A history row is < 1.3 KB there, a full history 512 dependent steps: the recursion is a pure
+// latency chain, so it runs on a single warp (no block barrier, no shared-memory partial sums) with NE = ceil(n / 32)
+// elements of the vector per lane, and the code of a round is kept short: the two loops are separate instantiations
+// (no per-element selects), the rows of step t sit in stage t mod 16 of a shared-memory ring filled by 16-byte
+// asynchronous copies, one commit group per step, so "at most 14 groups pending" is exactly "the two rows of this
+// round have landed". Two history rows per round (three dot products share one reduction), the same expansion as the
+// block-wide variant:
+//   loop 1:  a = s_A.q, b = s_B.q, c = s_B.y_A;  alpha_A = rho_A a,  alpha_B = rho_B (b - alpha_A c);  q -= alpha_A y_A + alpha_B y_B
+//   loop 2:  a = y_A.r, b = y_B.r, c = y_B.s_A;  k_A = alpha_A - rho_A a,  k_B = alpha_B - rho_B (b + k_A c);  r += k_A s_A + k_B s_B
+#define TP_SOLO_STAGES 16
+template <int NE>
+__device__ __forceinline__ void tp_two_loop_solo(double* q, int rowd, int bound, int end, int m,
+                                                 const double* __restrict__ lm_s, const double* __restrict__ lm_y, int xs,
+                                                 const double* s_rho, double* s_alpha, double* ring, double scale,
+                                                 int lane) {
+    const int total = 2 * bound;
+    const int chunks = rowd >> 1;     // 16-byte chunks per row
+    // row of step t: (end-1-t) mod m in the first loop, (end-bound+u) mod m in the second
+    auto row_of = [&](int t) {
+        int j = t < bound ? end - 1 - t : end - bound + (t - bound);
+        j = j < 0 ? j + m : j;
+        j = j < 0 ? j + m : j;
+        return j >= m ? j - m : j;
+    };
+    auto issue = [&](int t) {
+        if (t < total) {
+            const int j = row_of(t);
+            double* dst = ring + (t & (TP_SOLO_STAGES - 1)) * 2 * rowd;
+            const double* srs = lm_s + (size_t)j * xs;
+            const double* sry = lm_y + (size_t)j * xs;
+            for (int c = lane; c < chunks; c += 32) {
+                tp_cp_async16(dst + 2 * c, srs + 2 * c);
+                tp_cp_async16(dst + rowd + 2 * c, sry + 2 * c);
+            }
+        }
+        tp_cp_async_commit();         // also when the history has run out: one group per step, always
+    };
+    bool in[NE];
+#pragma unroll
+    for (int e = 0; e < NE; e++) in[e] = lane + 32 * e < rowd;
+    auto round = [&](auto first_tag, int t, bool pair) {
+        constexpr bool FIRST = decltype(first_tag)::value;
+        tp_cp_async_wait<TP_SOLO_STAGES - 2>();
+        __syncwarp();                 // every lane's chunks of steps t, t + 1 are in shared memory
+        const int jA = row_of(t);
+        const double* stA = ring + (t & (TP_SOLO_STAGES - 1)) * 2 * rowd;
+        const double* uAp = FIRST ? stA : stA + rowd;      // dotted with the vector
+        const double* vAp = FIRST ? stA + rowd : stA;      // added to it
+        double uA[NE], vA[NE], uB[NE], vB[NE];
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+            uA[e] = in[e] ? uAp[lane + 32 * e] : 0.0;
+            vA[e] = in[e] ? vAp[lane + 32 * e] : 0.0;
+        }
+        int jB = jA;
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+        if (pair) {
+            jB = row_of(t + 1);
+            const double* stB = ring + ((t + 1) & (TP_SOLO_STAGES - 1)) * 2 * rowd;
+            const double* uBp = FIRST ? stB : stB + rowd;
+            const double* vBp = FIRST ? stB + rowd : stB;
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                uB[e] = in[e] ? uBp[lane + 32 * e] : 0.0;
+                vB[e] = in[e] ? vBp[lane + 32 * e] : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                d0 += uA[e] * q[e];
+                d1 += uB[e] * q[e];
+                d2 += uB[e] * vA[e];
+            }
+#pragma unroll
+            for (int w = 16; w > 0; w >>= 1) {
+                d0 += tp_shfl_xor(d0, w);
+                d1 += tp_shfl_xor(d1, w);
+                d2 += tp_shfl_xor(d2, w);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < NE; e++) d0 += uA[e] * q[e];
+#pragma unroll
+            for (int w = 16; w > 0; w >>= 1) d0 += tp_shfl_xor(d0, w);
+        }
+        __syncwarp();                 // every lane has read both stages: refill them
+        issue(t + TP_SOLO_STAGES);
+        if (pair) issue(t + 1 + TP_SOLO_STAGES);
+        if (FIRST) {
+            const double alA = d0 * s_rho[jA];
+            const double alB = pair ? (d1 - alA * d2) * s_rho[jB] : 0.0;
+            if (lane == 0) {
+                s_alpha[jA] = alA;
+                if (pair) s_alpha[jB] = alB;
+            }
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                q[e] += (-alA) * vA[e];
+                if (pair) q[e] += (-alB) * vB[e];
+            }
+        } else {
+            const double kA = s_alpha[jA] - d0 * s_rho[jA];
+            const double kB = pair ? s_alpha[jB] - (d1 + kA * d2) * s_rho[jB] : 0.0;
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                q[e] += kA * vA[e];
+                if (pair) q[e] += kB * vB[e];
+            }
+        }
+    };
+    for (int t = 0; t < TP_SOLO_STAGES; t++) issue(t);
+    int t = 0;
+    while (t < bound) {
+        const bool pair = t + 1 < bound;
+        round(std::true_type{}, t, pair);
+        t += pair ? 2 : 1;
+    }
+    __syncwarp();                     // the alpha table is complete
+#pragma unroll
+    for (int e = 0; e < NE; e++) q[e] *= scale;      // between the loops: d *= ys / yy (lbfgs.hpp:701)
+    while (t < total) {
+        const bool pair = t + 1 < total;
+        round(std::false_type{}, t, pair);
+        t += pair ? 2 : 1;
+    }
+    tp_cp_async_wait<0>();
 }
 
 __device__ __forceinline__ bool tp_ok_code(int r) {
@@ -1366,6 +1505,9 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     if (i < n) {
                         se[i] = sv;
                         ye[i] = yv;
+                    } else if (i == n && (n & 1)) {
+                        se[i] = 0.0;      // the pad element of an odd-length row: the copies move rowd = n + 1 doubles
+                        ye[i] = 0.0;
                     }
                     q4[0] += yv * sv;
                     q4[1] += yv * yv;
@@ -1398,7 +1540,12 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                     const int rowd = (n + 1) & ~1;                       // 16-byte multiple
                     const uint32_t row_bytes = (uint32_t)(rowd * sizeof(double));
                     const int ring_doubles = smem_doubles - (512 + S.xs);
-                    const int nst = max(2, min(TP_RING_MAX, ring_doubles / (2 * rowd)) & ~1);   // even: rounds take two
+                    // Small problems (n <= 160, i.e. up to 16 pieces) run the whole recursion on warp 0
+                    // with the vector held 5 elements per lane: no block barrier, no shared-memory
+                    // partial sums — the 512 rounds of a full history are pure latency at that size.
+                    const bool solo = n <= TP_EPT * 32;
+                    // even: rounds take two; the single-warp variant keeps exactly 2 * TP_SOLO_GROUPS stages
+                    const int nst = solo ? 2 * TP_SOLO_GROUPS : max(2, min(TP_RING_MAX, ring_doubles / (2 * rowd)) & ~1);
                     double* ring = sm;
                     const uint64_t pol = tp_policy_evict_first();
                     // row of step t: (end-1-t) mod m in the first loop, (end-bound+u) mod m in the second;
@@ -1425,10 +1572,6 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                             tp_bulk_g2s(dst + rowd, lm_y + (size_t)j * S.xs, row_bytes, &s_bar[sg], pol);
                         }
                     };
-                    // Small problems (n <= 160, i.e. up to 16 pieces) run the whole recursion on warp 0
-                    // with the vector held 5 elements per lane: no block barrier, no shared-memory
-                    // partial sums — the 512 rounds of a full history are pure latency at that size.
-                    const bool solo = n <= TP_EPT * 32;
                     double* scratch = s_ys + 256;     // n doubles, behind the ring and the two tables
                     // Two history rows per reduction round. For rows A (first) and B (second) of a loop
                     //   loop 1:  a = s_A.q, b = s_B.q, c = s_B.y_A;  alpha_A = rho_A a,
@@ -1447,7 +1590,30 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                         // refill the stages of steps (t, t + 1) that were just read — stages sg0, sg0 + 1 —
                         // with steps t + nst, t + nst + 1; the four copies go to four different threads
                         auto issue_round = [&](int t, int sg0, int steps) {
-                            const int who = SOLO ? lane : (lane == 0 ? warp : -1);
+                            if (SOLO) {
+                                // the whole warp copies the rows of the round, 16 B per lane and instruction; ONE
+                                // commit group per round, committed even when the history has run out, so that
+                                // "all but the newest TP_SOLO_GROUPS - 1 groups have landed" always covers the
+                                // round about to be read
+#ifndef TP_DEBUG_NO_TMA
+                                const int chunks = rowd >> 1;             // 16-byte chunks per row
+                                for (int st_ = 0; st_ < steps; st_++) {
+                                    const int tt = t + st_;
+                                    if (tt >= total) break;
+                                    const int j = row_of(tt);
+                                    double* dst = ring + (size_t)(sg0 + st_) * 2 * rowd;
+                                    const double* srs = lm_s + (size_t)j * S.xs;
+                                    const double* sry = lm_y + (size_t)j * S.xs;
+                                    for (int c = lane; c < chunks; c += 32) {
+                                        tp_cp_async16(dst + 2 * c, srs + 2 * c);
+                                        tp_cp_async16(dst + rowd + 2 * c, sry + 2 * c);
+                                    }
+                                }
+                                tp_cp_async_commit();
+#endif
+                                return;
+                            }
+                            const int who = lane == 0 ? warp : -1;
                             if (who >= 0 && who < 2 * steps) {
                                 const int tt = t + (who >> 1);
                                 if (tt < total) issue_part(tt, sg0 + (who >> 1), who & 1);
@@ -1458,7 +1624,7 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                             const double* rs_ = lm_s + (size_t)jrow * S.xs;     // debug: plain loads, no ring
                             const double* ry_ = lm_y + (size_t)jrow * S.xs;
 #else
-                            tp_mbar_wait(&s_bar[sg], (uint32_t)ph);
+                            if (!SOLO) tp_mbar_wait(&s_bar[sg], (uint32_t)ph);
                             const double* rs_ = ring + (size_t)sg * 2 * rowd;
                             const double* ry_ = rs_ + rowd;
 #endif
@@ -1482,8 +1648,18 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                                 tp_block_sum<3>(d3, red, flip);   // one barrier: every thread has read both stages
                             }
                         };
-                        for (int t = 0; t < min(total, nst); t += 2) issue_round(t, t, 2);
+                        if (SOLO) {
+                            for (int t = 0; t < nst; t += 2) issue_round(t, t, 2);      // exactly TP_SOLO_GROUPS groups
+                        } else {
+                            for (int t = 0; t < min(total, nst); t += 2) issue_round(t, t, 2);
+                        }
                         for (int t = 0; t < total;) {
+                            if (SOLO) {
+#ifndef TP_DEBUG_NO_TMA
+                                tp_cp_async_wait<TP_SOLO_GROUPS - 1>();
+                                __syncwarp();             // every lane's chunks of the round are in shared memory
+#endif
+                            }
                             if (t == st.bound) {
                                 // between the loops: d *= ys / yy (lbfgs.hpp:701)
                                 const double sc = ys / yy;
@@ -1544,6 +1720,11 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                             if (SOLO) __syncwarp();       // alpha table writes visible to the warp
                             t += pair ? 2 : 1;
                         }
+                        if (SOLO) {
+#ifndef TP_DEBUG_NO_TMA
+                            tp_cp_async_wait<0>();
+#endif
+                        }
                     };
                     if (tid == 0) atomicAdd(S.node_count + 1, (unsigned long long)total * (unsigned long long)n);
                     // the ring region was last written through the generic proxy and the block's new
@@ -1560,7 +1741,14 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                             double q[TP_EPT];
 #pragma unroll
                             for (int e = 0; e < TP_EPT; e++) q[e] = lane + 32 * e < n ? scratch[lane + 32 * e] : 0.0;
-                            two_loop(std::true_type{}, q);
+                            const double sc = ys / yy;
+                            switch ((rowd + 31) >> 5) {
+                                case 1: tp_two_loop_solo<1>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, ring, sc, lane); break;
+                                case 2: tp_two_loop_solo<2>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, ring, sc, lane); break;
+                                case 3: tp_two_loop_solo<3>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, ring, sc, lane); break;
+                                case 4: tp_two_loop_solo<4>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, ring, sc, lane); break;
+                                default: tp_two_loop_solo<5>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, ring, sc, lane); break;
+                            }
 #pragma unroll
                             for (int e = 0; e < TP_EPT; e++)
                                 if (lane + 32 * e < n) scratch[lane + 32 * e] = q[e];
