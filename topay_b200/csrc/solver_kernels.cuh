@@ -937,20 +937,24 @@ __device__ __forceinline__ void tp_band_transpose(int n, double* lu) {
 
 // ---- two-loop recursion of small problems (n <= 160: up to 16 pieces) on ONE warp ----
 // lbfgs.hpp:691-710. A history row is < 1.3 KB there, a full history 512 dependent steps: the recursion is a pure
-// latency chain, so it runs on a single warp (no block barrier, no shared-memory partial sums) with NE = ceil(n / 32)
-// elements of the vector per lane, and the code of a round is kept short: the two loops are separate instantiations
-// (no per-element selects), the rows of step t sit in stage t mod 16 of a shared-memory ring filled by 16-byte
-// asynchronous copies, one commit group per step, so "at most 14 groups pending" is exactly "the two rows of this
-// round have landed". Two history rows per round (three dot products share one reduction), the same expansion as the
-// block-wide variant:
-//   loop 1:  a = s_A.q, b = s_B.q, c = s_B.y_A;  alpha_A = rho_A a,  alpha_B = rho_B (b - alpha_A c);  q -= alpha_A y_A + alpha_B y_B
-//   loop 2:  a = y_A.r, b = y_B.r, c = y_B.s_A;  k_A = alpha_A - rho_A a,  k_B = alpha_B - rho_B (b + k_A c);  r += k_A s_A + k_B s_B
+// latency chain, so it runs on a single warp (no block barrier) with NE = ceil(n / 32) elements of the vector per
+// lane, and the chain is cut four rows at a time. For rows A, B, C, D of a loop (in processing order), u = the vector
+// a row is dotted with (s in loop 1, y in loop 2), v = the vector it adds (y in loop 1, s in loop 2):
+//   a = u_A.q, b = u_B.q, c = u_C.q, d = u_D.q   and the six cross products  XY = u_X.v_Y  (Y before X)
+//   loop 1:  al_A = rho_A a,  al_B = rho_B (b - al_A BA),  al_C = rho_C (c - al_A CA - al_B CB),
+//            al_D = rho_D (d - al_A DA - al_B DB - al_C DC);          q -= al_A v_A + al_B v_B + al_C v_C + al_D v_D
+//   loop 2:  k_A = al_A - rho_A a,  k_B = al_B - rho_B (b + k_A BA),  ... ;   q += k_A v_A + k_B v_B + k_C v_C + k_D v_D
+// which is the recursion with u_X.(q -/+ ...) expanded, so that ten dot products share ONE reduction: a
+// transpose-reduce over the warp (16 exchanges instead of 50) and a broadcast through shared memory. The rows of
+// step t sit in stage t mod 16 of a shared-memory ring filled by 16-byte asynchronous copies, one commit group per
+// step, so "at most 12 groups pending" is exactly "the four rows of this round have landed". Loop tails of fewer than
+// four rows take single-row rounds.
 #define TP_SOLO_STAGES 16
 template <int NE>
 __device__ __forceinline__ void tp_two_loop_solo(double* q, int rowd, int bound, int end, int m,
                                                  const double* __restrict__ lm_s, const double* __restrict__ lm_y, int xs,
-                                                 const double* s_rho, double* s_alpha, double* ring, double scale,
-                                                 int lane) {
+                                                 const double* s_rho, double* s_alpha, double* s_red /*[16]*/,
+                                                 double* ring, double scale, int lane) {
     const int total = 2 * bound;
     const int chunks = rowd >> 1;     // 16-byte chunks per row
     // row of step t: (end-1-t) mod m in the first loop, (end-bound+u) mod m in the second
@@ -976,90 +980,157 @@ __device__ __forceinline__ void tp_two_loop_solo(double* q, int rowd, int bound,
     bool in[NE];
 #pragma unroll
     for (int e = 0; e < NE; e++) in[e] = lane + 32 * e < rowd;
-    auto round = [&](auto first_tag, int t, bool pair) {
+    // one row: the plain step of the recursion
+    auto round1 = [&](auto first_tag, int t) {
         constexpr bool FIRST = decltype(first_tag)::value;
-        tp_cp_async_wait<TP_SOLO_STAGES - 2>();
-        __syncwarp();                 // every lane's chunks of steps t, t + 1 are in shared memory
+        tp_cp_async_wait<TP_SOLO_STAGES - 4>();
+        __syncwarp();
         const int jA = row_of(t);
         const double* stA = ring + (t & (TP_SOLO_STAGES - 1)) * 2 * rowd;
-        const double* uAp = FIRST ? stA : stA + rowd;      // dotted with the vector
-        const double* vAp = FIRST ? stA + rowd : stA;      // added to it
-        double uA[NE], vA[NE], uB[NE], vB[NE];
+        const double* uAp = FIRST ? stA : stA + rowd;
+        const double* vAp = FIRST ? stA + rowd : stA;
+        double vA[NE], d0 = 0.0;
 #pragma unroll
         for (int e = 0; e < NE; e++) {
-            uA[e] = in[e] ? uAp[lane + 32 * e] : 0.0;
+            const double u = in[e] ? uAp[lane + 32 * e] : 0.0;
             vA[e] = in[e] ? vAp[lane + 32 * e] : 0.0;
+            d0 += u * q[e];
         }
-        int jB = jA;
-        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-        if (pair) {
-            jB = row_of(t + 1);
-            const double* stB = ring + ((t + 1) & (TP_SOLO_STAGES - 1)) * 2 * rowd;
-            const double* uBp = FIRST ? stB : stB + rowd;
-            const double* vBp = FIRST ? stB + rowd : stB;
 #pragma unroll
-            for (int e = 0; e < NE; e++) {
-                uB[e] = in[e] ? uBp[lane + 32 * e] : 0.0;
-                vB[e] = in[e] ? vBp[lane + 32 * e] : 0.0;
-            }
-#pragma unroll
-            for (int e = 0; e < NE; e++) {
-                d0 += uA[e] * q[e];
-                d1 += uB[e] * q[e];
-                d2 += uB[e] * vA[e];
-            }
-#pragma unroll
-            for (int w = 16; w > 0; w >>= 1) {
-                d0 += tp_shfl_xor(d0, w);
-                d1 += tp_shfl_xor(d1, w);
-                d2 += tp_shfl_xor(d2, w);
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < NE; e++) d0 += uA[e] * q[e];
-#pragma unroll
-            for (int w = 16; w > 0; w >>= 1) d0 += tp_shfl_xor(d0, w);
-        }
-        __syncwarp();                 // every lane has read both stages: refill them
+        for (int w = 16; w > 0; w >>= 1) d0 += tp_shfl_xor(d0, w);
+        __syncwarp();                 // every lane has read the stage: refill it
         issue(t + TP_SOLO_STAGES);
-        if (pair) issue(t + 1 + TP_SOLO_STAGES);
+        double k;
         if (FIRST) {
-            const double alA = d0 * s_rho[jA];
-            const double alB = pair ? (d1 - alA * d2) * s_rho[jB] : 0.0;
-            if (lane == 0) {
-                s_alpha[jA] = alA;
-                if (pair) s_alpha[jB] = alB;
-            }
-#pragma unroll
-            for (int e = 0; e < NE; e++) {
-                q[e] += (-alA) * vA[e];
-                if (pair) q[e] += (-alB) * vB[e];
-            }
+            k = -(d0 * s_rho[jA]);
+            if (lane == 0) s_alpha[jA] = -k;
         } else {
-            const double kA = s_alpha[jA] - d0 * s_rho[jA];
-            const double kB = pair ? s_alpha[jB] - (d1 + kA * d2) * s_rho[jB] : 0.0;
+            k = s_alpha[jA] - d0 * s_rho[jA];
+        }
+#pragma unroll
+        for (int e = 0; e < NE; e++) q[e] += k * vA[e];
+    };
+    // four rows
+    auto round4 = [&](auto first_tag, int t) {
+        constexpr bool FIRST = decltype(first_tag)::value;
+        tp_cp_async_wait<TP_SOLO_STAGES - 4>();
+        __syncwarp();                 // every lane's chunks of steps t .. t + 3 are in shared memory
+        int j[4];
+        double v[4][NE];
+        double dots[16];              // a b c d | BA CA CB DA DB DC | padding
+#pragma unroll
+        for (int i = 0; i < 16; i++) dots[i] = 0.0;
+        {
+            double u[4][NE];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                j[r] = row_of(t + r);
+                const double* stp = ring + ((t + r) & (TP_SOLO_STAGES - 1)) * 2 * rowd;
+                const double* up = FIRST ? stp : stp + rowd;
+                const double* vp = FIRST ? stp + rowd : stp;
+#pragma unroll
+                for (int e = 0; e < NE; e++) {
+                    u[r][e] = in[e] ? up[lane + 32 * e] : 0.0;
+                    v[r][e] = in[e] ? vp[lane + 32 * e] : 0.0;
+                }
+            }
 #pragma unroll
             for (int e = 0; e < NE; e++) {
-                q[e] += kA * vA[e];
-                if (pair) q[e] += kB * vB[e];
+                dots[0] += u[0][e] * q[e];
+                dots[1] += u[1][e] * q[e];
+                dots[2] += u[2][e] * q[e];
+                dots[3] += u[3][e] * q[e];
+                dots[4] += u[1][e] * v[0][e];     // BA
+                dots[5] += u[2][e] * v[0][e];     // CA
+                dots[6] += u[2][e] * v[1][e];     // CB
+                dots[7] += u[3][e] * v[0][e];     // DA
+                dots[8] += u[3][e] * v[1][e];     // DB
+                dots[9] += u[3][e] * v[2][e];     // DC
             }
         }
+        // transpose-reduce of 16 values over 32 lanes: after the steps 16, 8, 4, 2 a lane holds one partial sum, of
+        // value index (lane >> 1) & ... ; the last step completes it
+        {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {         // step xor 16: keep values [0,8) in the low half, [8,16) in the high
+                const bool hi = (lane & 16) != 0;
+                const double send = hi ? dots[i] : dots[i + 8];
+                const double keep = hi ? dots[i + 8] : dots[i];
+                dots[i] = keep + tp_shfl_xor(send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const bool hi = (lane & 8) != 0;
+                const double send = hi ? dots[i] : dots[i + 4];
+                const double keep = hi ? dots[i + 4] : dots[i];
+                dots[i] = keep + tp_shfl_xor(send, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const bool hi = (lane & 4) != 0;
+                const double send = hi ? dots[i] : dots[i + 2];
+                const double keep = hi ? dots[i + 2] : dots[i];
+                dots[i] = keep + tp_shfl_xor(send, 4);
+            }
+            {
+                const bool hi = (lane & 2) != 0;
+                const double send = hi ? dots[0] : dots[1];
+                const double keep = hi ? dots[1] : dots[0];
+                dots[0] = keep + tp_shfl_xor(send, 2);
+            }
+            dots[0] += tp_shfl_xor(dots[0], 1);
+            // lane holds value index  8 [lane & 16] + 4 [lane & 8] + 2 [lane & 4] + [lane & 2]
+            if (!(lane & 1)) s_red[((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = dots[0];
+        }
+        __syncwarp();                 // sums visible; every lane has read the four stages: refill them
+#pragma unroll
+        for (int r = 0; r < 4; r++) issue(t + r + TP_SOLO_STAGES);
+        const double a = s_red[0], b = s_red[1], c = s_red[2], d = s_red[3];
+        const double BA = s_red[4], CA = s_red[5], CB = s_red[6], DA = s_red[7], DB = s_red[8], DC = s_red[9];
+        const double rA = s_rho[j[0]], rB = s_rho[j[1]], rC = s_rho[j[2]], rD = s_rho[j[3]];
+        double kA, kB, kC, kD;
+        if (FIRST) {
+            const double alA = a * rA;
+            const double alB = (b - alA * BA) * rB;
+            const double alC = (c - alA * CA - alB * CB) * rC;
+            const double alD = (d - alA * DA - alB * DB - alC * DC) * rD;
+            if (lane == 0) {
+                s_alpha[j[0]] = alA;
+                s_alpha[j[1]] = alB;
+                s_alpha[j[2]] = alC;
+                s_alpha[j[3]] = alD;
+            }
+            kA = -alA; kB = -alB; kC = -alC; kD = -alD;
+        } else {
+            kA = s_alpha[j[0]] - a * rA;
+            kB = s_alpha[j[1]] - (b + kA * BA) * rB;
+            kC = s_alpha[j[2]] - (c + kA * CA + kB * CB) * rC;
+            kD = s_alpha[j[3]] - (d + kA * DA + kB * DB + kC * DC) * rD;
+        }
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+            q[e] += kA * v[0][e];
+            q[e] += kB * v[1][e];
+            q[e] += kC * v[2][e];
+            q[e] += kD * v[3][e];
+        }
+        __syncwarp();                 // s_red is free for the next round
     };
     for (int t = 0; t < TP_SOLO_STAGES; t++) issue(t);
     int t = 0;
-    while (t < bound) {
-        const bool pair = t + 1 < bound;
-        round(std::true_type{}, t, pair);
-        t += pair ? 2 : 1;
+    while (t + 4 <= bound) {
+        round4(std::true_type{}, t);
+        t += 4;
     }
+    while (t < bound) round1(std::true_type{}, t++);
     __syncwarp();                     // the alpha table is complete
 #pragma unroll
     for (int e = 0; e < NE; e++) q[e] *= scale;      // between the loops: d *= ys / yy (lbfgs.hpp:701)
-    while (t < total) {
-        const bool pair = t + 1 < total;
-        round(std::false_type{}, t, pair);
-        t += pair ? 2 : 1;
+    while (t + 4 <= total) {
+        round4(std::false_type{}, t);
+        t += 4;
     }
+    while (t < total) round1(std::false_type{}, t++);
     tp_cp_async_wait<0>();
 }
 
@@ -1743,11 +1814,11 @@ k_cand(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P
                             for (int e = 0; e < TP_EPT; e++) q[e] = lane + 32 * e < n ? scratch[lane + 32 * e] : 0.0;
                             const double sc = ys / yy;
                             switch ((rowd + 31) >> 5) {
-                                case 1: tp_two_loop_solo<1>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, ring, sc, lane); break;
-                                case 2: tp_two_loop_solo<2>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, ring, sc, lane); break;
-                                case 3: tp_two_loop_solo<3>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, ring, sc, lane); break;
-                                case 4: tp_two_loop_solo<4>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, ring, sc, lane); break;
-                                default: tp_two_loop_solo<5>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, ring, sc, lane); break;
+                                case 1: tp_two_loop_solo<1>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, red, ring, sc, lane); break;
+                                case 2: tp_two_loop_solo<2>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, red, ring, sc, lane); break;
+                                case 3: tp_two_loop_solo<3>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, red, ring, sc, lane); break;
+                                case 4: tp_two_loop_solo<4>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, red, ring, sc, lane); break;
+                                default: tp_two_loop_solo<5>(q, rowd, st.bound, st.end, m, lm_s, lm_y, S.xs, s_ys, s_alpha, red, ring, sc, lane); break;
                             }
 #pragma unroll
                             for (int e = 0; e < TP_EPT; e++)
