@@ -37,6 +37,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <array>
 #include <cstdlib>
 #include <limits>
 #include <vector>
@@ -480,6 +481,471 @@ struct RogEsdf {
             if (dist_flat[hash2_from_pos(pt)] < threshold) return false;
         }
         return true;
+    }
+};
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// rog_map::ProbMap — the probabilistic occupancy layer that drives the ESDF counter map from point clouds
+// (SURVEY §8 row N3). Restates, in the reference's operation order:
+//   src/rog_map/src/rog_map/prob_map.cpp:25-88    initProbMap (geometry, ceil / ground snapped to the grid)
+//   src/rog_map/src/rog_map/prob_map.cpp:291-300  slideAllMap
+//   src/rog_map/src/rog_map/prob_map.cpp:302-373  updateProbMap (incl. the first-frame sphere clearing)
+//   src/rog_map/src/rog_map/prob_map.cpp:512-541  resetCell (cells that leave the map when it slides)
+//   src/rog_map/src/rog_map/prob_map.cpp:543-569  probabilisticMapFromCache
+//   src/rog_map/src/rog_map/prob_map.cpp:571-664  hitPointUpdate / missPointUpdate (log-odds, type transitions)
+//   src/rog_map/src/rog_map/prob_map.cpp:666-778  raycastProcess (point filters, clipping, 3-D ray walk)
+//   src/rog_map/src/rog_map/prob_map.cpp:780-789  insertUpdateCandidate
+//   src/rog_map/src/rog_map/prob_map.cpp:791-820  updateLocalBox
+//   src/rog_map/include/utils/common_lib.hpp:148-170 lineBoxIntersectPoint
+//   src/rog_map/include/utils/raycaster.cpp:66-192   RayCaster::setInput / step
+// The inflation map (InfMap) and the frontier counter map receive the same notifications in the reference; they
+// do not feed the ESDF and are not restated (frontier_extraction_en = false).
+struct RogProb {
+    // SlidingMap of the probability grid
+    double res = 0, res_inv = 0;
+    int half[3] = {0, 0, 0}, size[3] = {0, 0, 0};
+    int64_t vox = 0;
+    bool sliding_en = true;
+    double sliding_thresh = 0;
+    int origin_i[3] = {0, 0, 0};
+    double origin_d[3] = {0, 0, 0}, bound_min_d[3] = {0, 0, 0}, bound_max_d[3] = {0, 0, 0};
+    // config (config.hpp:160-262, 336-382)
+    float l_hit = 0, l_miss = 0, l_min = 0, l_max = 0, l_occ = 0, l_free = 0;
+    double range_min = 0, range_max = 0, sqr_range_max = 0;
+    double ceil_h = 0, ground_h = 0;
+    int half_update_box_i[3] = {0, 0, 0};
+    int point_filt_num = 1, batch_update_size = 1, intensity_thresh = -1;
+    bool raycasting_en = true;
+    // state
+    std::vector<float> occupancy;
+    std::vector<uint16_t> op_cnt, hit_cnt;
+    std::vector<std::array<int, 3>> cache;      // update_cache_id_g (a queue: pushed and drained in order)
+    int batch_counter = 0;
+    bool inited = false, map_empty = true, first_frame = true;
+    double box_min[3] = {0, 0, 0}, box_max[3] = {0, 0, 0};   // local_update_box_min / max
+    RogEsdf* esdf = nullptr;
+
+    static int ifloor(double v) { return (int)std::floor(v); }
+    void pos_to_global(const double p[3], int id[3]) const {
+        for (int i = 0; i < 3; i++) id[i] = ifloor(p[i] * res_inv);
+    }
+    void global_to_pos(const int id[3], double p[3]) const {
+        for (int i = 0; i < 3; i++) p[i] = ((double)id[i] + 0.5) * res;
+    }
+    void global_to_local(const int g[3], int l[3]) const {
+        for (int i = 0; i < 3; i++) {
+            int v = g[i] % size[i];
+            if (v > half[i]) v -= size[i];
+            else if (v < -half[i]) v += size[i];
+            l[i] = v;
+        }
+    }
+    int64_t local_hash(const int l[3]) const {
+        return (int64_t)(l[0] + half[0]) * size[1] * size[2] + (int64_t)(l[1] + half[1]) * size[2] + (l[2] + half[2]);
+    }
+    int64_t hash_from_global(const int g[3]) const {
+        int l[3];
+        global_to_local(g, l);
+        return local_hash(l);
+    }
+    int64_t hash_from_pos(const double p[3]) const {
+        int g[3];
+        pos_to_global(p, g);
+        return hash_from_global(g);
+    }
+    bool inside_local_map_i(const int g[3]) const {
+        for (int i = 0; i < 3; i++)
+            if (std::abs(g[i] - origin_i[i]) - half[i] > 0) return false;
+        return true;
+    }
+    bool inside_local_map(const double p[3]) const {
+        int g[3];
+        pos_to_global(p, g);
+        return inside_local_map_i(g);
+    }
+    // sliding_map.cpp:262-268 + :234-259 (ORIGIN_AT_CORNER): position of a ring cell under the CURRENT origin
+    void hash_to_pos(int64_t h, double p[3]) const {
+        int l[3];
+        l[0] = (int)(h / ((int64_t)size[1] * size[2]));
+        l[1] = (int)((h - (int64_t)l[0] * size[1] * size[2]) / size[2]);
+        l[2] = (int)(h - (int64_t)l[0] * size[1] * size[2] - (int64_t)l[1] * size[2]);
+        for (int i = 0; i < 3; i++) {
+            l[i] -= half[i];
+            const int min_g = -half[i] + origin_i[i];
+            int min_l = min_g % size[i];
+            min_l -= min_l > half[i] ? size[i] : 0;
+            min_l += min_l < -half[i] ? size[i] : 0;
+            int d = l[i] - min_l;
+            d = d < 0 ? size[i] + d : d;
+            p[i] = ((double)(d + min_g) + 0.5) * res;
+        }
+    }
+    // sliding_map.cpp:85-97
+    void set_origin(const double od[3], const int oi[3]) {
+        int bmin[3], bmax[3];
+        for (int i = 0; i < 3; i++) {
+            origin_i[i] = oi[i];
+            origin_d[i] = od[i];
+            bmax[i] = oi[i] + half[i];
+            bmin[i] = oi[i] - half[i];
+        }
+        global_to_pos(bmin, bound_min_d);
+        global_to_pos(bmax, bound_max_d);
+    }
+    bool is_occupied(float v) const { return (double)v >= (double)l_occ; }      // prob_map.h:125-135 (double compare)
+    bool is_known_free(float v) const { return (double)v < (double)l_free; }
+    int type_of(float v) const { return is_occupied(v) ? ROG_OCCUPIED : (is_known_free(v) ? ROG_KNOWN_FREE : ROG_UNKNOWN); }
+
+    // prob_map.cpp:25-88 with config.hpp's derived quantities; `logit` in float as config.hpp:229-235
+    void init(RogEsdf* esdf_, const int half_map_size_i[3], double resolution, bool map_sliding_en,
+              double map_sliding_thresh, const double fix_origin[3], const float p[6] /*hit miss min max occ free*/,
+              double ray_min, double ray_max, double virtual_ceil, double virtual_ground,
+              const double local_update_box_d[3], int filt_num, int batch_size, int intensity, bool raycasting) {
+        esdf = esdf_;
+        res = resolution;
+        res_inv = 1.0 / resolution;
+        sliding_en = map_sliding_en;
+        sliding_thresh = map_sliding_thresh;
+        for (int i = 0; i < 3; i++) {
+            half[i] = half_map_size_i[i];
+            size[i] = 2 * half[i] + 1;
+        }
+        vox = (int64_t)size[0] * size[1] * size[2];
+        auto logit = [](float x) -> float { return std::log(x / (1 - x)); };
+        l_hit = logit(p[0]); l_miss = logit(p[1]); l_min = logit(p[2]);
+        l_max = logit(p[3]); l_occ = logit(p[4]); l_free = logit(p[5]);
+        range_min = ray_min;
+        range_max = ray_max;
+        sqr_range_max = ray_max * ray_max;
+        point_filt_num = filt_num <= 0 ? 1 : filt_num;
+        batch_update_size = batch_size <= 0 ? 1 : batch_size;
+        intensity_thresh = intensity;
+        raycasting_en = raycasting;
+        for (int i = 0; i < 3; i++) half_update_box_i[i] = (int)((local_update_box_d[i] / 2) / resolution);   // config.hpp:377-379
+        // prob_map.cpp:66-71: ceil / ground snapped to the grid
+        ceil_h = (double)ifloor(virtual_ceil * res_inv) * resolution;
+        ground_h = (double)ifloor(virtual_ground * res_inv) * resolution;
+        occupancy.assign(vox, 0.f);
+        op_cnt.assign(vox, 0);
+        hit_cnt.assign(vox, 0);
+        cache.clear();
+        batch_counter = 0;
+        inited = false;
+        map_empty = true;
+        first_frame = true;
+        if (!map_sliding_en) {
+            // sliding_map.cpp:58-61 + prob_map.cpp:73-77
+            int oi[3];
+            pos_to_global(fix_origin, oi);
+            for (int i = 0; i < 3; i++) {
+                origin_d[i] = fix_origin[i];
+                origin_i[i] = oi[i];
+            }
+            slide_all(fix_origin);
+        }
+    }
+
+    // prob_map.cpp:512-541 (inf / frontier notifications dropped)
+    void reset_cell(int64_t h) {
+        float& ret = occupancy[h];
+        if (is_occupied(ret)) {
+            double p[3];
+            hash_to_pos(h, p);
+            if (esdf) esdf->update_counter(p, ROG_OCCUPIED, ROG_UNKNOWN);
+        } else if (is_known_free(ret)) {
+            double p[3];
+            hash_to_pos(h, p);
+            if (esdf) esdf->update_counter(p, ROG_KNOWN_FREE, ROG_UNKNOWN);
+        }
+        ret = 0;
+    }
+    // prob_map.cpp:822-833
+    void reset_local_map() {
+        std::fill(occupancy.begin(), occupancy.end(), 0.f);
+        cache.clear();
+        batch_counter = 0;
+        std::fill(op_cnt.begin(), op_cnt.end(), (uint16_t)0);
+        std::fill(hit_cnt.begin(), hit_cnt.end(), (uint16_t)0);
+    }
+    // sliding_map.cpp:113-166 with ProbMap's resetCell / resetLocalMap
+    void map_sliding(const double odom[3]) {
+        int no[3];
+        pos_to_global(odom, no);
+        double nd[3];
+        for (int i = 0; i < 3; i++) nd[i] = (double)no[i] * res;
+        int shift[3];
+        for (int i = 0; i < 3; i++) shift[i] = no[i] - origin_i[i];
+        for (int i = 0; i < 3; i++)
+            if (std::fabs((double)shift[i]) > size[i]) {
+                reset_local_map();
+                set_origin(nd, no);
+                return;
+            }
+        auto normalize = [](int x, int a, int b) {
+            const int range = b - a + 1;
+            const int y = (x - a) % range;
+            return (y < 0 ? y + range : y) + a;
+        };
+        for (int i = 0; i < 3; i++) {
+            if (shift[i] == 0) continue;
+            const int min_g = -half[i] + origin_i[i];
+            const int min_l = min_g % size[i];
+            std::vector<int> clear_id;
+            if (shift[i] > 0)
+                for (int k = 0; k < shift[i]; k++) clear_id.push_back(normalize(min_l + k, -half[i], half[i]));
+            else
+                for (int k = -1; k >= shift[i]; k--) clear_id.push_back(normalize(min_l + k, -half[i], half[i]));
+            const int a1 = (i + 1) % 3, a2 = (i + 2) % 3;
+            for (int idd : clear_id)
+                for (int u = -half[a1]; u <= half[a1]; u++)
+                    for (int w = -half[a2]; w <= half[a2]; w++) {
+                        int l[3];
+                        l[i] = idd;
+                        l[a1] = u;
+                        l[a2] = w;
+                        reset_cell(local_hash(l));
+                    }
+        }
+        set_origin(nd, no);
+    }
+    // prob_map.cpp:291-300
+    void slide_all(const double pos[3]) {
+        map_sliding(pos);
+        if (esdf) esdf->slide(pos);
+    }
+
+    // prob_map.cpp:791-820
+    void update_local_box(const double odom[3]) {
+        int oi[3], lo[3], hi[3];
+        pos_to_global(odom, oi);
+        for (int i = 0; i < 3; i++) {
+            hi[i] = raycasting_en ? oi[i] + half_update_box_i[i] : 0;     // (uninitialised in the reference without raycasting)
+            lo[i] = raycasting_en ? oi[i] - half_update_box_i[i] : 0;
+        }
+        global_to_pos(lo, box_min);
+        global_to_pos(hi, box_max);
+        for (int i = 0; i < 3; i++) {
+            box_max[i] = std::min(box_max[i], bound_max_d[i]);
+            box_min[i] = std::max(box_min[i], bound_min_d[i]);
+        }
+    }
+    // prob_map.cpp:780-789
+    void insert_candidate(const int g[3], bool is_hit) {
+        const int64_t h = hash_from_global(g);
+        op_cnt[h]++;
+        if (op_cnt[h] == 1) cache.push_back({g[0], g[1], g[2]});
+        if (is_hit) hit_cnt[h]++;
+    }
+    // prob_map.cpp:571-664
+    void hit_miss_update(const double pos[3], int64_t h, int num, bool hit) {
+        float& ret = occupancy[h];
+        const int from = type_of(ret);
+        if (hit) {
+            ret += l_hit * num;
+            if (ret > l_max) ret = l_max;
+        } else {
+            ret += l_miss * num;
+            if (ret < l_min) ret = l_min;
+        }
+        const int to = type_of(ret);
+        if (from != to) {
+            int g[3];
+            double c[3];
+            pos_to_global(pos, g);
+            global_to_pos(g, c);
+            if (esdf) esdf->update_counter(c, from, to);
+        }
+    }
+    // prob_map.cpp:543-569
+    void from_cache() {
+        for (size_t k = 0; k < cache.size(); k++) {
+            const int g[3] = {cache[k][0], cache[k][1], cache[k][2]};
+            const int64_t h = hash_from_global(g);
+            double pos[3];
+            global_to_pos(g, pos);
+            if (hit_cnt[h] > 0) hit_miss_update(pos, h, hit_cnt[h], true);
+            else hit_miss_update(pos, h, (int)op_cnt[h] - (int)hit_cnt[h], false);
+            hit_cnt[h] = 0;
+            op_cnt[h] = 0;
+        }
+        cache.clear();
+    }
+    // common_lib.hpp:148-170
+    static void line_box_intersect(const double pt[3], const double pos[3], const double bmin[3], const double bmax[3],
+                                   double out[3]) {
+        double diff[3], max_tc[3], min_tc[3];
+        for (int i = 0; i < 3; i++) {
+            diff[i] = pt[i] - pos[i];
+            max_tc[i] = bmax[i] - pos[i];
+            min_tc[i] = bmin[i] - pos[i];
+        }
+        double min_t = 1000000;
+        for (int i = 0; i < 3; i++)
+            if (std::fabs(diff[i]) > 0) {
+                const double t1 = max_tc[i] / diff[i];
+                if (t1 > 0 && t1 < min_t) min_t = t1;
+                const double t2 = min_tc[i] / diff[i];
+                if (t2 > 0 && t2 < min_t) min_t = t2;
+            }
+        for (int i = 0; i < 3; i++) out[i] = pos[i] + (min_t - 1e-3) * diff[i];
+    }
+    // (p - o).normalized() * k + o   with Eigen's evaluation order: squaredNorm = (x^2 + y^2) + z^2, v / sqrt(.)
+    static void along(const double p[3], const double o[3], double k, double out[3]) {
+        const double d[3] = {p[0] - o[0], p[1] - o[1], p[2] - o[2]};
+        const double n2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        const double n = std::sqrt(n2);
+        for (int i = 0; i < 3; i++) out[i] = (n2 > 0.0 ? d[i] / n : d[i]) * k + o[i];
+    }
+    // prob_map.cpp:666-778. cloud: n x (x, y, z, intensity) float32
+    void raycast_process(const float* cloud, int64_t n, const double odom[3]) {
+        std::vector<std::array<double, 3>> rays;
+        int temporal = 0;
+        for (int64_t i = 0; i < n; i++) {
+            const float* c = cloud + 4 * i;
+            if (intensity_thresh > 0 && c[3] < intensity_thresh) continue;
+            if (temporal++ % point_filt_num) continue;
+            double p[3] = {(double)c[0], (double)c[1], (double)c[2]};
+            int g[3];
+            if (!raycasting_en) {
+                if (inside_local_map(p)) {
+                    pos_to_global(p, g);
+                    insert_candidate(g, true);
+                }
+                continue;
+            }
+            bool update_hit = true;
+            if (p[2] > ceil_h) {
+                update_hit = false;
+                const double dz = p[2] - odom[2], pc = ceil_h - odom[2];
+                double q[3];
+                along(p, odom, 1.0, q);     // (p - o).normalized() + o, then scaled below
+                const double d[3] = {p[0] - odom[0], p[1] - odom[1], p[2] - odom[2]};
+                const double nn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                for (int k = 0; k < 3; k++) p[k] = odom[k] + (d[k] / nn) * pc / dz;
+            } else if (p[2] < ground_h) {
+                update_hit = false;
+                const double dz = p[2] - odom[2], pc = ground_h - odom[2];
+                const double d[3] = {p[0] - odom[0], p[1] - odom[1], p[2] - odom[2]};
+                const double nn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                for (int k = 0; k < 3; k++) p[k] = odom[k] + (d[k] / nn) * pc / dz;
+            }
+            {
+                const double d[3] = {p[0] - odom[0], p[1] - odom[1], p[2] - odom[2]};
+                const double sqr = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                if (sqr > sqr_range_max) {
+                    const double k = range_max / std::sqrt(sqr);
+                    for (int a = 0; a < 3; a++) p[a] = k * d[a] + odom[a];
+                    update_hit = false;
+                }
+            }
+            {
+                double lo = p[0] - box_min[0], hi = p[0] - box_max[0];
+                for (int a = 1; a < 3; a++) {
+                    lo = std::min(lo, p[a] - box_min[a]);
+                    hi = std::max(hi, p[a] - box_max[a]);
+                }
+                if (lo < 0 || hi > 0) {
+                    double q[3];
+                    line_box_intersect(p, odom, box_min, box_max, q);
+                    for (int a = 0; a < 3; a++) p[a] = q[a];
+                    update_hit = false;
+                }
+            }
+            rays.push_back({p[0], p[1], p[2]});
+            if (update_hit) {
+                pos_to_global(p, g);
+                insert_candidate(g, true);
+            }
+        }
+        if (!raycasting_en) return;
+        const double DMAX = std::numeric_limits<double>::max();
+        // the reference keeps ONE RayCaster: a ray whose end points share a cell leaves the stepping tables of the
+        // previous ray in place (setInput returns early, raycaster.cpp:101-103) — harmless, its first step ends it
+        for (const auto& pr : rays) {
+            const double p[3] = {pr[0], pr[1], pr[2]};
+            double s[3];
+            {
+                const double d[3] = {p[0] - odom[0], p[1] - odom[1], p[2] - odom[2]};
+                const double nn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                for (int a = 0; a < 3; a++) s[a] = (d[a] / nn) * range_min + odom[a];
+            }
+            int si[3], ei[3], cur[3], dir[3];
+            for (int a = 0; a < 3; a++) {
+                si[a] = ifloor(s[a] / res);
+                ei[a] = ifloor(p[a] / res);
+                cur[a] = si[a];
+                const int dlt = ei[a] - si[a];
+                dir[a] = (0 < dlt) - (dlt < 0);
+            }
+            if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) continue;      // first step() returns false
+            double t_step[3], t_bound[3], dd[3];
+            for (int a = 0; a < 3; a++) dd[a] = std::fabs(p[a] - s[a]);
+            const double tmax = std::sqrt(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+            for (int a = 0; a < 3; a++) dd[a] /= tmax;
+            for (int a = 0; a < 3; a++) {
+                t_step[a] = dir[a] == 0 ? DMAX : std::fabs(res / dd[a]);
+                const double centre = ((double)si[a] + 0.5) * res;
+                const double nb = centre + dir[a] * res * 0.5;
+                t_bound[a] = dir[a] == 0 ? DMAX : std::fabs(nb - s[a]) / dd[a];
+            }
+            while (true) {
+                double pt[3];
+                for (int a = 0; a < 3; a++) pt[a] = ((double)cur[a] + 0.5) * res;
+                if (cur[0] == ei[0] && cur[1] == ei[1] && cur[2] == ei[2]) break;
+                if (t_bound[0] < t_bound[1]) {
+                    if (t_bound[0] < t_bound[2]) { cur[0] += dir[0]; t_bound[0] += t_step[0]; }
+                    else { cur[2] += dir[2]; t_bound[2] += t_step[2]; }
+                } else {
+                    if (t_bound[1] < t_bound[2]) { cur[1] += dir[1]; t_bound[1] += t_step[1]; }
+                    else { cur[2] += dir[2]; t_bound[2] += t_step[2]; }
+                }
+                int g[3];
+                pos_to_global(pt, g);
+                if (!inside_local_map_i(g)) break;
+                insert_candidate(g, false);
+            }
+        }
+    }
+    // prob_map.cpp:302-373
+    void update(const float* cloud, int64_t n, const double pos[3]) {
+        if (sliding_en && !inside_local_map(pos) && batch_counter == 0) {
+            slide_all(pos);
+            return;
+        }
+        if (pos[2] > ceil_h) return;
+        else if (pos[2] < ground_h) return;
+        {
+            const double d[3] = {pos[0] - origin_d[0], pos[1] - origin_d[1], pos[2] - origin_d[2]};
+            const double nrm = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            if (batch_counter == 0 && (map_empty || (sliding_en && nrm > sliding_thresh))) slide_all(pos);
+        }
+        if (!inited) {
+            inited = true;
+            slide_all(pos);
+        }
+        update_local_box(pos);
+        raycast_process(cloud, n, pos);
+        batch_counter++;
+        if (batch_counter >= batch_update_size) {
+            batch_counter = 0;
+            from_cache();
+            map_empty = false;
+        }
+        if (esdf) esdf->update_esdf(pos);
+        if (first_frame) {
+            // prob_map.cpp:357-372 (a function-level static in the reference: once per process)
+            first_frame = false;
+            for (double dx = -range_min; dx <= range_min; dx += res)
+                for (double dy = -range_min; dy <= range_min; dy += res)
+                    for (double dz = -range_min; dz <= range_min; dz += res) {
+                        const double nrm = std::sqrt(dx * dx + dy * dy + dz * dz);
+                        if (nrm <= range_min) {
+                            const double pp[3] = {pos[0] + dx, pos[1] + dy, pos[2] + dz};
+                            hit_miss_update(pp, hash_from_pos(pp), 999, false);
+                        }
+                    }
+        }
     }
 };
 
