@@ -270,6 +270,27 @@ enum {
 /* buffers topay_rogfield_download returns */
 enum { TOPAY_ROG_BUF_DIST3 = 0, TOPAY_ROG_BUF_NEG3 = 1, TOPAY_ROG_BUF_CRITICAL = 2, TOPAY_ROG_BUF_FLAT = 3 };
 
+/* rog_map::ProbMap — the probabilistic occupancy layer that drives the ESDF counter map from point clouds
+ * (src/rog_map/src/rog_map/prob_map.cpp; parameters of rog_map_core/config.hpp:160-262). The probability grid
+ * shares half_prob_map_size_i / prob_resolution / map_sliding_en / fix_map_origin with the ESDF ring it feeds. */
+typedef struct topay_prob_desc {
+    float   p_hit, p_miss, p_min, p_max, p_occ, p_free;   /* raycasting/p_*; the log-odds are logit() in float */
+    double  raycast_range_min, raycast_range_max;          /* raycasting/ray_range */
+    double  virtual_ceil_height, virtual_ground_height;    /* as configured: InfMap's constructor pulls them in by
+                                                            * inflation_step cells first (inf_map.cpp:81-89), then
+                                                            * initProbMap snaps them to the grid (prob_map.cpp:66-71) */
+    double  inflation_resolution;                          /* rounded up to a multiple of the resolution (config.hpp:338-349) */
+    int32_t inflation_step;
+    int32_t pad_;
+    double  local_update_box[3];                           /* raycasting/local_update_box, metres */
+    double  map_sliding_thresh;
+    int32_t point_filt_num;                                /* keep every point_filt_num-th point */
+    int32_t batch_update_size;                             /* clouds per probabilistic update */
+    int32_t intensity_thresh;                              /* <= 0: off */
+    int32_t raycasting_en;
+} topay_prob_desc;
+typedef struct topay_probmap topay_probmap;
+
 /* initESDFMap: sizes derived as CounterMap::initCounterMap does (counter_map.cpp:31-91,
  * inflation_step 0), buffers in HBM, counters reset (esdf_map.cpp:72-76). */
 int topay_rogfield_create(const topay_rog_desc* desc, int device, topay_rogfield** out);
@@ -298,6 +319,20 @@ int topay_rogfield_is_line_free2d(topay_rogfield* f, const double* start, const 
                                   double threshold, int8_t* out);
 int topay_rogfield_download(topay_rogfield* f, int which, double* out);
 int topay_rogfield_last_update_ms(topay_rogfield* f, float* ms_total, float* ms_3d);
+
+/* ProbMap over an ESDF ring (borrowed; must outlive the prob map): initProbMap (prob_map.cpp:25-88). */
+int topay_probmap_create(topay_rogfield* esdf, const topay_prob_desc* desc, topay_probmap** out);
+void topay_probmap_destroy(topay_probmap* m);
+/* ProbMap::updateProbMap(cloud, pose) (prob_map.cpp:302-373): slides the maps when the robot left them, clips
+ * and filters the points, walks the rays, applies the cached hits / misses to the log-odds, forwards every
+ * UNKNOWN / OCCUPIED / KNOWN_FREE transition to the ESDF counter map and runs updateESDF3D(pos). cloud: n x
+ * (x, y, z, intensity) float32, host memory. */
+int topay_probmap_update(topay_probmap* m, const float* cloud_xyzi, int64_t n, const double pos[3]);
+/* occupancy_buffer_ (log-odds, ring memory, (2h+1)^3 floats) and the map origin in cells. */
+int topay_probmap_download(topay_probmap* m, float* occupancy, int32_t origin_i[3]);
+/* the first-frame sphere clearing of updateProbMap is a function-level static in the reference (once per
+ * process); this re-arms (1) or disarms (0) it for this map */
+int topay_probmap_set_first_frame(topay_probmap* m, int armed);
 
 /* -------------------------------------- result post-processing + success gate */
 

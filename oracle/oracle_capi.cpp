@@ -479,4 +479,26 @@ void oracle_check_feasible(void* field, const topay_robot_params* rp, const topa
 }
 int oracle_select_shortest(const int32_t* succ, const double* dur, int n) { return select_shortest(succ, dur, n); }
 
+
+// ---- ProbMap (row N3)
+void* oracle_prob_create(void* esdf, const topay_rog_desc* d, const topay_prob_desc* p) {
+    RogProb* m = new RogProb();
+    const float pp[6] = {p->p_hit, p->p_miss, p->p_min, p->p_max, p->p_occ, p->p_free};
+    m->init((RogEsdf*)esdf, d->half_prob_map_size_i, d->prob_resolution, d->map_sliding_en != 0, p->map_sliding_thresh,
+            d->fix_map_origin, pp, p->raycast_range_min, p->raycast_range_max, p->virtual_ceil_height,
+            p->virtual_ground_height, p->inflation_resolution, p->inflation_step, p->local_update_box, p->point_filt_num, p->batch_update_size, p->intensity_thresh,
+            p->raycasting_en != 0);
+    return m;
+}
+void oracle_prob_destroy(void* h) { delete (RogProb*)h; }
+void oracle_prob_update(void* h, const float* cloud, int64_t n, const double* pos) { ((RogProb*)h)->update(cloud, n, pos); }
+void oracle_prob_set_first_frame(void* h, int armed) { ((RogProb*)h)->first_frame = armed != 0; }
+void oracle_prob_download(void* h, float* occ, int32_t* origin_i) {
+    RogProb* m = (RogProb*)h;
+    std::memcpy(occ, m->occupancy.data(), m->occupancy.size() * sizeof(float));
+    for (int i = 0; i < 3; i++) origin_i[i] = m->origin_i[i];
+}
+void oracle_prob_size(void* h, int32_t* size) {
+    for (int i = 0; i < 3; i++) size[i] = ((RogProb*)h)->size[i];
+}
 }  // extern "C"

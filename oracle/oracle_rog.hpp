@@ -600,8 +600,9 @@ struct RogProb {
     // prob_map.cpp:25-88 with config.hpp's derived quantities; `logit` in float as config.hpp:229-235
     void init(RogEsdf* esdf_, const int half_map_size_i[3], double resolution, bool map_sliding_en,
               double map_sliding_thresh, const double fix_origin[3], const float p[6] /*hit miss min max occ free*/,
-              double ray_min, double ray_max, double virtual_ceil, double virtual_ground,
-              const double local_update_box_d[3], int filt_num, int batch_size, int intensity, bool raycasting) {
+              double ray_min, double ray_max, double virtual_ceil, double virtual_ground, double inflation_resolution,
+              int inflation_step, const double local_update_box_d[3], int filt_num, int batch_size, int intensity,
+              bool raycasting) {
         esdf = esdf_;
         res = resolution;
         res_inv = 1.0 / resolution;
@@ -623,7 +624,15 @@ struct RogProb {
         intensity_thresh = intensity;
         raycasting_en = raycasting;
         for (int i = 0; i < 3; i++) half_update_box_i[i] = (int)((local_update_box_d[i] / 2) / resolution);   // config.hpp:377-379
-        // prob_map.cpp:66-71: ceil / ground snapped to the grid
+        // InfMap's constructor takes the Config by reference and pulls ceil / ground in by inflation_step cells of the
+        // inflation grid (inf_map.cpp:81-89; config.hpp:338-349 rounds that grid up to a multiple of the resolution) ...
+        const int inf_ratio = (int)std::ceil(inflation_resolution / resolution);
+        const double inf_res = resolution * inf_ratio;
+        const int ceil_id = (int)(virtual_ceil / inf_res + 0.5) - inflation_step;
+        const int ground_id = (int)(virtual_ground / inf_res + 0.5) + inflation_step;
+        virtual_ceil = ceil_id * inf_res;
+        virtual_ground = ground_id * inf_res;
+        // ... then prob_map.cpp:66-71 snaps them to the probability grid
         ceil_h = (double)ifloor(virtual_ceil * res_inv) * resolution;
         ground_h = (double)ifloor(virtual_ground * res_inv) * resolution;
         occupancy.assign(vox, 0.f);

@@ -398,3 +398,34 @@ def select_shortest(succ, dur):
     s = np.ascontiguousarray(succ, dtype=np.int32)
     d = _f64(dur)
     return lib().oracle_select_shortest(_p(s, C.c_int32), _p(d), len(s))
+
+
+class RogProb:
+    """oracle_rog.hpp RogProb (the rog_map::ProbMap restatement) over a RogField."""
+
+    def __init__(self, field: RogField, rog_desc, prob_desc):
+        lib().oracle_prob_create.restype = C.c_void_p
+        self.field = field
+        self.h = C.c_void_p(lib().oracle_prob_create(field.h, C.byref(rog_desc), C.byref(prob_desc)))
+        sz = (C.c_int32 * 3)()
+        lib().oracle_prob_size(self.h, sz)
+        self.size = tuple(sz)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_prob_destroy(self.h)
+            self.h = None
+
+    def update(self, cloud_xyzi, pos):
+        c = np.ascontiguousarray(cloud_xyzi, dtype=np.float32).reshape(-1, 4)
+        p = _f64(pos)
+        lib().oracle_prob_update(self.h, _p(c, C.c_float), C.c_int64(c.shape[0]), _p(p))
+
+    def set_first_frame(self, armed):
+        lib().oracle_prob_set_first_frame(self.h, int(armed))
+
+    def download(self):
+        occ = np.empty(self.size, dtype=np.float32)
+        org = (C.c_int32 * 3)()
+        lib().oracle_prob_download(self.h, _p(occ, C.c_float), org)
+        return occ, tuple(org)

@@ -288,3 +288,38 @@ class RogESDFMap:
         out = np.empty(self.size if which < 2 else self.size[:2])
         lib().ref_rog_download(self.h, which, _p(out))
         return out
+
+
+class RogProbMap:
+    """rog_map::ProbMap itself with its own ESDFMap (oracle/ref_driver_rog.cpp). `esdf` exposes the ESDF layer
+    through the RogESDFMap surface. The reference clears the first-frame sphere ONCE PER PROCESS (a function-level
+    static in updateProbMap): `first_frame_pending()` tells whether that has happened yet in this process."""
+    _first_done = False
+
+    def __init__(self, rog_desc, prob_desc):
+        l = lib()
+        l.ref_prob_create.restype = C.c_void_p
+        l.ref_prob_esdf.restype = C.c_void_p
+        self.h = C.c_void_p(l.ref_prob_create(C.byref(rog_desc), C.byref(prob_desc)))
+        sz = (C.c_int32 * 3)()
+        l.ref_prob_size(self.h, sz)
+        self.size = tuple(sz)
+        self.esdf = RogESDFMap.__new__(RogESDFMap)
+        self.esdf.h = C.c_void_p(l.ref_prob_esdf(self.h))
+        g = self.esdf._geometry()
+        self.esdf.half, self.esdf.size, self.esdf.half_box, self.esdf.resolution = g[0], g[1], g[3], g[4]
+
+    @classmethod
+    def first_frame_pending(cls):
+        return not cls._first_done
+
+    def update(self, cloud_xyzi, pos):
+        c = np.ascontiguousarray(cloud_xyzi, dtype=np.float32).reshape(-1, 4)
+        p = _f64(pos)
+        lib().ref_prob_update(self.h, _p(c, C.c_float), C.c_int64(c.shape[0]), _p(p))
+
+    def download(self):
+        occ = np.empty(self.size, dtype=np.float32)
+        org = (C.c_int32 * 3)()
+        lib().ref_prob_download(self.h, _p(occ, C.c_float), org)
+        return occ, tuple(org)

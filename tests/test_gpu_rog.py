@@ -220,3 +220,59 @@ def test_rog_error_paths():
     before = dev.getBuffer(0)
     dev.updateESDF3D((500.0, 0.0, 0.0))
     assert np.array_equal(before, dev.getBuffer(0))
+
+
+def _scan_cloud(rng, pos, n, spread, walls):
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = np.minimum(np.abs(walls[0] / np.where(np.abs(d[:, 0]) > 1e-3, d[:, 0], 1e-3)),
+                   np.abs(walls[1] / np.where(np.abs(d[:, 1]) > 1e-3, d[:, 1], 1e-3)))
+    r = np.minimum(r, rng.uniform(0.2, spread, n))
+    pts = pos + d * r[:, None]
+    pts[::17] += rng.normal(size=(len(pts[::17]), 3)) * 5.0
+    return np.concatenate([pts, rng.uniform(0, 100, (n, 1))], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(half=(20, 20, 8), res=0.1, esdf_res=0.1, box=(3.0, 3.0, 1.2), upd=(3.5, 3.5, 1.4), filt=1, batch=1, inten=-1, ray=True, step=1),
+    dict(half=(16, 18, 6), res=0.1, esdf_res=0.2, box=(2.5, 2.5, 1.0), upd=(99.0, 99.0, 99.0), filt=3, batch=2, inten=30, ray=True, step=1),
+    dict(half=(14, 14, 6), res=0.1, esdf_res=0.1, box=(2.0, 2.0, 1.0), upd=(2.0, 2.0, 1.0), filt=2, batch=1, inten=-1, ray=False, step=2),
+    dict(half=(60, 60, 12), res=0.05, esdf_res=0.05, box=(5.0, 5.0, 1.0), upd=(6.0, 6.0, 1.2), filt=1, batch=1, inten=-1, ray=True, step=1),
+])
+def test_prob_map_against_oracle(oracle, cfg):
+    """N3: ProbMap::updateProbMap on the device — point filters, clipping to ceiling / ground / range / update box,
+    the 3-D ray walks, batched hit / miss log-odds, type transitions into the ESDF counters, map sliding with
+    resetCell, poses outside the map / above the ceiling, the first-frame sphere — occupancy_buffer_ (float), the
+    ESDF counters and the ESDF buffers bit-identical to the oracle (= the reference's own ProbMap + ESDFMap,
+    tests/test_ref_pin.py::test_prob_map_bit_exact) after every frame."""
+    import topay_b200 as tp
+    d = tp.rog_desc(half_prob_map_size_i=cfg["half"], prob_resolution=cfg["res"], esdf_resolution=cfg["esdf_res"],
+                    local_update_box=cfg["box"], map_sliding_en=True)
+    p = tp.prob_desc(ray_range=(0.3, 2.4), virtual_ceil_height=0.62, virtual_ground_height=-0.48,
+                     local_update_box=cfg["upd"], map_sliding_thresh=0.25, point_filt_num=cfg["filt"],
+                     batch_update_size=cfg["batch"], intensity_thresh=cfg["inten"], raycasting_en=cfg["ray"],
+                     inflation_resolution=cfg["res"], inflation_step=cfg["step"])
+    esdf = tp.ESDFMap(d)
+    dev = tp.ProbMap(esdf, p)
+    of = oracle.RogField(d)
+    orc = oracle.RogProb(of, d, p)
+    rng = np.random.default_rng(cfg["half"][1])
+    poses = [(0.0, 0.0, 0.0), (0.05, 0.02, 0.0), (0.31, -0.22, 0.05), (0.33, -0.2, 0.05), (0.9, 0.7, 0.1),
+             (0.9, 0.7, 0.9), (9.0, 9.0, 0.0), (9.1, 9.0, 0.0), (8.7, 9.3, -0.1)]
+    touched = 0
+    for step, pos in enumerate(poses):
+        cloud = _scan_cloud(rng, np.array(pos), 3000, 3.0, (1.3, 1.7))
+        dev.updateProbMap(cloud, pos)
+        orc.update(cloud, pos)
+        (a, oa), (b, ob) = dev.getOccupancyBuffer(), orc.download()
+        assert oa == ob, step
+        assert np.array_equal(a, b), (step, int((a != b).sum()))
+        touched += int((b != 0).sum())
+        for x, y in zip(esdf.getCounters(), of.download_counters()):
+            assert np.array_equal(x, y), step
+        if cfg["half"][0] == cfg["half"][1]:
+            for which in range(4):
+                assert np.array_equal(esdf.getBuffer(which), of.download(which)), (step, which)
+    assert touched > 1000
+    dev.close()
+    esdf.close()

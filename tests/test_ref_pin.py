@@ -275,3 +275,63 @@ def test_rog_esdf_layer_bit_exact(oracle, half, box):
         s2 = rng.uniform(-1, 1, (200, 2)) * ext[:2] * 0.8 + np.array(odom[:2])
         e2 = s2 + rng.uniform(-0.6, 0.6, (200, 2))
         assert np.array_equal(ref.is_line_free2d(s2, e2, 0.05), orc.is_line_free2d(s2, e2, 0.05))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's ProbMap (prob_map.cpp) driving its ESDFMap from point clouds — row N3
+def _scan_cloud(rng, pos, n, spread, walls):
+    """A synthetic lidar frame: points on a few planes around the robot + far / high / low outliers + intensities."""
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = np.minimum(np.abs(walls[0] / np.where(np.abs(d[:, 0]) > 1e-3, d[:, 0], 1e-3)),
+                   np.abs(walls[1] / np.where(np.abs(d[:, 1]) > 1e-3, d[:, 1], 1e-3)))
+    r = np.minimum(r, rng.uniform(0.2, spread, n))
+    pts = pos + d * r[:, None]
+    pts[::17] += rng.normal(size=(len(pts[::17]), 3)) * 5.0          # far, above the ceiling, below the ground
+    inten = rng.uniform(0, 100, (n, 1))
+    return np.concatenate([pts, inten], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(half=(20, 20, 8), res=0.1, esdf_res=0.1, box=(3.0, 3.0, 1.2), upd=(3.5, 3.5, 1.4), filt=1, batch=1, inten=-1, ray=True),
+    dict(half=(16, 18, 6), res=0.1, esdf_res=0.2, box=(2.5, 2.5, 1.0), upd=(99.0, 99.0, 99.0), filt=3, batch=2, inten=30, ray=True),
+    dict(half=(14, 14, 6), res=0.1, esdf_res=0.1, box=(2.0, 2.0, 1.0), upd=(2.0, 2.0, 1.0), filt=2, batch=1, inten=-1, ray=False,
+         inf_step=2),
+])
+def test_prob_map_bit_exact(oracle, cfg):
+    """N3: ProbMap::updateProbMap over a sequence of clouds and poses — the point filters (intensity, every k-th),
+    clipping to ceiling / ground / range / update box, the 3-D ray walks, batched hit / miss log-odds updates, the type
+    transitions forwarded to the ESDF counter map, map sliding with resetCell, poses outside the map and outside the
+    ceiling, the first-frame sphere clearing — occupancy_buffer_ (float log-odds), the ESDF counters and the four ESDF
+    buffers IDENTICAL to the reference's own ProbMap + ESDFMap after every frame."""
+    from topay_b200._structs import prob_desc, rog_desc
+    d = rog_desc(half_prob_map_size_i=cfg["half"], prob_resolution=cfg["res"], esdf_resolution=cfg["esdf_res"],
+                 local_update_box=cfg["box"], map_sliding_en=True)
+    p = prob_desc(ray_range=(0.3, 2.4), virtual_ceil_height=0.62, virtual_ground_height=-0.48,
+                  local_update_box=cfg["upd"], map_sliding_thresh=0.25, point_filt_num=cfg["filt"],
+                  batch_update_size=cfg["batch"], intensity_thresh=cfg["inten"], raycasting_en=cfg["ray"],
+                  inflation_resolution=cfg["res"], inflation_step=cfg.get("inf_step", 1))
+    ref = R.RogProbMap(d, p)
+    of = oracle.RogField(d)
+    orc = oracle.RogProb(of, d, p)
+    assert ref.size == orc.size and ref.esdf.size == of.size
+    orc.set_first_frame(R.RogProbMap.first_frame_pending())
+    rng = np.random.default_rng(cfg["half"][1])
+    poses = [(0.0, 0.0, 0.0), (0.05, 0.02, 0.0), (0.31, -0.22, 0.05), (0.33, -0.2, 0.05), (0.9, 0.7, 0.1),
+             (0.9, 0.7, 0.9), (9.0, 9.0, 0.0), (9.1, 9.0, 0.0), (8.7, 9.3, -0.1)]
+    seen_occ = seen_free = False
+    for step, pos in enumerate(poses):
+        cloud = _scan_cloud(rng, np.array(pos), 700, 3.0, (1.3, 1.7))
+        ref.update(cloud, pos)
+        R.RogProbMap._first_done = True
+        orc.update(cloud, pos)
+        (a, oa), (b, ob) = ref.download(), orc.download()
+        assert oa == ob, step
+        assert np.array_equal(a, b), (step, int((a != b).sum()))
+        seen_occ, seen_free = seen_occ or bool((b > 0).any()), seen_free or bool((b < 0).any())
+        for x, y in zip(ref.esdf.download_counters(), of.download_counters()):
+            assert np.array_equal(x, y), step
+        if cfg["half"][0] == cfg["half"][1]:        # square rings only (the 2-D combine quirk, see above)
+            for which in range(4):
+                assert np.array_equal(ref.esdf.download(which), of.download(which)), (step, which)
+    assert seen_occ and (seen_free or not cfg["ray"])

@@ -5,11 +5,11 @@ this package is the host-side mirror of the two reference interfaces it replaces
 GridMap (field.py), rog_map::ESDFMap (rog.py) and MomaTrajOpt (optimizer.py).
 """
 from ._structs import (MAP2D_CRITICAL, MAP2D_FLAT, MAP2D_INFLATE, MAP3D, TERM_NAMES, GridDesc, OptParams,
-                       RobotParams, RogDesc, grid_desc, num_vars, rog_desc)
+                       RobotParams, RogDesc, grid_desc, num_vars, prob_desc, rog_desc)
 from .field import GridMap, robot_params_default
-from .rog import ESDFMap
+from .rog import ESDFMap, ProbMap
 from .optimizer import MomaTraj, MomaTrajOpt, opt_params_default, prepare_candidate
 
-__all__ = ["GridMap", "ESDFMap", "rog_desc", "RogDesc", "MomaTrajOpt", "MomaTraj", "grid_desc", "GridDesc", "OptParams", "RobotParams",
+__all__ = ["GridMap", "ESDFMap", "ProbMap", "prob_desc", "rog_desc", "RogDesc", "MomaTrajOpt", "MomaTraj", "grid_desc", "GridDesc", "OptParams", "RobotParams",
            "robot_params_default", "opt_params_default", "prepare_candidate", "num_vars", "TERM_NAMES",
            "MAP2D_FLAT", "MAP2D_INFLATE", "MAP2D_CRITICAL", "MAP3D"]

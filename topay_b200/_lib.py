@@ -8,7 +8,7 @@ import ctypes as C
 import os
 import subprocess
 
-from ._structs import Feasibility, GridDesc, RogDesc, TrajBatch, OptParams, ProblemBatch, ResultBatch, RobotParams, SolverStats
+from ._structs import Feasibility, GridDesc, ProbDesc, RogDesc, TrajBatch, OptParams, ProblemBatch, ResultBatch, RobotParams, SolverStats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("TOPAY_B200_LIB", os.path.join(_HERE, "libtopay_b200.so"))
@@ -78,6 +78,11 @@ PROTOTYPES = {
     "topay_rogfield_is_line_free2d": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_double, _i8p]),
     "topay_rogfield_download": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "topay_rogfield_last_update_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "topay_probmap_create": (C.c_int, [C.c_void_p, C.POINTER(ProbDesc), C.POINTER(C.c_void_p)]),
+    "topay_probmap_destroy": (None, [C.c_void_p]),
+    "topay_probmap_update": (C.c_int, [C.c_void_p, _fp, C.c_int64, _dp]),
+    "topay_probmap_download": (C.c_int, [C.c_void_p, _fp, _ip]),
+    "topay_probmap_set_first_frame": (C.c_int, [C.c_void_p, C.c_int]),
     "topay_traj_check_feasible": (C.c_int, [C.c_void_p, C.POINTER(RobotParams), C.POINTER(TrajBatch),
                                             C.POINTER(Feasibility)]),
     "topay_traj_car_seq": (C.c_int, [C.c_int, C.POINTER(TrajBatch), C.c_int, _dp, _ip]),

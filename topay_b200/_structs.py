@@ -93,6 +93,34 @@ def rog_desc(half_prob_map_size_i=(400, 400, 40), prob_resolution=0.05, esdf_res
     return d
 
 
+class ProbDesc(C.Structure):
+    _fields_ = [("p_hit", C.c_float), ("p_miss", C.c_float), ("p_min", C.c_float), ("p_max", C.c_float),
+                ("p_occ", C.c_float), ("p_free", C.c_float), ("raycast_range_min", C.c_double),
+                ("raycast_range_max", C.c_double), ("virtual_ceil_height", C.c_double),
+                ("virtual_ground_height", C.c_double), ("inflation_resolution", C.c_double),
+                ("inflation_step", C.c_int32), ("pad_", C.c_int32), ("local_update_box", C.c_double * 3),
+                ("map_sliding_thresh", C.c_double), ("point_filt_num", C.c_int32), ("batch_update_size", C.c_int32),
+                ("intensity_thresh", C.c_int32), ("raycasting_en", C.c_int32)]
+
+
+def prob_desc(p_hit=0.70, p_miss=0.35, p_min=0.12, p_max=0.97, p_occ=0.80, p_free=0.30, ray_range=(0.3, 10.0),
+              virtual_ceil_height=3.0, virtual_ground_height=-0.5, local_update_box=(20.0, 20.0, 4.0),
+              map_sliding_thresh=0.2, point_filt_num=1, batch_update_size=1, intensity_thresh=-1, raycasting_en=True,
+              inflation_resolution=0.05, inflation_step=1):
+    """Parameters of rog_map::ProbMap (rog_map_core/config.hpp:160-262); p_* are probabilities, the log-odds are
+    logit() in float as config.hpp:229-235."""
+    d = ProbDesc()
+    d.p_hit, d.p_miss, d.p_min, d.p_max, d.p_occ, d.p_free = p_hit, p_miss, p_min, p_max, p_occ, p_free
+    d.raycast_range_min, d.raycast_range_max = ray_range
+    d.virtual_ceil_height, d.virtual_ground_height = virtual_ceil_height, virtual_ground_height
+    d.inflation_resolution, d.inflation_step = inflation_resolution, inflation_step
+    d.local_update_box[:] = local_update_box
+    d.map_sliding_thresh = map_sliding_thresh
+    d.point_filt_num, d.batch_update_size = point_filt_num, batch_update_size
+    d.intensity_thresh, d.raycasting_en = intensity_thresh, int(raycasting_en)
+    return d
+
+
 class ProblemBatch(C.Structure):
     _fields_ = [("n_cand", C.c_int32), ("piece_num", C.POINTER(C.c_int32)),
                 ("head_pva", C.POINTER(C.c_double)), ("tail_pva", C.POINTER(C.c_double)),

@@ -17,6 +17,15 @@ void tp_field_grid(const topay_field* f, TpGrid* out);
 int tp_rogfield_device(const topay_rogfield* f);
 bool tp_rogfield_ready(const topay_rogfield* f);
 void tp_rogfield_grid(const topay_rogfield* f, TpGrid* out);   // kind = 1
+// what the probabilistic layer (probmap.cu) needs of the ESDF ring it feeds: geometry, the two counter arrays, its stream
+struct TpRogCounters {
+    TpRog view;
+    int16_t *occ_cnt, *unk_cnt;
+    cudaStream_t stream;
+    int device;
+    topay_rog_desc desc;
+};
+void tp_rogfield_counters(topay_rogfield* f, TpRogCounters* out);
 
 // Optional sink of the EDT's last pass: instead of a dense esdf array the two distances go straight into
 // the ROG ring buffers through the per-axis wrap rule (rogfield.cu; esdf_map.cpp:154-320).

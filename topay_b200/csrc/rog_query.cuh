@@ -182,3 +182,18 @@ TP_HD double tp_field_distance3d(const TpGrid& g, const double* p) {
     }
     return tp_distance3d(g, p);
 }
+
+#if defined(__CUDACC__)
+// 16-bit counter += delta by CAS on the enclosing 32-bit word (CounterMap's int16 counters, counter_map.h:100-110)
+__device__ __forceinline__ void tp_atomic_add16(int16_t* base, size_t idx, int delta) {
+    unsigned int* w = reinterpret_cast<unsigned int*>(base) + (idx >> 1);
+    const int sh = (idx & 1) ? 16 : 0;
+    unsigned int old = *w, assumed;
+    do {
+        assumed = old;
+        const unsigned int cur = (assumed >> sh) & 0xffffu;
+        const unsigned int nxt = (cur + (unsigned int)delta) & 0xffffu;
+        old = atomicCAS(w, assumed, (assumed & ~(0xffffu << sh)) | (nxt << sh));
+    } while (old != assumed);
+}
+#endif

@@ -138,18 +138,6 @@ __global__ void k_fill16(int16_t* p, int16_t v, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-__device__ __forceinline__ void atomic_add16(int16_t* base, size_t idx, int delta) {
-    unsigned int* w = reinterpret_cast<unsigned int*>(base) + (idx >> 1);
-    const int sh = (idx & 1) ? 16 : 0;
-    unsigned int old = *w, assumed;
-    do {
-        assumed = old;
-        const unsigned int cur = (assumed >> sh) & 0xffffu;
-        const unsigned int nxt = (cur + (unsigned int)delta) & 0xffffu;
-        old = atomicCAS(w, assumed, (assumed & ~(0xffffu << sh)) | (nxt << sh));
-    } while (old != assumed);
-}
-
 // updateGridCounter (counter_map.cpp:94-151); additions commute, so the batch order is immaterial
 __global__ void k_rog_counters(TpRog r, const double* __restrict__ pos, const uint8_t* __restrict__ from,
                                const uint8_t* __restrict__ to, int64_t n, int16_t* occ, int16_t* unk) {
@@ -159,8 +147,8 @@ __global__ void k_rog_counters(TpRog r, const double* __restrict__ pos, const ui
                                   tp_rog_cell(r, pos[3 * i + 2]));
     const int d_occ = (to[i] == TOPAY_ROG_OCCUPIED) - (from[i] == TOPAY_ROG_OCCUPIED);
     const int d_unk = (to[i] == TOPAY_ROG_UNKNOWN) - (from[i] == TOPAY_ROG_UNKNOWN);
-    if (d_occ) atomic_add16(occ, m, d_occ);
-    if (d_unk) atomic_add16(unk, m, d_unk);
+    if (d_occ) tp_atomic_add16(occ, m, d_occ);
+    if (d_unk) tp_atomic_add16(unk, m, d_unk);
 }
 
 __global__ void k_rog_query(TpRog r, int kind, const double* __restrict__ pos, int64_t n, double* dist, double* grad) {
@@ -247,6 +235,14 @@ int reset_counters(topay_rogfield* f) {   // esdf_map.cpp:72-76
 }  // namespace
 
 int tp_rogfield_device(const topay_rogfield* f) { return f->device; }
+void tp_rogfield_counters(topay_rogfield* f, TpRogCounters* out) {
+    out->view = rog_view(f);
+    out->occ_cnt = f->occ_cnt;
+    out->unk_cnt = f->unk_cnt;
+    out->stream = f->stream;
+    out->device = f->device;
+    out->desc = f->desc;
+}
 bool tp_rogfield_ready(const topay_rogfield* f) { return f->updated; }
 void tp_rogfield_grid(const topay_rogfield* f, TpGrid* out) {
     memset(out, 0, sizeof(*out));

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._structs import RogDesc, rog_desc
+from ._structs import ProbDesc, RogDesc, prob_desc, rog_desc
 
 # rog_map::GridType (include/utils/common_lib.hpp:74-81)
 UNDEFINED, UNKNOWN, OUT_OF_MAP, OCCUPIED, KNOWN_FREE = 0, 1, 2, 3, 4
@@ -134,3 +134,44 @@ class ESDFMap:
         out = np.empty(self.map_size_i if which <= BUF_NEG3 else self.map_size_i[:2])
         _lib.check(self._l.topay_rogfield_download(self.h, which, _p(out)), "topay_rogfield_download")
         return out
+
+
+class ProbMap:
+    """rog_map::ProbMap (src/rog_map/include/rog_map/prob_map.h) over an ESDFMap: the probabilistic occupancy layer
+    that ingests point clouds and drives the ESDF counter map (the inflation map and the frontier counters of the
+    reference are not built). `esdf_map_` is the ESDFMap it feeds, as in the reference."""
+
+    def __init__(self, esdf_map: ESDFMap, desc: ProbDesc = None):
+        """initProbMap (prob_map.cpp:25-88); the grid geometry (half_map_size_i, resolution, sliding, fixed origin)
+        is the ESDFMap descriptor's."""
+        self._l = _lib.lib()
+        self.esdf_map_ = esdf_map
+        self.cfg_ = desc if desc is not None else prob_desc(inflation_resolution=esdf_map.desc.prob_resolution)
+        self.h = C.c_void_p()
+        _lib.check(self._l.topay_probmap_create(esdf_map.h, C.byref(self.cfg_), C.byref(self.h)), "topay_probmap_create")
+        self.map_size_i = tuple(2 * int(h) + 1 for h in esdf_map.desc.half_prob_map_size_i)
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self._l.topay_probmap_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def updateProbMap(self, cloud_xyzi, pose_pos):
+        """ProbMap::updateProbMap(cloud, pose) (prob_map.cpp:302-373), incl. esdf_map_->updateESDF3D(pos).
+        cloud_xyzi: (n, 4) x, y, z, intensity."""
+        c = np.ascontiguousarray(cloud_xyzi, dtype=np.float32).reshape(-1, 4)
+        p = np.ascontiguousarray(pose_pos, dtype=np.float64)
+        _lib.check(self._l.topay_probmap_update(self.h, _p(c, C.c_float), C.c_int64(c.shape[0]), _p(p)),
+                   "topay_probmap_update")
+
+    def setFirstFrame(self, armed):
+        _lib.check(self._l.topay_probmap_set_first_frame(self.h, int(armed)), "topay_probmap_set_first_frame")
+
+    def getOccupancyBuffer(self):
+        """occupancy_buffer_ (float log-odds in ring memory) and local_map_origin_i_."""
+        occ = np.empty(self.map_size_i, dtype=np.float32)
+        org = (C.c_int32 * 3)()
+        _lib.check(self._l.topay_probmap_download(self.h, _p(occ, C.c_float), org), "topay_probmap_download")
+        return occ, tuple(org)
