@@ -283,7 +283,7 @@ def field_probe(tp, scenes, device, hbm_peak):
                     "8 taps x 8 B + 32 B result per point, points resident in HBM"}
 
 
-def sweep_probe(tp, scenes, local, rank, world, dist, per_rank=24, candidates=8, in_flight=8):
+def sweep_probe(tp, scenes, local, rank, world, dist, per_rank=48, candidates=8, in_flight=8):
     """BASELINE configs[4] (the scenario sweep, bounded): `per_rank` x world independent table / cuboid scenarios,
     static round-robin over the ranks (one process per GPU, no data-path collective). Every scenario runs the whole
     device pipeline the planner drives: rasterise its point cloud -> rebuild the field (4 x 2-D + 3-D ESDF) -> solve
@@ -379,6 +379,23 @@ def subpath_probe(tp, scenes, device, hbm_peak, solver, gm, rp, with_cpu):
                          "ms_total": tot, "ms_3d": d3, "Mvoxel_per_s": vox / (tot * 1e-3) / 1e6,
                          "algorithmic_GBps": vox * 9 / (d3 * 1e-3) / 1e9,
                          "frac_of_hbm_peak": vox * 9 / (d3 * 1e-3) / 1e9 / hbm_peak}
+    # ---- ProbMap ingest (N3): lidar-like frames of 10^5 points into the probability ring that feeds the same ESDF ring
+    from topay_b200.rog import ProbMap
+    pm = ProbMap(rog, tp.prob_desc(ray_range=(0.3, 10.0), virtual_ceil_height=3.0, virtual_ground_height=-0.5,
+                                   local_update_box=(20.0, 20.0, 4.0), inflation_resolution=res))
+    dirs = rng.normal(size=(100000, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    cloud = np.concatenate([dirs * rng.uniform(0.5, 9.0, (100000, 1)) + np.array([0.0, 0.0, 1.0]),
+                            np.full((100000, 1), 50.0)], axis=1).astype(np.float32)
+    tms = []
+    for k in range(4):
+        t0 = time.perf_counter()
+        pm.updateProbMap(cloud, (0.02 * k, 0.0, 1.0))
+        tms.append((time.perf_counter() - t0) * 1e3)
+    out["prob_map_update"] = {"frame": "10^5 points, rays up to 9 m at 0.05 m, ring 801x801x81 (incl. updateESDF3D of the "
+                                       "update box)", "ms_per_frame": float(np.median(tms[1:])),
+                              "Mpoints_per_s": 0.1 / (float(np.median(tms[1:])) * 1e-3)}
+    pm.close()
     rog.close()
     # ---- success gate on the candidates of the last solve, resident
     t = []
@@ -408,6 +425,15 @@ def subpath_probe(tp, scenes, device, hbm_peak, solver, gm, rp, with_cpu):
     bvox = int(np.prod([2 * h for h in orc.half_box]))
     out["rog_update"]["cpu"] = {"Mvoxel_per_s": bvox / dt / 1e6, "ms": dt * 1e3, "cores": 1, "kind": "port",
                                 "sample": f"ring {orc.size}, update box {bvox} voxels"}
+    # oracle: ProbMap ingest of a 10^4-point frame on the bounded ring
+    opm = O.RogProb(orc, small, tp.prob_desc(ray_range=(0.3, 10.0), virtual_ceil_height=3.0, virtual_ground_height=-0.5,
+                                             local_update_box=(20.0, 20.0, 4.0), inflation_resolution=res))
+    opm.update(cloud[:10000], (0.0, 0.0, 1.0))
+    t0 = time.perf_counter()
+    opm.update(cloud[10000:20000], (0.02, 0.0, 1.0))
+    dt = time.perf_counter() - t0
+    out["prob_map_update"]["cpu"] = {"Mpoints_per_s": 0.01 / dt, "ms": dt * 1e3, "cores": 1, "kind": "port",
+                                     "sample": f"10^4 points on ring {orc.size} (incl. updateESDF3D)"}
     # oracle: dense field rebuild + queries at the default 200 x 200 x 16 grid
     desc = tp.grid_desc()
     of = O.Field(desc)

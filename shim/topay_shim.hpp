@@ -407,4 +407,31 @@ private:
     topay_rogfield* f_ = nullptr;
 };
 
+// rog_map::ProbMap (src/rog_map/include/rog_map/prob_map.h:34-160): the probabilistic occupancy layer over an
+// ESDFMap. cfg is filled by the caller as Config's constructor would from the rosparams (config.hpp:160-262).
+class ProbMap {
+public:
+    typedef std::shared_ptr<ProbMap> Ptr;
+    topay_prob_desc cfg_ = {};
+    ESDFMap::Ptr esdf_map_;
+    ProbMap() = default;
+    ProbMap(const ProbMap&) = delete;               // owns the device ring
+    ProbMap& operator=(const ProbMap&) = delete;
+    ~ProbMap() { topay_probmap_destroy(m_); }
+    // initProbMap (prob_map.cpp:25-88): the grid geometry is the ESDFMap's descriptor
+    void initProbMap(ESDFMap::Ptr esdf_map) {
+        esdf_map_ = esdf_map;
+        nmoma_planner::topay_check(topay_probmap_create(esdf_map->handle(), &cfg_, &m_), "topay_probmap_create");
+    }
+    // updateProbMap(cloud, pose) (prob_map.cpp:302-373); cloud_xyzi: n x (x, y, z, intensity) float32
+    template <class V3> void updateProbMap(const float* cloud_xyzi, int64_t n, const V3& pose_pos) {
+        double p[3] = {pose_pos[0], pose_pos[1], pose_pos[2]};
+        nmoma_planner::topay_check(topay_probmap_update(m_, cloud_xyzi, n, p), "topay_probmap_update");
+    }
+    topay_probmap* handle() const { return m_; }
+
+private:
+    topay_probmap* m_ = nullptr;
+};
+
 }  // namespace rog_map
