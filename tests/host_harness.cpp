@@ -4,6 +4,7 @@
 // them in the same dataflow as the kernels (k_integrate -> k_penalty -> k_chain), serially,
 // so that the lane-level maths can be compared with the oracle without a GPU. This is not
 // a CPU path of the product: libtopay_b200.so neither contains nor calls any of it.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -333,4 +334,45 @@ void hh_edt_line(const int32_t* f_in, int n, int CH, int32_t* out_pos, int32_t* 
     }
 }
 int hh_sq16(int v) { return tp_sq16(v); }
+// ---- the same line in k_edt_scan's schedule: the line cut into NS segments of L cells, one envelope per segment
+// (its sources against the whole line), the positive transform of a free cell = minimum over the envelopes; an
+// occupied cell takes the outward search of the negative transform.
+void hh_edt_scan_line(const int32_t* f, int n, int NS, int32_t* out_pos, int32_t* out_neg, int32_t* depth) {
+    const int L = (((n + NS - 1) / NS) + 31) & ~31;
+    std::vector<TpEnvEntry> stk(L);
+    int deepest = 0;
+    for (int u = 0; u < n; u++) {
+        out_pos[u] = f[u] > 0 ? TP_INF32 : 0;
+        out_neg[u] = 0;
+    }
+    for (int j = 0; j < NS; j++) {
+        const int s0 = j * L, s1 = std::min(s0 + L, n);
+        if (s0 >= s1) continue;
+        TpEnv e{-1, 0, 0, 0};
+        int prev = s0 > 0 ? tp_env_val<false>(f[s0 - 1]) : 1, cur = tp_env_val<false>(f[s0]);
+        for (int u = s0; u < s1; u++) {
+            const int nxt = u + 1 < n ? tp_env_val<false>(f[u + 1]) : 1;
+            tp_env_push(e, stk.data(), n, u, cur, prev, nxt);
+            deepest = std::max(deepest, e.q + 1);
+            prev = cur;
+            cur = nxt;
+        }
+        for (int u = n - 1; u >= 0; u--) {
+            const int v = tp_env_pop(e, stk.data(), u);
+            if (f[u] > 0) out_pos[u] = std::min(out_pos[u], v);
+        }
+    }
+    for (int u = 0; u < n; u++) {
+        if (f[u] >= 0) continue;
+        int bn = tp_env_val<true>(f[u]);
+        for (int d = 1; d < n; d++) {
+            const int dd = d * d;
+            if (dd >= bn) break;
+            if (u - d >= 0) bn = std::min(bn, dd + tp_env_val<true>(f[u - d]));
+            if (u + d < n) bn = std::min(bn, dd + tp_env_val<true>(f[u + d]));
+        }
+        out_neg[u] = bn;
+    }
+    *depth = deepest;
+}
 }  // extern "C"

@@ -122,6 +122,15 @@ def traj_sample(T, coeff, car_seq, t):
     return st, ds, pva
 
 
+def edt_scan_line(f, segments=4):
+    """One line through the two-scan lower envelopes of k_edt_scan's schedule (edt_line.cuh): sign-packed int32 in, (pos, neg, deepest stack) out."""
+    f = np.ascontiguousarray(f, dtype=np.int32)
+    n = len(f)
+    pos, neg, depth = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32), C.c_int32(0)
+    lib().hh_edt_scan_line(_p(f, C.c_int32), n, int(segments), _p(pos, C.c_int32), _p(neg, C.c_int32), C.byref(depth))
+    return pos, neg, depth.value
+
+
 def edt_line(f, chunk=32):
     """One line through the strided EDT pass's schedule (edt_line.cuh): sign-packed int32 in, (pos, neg) out."""
     l = lib()

@@ -161,4 +161,9 @@ def test_edt_line_divide_and_conquer(n):
         for chunk in (4, 8, 32):
             got_p, got_n = hh.edt_line(packed, chunk)
             assert np.array_equal(got_p, np.minimum(exp_p, INF)) and np.array_equal(got_n, exp_n), chunk
+        # the two-scan lower envelope (thread per line on large grids) answers the same line
+        for segments in (1, 4):
+            got_p, got_n, depth = hh.edt_scan_line(packed, segments)
+            assert np.array_equal(got_p, np.minimum(exp_p, INF)) and np.array_equal(got_n, np.minimum(exp_n, INF))
+            assert depth <= max(32, (n + segments - 1) // segments + 31)
     assert hh.lib().hh_sq16(-16383) == -INF and hh.lib().hh_sq16(16383) == INF and hh.lib().hh_sq16(-5) == -25

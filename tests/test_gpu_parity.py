@@ -77,6 +77,34 @@ def test_field_ragged_and_degenerate(oracle, shape, fill):
         assert (gm.getSqDist(3)[0] == INT_MAX).all()
 
 
+@pytest.mark.parametrize("shape,fill", [((13, 10, 16), 0.05), ((37, 19, 32), 0.3), ((5, 70, 48), 0.9), ((40, 3, 128), 0.5),
+                                        ((21, 300, 80), 0.002), ((260, 9, 64), 0.6), ((6, 5, 4), 0.0), ((6, 5, 4), 1.0),
+                                        ((3, 2, 16), 0.0), ((3, 2, 16), 1.0), ((1, 1, 1), 1.0)])
+def test_field_thread_per_line_kernels(oracle, shape, fill, monkeypatch):
+    """a20: the kernels large grids take (one thread per line: k_edt_contig_thread for z lines of 16 NV cells, the two-scan
+    lower envelope k_edt_scan for the strided passes and the 2-D maps), forced onto small ragged / empty / full grids:
+    bit-identical to the oracle, and to the kernels small grids take."""
+    import topay_b200 as tp
+    res = 0.1
+    desc = tp.grid_desc(map_size=tuple((s - 0.5) * res for s in shape), resolution=res)
+    of = oracle.Field(desc)
+    rng = np.random.default_rng(sum(shape) + 1)
+    occ3 = (rng.random(shape) < fill).astype(np.int8)
+    occ2 = (rng.random(shape[:2]) < fill).astype(np.int8)
+    occ2c = (rng.random(shape[:2]) < fill).astype(np.int8)
+    of.set_occupancy(occ3, occ2, occ2c)
+    of.rebuild()
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("TOPAY_EDT_SCAN", mode)
+        gm = tp.GridMap(desc)
+        gm.loadMap(occ2, occ3, occ2c)
+        _compare_fields(gm, of)
+        got[mode] = gm._download(3)
+        gm.close()
+    assert np.array_equal(got["0"], got["1"])
+
+
 def test_rasterize_and_critical_quirk(oracle, small_scene):
     import topay_b200 as tp
     from topay_b200 import scenes

@@ -151,3 +151,74 @@ TP_HD int tp_dc_top(int len) {
     while (p < len) p <<= 1;
     return p;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Lower envelope by two scans, one thread per line (large grids: the lines of a pass outnumber the lanes of the
+// machine, so a line needs no parallelism inside it and the O(n) stack algorithm of the reference itself wins).
+// Integer form (Meijster et al.): the stack holds the parabolas of the envelope, entry k = (s_k, t_k, g_k):
+// source cell, first cell where it beats entry k - 1, its value. A new source u pops every entry it beats at
+// that entry's own start  ((t - s)^2 + g > (t - u)^2 + g_u),  then starts at
+//     w = 1 + floor((u^2 - s^2 + g_u - g) / (2 (u - s)))       (numerator >= 2 t (u - s) >= 0 after the pops)
+// if w is still inside the line. The backward scan reads the envelope off: cell u belongs to the top entry,
+// which is popped when u reaches its start. Everything is int32 (n < 2^14, values < 2^29).
+//
+// A cell is a source (value 0) of exactly one of the two transforms, and its own result for that transform is 0
+// without any search; so a scan only emits the cells that are NOT its sources, and a source strictly inside a
+// run of sources is not pushed at all (the run's end cells are at least as near to every cell outside the run).
+// With free space everywhere the negative transform's stack therefore stays a handful of entries deep.
+//
+// The top entry lives in registers (sv, tv, gv); stk[k] is written on every push.
+struct TpEnv {
+    int q, sv, tv, gv;      // q = index of the top entry, -1 = empty
+};
+struct alignas(8) TpEnvEntry {
+    unsigned st;            // s | t << 16
+    int g;
+};
+template <bool NEG>
+TP_HD int tp_env_val(int f) {                   // sign-packed cell -> its value in this transform (0 = source)
+    const int v = NEG ? -f : f;
+    return v <= 0 ? 0 : (v >= TP_INF32 ? TP_INF32 : v);
+}
+TP_HD void tp_env_load(TpEnv& e, const TpEnvEntry* stk) {
+    const TpEnvEntry w = stk[e.q];
+    e.sv = (int)(w.st & 0xffffu);
+    e.tv = (int)(w.st >> 16);
+    e.gv = w.g;
+}
+// one cell of the forward scan: value cur at cell u, prev / nxt = values of its neighbours (anything non-zero at the
+// line ends)
+TP_HD void tp_env_push(TpEnv& e, TpEnvEntry* stk, int n, int u, int cur, int prev, int nxt) {
+    if (cur >= TP_INF32 || (cur | prev | nxt) == 0) return;
+    while (e.q >= 0) {
+        const int a = e.tv - e.sv, b = e.tv - u;
+        if (a * a + e.gv <= b * b + cur) break;
+        if (--e.q >= 0) tp_env_load(e, stk);
+    }
+    if (e.q < 0) {
+        e.q = 0;
+        e.sv = u;
+        e.tv = 0;
+        e.gv = cur;
+        stk[0] = TpEnvEntry{(unsigned)u, cur};
+        return;
+    }
+    const unsigned num = (unsigned)(u * u - e.sv * e.sv + cur - e.gv), den = 2u * (unsigned)(u - e.sv);
+    const int w = 1 + (int)(num / den);
+    if (w < n) {
+        e.q++;
+        e.sv = u;
+        e.tv = w;
+        e.gv = cur;
+        stk[e.q] = TpEnvEntry{(unsigned)u | ((unsigned)w << 16), cur};
+    }
+}
+// one cell of the backward scan (u = n - 1 .. 0): the envelope's value at u (TP_INF32 = no source on the line)
+TP_HD int tp_env_pop(TpEnv& e, const TpEnvEntry* stk, int u) {
+    if (e.q < 0) return TP_INF32;
+    const int d = u - e.sv;
+    int val = d * d + e.gv;
+    val = val > TP_INF32 ? TP_INF32 : val;
+    if (u == e.tv && --e.q >= 0) tp_env_load(e, stk);
+    return val;
+}
