@@ -519,7 +519,7 @@ def main():
     ap.add_argument("--candidates", type=int, default=N_CAND, help="candidates per plan (dev only; bench = 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (dev only)")
     ap.add_argument("--no-extras", action="store_true", help="skip the latency and field sub-benchmarks")
-    ap.add_argument("--slots", type=int, default=1024,
+    ap.add_argument("--slots", type=int, default=2048,
                     help="candidates in flight on the device (continuous batching: a finished candidate's slot is "
                          "refilled from the queue of waiting plans on the device)")
     args = ap.parse_args()

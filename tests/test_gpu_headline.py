@@ -105,6 +105,37 @@ def test_pool_results_do_not_depend_on_the_slot_count(gpu_scene):
             assert np.array_equal(res[32][k], res[ns][k]), (ns, k)
 
 
+def test_two_lanes_give_the_single_lane_results(gpu_scene, monkeypatch):
+    """Large pools run their slots as two lanes (two parallel branches of the tick graph, each with its own live
+    lists, one shared queue and store). Forced onto a small pool: 32 candidates through 9 and 2 slots split into
+    lanes of 5 + 4 and 1 + 1 — every candidate's result bit-identical to the single-lane run, the gate and the
+    device-side selection included."""
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    paths, bv, ba = scenes.short_candidates(32, 11)
+    plans = [(paths[i:i + 8], bv[i:i + 8], ba[i:i + 8]) for i in range(0, 32, 8)]
+    res, win = {}, {}
+    for lanes, ns in ((1, 9), (2, 9), (2, 2)):
+        monkeypatch.setenv("TOPAY_LANE_MIN_SLOTS", "2" if lanes == 2 else "0")
+        s = tp.MomaTrajOpt(gpu_scene, max_cand=32, max_pieces=16, opt_param=opt, robot=rp, n_slots=ns)
+        res[lanes, ns] = s.optimizeTrajBatch(paths, bv, ba)
+        st = s.stats()
+        assert res[lanes, ns]["evals"].sum() <= st["slot_ticks"]
+        win[lanes, ns] = s.planWinners(plans, use_gate=True)
+        s.close()
+    for key in ((2, 9), (2, 2)):
+        for k in ("status", "lbfgs_code", "evals", "iters", "alm_rounds", "cost", "T", "coeff", "x", "final_xy_err"):
+            assert np.array_equal(res[1, 9][k], res[key][k]), (key, k)
+        for a, b in zip(win[1, 9], win[key]):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert a["index"] == b["index"]
+                for k, v in a.items():
+                    if isinstance(v, np.ndarray):
+                        assert np.array_equal(v, b[k]), (key, k)
+
+
 def test_headline_config_solve_against_the_oracle(gpu_scene, small_scene, oracle):
     """The headline workload itself: the first 4 candidates of scenes.synthetic_batch(256, 1234) at 64 pieces x
     int_K 32, solved on the device and by the oracle (= the reference, bit for bit). The solve is chaotic — the

@@ -64,6 +64,16 @@ struct topay_solver {
     // one CUDA graph per launch-grid bucket (live slots rounded up), rebuilt when max_N or a captured pointer changes
     std::map<int, cudaGraphExec_t> graphs;
     int graph_max_N;
+    // Two LANES (large pools only): the slots are split into two halves with their own live lists, and a batch runs
+    // the halves' tick chains as two parallel branches of one CUDA graph (second branch on stream2). The kernels of
+    // a tick are bound by different things (k_penalty: FP64 issue; the two-loop: HBM; the banded LU: one warp's
+    // latency chain), so one half's k_penalty overlaps the other half's k_cand. Store, queue and results are shared:
+    // which lane solves a candidate does not change its result.
+    int lanes;                  // lanes of the run in progress (1 or 2)
+    int lane_min_slots;         // two lanes from this many seeded slots on (TOPAY_LANE_MIN_SLOTS; 0 = never)
+    int32_t *list_b, *count_b;  // lane B's live lists / counts (lane A uses dev.list / dev.count)
+    cudaStream_t stream2;
+    cudaEvent_t ev_fork, ev_join;
     // success gate (topay_solver_check_feasible): built on first use
     TpTrajChecker* checker;
     int32_t* d_pn;
@@ -161,6 +171,23 @@ void drop_graphs(topay_solver* s) {
     for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second);
     s->graphs.clear();
 }
+
+// While alive, the launch helpers address lane B: its lists, its stream.
+struct TpLaneB {
+    topay_solver* s;
+    int32_t *list, *count;
+    cudaStream_t stream;
+    explicit TpLaneB(topay_solver* s_) : s(s_), list(s_->dev.list), count(s_->dev.count), stream(s_->stream) {
+        s->dev.list = s->list_b;
+        s->dev.count = s->count_b;
+        s->stream = s->stream2;
+    }
+    ~TpLaneB() {
+        s->dev.list = list;
+        s->dev.count = count;
+        s->stream = stream;
+    }
+};
 
 }  // namespace
 
@@ -262,6 +289,8 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     ALLOC(D.slot_gid, C);
     ALLOC(D.list, (size_t)(TP_TICKS + 1) * C);
     ALLOC(D.count, (size_t)TP_TICKS + 1);
+    ALLOC(s->list_b, (size_t)(TP_TICKS + 1) * C);
+    ALLOC(s->count_b, (size_t)TP_TICKS + 1);
     ALLOC(D.queue, 4);
     // slots
     ALLOC(D.st, C);
@@ -312,6 +341,11 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     cudaEventCreate(&s->ev_begin);
     cudaEventCreate(&s->ev_end);
     cudaEventCreateWithFlags(&s->ev_batch, cudaEventBlockingSync | cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
+    s->lanes = 1;
+    s->lane_min_slots = getenv("TOPAY_LANE_MIN_SLOTS") ? atoi(getenv("TOPAY_LANE_MIN_SLOTS")) : 512;
     // LU band + one right-hand-side matrix, or the two-loop's TMA ring + its two 256-entry tables + one
     // vector of scratch (single-warp variant)
     // at least six full-width stages; small solvers still get 64 KB so that short rows ride a deep ring
@@ -387,6 +421,9 @@ extern "C" void topay_solver_destroy(topay_solver* s) {
     if (s->ev_begin) cudaEventDestroy(s->ev_begin);
     if (s->ev_end) cudaEventDestroy(s->ev_end);
     if (s->ev_batch) cudaEventDestroy(s->ev_batch);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->stream2) cudaStreamDestroy(s->stream2);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -455,6 +492,16 @@ static int seed_slots(topay_solver* s) {
     s->n_slots_used = n0;
     k_slot_init<<<n0, 128, 0, s->stream>>>(D, n0, s->n_cand);
     return n0;
+}
+
+// Two lanes: slots [0, na) stay on lane A's list, slots [na, n0) move to lane B's.
+__global__ void k_lane_split(const __grid_constant__ TpSolverDev S, int32_t* list_b, int32_t* count_b, int na, int n0) {
+    for (int i = threadIdx.x; i < n0 - na; i += blockDim.x) list_b[(size_t)TP_TICKS * S.n_slots + i] = na + i;
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < TP_TICKS; t++) count_b[t] = 0;
+        count_b[TP_TICKS] = n0 - na;
+        S.count[TP_TICKS] = na;
+    }
 }
 
 extern "C" int topay_solver_eval(topay_solver* s, int stage, const topay_problem_batch* prob, const double* x,
@@ -531,7 +578,7 @@ extern "C" int topay_solver_upload(topay_solver* s, int n_cand, const int32_t* p
 
 // One batch of TP_TICKS ticks over at most `ny` live slots: roll the list, then per tick the three evaluation
 // kernels and k_cand; the live count after the batch and the queue state return through pinned memory.
-static void enqueue_batch(topay_solver* s, int ny, bool timed) {
+static void enqueue_lane(topay_solver* s, int ny, bool timed, int32_t* h_live) {
     const TpSolverDev& D = s->dev;
     cudaStream_t q = s->stream;
     k_list_roll<<<1, 1024, 0, q>>>(D);
@@ -552,9 +599,25 @@ static void enqueue_batch(topay_solver* s, int ny, bool timed) {
         launch_cand(s, TP_MODE_GEN, t, t + 1, ny);
         if (timed) cudaEventRecord(s->ev[TP_EV * t + 6], q);
     }
-    cudaMemcpyAsync(s->h_active, D.count + TP_TICKS, sizeof(int32_t), cudaMemcpyDeviceToHost, q);
-    cudaMemcpyAsync(s->h_active + 1, D.queue, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
+    cudaMemcpyAsync(h_live, D.count + TP_TICKS, sizeof(int32_t), cudaMemcpyDeviceToHost, q);
     s->stats.kernel_launches += 1;
+}
+
+static void enqueue_batch(topay_solver* s, int ny, int ny_b, bool timed) {
+    cudaStream_t q = s->stream;
+    if (s->lanes == 2) {
+        // fork: lane B's chain is a second branch of the captured graph
+        cudaEventRecord(s->ev_fork, q);
+        cudaStreamWaitEvent(s->stream2, s->ev_fork, 0);
+        {
+            TpLaneB lane_b(s);
+            enqueue_lane(s, ny_b, timed, s->h_active + 4);
+        }
+        cudaEventRecord(s->ev_join, s->stream2);
+    }
+    enqueue_lane(s, ny, timed, s->h_active);
+    if (s->lanes == 2) cudaStreamWaitEvent(q, s->ev_join, 0);
+    cudaMemcpyAsync(s->h_active + 1, s->dev.queue, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, q);
 }
 
 // Marks every candidate that is still live (or was never started) as stopped by the tick cap.
@@ -595,9 +658,16 @@ extern "C" int topay_solver_run(topay_solver* s) {
     if (D.trace) cudaMemsetAsync(D.trace_len, 0, (size_t)D.max_cand * sizeof(int32_t), q);
     cudaEventRecord(s->ev_begin, q);
     // the store holds the uploaded initial state, so repeated runs do identical work
-    int live = seed_slots(s);
+    int live = seed_slots(s), live_b = 0;
     launch_cand(s, TP_MODE_GEN, TP_TICKS, -1, live);
     s->stats.kernel_launches += 1;
+    s->lanes = (!s->timed && s->lane_min_slots > 0 && live >= s->lane_min_slots) ? 2 : 1;
+    if (s->lanes == 2) {
+        const int na = (live + 1) / 2;
+        k_lane_split<<<1, 1024, 0, q>>>(D, s->list_b, s->count_b, na, live);
+        live_b = live - na;
+        live = na;
+    }
     double ms_eval = 0.0, ms_k[3] = {0.0, 0.0, 0.0}, ms_c[3] = {0.0, 0.0, 0.0}, full_ms_cand = 0.0;
     unsigned long long hist_prev = 0, full_hist = 0;
     long long full_ticks = 0;
@@ -620,30 +690,32 @@ extern "C" int topay_solver_run(topay_solver* s) {
         s->graph_max_N = s->max_N;
     }
     while (!done && ticks < max_ticks) {
-        const int ny = grid_bucket(live);
+        const int ny = grid_bucket(live), ny_b = s->lanes == 2 ? grid_bucket(live_b) : 0;
+        const int key = ny | (ny_b << 16);
         if (use_graph) {
-            auto it = s->graphs.find(ny);
+            auto it = s->graphs.find(key);
             if (it == s->graphs.end()) {
                 cudaGraph_t g = nullptr;
                 cudaGraphExec_t ge = nullptr;
                 const topay_solver_stats keep = s->stats;
                 TP_CUDA_OK(cudaStreamBeginCapture(q, cudaStreamCaptureModeThreadLocal), {});
-                enqueue_batch(s, ny, false);
+                enqueue_batch(s, ny, ny_b, false);
                 TP_CUDA_OK(cudaStreamEndCapture(q, &g), {});
                 TP_CUDA_OK(cudaGraphInstantiate(&ge, g, 0), { cudaGraphDestroy(g); });
                 cudaGraphDestroy(g);
                 s->stats = keep;   // the capture pass launched nothing
-                it = s->graphs.emplace(ny, ge).first;
+                it = s->graphs.emplace(key, ge).first;
             }
             TP_CUDA_OK(cudaGraphLaunch(it->second, q), {});
             s->stats.kernel_launches += (ny <= s->fuse_max ? 4 : 6) * TP_TICKS + 1;
-            s->stats.eval_launches += TP_TICKS;
+            if (s->lanes == 2) s->stats.kernel_launches += (ny_b <= s->fuse_max ? 4 : 6) * TP_TICKS + 1;
+            s->stats.eval_launches += TP_TICKS * s->lanes;
         } else {
-            enqueue_batch(s, ny, true);
+            enqueue_batch(s, ny, 0, true);
             cudaMemcpyAsync(s->h_nodes, D.node_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q);
         }
         ticks += TP_TICKS;
-        slot_ticks += (long long)live * TP_TICKS;
+        slot_ticks += (long long)(live + live_b) * TP_TICKS;
         if (s->spin_sync || g_solves_running.load(std::memory_order_relaxed) <= 2) {
             TP_CUDA_OK(cudaStreamSynchronize(q), {});
         } else {
@@ -681,9 +753,14 @@ extern "C" int topay_solver_run(topay_solver* s) {
             hist_prev = hist_now;
         }
         live = live_after;
-        done = live == 0;
+        if (s->lanes == 2) live_b = s->h_active[4];
+        done = live + live_b == 0;
     }
     if (!done) {
+        if (s->lanes == 2) {
+            TpLaneB lane_b(s);
+            k_mark_tick_cap<<<(D.n_slots + 127) / 128, 128, 0, q>>>(s->dev, 0);
+        }
         k_mark_tick_cap<<<(std::max(s->n_cand, D.n_slots) + 127) / 128, 128, 0, q>>>(D, s->n_cand);
         tp_set_error("tick cap reached: unfinished candidates carry TOPAY_LBFGSERR_TICK_CAP");
     }
