@@ -658,10 +658,12 @@ def main():
         "config": base_config(n_cand),
         "details": {"scheduling": f"continuous batching: the K plans of a rank ({K} x {n_cand} candidates, distinct per "
                                   f"rank and step) are queued on the device and stream through {n_slots} candidate "
-                                  f"slots; a finished candidate's slot takes the next waiting candidate inside the kernel",
+                                  f"slots; a finished candidate's slot takes the next waiting candidate inside the kernel; pools of 512+ "
+                                  f"slots run as two lanes (two parallel branches of the tick graph) so that one half's "
+                                  f"FP64-bound penalty kernel overlaps the other half's HBM- / latency-bound L-BFGS kernels",
                     "slots": n_slots,
-                    "l2": "working set larger than L2: the L-BFGS history is 2.6 MB per slot (2.7 GB at 1024 slots, "
-                          "126 MB L2); a 512 MiB buffer is rewritten before each timed region",
+                    "l2": f"working set larger than L2: the L-BFGS history is 2.6 MB per slot ({2.6e-3 * n_slots:.1f} GB at "
+                          f"{n_slots} slots, 126 MB L2); a 512 MiB buffer is rewritten before each timed region",
                     "successes": n_ok},
         "e2e": {"value": total / dt_e2e, "unit": "trajectories/s", "h2d_bytes_per_step": h2d // K,
                 "d2h_bytes_per_step": d2h // K,
