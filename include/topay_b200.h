@@ -214,6 +214,14 @@ int topay_field_is_line_collision_grid2d(topay_field* f, const double* p1, const
  * grid) of the critical map, else of the inflated map. idx is n x 2 int32. */
 int topay_field_dist_coarse2d(topay_field* f, const double* pos, int64_t n, int critical, double* out);
 int topay_field_dist_coarse2i(topay_field* f, const int32_t* idx, int64_t n, int critical, double* out);
+/* TopologyPRM::lineVisib (src/planner/src/topo_prm.cpp:278-315) on n segments p1 -> p2 (both n x 3, z is
+ * carried through the ray walk as in the reference): the planner's RayCaster (src/planner/src/utils/raycast.cpp:
+ * 253-346) steps through the cells from p1 / res to p2 / res, every cell but the end cell is looked up through
+ * getDistCoarse2i in the inflated (use_critical = 0) or critical map; visible[i] = 0 when a cell at or below `thresh`
+ * blocks the ray, and pc[i] (n x 3, in/out) then holds the midpoint of that cell's centre and the previous
+ * cell's, z = 0; pc of a visible segment is left as passed in. Front-end row N2 of SURVEY.md §8f. */
+int topay_field_line_visible(topay_field* f, const double* p1, const double* p2, int64_t n, double thresh,
+                             int use_critical, int8_t* visible, double* pc);
 /* Same queries with DEVICE pointers (inputs and outputs already in HBM), asynchronous
  * on the field's stream; used by the resident benchmark and by the solver. */
 int topay_field_query3d_dev(topay_field* f, const double* pos_dev, int64_t n, double* dist_dev,
@@ -432,6 +440,14 @@ int topay_solver_eval(topay_solver* s, int stage, const topay_problem_batch* pro
 
 /* Number of optimisation variables of an N-piece candidate: 9(N-1)+N+1. */
 static inline int topay_num_vars(int piece_num) { return 10 * piece_num - 8; }
+
+/* GraphSearch::getDensePath (src/planner/src/graph_search.cpp:119-176; called by every planning worker right
+ * before the sampler and the solve, planner.cpp:858): raw 2-D waypoints (n x 2) -> rows (x, y, theta, dt): every
+ * segment cut into ceil(len / step_size) steps, a turn-in-place row before and after every move, yaw unwrapped
+ * against the previous row, rows shorter than 1e-3 s dropped. Host arithmetic. Writes at most `cap` rows to out
+ * (cap x 4) and returns the number of rows the path has (> cap: call again), or a negative TOPAY_ERR_*. */
+int topay_dense_path(const double* raw_xy, int n, double step_size, double start_yaw, double end_yaw, double v_max,
+                     double w_max, double* out, int cap);
 
 /* MomaTrajOpt::optimizeTraj pre-processing (moma_traj_opt.cpp:146-344): waypoints ->
  * problem data + initial x. Host-side helper of solve_batch, exported for parity

@@ -7,6 +7,7 @@
 #include <thread>
 
 #include "oracle_field.hpp"
+#include "oracle_front.hpp"
 #include "oracle_robot.hpp"
 #include "oracle_rog.hpp"
 #include "oracle_solve.hpp"
@@ -501,4 +502,19 @@ void oracle_prob_download(void* h, float* occ, int32_t* origin_i) {
 void oracle_prob_size(void* h, int32_t* size) {
     for (int i = 0; i < 3; i++) size[i] = ((RogProb*)h)->size[i];
 }
+
+// ------------------------------------------------------------------ front-end pieces (row N2)
+int oracle_dense_path(const double* raw_xy, int n, double step_size, double start_yaw, double end_yaw, double v_max,
+                      double w_max, double* out, int cap) {
+    const auto r = dense_path(raw_xy, n, step_size, start_yaw, end_yaw, v_max, w_max);
+    for (size_t i = 0; i < r.size() && (int)i < cap; i++)
+        for (int k = 0; k < 4; k++) out[4 * i + k] = r[i][k];
+    return (int)r.size();
+}
+void oracle_line_visib(void* h, const double* p1, const double* p2, int64_t n, double thresh, int use_critical,
+                       int8_t* visible, double* pc) {
+    const Field* f = (const Field*)h;
+    for (int64_t i = 0; i < n; i++) visible[i] = line_visib(*f, p1 + 3 * i, p2 + 3 * i, thresh, use_critical != 0, pc + 3 * i) ? 1 : 0;
+}
+
 }  // extern "C"

@@ -8,6 +8,9 @@
 //   src/map/src/grid_map.cpp + include/map/grid_map.h                     GridMap (cloudCallback rasterisation,
 //                                                                         updateESDF / fillESDF, all lookups)
 //   src/simulator/random_map_generator/src/random_map_generator.cpp      (GridMap owns one; never called here)
+//   src/planner/src/graph_search.cpp, src/planner/src/topo_prm.cpp,       front-end pieces next to the solve (row N2):
+//   src/planner/src/utils/raycast.cpp                                     GraphSearch::getDensePath,
+//                                                                         TopologyPRM::lineVisib over RayCaster
 // against the Eigen / ROS / PCL / boost stand-ins of oracle/ref_stubs. rog_map is not compiled: GridMap runs
 // with `use_rog: false` (params/grid_map.yaml:3). `#define private public` below only opens the classes to
 // this driver (problem set-up for single evaluations, buffer downloads); the reference's translation units
@@ -39,6 +42,9 @@
 #define private public
 #define protected public
 #include "planner/moma_traj_opt.h"
+#include <list>
+#include "planner/graph_search.h"
+#include "planner/topo_prm.h"
 #undef private
 #undef protected
 
@@ -396,6 +402,39 @@ int ref_solve_batch(void* grid, const topay_opt_params* p, int n_cand, const int
     for (int t = 0; t < std::max(1, n_threads); t++) th.emplace_back(worker);
     for (auto& t : th) t.join();
     return 0;
+}
+
+
+// ------------------------------------------------------------------ front-end pieces (row N2)
+// GraphSearch::getDensePath (graph_search.cpp:119-176); out rows (x, y, theta, dt); returns the row count
+int ref_dense_path(void* grid, const double* raw_xy, int n, double step_size, double start_yaw, double end_yaw,
+                   double v_max, double w_max, double* out, int cap) {
+    Quiet q;
+    JPS::GraphSearch gs(((RefGrid*)grid)->gm, 0.0);
+    std::vector<Eigen::Vector2d> raw;
+    for (int i = 0; i < n; i++) raw.push_back(Eigen::Vector2d(raw_xy[2 * i], raw_xy[2 * i + 1]));
+    const std::vector<Eigen::Vector4d> r = gs.getDensePath(raw, step_size, start_yaw, end_yaw, v_max, w_max);
+    for (size_t i = 0; i < r.size() && (int)i < cap; i++)
+        for (int k = 0; k < 4; k++) out[4 * i + k] = r[i](k);
+    return (int)r.size();
+}
+// TopologyPRM::lineVisib (topo_prm.cpp:278-315) on n segments; visible[i], pc[i] (untouched when visible)
+void ref_line_visib(void* grid, const double* p1, const double* p2, int64_t n, double thresh, int use_critical,
+                    int8_t* visible, double* pc) {
+    Quiet q;
+    auto& P = ros::stub_params();
+    P["topo_prm/max_raw_path"] = {1.0};
+    ros::NodeHandle nh;
+    nmoma_planner::TopologyPRM prm;
+    prm.grid_map_ptr = ((RefGrid*)grid)->gm;
+    prm.init(nh);
+    prm.use_critical = use_critical != 0;
+    for (int64_t i = 0; i < n; i++) {
+        Eigen::Vector3d a(p1[3 * i], p1[3 * i + 1], p1[3 * i + 2]), b(p2[3 * i], p2[3 * i + 1], p2[3 * i + 2]), c;
+        c << pc[3 * i], pc[3 * i + 1], pc[3 * i + 2];
+        visible[i] = prm.lineVisib(a, b, thresh, c, 0) ? 1 : 0;
+        for (int k = 0; k < 3; k++) pc[3 * i + k] = c(k);
+    }
 }
 
 }  // extern "C"

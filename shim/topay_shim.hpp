@@ -11,6 +11,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "../include/topay_b200.h"
@@ -172,6 +173,19 @@ public:
         topay_check(topay_field_dist_coarse2i(f_, i2, 1, critical, &d), "topay_field_dist_coarse2i");
         return d;
     }
+    // TopologyPRM::lineVisib (topo_prm.cpp:278-315; the PRM's guard / connection / shortcut visibility test) on this
+    // field: single segment, and the batched form (one launch for all rays of a roadmap pass)
+    template <class V3> bool lineVisib(const V3& p1, const V3& p2, double thresh, V3& pc, bool use_critical = false) {
+        double a[3] = {p1[0], p1[1], p1[2]}, b[3] = {p2[0], p2[1], p2[2]}, c[3] = {pc[0], pc[1], pc[2]};
+        int8_t vis = 0;
+        topay_check(topay_field_line_visible(f_, a, b, 1, thresh, use_critical, &vis, c), "topay_field_line_visible");
+        pc[0] = c[0]; pc[1] = c[1]; pc[2] = c[2];
+        return vis != 0;
+    }
+    void lineVisibBatch(const double* p1, const double* p2, int64_t n, double thresh, bool use_critical, int8_t* visible,
+                        double* pc) {
+        topay_check(topay_field_line_visible(f_, p1, p2, n, thresh, use_critical, visible, pc), "topay_field_line_visible");
+    }
     // batched forms for the front-end (one launch for many samples)
     void isWholeBodyCollisionBatch(const double* states, int64_t n, int8_t* out) {
         topay_robot_params rp;
@@ -217,6 +231,32 @@ private:
     topay_field* f_ = nullptr;
     bool map_ready_ = false;
 };
+
+// JPS::GraphSearch::getDensePath (graph_search.cpp:119-176): rows (x, y, theta, dt) as std::array<double, 4>.
+namespace JPS {
+struct GraphSearch {
+    template <class V2>
+    static std::vector<std::array<double, 4>> getDensePath(const std::vector<V2>& raw_path, double step_size,
+                                                           double start_yaw, double end_yaw, double v_max,
+                                                           double w_max) {
+        std::vector<double> raw;
+        for (const auto& p : raw_path) {
+            raw.push_back(p[0]);
+            raw.push_back(p[1]);
+        }
+        std::vector<std::array<double, 4>> out(64);
+        for (;;) {
+            const int n = topay_dense_path(raw.data(), (int)raw_path.size(), step_size, start_yaw, end_yaw, v_max, w_max,
+                                           &out[0][0], (int)out.size());
+            if (n < 0) topay_check(n, "topay_dense_path");
+            const bool fits = n <= (int)out.size();
+            out.resize(n);
+            if (fits) return out;
+        }
+    }
+};
+}  // namespace JPS
+
 
 class MomaTrajOpt {
 public:

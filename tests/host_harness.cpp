@@ -56,6 +56,11 @@ void hh_query2d(const TpGrid* g, int which, const double* pos, int64_t n, double
     for (int64_t i = 0; i < n; i++) tp_query2d(*g, buf, pos + 2 * i, dist[i], grad + 2 * i);
 }
 
+void hh_line_visib(const TpGrid* g, const double* p1, const double* p2, int64_t n, double thresh, int critical,
+                   int8_t* visible, double* pc) {
+    for (int64_t i = 0; i < n; i++) visible[i] = tp_line_visib(*g, p1 + 3 * i, p2 + 3 * i, thresh, critical != 0, pc + 3 * i) ? 1 : 0;
+}
+
 void hh_fk(const TpParams* P, const double* pos10, double* pts36) {
     TpFK fk;
     TpSphereStoreLocal pts;

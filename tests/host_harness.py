@@ -47,6 +47,13 @@ class Harness:
         self.l.hh_query2d(self.G, which, _p(pos), C.c_int64(len(pos)), _p(d), _p(g))
         return d, g
 
+    def line_visib(self, p1, p2, thresh, critical=False):
+        p1, p2 = np.ascontiguousarray(p1, dtype=np.float64), np.ascontiguousarray(p2, dtype=np.float64)
+        n = len(p1)
+        vis, pc = np.zeros(n, dtype=np.int8), np.full((n, 3), np.nan)
+        self.l.hh_line_visib(self.G, _p(p1), _p(p2), C.c_int64(n), C.c_double(thresh), int(critical), _p(vis, C.c_int8), _p(pc))
+        return vis.astype(bool), pc
+
     def fk(self, pos10):
         pos10 = np.ascontiguousarray(pos10, dtype=np.float64)
         out = np.zeros((12, 3))

@@ -67,6 +67,17 @@ def opt_defaults():
     return o
 
 
+def dense_path(raw_xy, step_size, start_yaw, end_yaw, v_max, w_max):
+    """graph_search.cpp:119-176: rows (x, y, theta, dt)."""
+    raw = _f64(raw_xy)
+    cap = 16 * len(raw) + int(np.abs(np.diff(raw, axis=0)).sum() / step_size * 4) + 64
+    out = np.zeros((cap, 4))
+    n = lib().oracle_dense_path(_p(raw), len(raw), C.c_double(step_size), C.c_double(start_yaw), C.c_double(end_yaw),
+                                C.c_double(v_max), C.c_double(w_max), _p(out), cap)
+    assert n <= cap
+    return out[:n]
+
+
 class Field:
     def __init__(self, desc: GridDesc):
         self.h = C.c_void_p(lib().oracle_field_create(C.byref(desc)))
@@ -92,6 +103,15 @@ class Field:
 
     def rebuild(self):
         lib().oracle_field_rebuild(self.h)
+
+    def line_visib(self, p1, p2, thresh, use_critical=False):
+        """topo_prm.cpp:278-315 on n segments: (visible, pc); pc = nan where visible."""
+        p1, p2 = _f64(p1), _f64(p2)
+        n = len(p1)
+        vis, pc = np.zeros(n, dtype=np.int8), np.full((n, 3), np.nan)
+        lib().oracle_line_visib(self.h, _p(p1), _p(p2), C.c_int64(n), C.c_double(thresh), int(use_critical),
+                                _p(vis, C.c_int8), _p(pc))
+        return vis.astype(bool), pc
 
     def query3d(self, pos):
         pos = _f64(pos)

@@ -171,6 +171,26 @@ class GridMap:
         return out.astype(bool)
 
 
+def dense_path(grid, raw_xy, step_size, start_yaw, end_yaw, v_max, w_max):
+    """GraphSearch::getDensePath of the compiled reference: rows (x, y, theta, dt)."""
+    raw = _f64(raw_xy)
+    cap = 16 * len(raw) + int(np.abs(np.diff(raw, axis=0)).sum() / step_size * 4) + 64
+    out = np.zeros((cap, 4))
+    n = lib().ref_dense_path(grid.h, _p(raw), len(raw), C.c_double(step_size), C.c_double(start_yaw), C.c_double(end_yaw),
+                             C.c_double(v_max), C.c_double(w_max), _p(out), cap)
+    assert n <= cap
+    return out[:n]
+
+
+def line_visib(grid, p1, p2, thresh, use_critical=False):
+    """TopologyPRM::lineVisib of the compiled reference on n segments: (visible, pc); pc = nan where visible."""
+    p1, p2 = _f64(p1), _f64(p2)
+    n = len(p1)
+    vis, pc = np.zeros(n, dtype=np.int8), np.full((n, 3), np.nan)
+    lib().ref_line_visib(grid.h, _p(p1), _p(p2), C.c_int64(n), C.c_double(thresh), int(use_critical), _p(vis, C.c_int8), _p(pc))
+    return vis.astype(bool), pc
+
+
 class MomaTrajOpt:
     """nmoma_planner::MomaTrajOpt (src/planner), parameters taken from a topay_opt_params."""
 

@@ -158,3 +158,34 @@ def test_plain_c_caller_links_and_runs(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     assert "select_shortest -> 2" in out.stdout
     assert ("no CUDA device" in out.stdout) or ("status 1" in out.stdout)
+
+
+def test_dense_path_matches_the_oracle(oracle):
+    """N2: topay_dense_path (host arithmetic, no GPU) against the oracle (= the reference's getDensePath bit for bit,
+    test_ref_pin.py::test_dense_path_bit_exact): ragged polylines, short and zero-length segments, straight
+    continuations, a capacity too small for the path, bad arguments."""
+    import topay_b200 as tp
+    rng = np.random.default_rng(15)
+    for i in range(80):
+        k = int(rng.integers(2, 8))
+        raw = rng.uniform(-9, 9, (k, 2))
+        if i % 4 == 0:
+            raw[1] = raw[0] + np.array([0.2, 0.1])
+        if i % 6 == 0 and k > 2:
+            raw[2] = raw[1] + (raw[1] - raw[0])
+        if i % 9 == 0 and k > 2:
+            raw[2] = raw[1]
+        y0, y1 = rng.uniform(-np.pi, np.pi, 2)
+        for step in (1.414, 0.3):
+            a = tp.getDensePath(raw, step, y0, y1, 1.0, 1.25)
+            b = oracle.dense_path(raw, step, y0, y1, 1.0, 1.25)
+            assert a.shape == b.shape and np.array_equal(a, b), (i, step)
+    from topay_b200 import _lib
+    import ctypes as C
+    raw = np.array([[0.0, 0.0], [5.0, 0.0]])
+    out = np.zeros((2, 4))
+    dp = C.POINTER(C.c_double)
+    n = _lib.lib().topay_dense_path(raw.ctypes.data_as(dp), 2, 1.0, 0.0, 0.0, 1.0, 1.0, out.ctypes.data_as(dp), 2)
+    assert n == len(tp.getDensePath(raw, 1.0, 0.0, 0.0, 1.0, 1.0)) > 2
+    assert _lib.lib().topay_dense_path(raw.ctypes.data_as(dp), 1, 1.0, 0.0, 0.0, 1.0, 1.0, out.ctypes.data_as(dp), 2) < 0
+    assert _lib.lib().topay_dense_path(raw.ctypes.data_as(dp), 2, 0.0, 0.0, 0.0, 1.0, 1.0, out.ctypes.data_as(dp), 2) < 0

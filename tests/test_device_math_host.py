@@ -114,6 +114,22 @@ def test_field_predicates_bit_exact(oracle, small_scene, harness):
         assert np.array_equal(cd, f.dist_coarse2d(p2, crit)) and np.array_equal(ci, f.dist_coarse2i(idx, crit))
 
 
+def test_line_visibility_ray_bit_exact(oracle, small_scene, harness):
+    """N2: tp_line_visib (field_query.cuh; TopologyPRM::lineVisib over the planner's RayCaster) instantiated on the CPU
+    against the oracle: verdicts and blocking points of segments across the scene, ends outside the map, degenerate rays."""
+    f = small_scene["field"]
+    rng = np.random.default_rng(9)
+    n = 6000
+    p1 = np.concatenate([rng.uniform(-9.8, 9.8, (n, 2)), np.zeros((n, 1))], axis=1)
+    p2 = p1 + np.concatenate([rng.normal(size=(n, 2)) * rng.choice([0.05, 0.5, 4.0], (n, 1)), np.zeros((n, 1))], axis=1)
+    p2[::40] = p1[::40]
+    p2[1::40, :2] *= 1.3
+    for thr, crit in ((0.0, False), (0.25, True)):
+        va, pa = harness.line_visib(p1, p2, thr, crit)
+        vb, pb = f.line_visib(p1, p2, thr, crit)
+        assert np.array_equal(va, vb) and np.array_equal(pa[~va], pb[~vb]) and np.isnan(pa[va]).all()
+
+
 def test_traj_evaluation_bit_exact(oracle):
     """traj.cuh (locatePieceIdx, Piece::getPos/getVel/getAcc, MomaTraj::getState/getDState) on the CPU against
     the oracle, fed with the oracle's pose table."""

@@ -345,6 +345,27 @@ def test_front_end_predicates_and_coarse_lookups(gpu_scene, small_scene):
         assert np.array_equal(gpu_scene.getDistCoarse2i(idx, crit), of.dist_coarse2i(idx, crit))
 
 
+def test_line_visibility_rays(gpu_scene, small_scene):
+    """N2: TopologyPRM::lineVisib on the device (topay_field_line_visible) — verdict and blocking point of 20 000
+    segments (long, short, degenerate, leaving the map) against the oracle (= the reference's lineVisib over its own
+    RayCaster, test_ref_pin.py::test_line_visib_bit_exact), inflated and critical map: bit-identical."""
+    of = small_scene["field"]
+    rng = np.random.default_rng(21)
+    n = 20000
+    p1 = np.concatenate([rng.uniform(-9.8, 9.8, (n, 2)), np.zeros((n, 1))], axis=1)
+    p2 = p1 + np.concatenate([rng.normal(size=(n, 2)) * rng.choice([0.05, 0.5, 4.0], (n, 1)), np.zeros((n, 1))], axis=1)
+    p2[::40] = p1[::40]
+    p2[1::40, :2] *= 1.3          # some ends outside the map (cells clamped by getDistCoarse2i)
+    for crit in (False, True):
+        for thresh in (0.0, 0.25):
+            vg, pg = gpu_scene.lineVisib(p1, p2, thresh, crit)
+            vo, po = of.line_visib(p1, p2, thresh, crit)
+            assert np.array_equal(vg, vo)
+            assert np.array_equal(pg[~vg], po[~vo])
+            assert np.isnan(pg[vg]).all()
+    assert 0.05 < vg.mean() < 0.98
+
+
 def test_solvers_of_different_capacity_coexist(gpu_scene):
     """Kernel attributes (dynamic shared memory) are per kernel, not per solver: a small solver created after a
     large one must not break the large one, and results do not depend on what else was created."""

@@ -181,6 +181,49 @@ def test_gridmap_queries_bit_exact(oracle, small_scene, ref_scene):
     assert np.array_equal(ref_scene.whole_body_collision(st), of.whole_body_collision(rp, st))
 
 
+def _front_cases(rng, n):
+    """Polylines as the topological front end produces them: 2-6 waypoints inside the 20 m map."""
+    out = []
+    for i in range(n):
+        k = int(rng.integers(2, 7))
+        raw = rng.uniform(-8.5, 8.5, (k, 2))
+        if i % 5 == 0:
+            raw[1] = raw[0] + np.array([0.3, 0.0])          # a segment shorter than one step
+        if i % 7 == 0 and k > 2:
+            raw[2] = raw[1] + (raw[1] - raw[0])               # a straight continuation (zero turn: dropped rows)
+        out.append((raw, rng.uniform(-np.pi, np.pi), rng.uniform(-np.pi, np.pi)))
+    return out
+
+
+def test_dense_path_bit_exact(oracle, ref_scene):
+    """N2: GraphSearch::getDensePath (graph_search.cpp:119-176) — segment subdivision, turn-in-place rows, angle
+    unwrapping against the previous row, the 1e-3 s filter — row count and every (x, y, theta, dt) bit for bit."""
+    rng = np.random.default_rng(5)
+    for raw, y0, y1 in _front_cases(rng, 60):
+        for step in (1.414, 0.5):
+            a = R.dense_path(ref_scene, raw, step, y0, y1, 1.0, 1.25)
+            b = oracle.dense_path(raw, step, y0, y1, 1.0, 1.25)
+            assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_line_visib_bit_exact(oracle, small_scene, ref_scene):
+    """N2: TopologyPRM::lineVisib (topo_prm.cpp:278-315) over the planner's RayCaster (raycast.cpp:253-346): verdict and
+    blocking point of 4000 segments across the cuboids scene, inflated and critical map, several clearances."""
+    of = small_scene["field"]
+    rng = np.random.default_rng(6)
+    p1 = np.concatenate([rng.uniform(-9.5, 9.5, (4000, 2)), np.zeros((4000, 1))], axis=1)
+    p2 = p1 + np.concatenate([rng.normal(size=(4000, 2)) * rng.choice([0.05, 0.5, 3.0], (4000, 1)), np.zeros((4000, 1))], axis=1)
+    p2[:, :2] = np.clip(p2[:, :2], -9.9, 9.9)
+    p2[::50] = p1[::50]                     # degenerate rays (setInput returns false)
+    for crit in (False, True):
+        for thresh in (0.0, 0.1, 0.3):
+            va, pa = R.line_visib(ref_scene, p1, p2, thresh, crit)
+            vb, pb = of.line_visib(p1, p2, thresh, crit)
+            assert np.array_equal(va, vb)
+            assert np.array_equal(pa[~va], pb[~vb])
+            assert 0.05 < va.mean() < 0.98
+
+
 @pytest.mark.parametrize("int_K,pieces", [(12, 0), (5, 0), (32, 64)])
 def test_cost_callbacks_bit_exact(oracle, small_scene, ref_scene, int_K, pieces):
     """a2, a6, a7, a12: first/secondStageCostCallback (moma_traj_opt.cpp:817-955) = generate + jerk + the penalty loops

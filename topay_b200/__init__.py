@@ -8,8 +8,8 @@ from ._structs import (MAP2D_CRITICAL, MAP2D_FLAT, MAP2D_INFLATE, MAP3D, TERM_NA
                        RobotParams, RogDesc, grid_desc, num_vars, prob_desc, rog_desc)
 from .field import GridMap, robot_params_default
 from .rog import ESDFMap, ProbMap
-from .optimizer import MomaTraj, MomaTrajOpt, opt_params_default, prepare_candidate
+from .optimizer import MomaTraj, MomaTrajOpt, getDensePath, opt_params_default, prepare_candidate
 
 __all__ = ["GridMap", "ESDFMap", "ProbMap", "prob_desc", "rog_desc", "RogDesc", "MomaTrajOpt", "MomaTraj", "grid_desc", "GridDesc", "OptParams", "RobotParams",
-           "robot_params_default", "opt_params_default", "prepare_candidate", "num_vars", "TERM_NAMES",
+           "robot_params_default", "opt_params_default", "prepare_candidate", "getDensePath", "num_vars", "TERM_NAMES",
            "MAP2D_FLAT", "MAP2D_INFLATE", "MAP2D_CRITICAL", "MAP3D"]

@@ -58,6 +58,9 @@ PROTOTYPES = {
     "topay_field_is_collision3d": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_double, _i8p]),
     "topay_field_is_line_collision_grid2d": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_double, _i8p]),
     "topay_field_dist_coarse2d": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int, _dp]),
+    "topay_field_line_visible": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_double, C.c_int, _i8p, _dp]),
+    "topay_dense_path": (C.c_int, [_dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _dp,
+                                   C.c_int]),
     "topay_field_dist_coarse2i": (C.c_int, [C.c_void_p, _ip, C.c_int64, C.c_int, _dp]),
     "topay_field_query3d_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "topay_field_sync": (C.c_int, [C.c_void_p]),

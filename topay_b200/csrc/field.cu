@@ -660,6 +660,19 @@ __global__ void k_field_misc(TpGrid g, int kind, const double* __restrict__ a, c
     }
 }
 
+// TopologyPRM::lineVisib (topo_prm.cpp:278-315), one thread per segment.
+__global__ void k_line_visib(TpGrid g, const double* __restrict__ p1, const double* __restrict__ p2, int64_t n,
+                             double thresh, int critical, int8_t* visible, double* pc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a[3] = {p1[3 * i], p1[3 * i + 1], p1[3 * i + 2]}, b[3] = {p2[3 * i], p2[3 * i + 1], p2[3 * i + 2]};
+    double c[3] = {pc[3 * i], pc[3 * i + 1], pc[3 * i + 2]};
+    visible[i] = tp_line_visib(g, a, b, thresh, critical != 0, c) ? 1 : 0;
+    pc[3 * i] = c[0];
+    pc[3 * i + 1] = c[1];
+    pc[3 * i + 2] = c[2];
+}
+
 // GridMap::isWholeBodyCollision (grid_map.h:613-650), one thread per 10-D state.
 __global__ void k_whole_body(TpGrid g, TpParams P, const double* __restrict__ states, int64_t n, int8_t* out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1169,6 +1182,33 @@ extern "C" int topay_field_dist_coarse2d(topay_field* f, const double* pos, int6
 }
 extern "C" int topay_field_dist_coarse2i(topay_field* f, const int32_t* idx, int64_t n, int critical, double* out) {
     return field_misc(f, 4, nullptr, 2, nullptr, idx, n, 0.0, critical, nullptr, out);
+}
+
+extern "C" int topay_field_line_visible(topay_field* f, const double* p1, const double* p2, int64_t n, double thresh,
+                                        int use_critical, int8_t* visible, double* pc) {
+    if (!f || n < 0 || (n > 0 && (!p1 || !p2 || !visible || !pc))) return TOPAY_ERR_INVALID_ARG;
+    if (!f->ready) {
+        tp_set_error("field queried before topay_field_rebuild");
+        return TOPAY_ERR_NOT_READY;
+    }
+    if (n == 0) return TOPAY_OK;
+    cudaSetDevice(f->device);
+    const size_t bp = (size_t)n * 3 * 8;
+    char* d = nullptr;
+    TP_CUDA_OK(cudaMalloc(&d, 3 * bp + (size_t)n + 64), {});
+    double *d1 = (double*)d, *d2 = (double*)(d + bp), *dc = (double*)(d + 2 * bp);
+    int8_t* dv = (int8_t*)(d + 3 * bp);
+    cudaMemcpyAsync(d1, p1, bp, cudaMemcpyHostToDevice, f->stream);
+    cudaMemcpyAsync(d2, p2, bp, cudaMemcpyHostToDevice, f->stream);
+    cudaMemcpyAsync(dc, pc, bp, cudaMemcpyHostToDevice, f->stream);      // pc of a visible segment stays as passed in
+    k_line_visib<<<(unsigned)((n + 127) / 128), 128, 0, f->stream>>>(f->grid, d1, d2, n, thresh, use_critical, dv, dc);
+    cudaMemcpyAsync(visible, dv, (size_t)n, cudaMemcpyDeviceToHost, f->stream);
+    cudaMemcpyAsync(pc, dc, bp, cudaMemcpyDeviceToHost, f->stream);
+    cudaError_t e = cudaStreamSynchronize(f->stream);
+    cudaFree(d);
+    TP_CUDA_OK(e, {});
+    TP_CUDA_OK(cudaGetLastError(), {});
+    return TOPAY_OK;
 }
 
 extern "C" int topay_field_download(topay_field* f, int which, double* esdf_out) {

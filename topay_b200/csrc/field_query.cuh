@@ -154,3 +154,77 @@ TP_HD bool tp_line_collision_grid2d(const TpGrid& g, const double* p1, const dou
     }
     return false;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Front-end visibility ray (row N2): TopologyPRM::lineVisib (src/planner/src/topo_prm.cpp:278-315) over the planner's
+// RayCaster (src/planner/src/utils/raycast.cpp:27-45 signum / mod / intbound, :253-299 setInput, :301-346 step) — an
+// Amanatides & Woo walk in cell units from p1 / res to p2 / res; every cell but the end cell is looked up in the
+// inflated (or critical) 2-D map through getDistCoarse2i; the first cell at or below `thresh` blocks the ray and
+// pc = midpoint of that cell's centre and the previous cell's (z = 0). Divisions, fmod and floor are exact on both
+// sides; the two multiply-adds of indexToPos3d are kept un-contracted, so verdict and pc are bit-identical.
+// The walk is capped at the Manhattan cell distance + 2 steps (a ray that steps past its end cell loops for ever in
+// the reference; stated deviation).
+#if defined(__CUDA_ARCH__)
+#define TP_FQ_MUL(a, b) __dmul_rn((a), (b))
+#define TP_FQ_ADD(a, b) __dadd_rn((a), (b))
+#else
+#define TP_FQ_MUL(a, b) ((a) * (b))
+#define TP_FQ_ADD(a, b) ((a) + (b))
+#endif
+TP_HD int tp_signum(int v) { return v == 0 ? 0 : (v < 0 ? -1 : 1); }
+TP_HD double tp_intbound(double s, double ds) {
+    if (ds < 0) {
+        s = -s;
+        ds = -ds;
+    }
+    s = fmod(fmod(s, 1.0) + 1.0, 1.0);
+    return (1 - s) / ds;
+}
+TP_HD bool tp_line_visib(const TpGrid& g, const double* p1, const double* p2, double thresh, bool critical, double* pc) {
+    const double res = g.resolution;
+    double s[3], e[3], off[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        s[i] = p1[i] / res;
+        e[i] = p2[i] / res;
+    }
+    off[0] = 0.5 - g.origin[0] / res;
+    off[1] = 0.5 - g.origin[1] / res;
+    int c[3], en[3], st[3];
+    double tm[3], td[3];
+    long budget = 2;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        c[i] = (int)floor(s[i]);
+        en[i] = (int)floor(e[i]);
+        const double d = en[i] - c[i];
+        st[i] = tp_signum((int)d);
+        tm[i] = tp_intbound(s[i], d);
+        td[i] = ((double)st[i]) / d;
+        budget += en[i] > c[i] ? en[i] - c[i] : c[i] - en[i];
+    }
+    if (st[0] == 0 && st[1] == 0 && st[2] == 0) return true;
+    int prev[2] = {c[0], c[1]};
+    while (budget-- > 0) {
+        if (c[0] == en[0] && c[1] == en[1] && c[2] == en[2]) return true;
+        const int id[2] = {(int)(c[0] + off[0]), (int)(c[1] + off[1])};     // double -> int truncation, as the reference
+        if (tp_dist_coarse2i(g, id[0], id[1], critical) <= thresh) {
+            const double ax = TP_FQ_ADD(TP_FQ_MUL(id[0] + 0.5, res), g.origin[0]);
+            const double ay = TP_FQ_ADD(TP_FQ_MUL(id[1] + 0.5, res), g.origin[1]);
+            const double bx = TP_FQ_ADD(TP_FQ_MUL(prev[0] + 0.5, res), g.origin[0]);
+            const double by = TP_FQ_ADD(TP_FQ_MUL(prev[1] + 0.5, res), g.origin[1]);
+            pc[0] = TP_FQ_MUL(0.5, TP_FQ_ADD(ax, bx));
+            pc[1] = TP_FQ_MUL(0.5, TP_FQ_ADD(ay, by));
+            pc[2] = 0.0;
+            return false;
+        }
+        prev[0] = id[0];
+        prev[1] = id[1];
+        if (tm[0] < tm[1]) {
+            if (tm[0] < tm[2]) { c[0] += st[0]; tm[0] += td[0]; } else { c[2] += st[2]; tm[2] += td[2]; }
+        } else {
+            if (tm[1] < tm[2]) { c[1] += st[1]; tm[1] += td[1]; } else { c[2] += st[2]; tm[2] += td[2]; }
+        }
+    }
+    return true;
+}

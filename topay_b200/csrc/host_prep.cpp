@@ -316,3 +316,100 @@ extern "C" void topay_opt_params_default(topay_opt_params* o) {
     o->alm_tolerance = 0.01;
     o->alm_max_rounds = 20;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// GraphSearch::getDensePath (src/planner/src/graph_search.cpp:119-176, normalizeAngle :6-13). Two passes over the
+// waypoints instead of the reference's three vectors: rows are produced in order and filtered on the fly (a row's
+// dt is final once the next row has been started). Same operations on the same operands, so the rows are
+// bit-identical.
+namespace {
+struct DenseRows {
+    double* out;
+    int cap, count;
+    double cur[4];
+    bool has;
+    void flush(bool last) {
+        if (!has) return;
+        if (last || cur[3] > 1.0e-3) {
+            if (count < cap) memcpy(out + 4 * (size_t)count, cur, sizeof(cur));
+            count++;
+        }
+    }
+    void start(double x, double y, double th) {
+        flush(false);
+        cur[0] = x; cur[1] = y; cur[2] = th; cur[3] = 0.0;
+        has = true;
+    }
+};
+inline void unwrap(double ref, double& a) {
+    while (ref - a > M_PI) a += 2 * M_PI;
+    while (ref - a < -M_PI) a -= 2 * M_PI;
+}
+}  // namespace
+
+extern "C" int topay_dense_path(const double* raw, int n, double step_size, double start_yaw, double end_yaw,
+                                double v_max, double w_max, double* out, int cap) {
+    if (!raw || n < 2 || !(step_size > 0.0) || !(v_max > 0.0) || !(w_max > 0.0) || cap < 0 || (cap > 0 && !out))
+        return TOPAY_ERR_INVALID_ARG;
+    // the dense polyline, point by point
+    struct Walker {
+        const double* raw;
+        int n, i, j, times;
+        double step, dx, dy, step_size;
+        void segment() {
+            const double ex = raw[2 * i] - raw[2 * i - 2], ey = raw[2 * i + 1] - raw[2 * i - 1];
+            const double z = ex * ex + ey * ey, len = sqrt(z);
+            dx = ex;
+            dy = ey;
+            if (z > 0.0) {
+                dx = ex / len;
+                dy = ey / len;
+            }
+            times = (int)std::max(ceil(len / step_size), 1.0);
+            step = len / times;
+            j = 1;
+        }
+        bool next(double* p) {          // false after the last point
+            if (i >= n) return false;
+            p[0] = raw[2 * i - 2] + (step * j) * dx;
+            p[1] = raw[2 * i - 1] + (step * j) * dy;
+            if (++j > times && ++i < n) segment();
+            return true;
+        }
+    } w{raw, n, 1, 1, 1, 0.0, 0.0, 0.0, step_size};
+    w.segment();
+    DenseRows rows{out, cap, 0, {0, 0, 0, 0}, false};
+    double p0[2] = {raw[0], raw[1]}, p1[2], p2[2];
+    w.next(p1);                                         // dense[1] exists: every segment has at least one step
+    rows.start(p0[0], p0[1], start_yaw);
+    double th = atan2(p1[1] - p0[1], p1[0] - p0[0]);
+    unwrap(start_yaw, th);
+    rows.cur[3] = fabs(th - start_yaw) / w_max;
+    rows.start(p0[0], p0[1], th);
+    // interior points: a move row ending at the point, then a turn row towards the next point
+    while (w.next(p2)) {
+        const double ax = p1[0] - rows.cur[0], ay = p1[1] - rows.cur[1];
+        rows.cur[3] = sqrt(ax * ax + ay * ay) / v_max;
+        const double keep = rows.cur[2];
+        rows.start(p1[0], p1[1], keep);
+        th = atan2(p2[1] - p1[1], p2[0] - p1[0]);
+        unwrap(keep, th);
+        rows.cur[3] = fabs(th - keep) / w_max;
+        rows.start(p1[0], p1[1], th);
+        p1[0] = p2[0];
+        p1[1] = p2[1];
+    }
+    // the last point: move, then turn to the goal yaw
+    {
+        const double ax = p1[0] - rows.cur[0], ay = p1[1] - rows.cur[1];
+        rows.cur[3] = sqrt(ax * ax + ay * ay) / v_max;
+        const double keep = rows.cur[2];
+        rows.start(p1[0], p1[1], keep);
+        th = end_yaw;
+        unwrap(keep, th);
+        rows.cur[3] = fabs(th - keep) / w_max;
+        rows.start(p1[0], p1[1], th);
+        rows.flush(true);
+    }
+    return rows.count;
+}

@@ -148,6 +148,18 @@ class GridMap:
                    "dist_coarse2i")
         return out
 
+    def lineVisib(self, p1, p2, thresh, use_critical=False, pc=None):
+        """TopologyPRM::lineVisib (topo_prm.cpp:278-315) for (n, 3) end points on the device: (visible, pc). pc rows of
+        visible segments keep what was passed in (nan by default)."""
+        p1 = np.ascontiguousarray(p1, dtype=np.float64).reshape(-1, 3)
+        p2 = np.ascontiguousarray(p2, dtype=np.float64).reshape(-1, 3)
+        n = p1.shape[0]
+        vis = np.zeros(n, dtype=np.int8)
+        pc = np.full((n, 3), np.nan) if pc is None else np.ascontiguousarray(pc, dtype=np.float64).reshape(n, 3).copy()
+        _lib.check(self._l.topay_field_line_visible(self.h, _p(p1), _p(p2), n, C.c_double(thresh), int(use_critical),
+                                                    _p(vis, C.c_int8), _p(pc)), "line_visible")
+        return vis.astype(bool), pc
+
     # ---- index helpers (pure host arithmetic, grid_map.h:727-885) ---------------
     @property
     def map_origin(self):

@@ -357,3 +357,19 @@ def prepare_candidate(opt, rp, init_path, bvel, bacc, max_pieces):
                                             _p(inner_xy), _p(x0), C.byref(past))
     return dict(rc=rc, piece_num=N.value, head_pva=head, tail_pva=tail, start_xy=sxy, end_xy=exy,
                 init_inner_xy=inner_xy, x0=x0[:num_vars(N.value)] if rc == 0 else x0, s1_past=past.value)
+
+
+def getDensePath(raw_path, step_size, start_yaw, end_yaw, v_max, w_max):
+    """GraphSearch::getDensePath (graph_search.cpp:119-176) through topay_dense_path: (n, 2) raw waypoints -> rows
+    (x, y, theta, dt). Host arithmetic (the call every planning worker makes before the sampler and the solve,
+    planner.cpp:858)."""
+    raw = np.ascontiguousarray(raw_path, dtype=np.float64).reshape(-1, 2)
+    cap = 64
+    while True:
+        out = np.zeros((cap, 4))
+        n = _lib.lib().topay_dense_path(_p(raw), raw.shape[0], step_size, start_yaw, end_yaw, v_max, w_max, _p(out), cap)
+        if n < 0:
+            _lib.check(n, "topay_dense_path")
+        if n <= cap:
+            return out[:n]
+        cap = n
