@@ -645,7 +645,11 @@ def main():
     pen_achieved = pen_bytes / (pen_ms * 1e-3) / 1e9
     flop = nodes_per_launch * NODE_FLOP + nodes_per_launch * INT_K / (INT_K + 1) * MID_FLOP
     roof_pen = {"bound": "hbm", "kernel": "k_penalty", "achieved": pen_achieved, "peak": peak, "unit": "GB/s",
-                "frac": pen_achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": pen_achieved / peak, "traffic": 127.6e6,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one mid-run launch with 1024 live "
+                                  "candidates (2.16 M nodes, 1.73 GB algorithmic), ncu --set full, "
+                                  "profiles/r02_summary.md section 4: the 5 MB field stays in L2",
+                "peak_source": peak_src,
                 "avg_launch_ms": pen_ms, "nodes_per_launch": nodes_per_launch,
                 "algorithmic_bytes_per_launch": pen_bytes,
                 "algorithmic_bytes": "800 B of ESDF taps per penalty node (12 x 3-D + 1 x 2-D lookups, SURVEY §8d) x the "
@@ -656,7 +660,10 @@ def main():
                          "note": "4.0 kflop per penalty node + 0.15 kflop per midpoint (SURVEY §8d); MEASURED_PEAKS.json "
                                  "has no FP64 figure, 40 TFLOP/s is the nominal B200 FP64 rate"}}
     roof_lb = {"bound": "hbm", "kernel": "k_cand<lbfgs>", "achieved": lb_achieved, "peak": peak, "unit": "GB/s",
-               "frac": lb_achieved / peak, "traffic": None, "peak_source": peak_src, "avg_launch_ms": lb_ms,
+               "frac": lb_achieved / peak, "traffic": 3.455e9,
+               "traffic_source": "dram bytes of one mid-solve launch with 1024 live candidates in 0.60 ms (5.7 TB/s, "
+                                 "gpu__dram_throughput 70.5 % of peak), ncu --set full, profiles/r02_summary.md section 4",
+               "peak_source": peak_src, "avg_launch_ms": lb_ms,
                "algorithmic_bytes_per_launch": lb_bytes,
                "algorithmic_bytes": "L-BFGS history walked by the two-loop recursions: 2 loops x bound rows x (s_j, y_j) "
                                     "x n x 8 B per accepted iteration (5.2 MB at m = 256, n = 632), counted on the device; "
