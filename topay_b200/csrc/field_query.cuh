@@ -72,6 +72,54 @@ TP_HD void tp_query3d(const TpGrid& g, const double* pos, double& distance, doub
     }
 }
 
+// The same lookup in two steps for callers that need the gradient only when a hinge on the value is active (the
+// sphere penalties of the stage-2 node: a sphere is almost always clear of its margin): tp_query3d_taps fetches the
+// eight taps and returns the value, tp_query3d_grad finishes the gradient from them. Same operations in the same
+// order as tp_query3d, so the two paths are bit-identical.
+struct TpTaps3 {
+    double v000, v001, v010, v011, v100, v101, v110, v111, dx, dy, dz;
+    double v00, v01, v10, v11, v0, v1;
+    bool in_map;
+};
+TP_HD double tp_query3d_taps(const TpGrid& g, const double* pos, TpTaps3& t) {
+    t.in_map = tp_in_map3(g, pos);
+    if (!t.in_map) return 0.0;
+    int ix, iy, iz;
+    tp_anchor(g, pos[0], 0, ix, t.dx);
+    tp_anchor(g, pos[1], 1, iy, t.dy);
+    tp_anchor(g, pos[2], 2, iz, t.dz);
+    const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+    const int x0 = tp_clampi(ix, nx - 1), x1 = tp_clampi(ix + 1, nx - 1);
+    const int y0 = tp_clampi(iy, ny - 1), y1 = tp_clampi(iy + 1, ny - 1);
+    const int z0 = tp_clampi(iz, nz - 1), z1 = tp_clampi(iz + 1, nz - 1);
+    const double* b = g.esdf3d;
+    const size_t sx = (size_t)ny * nz, sy = (size_t)nz;
+    t.v000 = TP_LDG(b + x0 * sx + y0 * sy + z0); t.v001 = TP_LDG(b + x0 * sx + y0 * sy + z1);
+    t.v010 = TP_LDG(b + x0 * sx + y1 * sy + z0); t.v011 = TP_LDG(b + x0 * sx + y1 * sy + z1);
+    t.v100 = TP_LDG(b + x1 * sx + y0 * sy + z0); t.v101 = TP_LDG(b + x1 * sx + y0 * sy + z1);
+    t.v110 = TP_LDG(b + x1 * sx + y1 * sy + z0); t.v111 = TP_LDG(b + x1 * sx + y1 * sy + z1);
+    t.v00 = t.v000 * (1 - t.dx) + t.v100 * t.dx;
+    t.v01 = t.v001 * (1 - t.dx) + t.v101 * t.dx;
+    t.v10 = t.v010 * (1 - t.dx) + t.v110 * t.dx;
+    t.v11 = t.v011 * (1 - t.dx) + t.v111 * t.dx;
+    t.v0 = t.v00 * (1 - t.dy) + t.v10 * t.dy;
+    t.v1 = t.v01 * (1 - t.dy) + t.v11 * t.dy;
+    return t.v0 * (1.0 - t.dz) + t.v1 * t.dz;
+}
+TP_HD void tp_query3d_grad(const TpGrid& g, const TpTaps3& t, double* grad) {
+    if (!t.in_map) {
+        grad[0] = grad[1] = grad[2] = 0.0;
+        return;
+    }
+    grad[2] = (t.v1 - t.v0) * g.resolution_inv;
+    grad[1] = ((t.v10 - t.v00) * (1.0 - t.dz) + (t.v11 - t.v01) * t.dz) * g.resolution_inv;
+    double gx = (1.0 - t.dz) * (1 - t.dy) * (t.v100 - t.v000);
+    gx += (1.0 - t.dz) * t.dy * (t.v110 - t.v010);
+    gx += t.dz * (1 - t.dy) * (t.v101 - t.v001);
+    gx += t.dz * t.dy * (t.v111 - t.v011);
+    grad[0] = gx * g.resolution_inv;
+}
+
 // getDistance3d (grid_map.h:307-362): value only, 1e10 outside the map.
 TP_HD double tp_distance3d(const TpGrid& g, const double* pos) {
     if (!tp_in_map3(g, pos)) return 1e+10;

@@ -211,13 +211,21 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
     const double cost_scale = 10.0;
     const double w_mc = op.s2_mani_colli_weight, w_sc = op.s2_self_colli_weight;
     // sphere vs the 3-D field (:1477-1520) and vs the chassis top (:1525-1564)
+    // `active`: some sphere carries a gradient. Spheres are almost always clear of their margins, and with every
+    // sphere gradient zero the FK adjoint below returns exact zeros — it is skipped then.
+    bool active = false;
     for (int ci = 0; ci < P.n_sphere; ci++) {
         const double pc[3] = {pts.at(ci, 0), pts.at(ci, 1), pts.at(ci, 2)};
         double sdf, gp[3];
-        tp_field_query3d(g, pc, sdf, gp);
+        TpTaps3 taps;
+        const bool dense = g.kind == 0;
+        if (dense) sdf = tp_query3d_taps(g, pc, taps);      // the gradient only when the hinge is active
+        else tp_field_query3d(g, pc, sdf, gp);
         const double v = P.sphere_r[ci] * cost_scale * 1.1 - sdf * cost_scale;
         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
         if (v > 0) {
+            if (dense) tp_query3d_grad(g, taps, gp);
+            active = true;
             double f, df;
             tp_smoothL1(P, v, f, df);
             const double k = -omg * step * w_mc * df;
@@ -230,6 +238,7 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
         if (ci > 2) {
             const double height = rp.chassis_height + rp.relative_t[2] + P.sphere_r[ci] - pc[2];
             if (height > 0) {
+                active = true;
                 double f, df;
                 tp_smoothL1(P, height, f, df);
                 g2 += -omg * step * w_sc * df;
@@ -260,6 +269,7 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
         }
         hit &= mask;          // pair_mask holds bits c2 > ci, c2 < n_sphere only
         if (hit == 0u) continue;
+        active = true;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
         for (int cj = ci + 1; cj < P.n_sphere; cj++) {
             if (!((hit >> cj) & 1u)) continue;
@@ -284,7 +294,12 @@ TP_HD void tp_node_stage2(const TpParams& P, const TpGrid& g, const double* c, d
         pg.at(ci, 2) += a2;
     }
     double mu[10];
-    tp_fk_adjoint(P, fk, pg, mu);
+    if (active) {
+        tp_fk_adjoint(P, fk, pg, mu);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 10; q++) mu[q] = 0.0;
+    }
 
     // joint position limits (:1616-1666)
     const double w_mp = op.s2_mani_pos_weight;
