@@ -300,7 +300,7 @@ def field_probe(tp, scenes, device, hbm_peak):
                     "8 taps x 8 B + 32 B result per point, points resident in HBM"}
 
 
-def sweep_probe(tp, scenes, local, rank, world, dist, per_rank=48, candidates=8, in_flight=8):
+def sweep_probe(tp, scenes, local, rank, world, dist, per_rank=256, candidates=8, in_flight=32):
     """BASELINE configs[4] (the scenario sweep, bounded): `per_rank` x world independent table / cuboid scenarios,
     static round-robin over the ranks (one process per GPU, no data-path collective). Every scenario runs the whole
     device pipeline the planner drives: rasterise its point cloud -> rebuild the field (4 x 2-D + 3-D ESDF) -> solve

@@ -50,6 +50,17 @@ struct TpEdtScratch {
 int tp_signed_edt(const TpEdtScratch& s, const int8_t* src, int A, int B, int C, double* esdf, int32_t* sqp,
                   int32_t* sqn);
 
+// Per-call device scratch comes from the stream-ordered allocator: cudaFree synchronises the whole device, which
+// stalls every other stream (concurrent solves of a scenario sweep, the plans of other host threads).
+// tp_pool_keep keeps the default pool's memory across synchronisations (set once per device).
+inline void tp_pool_keep(int device) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+}
+
 #define TP_CUDA_OK(call, cleanup)                                                              \
     do {                                                                                       \
         cudaError_t e_ = (call);                                                               \

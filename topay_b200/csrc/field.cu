@@ -863,6 +863,7 @@ extern "C" int topay_field_create(const topay_grid_desc* desc, int device, topay
     f->device = device;
     f->keep_sq = true;
     cudaSetDevice(device);
+    tp_pool_keep(device);
     // grid_map.cpp:33-54
     TpGrid& g = f->grid;
     g.resolution = desc->resolution;
@@ -990,12 +991,13 @@ extern "C" int topay_field_rasterize_points(topay_field* f, const float* xyz, in
     if (n == 0) return TOPAY_OK;
     cudaSetDevice(f->device);
     float* d = nullptr;
-    TP_CUDA_OK(cudaMalloc(&d, (size_t)n * 3 * sizeof(float)), {});
-    TP_CUDA_OK(cudaMemcpyAsync(d, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, f->stream), { cudaFree(d); });
+    TP_CUDA_OK(cudaMallocAsync(&d, (size_t)n * 3 * sizeof(float), f->stream), {});
+    TP_CUDA_OK(cudaMemcpyAsync(d, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, f->stream),
+               { cudaFreeAsync(d, f->stream); });
     k_rasterize<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(d, n, f->grid, f->desc.chassis_height, f->occ3d,
                                                                   f->occ2d, f->occ2d_crit);
-    TP_CUDA_OK(cudaStreamSynchronize(f->stream), { cudaFree(d); });
-    cudaFree(d);
+    cudaFreeAsync(d, f->stream);
+    TP_CUDA_OK(cudaStreamSynchronize(f->stream), {});
     f->ready = false;
     f->grid.ready = 0;
     return TOPAY_OK;
@@ -1052,9 +1054,11 @@ static int query_common(topay_field* f, const double* pos, int64_t n, int dim, i
     if (n == 0) return TOPAY_OK;
     cudaSetDevice(f->device);
     double *dpos = nullptr, *dd = nullptr, *dg = nullptr;
-    TP_CUDA_OK(cudaMalloc(&dpos, (size_t)n * dim * 8), {});
-    TP_CUDA_OK(cudaMalloc(&dd, (size_t)n * 8), { cudaFree(dpos); });
-    if (grad) TP_CUDA_OK(cudaMalloc(&dg, (size_t)n * dim * 8), { cudaFree(dpos); cudaFree(dd); });
+    TP_CUDA_OK(cudaMallocAsync(&dpos, (size_t)n * dim * 8, f->stream), {});
+    TP_CUDA_OK(cudaMallocAsync(&dd, (size_t)n * 8, f->stream), { cudaFreeAsync(dpos, f->stream); });
+    if (grad)
+        TP_CUDA_OK(cudaMallocAsync(&dg, (size_t)n * dim * 8, f->stream),
+                   { cudaFreeAsync(dpos, f->stream); cudaFreeAsync(dd, f->stream); });
     cudaMemcpyAsync(dpos, pos, (size_t)n * dim * 8, cudaMemcpyHostToDevice, f->stream);
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (dim == 3)
@@ -1066,10 +1070,10 @@ static int query_common(topay_field* f, const double* pos, int64_t n, int dim, i
     }
     cudaMemcpyAsync(dist, dd, (size_t)n * 8, cudaMemcpyDeviceToHost, f->stream);
     if (grad) cudaMemcpyAsync(grad, dg, (size_t)n * dim * 8, cudaMemcpyDeviceToHost, f->stream);
+    cudaFreeAsync(dpos, f->stream);
+    cudaFreeAsync(dd, f->stream);
+    if (dg) cudaFreeAsync(dg, f->stream);
     cudaError_t e = cudaStreamSynchronize(f->stream);
-    cudaFree(dpos);
-    cudaFree(dd);
-    if (dg) cudaFree(dg);
     TP_CUDA_OK(e, {});
     TP_CUDA_OK(cudaGetLastError(), {});
     return TOPAY_OK;
@@ -1120,14 +1124,14 @@ extern "C" int topay_field_whole_body_collision(topay_field* f, const topay_robo
     tp_derive_params(P);
     double* ds = nullptr;
     int8_t* dout = nullptr;
-    TP_CUDA_OK(cudaMalloc(&ds, (size_t)n * 10 * 8), {});
-    TP_CUDA_OK(cudaMalloc(&dout, (size_t)n), { cudaFree(ds); });
+    TP_CUDA_OK(cudaMallocAsync(&ds, (size_t)n * 10 * 8, f->stream), {});
+    TP_CUDA_OK(cudaMallocAsync(&dout, (size_t)n, f->stream), { cudaFreeAsync(ds, f->stream); });
     cudaMemcpyAsync(ds, states, (size_t)n * 10 * 8, cudaMemcpyHostToDevice, f->stream);
     k_whole_body<<<(unsigned)((n + 127) / 128), 128, 0, f->stream>>>(f->grid, P, ds, n, dout);
     cudaMemcpyAsync(out, dout, (size_t)n, cudaMemcpyDeviceToHost, f->stream);
+    cudaFreeAsync(ds, f->stream);
+    cudaFreeAsync(dout, f->stream);
     cudaError_t e = cudaStreamSynchronize(f->stream);
-    cudaFree(ds);
-    cudaFree(dout);
     TP_CUDA_OK(e, {});
     return TOPAY_OK;
 }
@@ -1147,7 +1151,7 @@ static int field_misc(topay_field* f, int kind, const double* in_a, int wa, cons
     const size_t ba = in_a ? (size_t)n * wa * 8 : 0, bb = in_b ? (size_t)n * wa * 8 : 0, bi = in_i ? (size_t)n * 8 : 0;
     const size_t bv = (size_t)n * 8, bf = (size_t)n;
     char* d = nullptr;
-    TP_CUDA_OK(cudaMalloc(&d, ba + bb + bi + bv + bf + 64), {});
+    TP_CUDA_OK(cudaMallocAsync(&d, ba + bb + bi + bv + bf + 64, f->stream), {});
     double* da = (double*)d;
     double* db = (double*)(d + ba);
     int32_t* di = (int32_t*)(d + ba + bb);
@@ -1160,8 +1164,8 @@ static int field_misc(topay_field* f, int kind, const double* in_a, int wa, cons
                                                                     df, dv);
     if (kind <= 2) cudaMemcpyAsync(flag, df, bf, cudaMemcpyDeviceToHost, f->stream);
     else cudaMemcpyAsync(val, dv, bv, cudaMemcpyDeviceToHost, f->stream);
+    cudaFreeAsync(d, f->stream);
     cudaError_t e = cudaStreamSynchronize(f->stream);
-    cudaFree(d);
     TP_CUDA_OK(e, {});
     TP_CUDA_OK(cudaGetLastError(), {});
     return TOPAY_OK;
@@ -1195,7 +1199,7 @@ extern "C" int topay_field_line_visible(topay_field* f, const double* p1, const 
     cudaSetDevice(f->device);
     const size_t bp = (size_t)n * 3 * 8;
     char* d = nullptr;
-    TP_CUDA_OK(cudaMalloc(&d, 3 * bp + (size_t)n + 64), {});
+    TP_CUDA_OK(cudaMallocAsync(&d, 3 * bp + (size_t)n + 64, f->stream), {});
     double *d1 = (double*)d, *d2 = (double*)(d + bp), *dc = (double*)(d + 2 * bp);
     int8_t* dv = (int8_t*)(d + 3 * bp);
     cudaMemcpyAsync(d1, p1, bp, cudaMemcpyHostToDevice, f->stream);
@@ -1204,8 +1208,8 @@ extern "C" int topay_field_line_visible(topay_field* f, const double* p1, const 
     k_line_visib<<<(unsigned)((n + 127) / 128), 128, 0, f->stream>>>(f->grid, d1, d2, n, thresh, use_critical, dv, dc);
     cudaMemcpyAsync(visible, dv, (size_t)n, cudaMemcpyDeviceToHost, f->stream);
     cudaMemcpyAsync(pc, dc, bp, cudaMemcpyDeviceToHost, f->stream);
+    cudaFreeAsync(d, f->stream);
     cudaError_t e = cudaStreamSynchronize(f->stream);
-    cudaFree(d);
     TP_CUDA_OK(e, {});
     TP_CUDA_OK(cudaGetLastError(), {});
     return TOPAY_OK;

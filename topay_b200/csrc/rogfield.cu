@@ -394,16 +394,16 @@ extern "C" int topay_rogfield_update_counters(topay_rogfield* f, const double* p
     cudaSetDevice(f->device);
     double* dp = nullptr;
     uint8_t* dt = nullptr;
-    TP_CUDA_OK(cudaMalloc(&dp, (size_t)n * 24), {});
-    TP_CUDA_OK(cudaMalloc(&dt, (size_t)n * 2), { cudaFree(dp); });
+    TP_CUDA_OK(cudaMallocAsync(&dp, (size_t)n * 24, f->stream), {});
+    TP_CUDA_OK(cudaMallocAsync(&dt, (size_t)n * 2, f->stream), { cudaFreeAsync(dp, f->stream); });
     cudaMemcpyAsync(dp, pos, (size_t)n * 24, cudaMemcpyHostToDevice, f->stream);
     cudaMemcpyAsync(dt, from_type, (size_t)n, cudaMemcpyHostToDevice, f->stream);
     cudaMemcpyAsync(dt + n, to_type, (size_t)n, cudaMemcpyHostToDevice, f->stream);
     k_rog_counters<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(rog_view(f), dp, dt, dt + n, n, f->occ_cnt,
                                                                       f->unk_cnt);
+    cudaFreeAsync(dp, f->stream);
+    cudaFreeAsync(dt, f->stream);
     cudaError_t e = cudaStreamSynchronize(f->stream);
-    cudaFree(dp);
-    cudaFree(dt);
     TP_CUDA_OK(e, {});
     TP_CUDA_OK(cudaGetLastError(), {});
     return TOPAY_OK;
@@ -527,7 +527,7 @@ extern "C" int topay_rogfield_query(topay_rogfield* f, int kind, const double* p
     if (n == 0) return TOPAY_OK;
     cudaSetDevice(f->device);
     double* d = nullptr;
-    TP_CUDA_OK(cudaMalloc(&d, (size_t)n * 7 * 8), {});
+    TP_CUDA_OK(cudaMallocAsync(&d, (size_t)n * 7 * 8, f->stream), {});
     double *dpos = d, *ddist = d + 3 * n, *dgrad = d + 4 * n;
     cudaMemcpyAsync(dpos, pos, (size_t)n * 24, cudaMemcpyHostToDevice, f->stream);
     if (grad) cudaMemcpyAsync(dgrad, grad, (size_t)n * 24, cudaMemcpyHostToDevice, f->stream);   // cell kinds leave it
@@ -535,8 +535,8 @@ extern "C" int topay_rogfield_query(topay_rogfield* f, int kind, const double* p
                                                                    grad ? dgrad : nullptr);
     cudaMemcpyAsync(dist, ddist, (size_t)n * 8, cudaMemcpyDeviceToHost, f->stream);
     if (grad) cudaMemcpyAsync(grad, dgrad, (size_t)n * 24, cudaMemcpyDeviceToHost, f->stream);
+    cudaFreeAsync(d, f->stream);
     cudaError_t e = cudaStreamSynchronize(f->stream);
-    cudaFree(d);
     TP_CUDA_OK(e, {});
     TP_CUDA_OK(cudaGetLastError(), {});
     return TOPAY_OK;
@@ -548,14 +548,14 @@ extern "C" int topay_rogfield_is_line_free2d(topay_rogfield* f, const double* st
     if (n == 0) return TOPAY_OK;
     cudaSetDevice(f->device);
     double* d = nullptr;
-    TP_CUDA_OK(cudaMalloc(&d, (size_t)n * 4 * 8 + (size_t)n), {});
+    TP_CUDA_OK(cudaMallocAsync(&d, (size_t)n * 4 * 8 + (size_t)n, f->stream), {});
     int8_t* dout = reinterpret_cast<int8_t*>(d + 4 * n);
     cudaMemcpyAsync(d, start, (size_t)n * 16, cudaMemcpyHostToDevice, f->stream);
     cudaMemcpyAsync(d + 2 * n, end, (size_t)n * 16, cudaMemcpyHostToDevice, f->stream);
     k_rog_line<<<(unsigned)((n + 127) / 128), 128, 0, f->stream>>>(rog_view(f), d, d + 2 * n, n, threshold, dout);
     cudaMemcpyAsync(out, dout, (size_t)n, cudaMemcpyDeviceToHost, f->stream);
+    cudaFreeAsync(d, f->stream);
     cudaError_t e = cudaStreamSynchronize(f->stream);
-    cudaFree(d);
     TP_CUDA_OK(e, {});
     TP_CUDA_OK(cudaGetLastError(), {});
     return TOPAY_OK;

@@ -470,7 +470,7 @@ extern "C" int topay_traj_sample(int device, const topay_traj_batch* trajs, cons
         if (rc == TOPAY_OK) rc = ck.prepare(hb.V);
         if (rc == TOPAY_OK) {
             const size_t nm = (size_t)hb.V.n * m;
-            if (cudaMalloc(&d, nm * 21 * 8) != cudaSuccess) {
+            if (cudaMallocAsync(&d, nm * 21 * 8, q) != cudaSuccess) {
                 tp_set_error("traj_sample: cudaMalloc failed");
                 rc = TOPAY_ERR_ALLOC;
             } else {
@@ -482,8 +482,8 @@ extern "C" int topay_traj_sample(int device, const topay_traj_batch* trajs, cons
                 if (dstate) cudaMemcpyAsync(dstate, d + nm * 11, nm * 80, cudaMemcpyDeviceToHost, q);
             }
         }
+        if (d) cudaFreeAsync(d, q);
         cudaError_t e = cudaStreamSynchronize(q);
-        if (d) cudaFree(d);
         if (rc == TOPAY_OK && e != cudaSuccess) {
             tp_set_error(std::string("traj_sample: ") + cudaGetErrorString(e));
             rc = TOPAY_ERR_CUDA;
