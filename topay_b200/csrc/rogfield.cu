@@ -266,6 +266,7 @@ extern "C" int topay_rogfield_create(const topay_rog_desc* d, int device, topay_
     f->desc = *d;
     f->device = device;
     cudaSetDevice(device);
+    tp_pool_keep(device);
     // counter_map.cpp:58-86 with inflation_step = 0 (esdf_map.cpp:37-44)
     const int ratio = (int)std::round(d->esdf_resolution / d->prob_resolution);
     const double cres = d->prob_resolution * ratio;

@@ -251,6 +251,7 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
     s->d_start = nullptr;
     memset(&s->stats, 0, sizeof(s->stats));
     cudaSetDevice(s->device);
+    tp_pool_keep(s->device);
     TP_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), { delete s; });
     memset(&s->params, 0, sizeof(s->params));
     s->params.robot = *robot;
