@@ -204,7 +204,19 @@ TP_HD void tp_env_push(TpEnv& e, TpEnvEntry* stk, int n, int u, int cur, int pre
         return;
     }
     const unsigned num = (unsigned)(u * u - e.sv * e.sv + cur - e.gv), den = 2u * (unsigned)(u - e.sv);
+#if defined(__CUDA_ARCH__)
+    // floor(num / den) is only needed while it is below n < 2^14: a float estimate (relative error < 2^-21, i.e.
+    // less than one unit there) corrected by the exact integer remainder; anything estimated at 2^15 or more starts
+    // past the line's end. (num < 2^30, den < 2^15.)
+    const float qf = __fdividef(__uint2float_rn(num), __uint2float_rn(den));     // MUFU.RCP + multiply, 2 ulp
+    if (qf >= 32768.0f) return;
+    int qi = (int)qf;
+    const int rem = (int)num - qi * (int)den;
+    qi += rem < 0 ? -1 : (rem >= (int)den ? 1 : 0);
+    const int w = 1 + qi;
+#else
     const int w = 1 + (int)(num / den);
+#endif
     if (w < n) {
         e.q++;
         e.sv = u;

@@ -543,6 +543,7 @@ k_edt_scan(const void* __restrict__ in_, int32_t* __restrict__ out32, int32_t* _
     for (int k = 1; k <= 8; k++) tp_touch(&stk[max(e.q - k, 0)]);
     __syncthreads();
     // ---- 2. sweep from the far end, 32 cells at a time
+    const double r_inf = __dmul_rn(res, __dsqrt_rn(DBL_MAX));      // "no obstacle anywhere" (fillESDF's DBL_MAX)
     if (e.q < 0) {          // no source in the segment: a sentinel entry that never pops and never wins
         e.sv = 0;
         e.gv = TP_INF32;
@@ -581,8 +582,22 @@ k_edt_scan(const void* __restrict__ in_, int32_t* __restrict__ out32, int32_t* _
                 }
             }
             const size_t idx = base + (size_t)u * line_stride;
-            if (FINAL) tp_edt_store(true, bp, bn, idx, res, out_pos, out_neg, esdf, sink, u, outer, c);
-            else out32[idx] = bn > 0 ? -bn : bp;
+            if (!FINAL) {
+                out32[idx] = bn > 0 ? -bn : bp;
+            } else if (sink.enabled) {
+                tp_edt_store(true, bp, bn, idx, res, out_pos, out_neg, esdf, sink, u, outer, c);
+            } else {
+                // the dense field's store (tp_edt_store without the ring sink): one square root per cell, rounded
+                // products and sums (grid_map.cpp:457, 503, 515-517)
+                const bool oc = bn > 0;
+                const int x = oc ? bn : bp;
+                const double r = x >= TP_INF32 ? r_inf : __dmul_rn(res, __dsqrt_rn((double)x));
+                if (esdf) esdf[idx] = oc ? __dadd_rn(-r, res) : r;
+                if (out_pos) {
+                    out_pos[idx] = bp >= TP_INF32 ? INT32_MAX : bp;
+                    out_neg[idx] = bn >= TP_INF32 ? INT32_MAX : bn;
+                }
+            }
         }
         __syncthreads();
     }
