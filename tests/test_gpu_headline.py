@@ -136,6 +136,31 @@ def test_two_lanes_give_the_single_lane_results(gpu_scene, monkeypatch):
                         assert np.array_equal(v, b[k]), (key, k)
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_tick_cap_marks_unfinished_candidates(gpu_scene, monkeypatch, lanes):
+    """The hard cap on ticks (a runaway guard; forced here through TOPAY_MAX_TICKS): candidates still solving when it
+    strikes — in a slot of either lane, or still waiting in the queue — come back with status 0 and the distinct
+    code TOPAY_LBFGSERR_TICK_CAP; candidates that had finished keep their results."""
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    paths, bv, ba = scenes.short_candidates(24, 11)
+    monkeypatch.setenv("TOPAY_LANE_MIN_SLOTS", "2" if lanes == 2 else "0")
+    s = tp.MomaTrajOpt(gpu_scene, max_cand=24, max_pieces=16, opt_param=opt, robot=rp, n_slots=6)
+    full = s.optimizeTrajBatch(paths, bv, ba)
+    monkeypatch.setenv("TOPAY_MAX_TICKS", "160")
+    cut = s.optimizeTrajBatch(paths, bv, ba)
+    monkeypatch.delenv("TOPAY_MAX_TICKS")
+    s.close()
+    capped = cut["lbfgs_code"] == tp.LBFGSERR_TICK_CAP
+    assert capped.any() and (cut["status"][capped] == 0).all()
+    assert capped[6:].sum() >= 12                  # most of the queue never reached a slot in 160 ticks
+    done = ~capped
+    for k in ("status", "lbfgs_code", "evals", "cost", "T"):
+        assert np.array_equal(cut[k][done], full[k][done]), k
+    assert (full["evals"][done] <= 160).all()
+
+
 def test_headline_config_solve_against_the_oracle(gpu_scene, small_scene, oracle):
     """The headline workload itself: the first 4 candidates of scenes.synthetic_batch(256, 1234) at 64 pieces x
     int_K 32, solved on the device and by the oracle (= the reference, bit for bit). The solve is chaotic — the

@@ -7,6 +7,7 @@ DOF, DIM, NSPHERE, NTERMS = 7, 9, 12, 13
 TERM_NAMES = ["jerk", "time", "chassis_colli", "moment", "acc", "domega", "mani_colli",
               "self_colli", "mani_pos", "mani_vel", "mani_acc", "mean_time", "endp"]
 MAP2D_FLAT, MAP2D_INFLATE, MAP2D_CRITICAL, MAP3D = 0, 1, 2, 3
+LBFGSERR_TICK_CAP = -2000      # TOPAY_LBFGSERR_TICK_CAP: stopped by the solver's hard cap on ticks
 
 
 class RobotParams(C.Structure):

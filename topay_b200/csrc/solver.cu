@@ -681,7 +681,8 @@ extern "C" int topay_solver_run(topay_solver* s) {
     };
     const double per_cand = evals_of(op.s1_lbfgs) + (op.alm_max_rounds + 1.0) * evals_of(op.s2_lbfgs);
     const double waves = std::ceil((double)s->n_cand / std::max(1, s->n_slots_used));
-    const long long max_ticks = (long long)std::min(per_cand * waves, 4e15);
+    long long max_ticks = (long long)std::min(per_cand * waves, 4e15);
+    if (const char* e = getenv("TOPAY_MAX_TICKS")) max_ticks = std::max(1LL, atoll(e));   // tests: force the cap
     long long ticks = 0;
     long long slot_ticks = 0;      // live slots summed over the batches (upper bound of the evaluations done)
     bool done = false;
