@@ -222,6 +222,13 @@ int topay_field_dist_coarse2i(topay_field* f, const int32_t* idx, int64_t n, int
  * cell's, z = 0; pc of a visible segment is left as passed in. Front-end row N2 of SURVEY.md §8f. */
 int topay_field_line_visible(topay_field* f, const double* p1, const double* p2, int64_t n, double thresh,
                              int use_critical, int8_t* visible, double* pc);
+/* TopologyPRM::sameTopoPath (topo_prm.cpp:424-448) for n_pairs pairs of paths in one launch (the PRM's
+ * pruneEquivalent compares every path with every kept one): path p is the polyline pts[offsets[p] .. offsets[p+1])
+ * (rows of 3), pairs is n_pairs x 2 path indices; same[k] = 1 when every pair of the ceil(max length / resolution)
+ * equally spaced points (discretizePath) of the two paths sees each other (lineVisib with `thresh`). Paths must be
+ * longer than one cell. */
+int topay_field_same_topo_paths(topay_field* f, const double* pts, const int32_t* offsets, int n_paths,
+                                const int32_t* pairs, int n_pairs, double thresh, int use_critical, int8_t* same);
 /* Same queries with DEVICE pointers (inputs and outputs already in HBM), asynchronous
  * on the field's stream; used by the resident benchmark and by the solver. */
 int topay_field_query3d_dev(topay_field* f, const double* pos_dev, int64_t n, double* dist_dev,
@@ -448,6 +455,11 @@ static inline int topay_num_vars(int piece_num) { return 10 * piece_num - 8; }
  * (cap x 4) and returns the number of rows the path has (> cap: call again), or a negative TOPAY_ERR_*. */
 int topay_dense_path(const double* raw_xy, int n, double step_size, double start_yaw, double end_yaw, double v_max,
                      double w_max, double* out, int cap);
+
+/* TopologyPRM::pathLength / discretizePath (src/planner/src/topo_prm.cpp:462-506): length of a 3-D polyline (n rows
+ * of 3) and pt_num >= 2 points at equal arc-length spacing along it (out: pt_num x 3). Host arithmetic. */
+double topay_path_length(const double* path, int n);
+int topay_discretize_path(const double* path, int n, int pt_num, double* out);
 
 /* MomaTrajOpt::optimizeTraj pre-processing (moma_traj_opt.cpp:146-344): waypoints ->
  * problem data + initial x. Host-side helper of solve_batch, exported for parity

@@ -517,4 +517,15 @@ void oracle_line_visib(void* h, const double* p1, const double* p2, int64_t n, d
     for (int64_t i = 0; i < n; i++) visible[i] = line_visib(*f, p1 + 3 * i, p2 + 3 * i, thresh, use_critical != 0, pc + 3 * i) ? 1 : 0;
 }
 
+int oracle_discretize_path(const double* path, int n, int pt_num, double* out) {
+    const auto r = discretize_path(path, n, pt_num);
+    for (size_t i = 0; i < r.size(); i++)
+        for (int k = 0; k < 3; k++) out[3 * i + k] = r[i][k];
+    return (int)r.size();
+}
+double oracle_path_length(const double* path, int n) { return path_length(path, n); }
+int oracle_same_topo_path(void* h, const double* p1, int n1, const double* p2, int n2, double thresh, int use_critical) {
+    return same_topo_path(*(const Field*)h, p1, n1, p2, n2, thresh, use_critical != 0) ? 1 : 0;
+}
+
 }  // extern "C"

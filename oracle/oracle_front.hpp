@@ -3,6 +3,7 @@
 //   GraphSearch::getDensePath      src/planner/src/graph_search.cpp:119-176 (+ normalizeAngle :6-13)
 //   RayCaster::setInput / step     src/planner/src/utils/raycast.cpp:27-45, 253-346
 //   TopologyPRM::lineVisib         src/planner/src/topo_prm.cpp:278-315
+//   TopologyPRM::sameTopoPath      src/planner/src/topo_prm.cpp:424-448 (+ pathLength :462-470, discretizePath :472-506)
 // in the reference's operation order. Pinned bit for bit against the reference's own code compiled unmodified
 // (oracle/_ref, tests/test_ref_pin.py::test_dense_path_bit_exact / test_line_visib_bit_exact).
 #pragma once
@@ -134,6 +135,55 @@ inline bool line_visib(const Field& f, const double* p1, const double* p2, doubl
         }
         prev[0] = id[0]; prev[1] = id[1]; prev[2] = id[2];
     }
+    return true;
+}
+
+// topo_prm.cpp:462-470
+inline double path_length(const double* path, int n) {
+    double length = 0.0;
+    if (n < 2) return length;
+    for (int i = 0; i < n - 1; ++i) {
+        const double dx = path[3 * i + 3] - path[3 * i], dy = path[3 * i + 4] - path[3 * i + 1], dz = path[3 * i + 5] - path[3 * i + 2];
+        length += std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    return length;
+}
+// topo_prm.cpp:472-506: pt_num points at equal arc-length spacing along the polyline
+inline std::vector<std::array<double, 3>> discretize_path(const double* path, int n, int pt_num) {
+    std::vector<double> len_list;
+    len_list.push_back(0.0);
+    for (int i = 0; i < n - 1; ++i) {
+        const double dx = path[3 * i + 3] - path[3 * i], dy = path[3 * i + 4] - path[3 * i + 1], dz = path[3 * i + 5] - path[3 * i + 2];
+        len_list.push_back(std::sqrt(dx * dx + dy * dy + dz * dz) + len_list[i]);
+    }
+    const double len_total = len_list.back();
+    const double dl = len_total / double(pt_num - 1);
+    std::vector<std::array<double, 3>> out;
+    for (int i = 0; i < pt_num; ++i) {
+        const double cur_l = double(i) * dl;
+        int idx = -1;
+        for (int j = 0; j < (int)len_list.size() - 1; ++j)
+            if (cur_l >= len_list[j] - 1e-4 && cur_l <= len_list[j + 1] + 1e-4) {
+                idx = j;
+                break;
+            }
+        const double lambda = (cur_l - len_list[idx]) / (len_list[idx + 1] - len_list[idx]);
+        out.push_back({(1 - lambda) * path[3 * idx] + lambda * path[3 * idx + 3],
+                       (1 - lambda) * path[3 * idx + 1] + lambda * path[3 * idx + 4],
+                       (1 - lambda) * path[3 * idx + 2] + lambda * path[3 * idx + 5]});
+    }
+    return out;
+}
+// topo_prm.cpp:424-448: two paths are the same topological class when every pair of equally spaced points sees
+// each other. (Callers pass paths longer than one cell: pt_num >= 2.)
+inline bool same_topo_path(const Field& f, const double* p1, int n1, const double* p2, int n2, double thresh,
+                           bool use_critical) {
+    const double max_len = std::max(path_length(p1, n1), path_length(p2, n2));
+    const int pt_num = (int)std::ceil(max_len / f.resolution);
+    const auto a = discretize_path(p1, n1, pt_num), b = discretize_path(p2, n2, pt_num);
+    double pc[3];
+    for (int i = 0; i < pt_num; ++i)
+        if (!line_visib(f, a[i].data(), b[i].data(), thresh, use_critical, pc)) return false;
     return true;
 }
 

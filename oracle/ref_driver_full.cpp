@@ -437,4 +437,40 @@ void ref_line_visib(void* grid, const double* p1, const double* p2, int64_t n, d
     }
 }
 
+// TopologyPRM::sameTopoPath / discretizePath / pathLength (topo_prm.cpp:424-506)
+static void make_prm(nmoma_planner::TopologyPRM& prm, void* grid, int use_critical) {
+    auto& P = ros::stub_params();
+    P["topo_prm/max_raw_path"] = {1.0};
+    ros::NodeHandle nh;
+    prm.grid_map_ptr = ((RefGrid*)grid)->gm;
+    prm.init(nh);
+    prm.use_critical = use_critical != 0;
+}
+static std::vector<Eigen::Vector3d> to_path(const double* p, int n) {
+    std::vector<Eigen::Vector3d> v;
+    for (int i = 0; i < n; i++) v.push_back(Eigen::Vector3d(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
+    return v;
+}
+int ref_same_topo_path(void* grid, const double* p1, int n1, const double* p2, int n2, double thresh, int use_critical) {
+    Quiet q;
+    nmoma_planner::TopologyPRM prm;
+    make_prm(prm, grid, use_critical);
+    return prm.sameTopoPath(to_path(p1, n1), to_path(p2, n2), thresh) ? 1 : 0;
+}
+int ref_discretize_path(void* grid, const double* path, int n, int pt_num, double* out) {
+    Quiet q;
+    nmoma_planner::TopologyPRM prm;
+    make_prm(prm, grid, 0);
+    const std::vector<Eigen::Vector3d> r = prm.discretizePath(to_path(path, n), pt_num);
+    for (size_t i = 0; i < r.size(); i++)
+        for (int k = 0; k < 3; k++) out[3 * i + k] = r[i](k);
+    return (int)r.size();
+}
+double ref_path_length(void* grid, const double* path, int n) {
+    Quiet q;
+    nmoma_planner::TopologyPRM prm;
+    make_prm(prm, grid, 0);
+    return prm.pathLength(to_path(path, n));
+}
+
 }  // extern "C"

@@ -186,6 +186,12 @@ public:
                         double* pc) {
         topay_check(topay_field_line_visible(f_, p1, p2, n, thresh, use_critical, visible, pc), "topay_field_line_visible");
     }
+    // TopologyPRM::sameTopoPath (topo_prm.cpp:424-448) for many pairs in one launch (pruneEquivalent)
+    void sameTopoPaths(const double* pts, const int32_t* offsets, int n_paths, const int32_t* pairs, int n_pairs,
+                       double thresh, bool use_critical, int8_t* same) {
+        topay_check(topay_field_same_topo_paths(f_, pts, offsets, n_paths, pairs, n_pairs, thresh, use_critical, same),
+                    "topay_field_same_topo_paths");
+    }
     // batched forms for the front-end (one launch for many samples)
     void isWholeBodyCollisionBatch(const double* states, int64_t n, int8_t* out) {
         topay_robot_params rp;

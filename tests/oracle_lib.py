@@ -78,6 +78,21 @@ def dense_path(raw_xy, step_size, start_yaw, end_yaw, v_max, w_max):
     return out[:n]
 
 
+def discretize_path(path, pt_num):
+    """topo_prm.cpp:472-506."""
+    path = _f64(path)
+    out = np.zeros((pt_num, 3))
+    n = lib().oracle_discretize_path(_p(path), len(path), int(pt_num), _p(out))
+    assert n == pt_num
+    return out
+
+
+def path_length(path):
+    path = _f64(path)
+    lib().oracle_path_length.restype = C.c_double
+    return lib().oracle_path_length(_p(path), len(path))
+
+
 class Field:
     def __init__(self, desc: GridDesc):
         self.h = C.c_void_p(lib().oracle_field_create(C.byref(desc)))
@@ -103,6 +118,11 @@ class Field:
 
     def rebuild(self):
         lib().oracle_field_rebuild(self.h)
+
+    def same_topo_path(self, p1, p2, thresh, use_critical=False):
+        """topo_prm.cpp:424-448."""
+        p1, p2 = _f64(p1), _f64(p2)
+        return bool(lib().oracle_same_topo_path(self.h, _p(p1), len(p1), _p(p2), len(p2), C.c_double(thresh), int(use_critical)))
 
     def line_visib(self, p1, p2, thresh, use_critical=False):
         """topo_prm.cpp:278-315 on n segments: (visible, pc); pc = nan where visible."""

@@ -191,6 +191,26 @@ def line_visib(grid, p1, p2, thresh, use_critical=False):
     return vis.astype(bool), pc
 
 
+def same_topo_path(grid, p1, p2, thresh, use_critical=False):
+    """TopologyPRM::sameTopoPath of the compiled reference."""
+    p1, p2 = _f64(p1), _f64(p2)
+    return bool(lib().ref_same_topo_path(grid.h, _p(p1), len(p1), _p(p2), len(p2), C.c_double(thresh), int(use_critical)))
+
+
+def discretize_path(grid, path, pt_num):
+    path = _f64(path)
+    out = np.zeros((pt_num, 3))
+    n = lib().ref_discretize_path(grid.h, _p(path), len(path), int(pt_num), _p(out))
+    assert n == pt_num
+    return out
+
+
+def path_length(grid, path):
+    path = _f64(path)
+    lib().ref_path_length.restype = C.c_double
+    return lib().ref_path_length(grid.h, _p(path), len(path))
+
+
 class MomaTrajOpt:
     """nmoma_planner::MomaTrajOpt (src/planner), parameters taken from a topay_opt_params."""
 

@@ -189,3 +189,25 @@ def test_dense_path_matches_the_oracle(oracle):
     assert n == len(tp.getDensePath(raw, 1.0, 0.0, 0.0, 1.0, 1.0)) > 2
     assert _lib.lib().topay_dense_path(raw.ctypes.data_as(dp), 1, 1.0, 0.0, 0.0, 1.0, 1.0, out.ctypes.data_as(dp), 2) < 0
     assert _lib.lib().topay_dense_path(raw.ctypes.data_as(dp), 2, 0.0, 0.0, 0.0, 1.0, 1.0, out.ctypes.data_as(dp), 2) < 0
+
+
+def test_discretize_path_matches_the_oracle(oracle):
+    """N2: topay_path_length / topay_discretize_path (host arithmetic) against the oracle (= TopologyPRM::pathLength /
+    discretizePath of the compiled reference, test_ref_pin.py::test_same_topo_path_bit_exact): ragged polylines, a
+    repeated waypoint (zero-length segment: the reference's 0 / 0 is reproduced), bad arguments."""
+    import topay_b200 as tp
+    from topay_b200 import _lib
+    import ctypes as C
+    rng = np.random.default_rng(31)
+    for i in range(200):
+        k = int(rng.integers(2, 8))
+        p = rng.uniform(-9, 9, (k, 3))
+        if i % 5 == 0 and k > 2:
+            p[2] = p[1]
+        n = int(rng.integers(2, 200))
+        assert np.array_equal(tp.discretizePath(p, n), oracle.discretize_path(p, n), equal_nan=True)
+        assert tp.pathLength(p) == oracle.path_length(p)
+    dp = C.POINTER(C.c_double)
+    p, out = np.zeros((2, 3)), np.zeros((4, 3))
+    assert _lib.lib().topay_discretize_path(p.ctypes.data_as(dp), 2, 1, out.ctypes.data_as(dp)) < 0
+    assert _lib.lib().topay_discretize_path(p.ctypes.data_as(dp), 1, 4, out.ctypes.data_as(dp)) < 0

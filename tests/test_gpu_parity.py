@@ -366,6 +366,27 @@ def test_line_visibility_rays(gpu_scene, small_scene):
     assert 0.05 < vg.mean() < 0.98
 
 
+def test_same_topo_paths_batch(gpu_scene, small_scene):
+    """N2: TopologyPRM::sameTopoPath for all pairs of a set of paths in one launch (topay_field_same_topo_paths:
+    host discretizePath + one batch of visibility rays) against the oracle's verdict pair by pair (= the reference's,
+    test_ref_pin.py::test_same_topo_path_bit_exact)."""
+    of = small_scene["field"]
+    rng = np.random.default_rng(41)
+    a, b = np.array([-7.5, -6.0]), np.array([7.0, 6.5])
+    paths = []
+    for _ in range(14):
+        k = int(rng.integers(0, 4))
+        mid = [a + (b - a) * t + rng.normal(size=2) * rng.choice([0.05, 1.0, 3.0]) for t in np.sort(rng.uniform(0.1, 0.9, k))]
+        xy = np.clip(np.array([a] + mid + [b]), -9.5, 9.5)
+        paths.append(np.concatenate([xy, np.zeros((len(xy), 1))], axis=1))
+    pairs = np.array([(i, j) for i in range(len(paths)) for j in range(i + 1, len(paths))])
+    for crit in (False, True):
+        got = gpu_scene.sameTopoPaths(paths, pairs, 0.0, crit)
+        exp = np.array([of.same_topo_path(paths[i], paths[j], 0.0, crit) for i, j in pairs])
+        assert np.array_equal(got, exp)
+    assert 0 < exp.sum() < len(exp)
+
+
 def test_solvers_of_different_capacity_coexist(gpu_scene):
     """Kernel attributes (dynamic shared memory) are per kernel, not per solver: a small solver created after a
     large one must not break the large one, and results do not depend on what else was created."""

@@ -224,6 +224,40 @@ def test_line_visib_bit_exact(oracle, small_scene, ref_scene):
             assert 0.05 < va.mean() < 0.98
 
 
+def _topo_paths(rng, n):
+    """Pairs of polylines between common end points, as the PRM's path search returns them: some hug each other (same
+    class), some pass on different sides of obstacles."""
+    out = []
+    for i in range(n):
+        a, b = rng.uniform(-8.5, 8.5, 2), rng.uniform(-8.5, 8.5, 2)
+        paths = []
+        for _ in range(2):
+            k = int(rng.integers(0, 4))
+            mid = [a + (b - a) * t + rng.normal(size=2) * rng.choice([0.05, 0.8, 2.5]) for t in np.sort(rng.uniform(0.1, 0.9, k))]
+            xy = np.clip(np.array([a] + mid + [b]), -9.5, 9.5)
+            paths.append(np.concatenate([xy, np.zeros((len(xy), 1))], axis=1))
+        out.append(paths)
+    return out
+
+
+def test_same_topo_path_bit_exact(oracle, small_scene, ref_scene):
+    """N2: TopologyPRM::pathLength, discretizePath and sameTopoPath (topo_prm.cpp:424-506): lengths and the equally
+    spaced points bit for bit, the equivalence verdict on 300 path pairs (inflated and critical map)."""
+    of = small_scene["field"]
+    rng = np.random.default_rng(8)
+    pairs = _topo_paths(rng, 300)
+    verdicts = []
+    for p1, p2 in pairs:
+        assert R.path_length(ref_scene, p1) == oracle.path_length(p1)
+        pt = int(rng.integers(2, 120))
+        assert np.array_equal(R.discretize_path(ref_scene, p1, pt), oracle.discretize_path(p1, pt))
+        for crit in (False, True):
+            a = R.same_topo_path(ref_scene, p1, p2, 0.0, crit)
+            assert a == of.same_topo_path(p1, p2, 0.0, crit)
+            verdicts.append(a)
+    assert 0.05 < np.mean(verdicts) < 0.95
+
+
 @pytest.mark.parametrize("int_K,pieces", [(12, 0), (5, 0), (32, 64)])
 def test_cost_callbacks_bit_exact(oracle, small_scene, ref_scene, int_K, pieces):
     """a2, a6, a7, a12: first/secondStageCostCallback (moma_traj_opt.cpp:817-955) = generate + jerk + the penalty loops

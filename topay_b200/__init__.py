@@ -8,8 +8,9 @@ from ._structs import (LBFGSERR_TICK_CAP, MAP2D_CRITICAL, MAP2D_FLAT, MAP2D_INFL
                        RobotParams, RogDesc, grid_desc, num_vars, prob_desc, rog_desc)
 from .field import GridMap, robot_params_default
 from .rog import ESDFMap, ProbMap
-from .optimizer import MomaTraj, MomaTrajOpt, getDensePath, opt_params_default, prepare_candidate
+from .optimizer import (MomaTraj, MomaTrajOpt, discretizePath, getDensePath, opt_params_default, pathLength,
+                        prepare_candidate)
 
 __all__ = ["GridMap", "ESDFMap", "ProbMap", "prob_desc", "rog_desc", "RogDesc", "MomaTrajOpt", "MomaTraj", "grid_desc", "GridDesc", "OptParams", "RobotParams",
-           "robot_params_default", "opt_params_default", "prepare_candidate", "getDensePath", "num_vars", "TERM_NAMES",
+           "robot_params_default", "opt_params_default", "prepare_candidate", "getDensePath", "discretizePath", "pathLength", "num_vars", "TERM_NAMES",
            "MAP2D_FLAT", "MAP2D_INFLATE", "MAP2D_CRITICAL", "MAP3D", "LBFGSERR_TICK_CAP"]

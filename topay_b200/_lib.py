@@ -59,6 +59,9 @@ PROTOTYPES = {
     "topay_field_is_line_collision_grid2d": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_double, _i8p]),
     "topay_field_dist_coarse2d": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int, _dp]),
     "topay_field_line_visible": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_double, C.c_int, _i8p, _dp]),
+    "topay_field_same_topo_paths": (C.c_int, [C.c_void_p, _dp, _ip, C.c_int, _ip, C.c_int, C.c_double, C.c_int, _i8p]),
+    "topay_path_length": (C.c_double, [_dp, C.c_int]),
+    "topay_discretize_path": (C.c_int, [_dp, C.c_int, C.c_int, _dp]),
     "topay_dense_path": (C.c_int, [_dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _dp,
                                    C.c_int]),
     "topay_field_dist_coarse2i": (C.c_int, [C.c_void_p, _ip, C.c_int64, C.c_int, _dp]),

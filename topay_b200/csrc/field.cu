@@ -1230,6 +1230,52 @@ extern "C" int topay_field_line_visible(topay_field* f, const double* p1, const 
     return TOPAY_OK;
 }
 
+extern "C" int topay_discretize_path(const double* path, int n, int pt_num, double* out);
+extern "C" double topay_path_length(const double* path, int n);
+
+// TopologyPRM::sameTopoPath (topo_prm.cpp:424-448) for many pairs of paths at once: the equally spaced points of
+// both paths of every pair (host arithmetic) become one batch of visibility rays (one launch), a pair is the same
+// class when all of its rays are free.
+extern "C" int topay_field_same_topo_paths(topay_field* f, const double* pts, const int32_t* offsets, int n_paths,
+                                           const int32_t* pairs, int n_pairs, double thresh, int use_critical,
+                                           int8_t* same) {
+    if (!f || !pts || !offsets || !pairs || !same || n_paths < 1 || n_pairs < 0) return TOPAY_ERR_INVALID_ARG;
+    std::vector<double> p1, p2;
+    std::vector<int64_t> first(n_pairs + 1, 0);
+    std::vector<double> a, b;
+    for (int k = 0; k < n_pairs; k++) {
+        const int i = pairs[2 * k], j = pairs[2 * k + 1];
+        if (i < 0 || j < 0 || i >= n_paths || j >= n_paths) return TOPAY_ERR_INVALID_ARG;
+        const double *pa = pts + 3 * (size_t)offsets[i], *pb = pts + 3 * (size_t)offsets[j];
+        const int na = offsets[i + 1] - offsets[i], nb = offsets[j + 1] - offsets[j];
+        if (na < 2 || nb < 2) return TOPAY_ERR_INVALID_ARG;
+        const double max_len = std::max(topay_path_length(pa, na), topay_path_length(pb, nb));
+        const int pt_num = (int)ceil(max_len / f->desc.resolution);
+        if (pt_num < 2) {       // both paths inside one cell: the reference divides by pt_num - 1 = 0 here
+            tp_set_error("same_topo_paths: paths shorter than one cell");
+            return TOPAY_ERR_INVALID_ARG;
+        }
+        a.resize((size_t)pt_num * 3);
+        b.resize((size_t)pt_num * 3);
+        topay_discretize_path(pa, na, pt_num, a.data());
+        topay_discretize_path(pb, nb, pt_num, b.data());
+        p1.insert(p1.end(), a.begin(), a.end());
+        p2.insert(p2.end(), b.begin(), b.end());
+        first[k + 1] = first[k] + pt_num;
+    }
+    const int64_t n = first[n_pairs];
+    std::vector<int8_t> vis((size_t)std::max<int64_t>(n, 1));
+    std::vector<double> pc((size_t)std::max<int64_t>(n, 1) * 3, 0.0);
+    const int rc = topay_field_line_visible(f, p1.data(), p2.data(), n, thresh, use_critical, vis.data(), pc.data());
+    if (rc != TOPAY_OK) return rc;
+    for (int k = 0; k < n_pairs; k++) {
+        int8_t all = 1;
+        for (int64_t r = first[k]; r < first[k + 1]; r++) all &= vis[r];
+        same[k] = all;
+    }
+    return TOPAY_OK;
+}
+
 extern "C" int topay_field_download(topay_field* f, int which, double* esdf_out) {
     if (!f || !esdf_out || which < 0 || which > 3) return TOPAY_ERR_INVALID_ARG;
     cudaSetDevice(f->device);

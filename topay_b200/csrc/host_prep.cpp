@@ -413,3 +413,39 @@ extern "C" int topay_dense_path(const double* raw, int n, double step_size, doub
     }
     return rows.count;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// TopologyPRM::pathLength / discretizePath (src/planner/src/topo_prm.cpp:462-506): pt_num points at equal arc-length
+// spacing along a 3-D polyline. The reference looks the segment of every point up from the start of the path with
+// a 1e-4 tolerance window and takes the first hit; arc length only grows along the points, so a moving index
+// finds the same segment. Same arithmetic per point, bit-identical.
+extern "C" double topay_path_length(const double* path, int n) {
+    double length = 0.0;
+    if (!path || n < 2) return length;
+    for (int i = 0; i + 1 < n; i++) {
+        const double dx = path[3 * i + 3] - path[3 * i], dy = path[3 * i + 4] - path[3 * i + 1],
+                     dz = path[3 * i + 5] - path[3 * i + 2];
+        length += sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    return length;
+}
+
+extern "C" int topay_discretize_path(const double* path, int n, int pt_num, double* out) {
+    if (!path || !out || n < 2 || pt_num < 2) return TOPAY_ERR_INVALID_ARG;
+    std::vector<double> cum(n);
+    cum[0] = 0.0;
+    for (int i = 0; i + 1 < n; i++) {
+        const double dx = path[3 * i + 3] - path[3 * i], dy = path[3 * i + 4] - path[3 * i + 1],
+                     dz = path[3 * i + 5] - path[3 * i + 2];
+        cum[i + 1] = sqrt(dx * dx + dy * dy + dz * dz) + cum[i];
+    }
+    const double dl = cum[n - 1] / double(pt_num - 1);
+    int j = 0;
+    for (int i = 0; i < pt_num; i++) {
+        const double cur_l = double(i) * dl;
+        while (j < n - 2 && !(cur_l >= cum[j] - 1e-4 && cur_l <= cum[j + 1] + 1e-4)) j++;
+        const double lambda = (cur_l - cum[j]) / (cum[j + 1] - cum[j]);
+        for (int k = 0; k < 3; k++) out[3 * i + k] = (1 - lambda) * path[3 * j + k] + lambda * path[3 * j + 3 + k];
+    }
+    return TOPAY_OK;
+}

@@ -160,6 +160,19 @@ class GridMap:
                                                     _p(vis, C.c_int8), _p(pc)), "line_visible")
         return vis.astype(bool), pc
 
+    def sameTopoPaths(self, paths, pairs, thresh, use_critical=False):
+        """TopologyPRM::sameTopoPath (topo_prm.cpp:424-448) for many pairs at once: `paths` is a list of (n_i, 3)
+        polylines, `pairs` an (m, 2) array of path indices; returns m booleans."""
+        paths = [np.ascontiguousarray(p, dtype=np.float64).reshape(-1, 3) for p in paths]
+        pts = np.ascontiguousarray(np.concatenate(paths))
+        off = np.cumsum([0] + [len(p) for p in paths]).astype(np.int32)
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        same = np.zeros(len(pairs), dtype=np.int8)
+        _lib.check(self._l.topay_field_same_topo_paths(self.h, _p(pts), _p(off, C.c_int32), len(paths), _p(pairs, C.c_int32),
+                                                       len(pairs), C.c_double(thresh), int(use_critical), _p(same, C.c_int8)),
+                   "same_topo_paths")
+        return same.astype(bool)
+
     # ---- index helpers (pure host arithmetic, grid_map.h:727-885) ---------------
     @property
     def map_origin(self):

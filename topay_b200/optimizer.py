@@ -373,3 +373,18 @@ def getDensePath(raw_path, step_size, start_yaw, end_yaw, v_max, w_max):
         if n <= cap:
             return out[:n]
         cap = n
+
+
+def discretizePath(path, pt_num):
+    """TopologyPRM::discretizePath (topo_prm.cpp:472-506) through topay_discretize_path: pt_num points at equal
+    arc-length spacing along an (n, 3) polyline. Host arithmetic."""
+    path = np.ascontiguousarray(path, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((int(pt_num), 3))
+    _lib.check(_lib.lib().topay_discretize_path(_p(path), path.shape[0], int(pt_num), _p(out)), "topay_discretize_path")
+    return out
+
+
+def pathLength(path):
+    """TopologyPRM::pathLength (topo_prm.cpp:462-470)."""
+    path = np.ascontiguousarray(path, dtype=np.float64).reshape(-1, 3)
+    return float(_lib.lib().topay_path_length(_p(path), path.shape[0]))
