@@ -506,6 +506,14 @@ int topay_solver_solve_batch(topay_solver* s, int n_cand, const int32_t* path_le
 int topay_solver_upload(topay_solver* s, int n_cand, const int32_t* path_len,
                         const double* init_paths, const double* bvel, const double* bacc);
 int topay_solver_run(topay_solver* s);          /* device solve of the uploaded batch, blocking */
+/* Scenario sweeps (BASELINE configs[4]: thousands of independent scenarios, each with its own 200 x 200 x 16 field and
+ * a handful of candidates; the reference plans them one after the other, planner.cpp:494-548 + :847-1010): the
+ * candidates of ONE upload may belong to different scenarios. field_of[c] (one entry per uploaded candidate) indexes
+ * `fields` (dense fields on the solver's device, rebuilt before the run); the solve, the success gate
+ * (topay_solver_check_feasible) and the selection then read every candidate against its own field, so that a whole
+ * group of scenarios shares the launches of one solve. The assignment holds for uploads of the same size until it is
+ * changed; n_fields <= 1 returns to the solver's own field. Call after topay_solver_upload. */
+int topay_solver_assign_fields(topay_solver* s, topay_field* const* fields, int n_fields, const int32_t* field_of);
 int topay_solver_download(topay_solver* s, topay_result_batch* out, int32_t* best_by_duration,
                           int32_t* best_by_cost);
 

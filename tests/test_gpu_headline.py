@@ -161,6 +161,46 @@ def test_tick_cap_marks_unfinished_candidates(gpu_scene, monkeypatch, lanes):
     assert (full["evals"][done] <= 160).all()
 
 
+def test_scenarios_with_their_own_fields_share_one_solve():
+    """BASELINE configs[4]: the candidates of several scenarios, each with its own field, in ONE upload
+    (topay_solver_assign_fields). Every scenario's winner, trajectory and gate verdicts are bit-identical to solving that
+    scenario alone against its field — also when the plans are handed over in another order and with two lanes."""
+    import topay_b200 as tp
+    from topay_b200 import scenes
+    opt, rp = tp.opt_params_default(), tp.robot_params_default()
+    n_sc, n_c = 5, 6
+    fields, plans, alone = [], [], []
+    for sc in range(n_sc):
+        g = tp.GridMap(tp.grid_desc())
+        g.regenerateMap(scenes.tables_scene(70 + sc)[0] if sc % 2 == 0 else scenes.cuboids_scene(70 + sc)[0])
+        fields.append(g)
+        plans.append(scenes.short_candidates(n_c, 3000 + sc))
+        one = tp.MomaTrajOpt(g, max_cand=n_c, max_pieces=16, opt_param=opt, robot=rp)
+        alone.append((one.planWinners([plans[sc]], use_gate=True)[0], {k: v.copy() for k, v in one.constraints.items()}))
+        one.close()
+    pool = tp.MomaTrajOpt(fields[0], max_cand=n_sc * n_c, max_pieces=16, opt_param=opt, robot=rp, n_slots=16)
+    for order in (list(range(n_sc)), [3, 0, 4, 2, 1]):
+        got = pool.planWinners([plans[i] for i in order], use_gate=True, fields=[fields[i] for i in order])
+        gate = pool.constraints
+        for pos, sc in enumerate(order):
+            w, (a, ag) = got[pos], alone[sc]
+            assert (w is None) == (a is None)
+            if w is not None:
+                assert w["index"] == a["index"]
+                for k, v in a.items():
+                    if isinstance(v, np.ndarray):
+                        assert np.array_equal(v, w[k]), (sc, k)
+            for k in ("feasible", "feasible_print"):
+                assert np.array_equal(gate[k][pos * n_c:(pos + 1) * n_c], ag[k]), (sc, k)
+    # back to the solver's own field
+    pool.assign_fields(None, None)
+    back = pool.planWinners([plans[0]], use_gate=True)[0]
+    assert (back is None) == (alone[0][0] is None) and (back is None or back["index"] == alone[0][0]["index"])
+    pool.close()
+    for g in fields:
+        g.close()
+
+
 def test_headline_config_solve_against_the_oracle(gpu_scene, small_scene, oracle):
     """The headline workload itself: the first 4 candidates of scenes.synthetic_batch(256, 1234) at 64 pieces x
     int_K 32, solved on the device and by the oracle (= the reference, bit for bit). The solve is chaotic — the

@@ -74,6 +74,11 @@ struct topay_solver {
     int32_t *list_b, *count_b;  // lane B's live lists / counts (lane A uses dev.list / dev.count)
     cudaStream_t stream2;
     cudaEvent_t ev_fork, ev_join;
+    // scenario sweeps: candidates of one upload may belong to different fields (topay_solver_assign_fields)
+    std::vector<topay_field*> fields;
+    TpGrid* d_grids;            // [max_cand] (a field per candidate at most), allocated on first use
+    int32_t* d_field_of;        // [max_cand]
+    int fields_n_cand;          // the upload size the assignment was made for
     // success gate (topay_solver_check_feasible): built on first use
     TpTrajChecker* checker;
     int32_t* d_pn;
@@ -86,7 +91,14 @@ void solver_grid(const topay_solver* s, TpGrid* G) {
     if (s->rog) tp_rogfield_grid(s->rog, G);
     else tp_field_grid(s->field, G);
 }
-bool solver_field_ready(const topay_solver* s) { return s->rog ? tp_rogfield_ready(s->rog) : tp_field_ready(s->field); }
+bool solver_field_ready(const topay_solver* s) {
+    if (s->dev.n_fields > 1) {
+        for (const topay_field* f : s->fields)
+            if (!tp_field_ready(f)) return false;
+        return true;
+    }
+    return s->rog ? tp_rogfield_ready(s->rog) : tp_field_ready(s->field);
+}
 
 template <typename T>
 int dev_alloc(topay_solver* s, T** p, size_t count) {
@@ -139,11 +151,20 @@ void launch_eval(topay_solver* s, bool timed, int tick, int ny) {
     if (timed) cudaEventRecord(s->ev[TP_EV * te], s->stream);
     k_integrate<<<g1, blk, sm_int, s->stream>>>(D, tick);
     if (timed) cudaEventRecord(s->ev[TP_EV * te + 1], s->stream);
-    switch (D.Kpad) {
-        case 4: k_penalty<4><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
-        case 8: k_penalty<8><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
-        case 16: k_penalty<16><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
-        default: k_penalty<32><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+    if (D.n_fields > 1) {
+        switch (D.Kpad) {
+            case 4: k_penalty<4, true><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+            case 8: k_penalty<8, true><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+            case 16: k_penalty<16, true><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+            default: k_penalty<32, true><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+        }
+    } else {
+        switch (D.Kpad) {
+            case 4: k_penalty<4><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+            case 8: k_penalty<8><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+            case 16: k_penalty<16><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+            default: k_penalty<32><<<g2, blk2, sm_pen, s->stream>>>(D, s->params, G, groups, tick); break;
+        }
     }
     if (timed) cudaEventRecord(s->ev[TP_EV * te + 2], s->stream);
     k_chain<<<g1, blk, 0, s->stream>>>(D, s->params, tick);
@@ -399,6 +420,10 @@ static int solver_create(const topay_opt_params* opt, const topay_robot_params* 
         TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(8)), { topay_solver_destroy(s); });
         TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(16)), { topay_solver_destroy(s); });
         TP_CUDA_OK(cudaFuncSetAttribute(k_penalty<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(32)), { topay_solver_destroy(s); });
+        cudaFuncSetAttribute(k_penalty<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(4));
+        cudaFuncSetAttribute(k_penalty<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(8));
+        cudaFuncSetAttribute(k_penalty<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(16));
+        cudaFuncSetAttribute(k_penalty<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)penalty_smem(32));
     }
     TP_CUDA_OK(cudaStreamSynchronize(s->stream), { topay_solver_destroy(s); });
     *out = s;
@@ -549,6 +574,46 @@ extern "C" int topay_solver_eval(topay_solver* s, int stage, const topay_problem
     return TOPAY_OK;
 }
 
+// Scenario sweeps (BASELINE configs[4]): the candidates of ONE upload may belong to different scenarios, each with its
+// own field. field_of[c] (n_cand entries, the uploaded batch) indexes `fields`; all fields live on the solver's device
+// and are dense GridMap fields. The assignment holds for uploads of the same size until it is changed; n_fields <= 1
+// returns to the solver's own field. Call after topay_solver_upload, before topay_solver_run; rebuild the fields first.
+extern "C" int topay_solver_assign_fields(topay_solver* s, topay_field* const* fields, int n_fields,
+                                          const int32_t* field_of) {
+    if (!s) return TOPAY_ERR_INVALID_ARG;
+    cudaSetDevice(s->device);
+    TpSolverDev& D = s->dev;
+    if (n_fields <= 1) {
+        if (D.n_fields > 1) drop_graphs(s);     // the captured kernel arguments change
+        D.n_fields = 0;
+        s->fields.clear();
+        return TOPAY_OK;
+    }
+    if (!fields || !field_of || s->rog || s->n_cand < 1 || n_fields > D.max_cand) return TOPAY_ERR_INVALID_ARG;
+    std::vector<TpGrid> hg(n_fields);
+    for (int i = 0; i < n_fields; i++) {
+        if (!fields[i] || tp_field_device(fields[i]) != s->device) return TOPAY_ERR_INVALID_ARG;
+        tp_field_grid(fields[i], &hg[i]);
+    }
+    for (int c = 0; c < s->n_cand; c++)
+        if (field_of[c] < 0 || field_of[c] >= n_fields) return TOPAY_ERR_INVALID_ARG;
+    int rc;
+    if (!s->d_grids) {
+        if ((rc = dev_alloc(s, &s->d_grids, (size_t)D.max_cand)) != TOPAY_OK) return rc;
+        if ((rc = dev_alloc(s, &s->d_field_of, (size_t)D.max_cand)) != TOPAY_OK) return rc;
+    }
+    TP_CUDA_OK(cudaMemcpyAsync(s->d_grids, hg.data(), (size_t)n_fields * sizeof(TpGrid), cudaMemcpyHostToDevice, s->stream), {});
+    TP_CUDA_OK(cudaMemcpyAsync(s->d_field_of, field_of, (size_t)s->n_cand * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream), {});
+    TP_CUDA_OK(cudaStreamSynchronize(s->stream), {});
+    if (D.n_fields <= 1) drop_graphs(s);
+    D.grids = s->d_grids;
+    D.field_of = s->d_field_of;
+    D.n_fields = 2;             // "one field per candidate" (the kernels only test > 1)
+    s->fields.assign(fields, fields + n_fields);
+    s->fields_n_cand = s->n_cand;
+    return TOPAY_OK;
+}
+
 extern "C" int topay_solver_upload(topay_solver* s, int n_cand, const int32_t* path_len, const double* init_paths,
                                    const double* bvel, const double* bacc) {
     if (!s || !path_len || !init_paths || !bvel || !bacc) return TOPAY_ERR_INVALID_ARG;
@@ -648,6 +713,10 @@ extern "C" int topay_solver_run(topay_solver* s) {
     if (!s || s->n_cand < 1) return TOPAY_ERR_INVALID_ARG;
     if (!solver_field_ready(s)) {
         tp_set_error("field not built: call topay_field_rebuild first");
+        return TOPAY_ERR_NOT_READY;
+    }
+    if (s->dev.n_fields > 1 && s->fields_n_cand != s->n_cand) {
+        tp_set_error("the field assignment was made for an upload of another size: call topay_solver_assign_fields again");
         return TOPAY_ERR_NOT_READY;
     }
     cudaSetDevice(s->device);
@@ -887,7 +956,7 @@ extern "C" int topay_solver_check_feasible(topay_solver* s, topay_feasibility* o
         fp.resize(n);
         out->feasible_print = fp.data();
     }
-    rc = s->checker->check(V, s->params, G, out);
+    rc = s->checker->check(V, s->params, G, out, D.n_fields > 1 ? D.grids : nullptr, D.field_of);
     s->checker->checked_n = rc == TOPAY_OK ? n : 0;
     out->feasible_print = keep_fp;
     if (rc == TOPAY_OK && best_success) {

@@ -63,6 +63,11 @@ struct TpSolverDev {
     double *res_T;            // [store][max_pieces]
     double *res_coeff;        // [store][6*max_pieces][9]   coefficients of the last evaluation (what getTraj() returns)
     double *res_x;            // [store][xs]
+    // fields: one per solver (the kernels' grid argument), or — scenario sweeps — one per candidate: grids[field_of[gid]]
+    const TpGrid* grids;      // [n_fields] or null
+    const int32_t* field_of;  // [store]
+    int32_t n_fields;         // 0 / 1: the solver's own field
+    int32_t pad_fields_;
     // scheduling
     int32_t *slot_gid;        // [slot] candidate in the slot
     int32_t *list;            // [TP_TICKS + 1][n_slots] live slots before tick t
@@ -272,15 +277,25 @@ __device__ __forceinline__ void tp_transpose_reduce64(Gen gen, double* v /*[32]*
     }
 }
 
-template <int KPAD>
+// MULTI: every candidate reads the field of its own scenario (S.grids[S.field_of[gid]], staged in shared memory once per
+// block) instead of the solver's one field (the constant-bank argument G0).
+template <int KPAD, bool MULTI = false>
 __global__ void __launch_bounds__(TP_PEN_WARPS * 32, TP_PEN_MIN_BLOCKS)
 k_penalty(const __grid_constant__ TpSolverDev S, const __grid_constant__ TpParams P,
-          const __grid_constant__ TpGrid G, int n_groups, int tick) {
+          const __grid_constant__ TpGrid G0, int n_groups, int tick) {
     const int cand = tp_live_slot(S, tick, blockIdx.y);   // slot
     if (cand < 0) return;
     const TpCandState& cs = S.st[cand];
     if (cs.phase == 0) return;
     const int gid = S.slot_gid[cand];
+    __shared__ TpGrid s_grid;
+    if (MULTI) {
+        const double* src = reinterpret_cast<const double*>(S.grids + S.field_of[gid]);
+        double* dst = reinterpret_cast<double*>(&s_grid);
+        for (int i = threadIdx.x; i < (int)(sizeof(TpGrid) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const TpGrid& G = MULTI ? s_grid : G0;
     const int STAGE = cs.phase;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = S.K, N = cs.N;

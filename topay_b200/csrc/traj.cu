@@ -149,8 +149,18 @@ __device__ __forceinline__ void maxabs_merge(MaxAbs& m, double oa, double ov, in
 
 // moma_traj_opt.h:948-1045 / :1047-1210
 __global__ void __launch_bounds__(TP_TRAJ_THREADS)
-k_feasible(TpTrajView V, const __grid_constant__ TpParams P, TpGrid g, const TpTrajMeta* __restrict__ meta,
+k_feasible(TpTrajView V, const __grid_constant__ TpParams P, const __grid_constant__ TpGrid g0,
+           const TpGrid* __restrict__ grids, const int32_t* __restrict__ field_of, const TpTrajMeta* __restrict__ meta,
            const double* __restrict__ car_seq, const double* __restrict__ ttab, TpFeasOut* out) {
+    // scenario sweeps: trajectory i is checked against the field of its own scenario, grids[field_of[i]]
+    __shared__ TpGrid s_grid;
+    if (grids) {
+        const double* src = reinterpret_cast<const double*>(grids + field_of[blockIdx.x]);
+        double* dst = reinterpret_cast<double*>(&s_grid);
+        for (int w = threadIdx.x; w < (int)(sizeof(TpGrid) / sizeof(double)); w += TP_TRAJ_THREADS) dst[w] = src[w];
+        __syncthreads();
+    }
+    const TpGrid& g = grids ? s_grid : g0;
     __shared__ double s_a[TP_TRAJ_THREADS / 32][TP_NMAXABS], s_v[TP_TRAJ_THREADS / 32][TP_NMAXABS];
     __shared__ int s_i[TP_TRAJ_THREADS / 32][TP_NMAXABS];
     __shared__ double s_m[TP_TRAJ_THREADS / 32][TP_NMIN];
@@ -319,10 +329,11 @@ int TpTrajChecker::prepare(const TpTrajView& V) {
     return TOPAY_OK;
 }
 
-int TpTrajChecker::check(const TpTrajView& V, const TpParams& P, const TpGrid& g, topay_feasibility* out) {
+int TpTrajChecker::check(const TpTrajView& V, const TpParams& P, const TpGrid& g, topay_feasibility* out,
+                         const TpGrid* grids, const int32_t* field_of) {
     int rc = prepare(V);
     if (rc != TOPAY_OK) return rc;
-    k_feasible<<<V.n, TP_TRAJ_THREADS, 0, stream>>>(V, P, g, meta, car_seq, ttab, feas);
+    k_feasible<<<V.n, TP_TRAJ_THREADS, 0, stream>>>(V, P, g, grids, field_of, meta, car_seq, ttab, feas);
     std::vector<TpFeasOut> h(V.n);
     TP_CUDA_OK(cudaMemcpyAsync(h.data(), feas, (size_t)V.n * sizeof(TpFeasOut), cudaMemcpyDeviceToHost, stream), {});
     TP_CUDA_OK(cudaStreamSynchronize(stream), {});

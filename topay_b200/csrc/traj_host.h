@@ -47,5 +47,6 @@ struct TpTrajChecker {
     int init(int device, cudaStream_t stream);
     // durations, sample counts and the pose tables of the batch (one host round trip for the sizes)
     int prepare(const TpTrajView& V);
-    int check(const TpTrajView& V, const TpParams& P, const TpGrid& g, topay_feasibility* out);
+    int check(const TpTrajView& V, const TpParams& P, const TpGrid& g, topay_feasibility* out,
+              const TpGrid* grids = nullptr, const int32_t* field_of = nullptr);   // per-trajectory fields (sweeps)
 };

@@ -170,6 +170,20 @@ class MomaTrajOpt:
         self._starts = [np.asarray(p)[0, :3].copy() for p in paths]
         self.h2d_bytes = int(plen.nbytes + flat.nbytes + bvel.nbytes + bacc.nbytes)
 
+    def assign_fields(self, fields, field_of):
+        """topay_solver_assign_fields: candidate c of the uploaded batch is solved (and gated) against fields[field_of[c]]
+        — scenario sweeps, where one upload carries the candidates of many scenarios. `fields` = GridMap objects on
+        this solver's device, rebuilt before run(); None / a single field returns to the solver's own field."""
+        if not fields or len(fields) <= 1:
+            _lib.check(self._l.topay_solver_assign_fields(self.h, None, 0, None), "topay_solver_assign_fields")
+            self._fields = None
+            return
+        hs = (C.c_void_p * len(fields))(*[f.h for f in fields])
+        fo = np.ascontiguousarray(field_of, dtype=np.int32)
+        assert len(fo) == self._n
+        _lib.check(self._l.topay_solver_assign_fields(self.h, hs, len(fields), _p(fo, C.c_int32)), "topay_solver_assign_fields")
+        self._fields = list(fields)       # keep them alive
+
     def run(self):
         _lib.check(self._l.topay_solver_run(self.h), "topay_solver_run")
 
@@ -216,16 +230,19 @@ class MomaTrajOpt:
         out["nbytes"] = int(sum(v.nbytes for v in r.values()))
         return out
 
-    def planWinners(self, plans, use_gate=True):
+    def planWinners(self, plans, use_gate=True, fields=None):
         """The worker loop of planner.cpp:847-1010 for several plans in one device solve: every candidate is optimised
         (continuous batching), passed through the success gate (optimizeTraj && printConstraintsSituations,
         :877-880) and the shortest trajectory of each plan is picked (:999-1010) — all on the device; only each
         plan's winner crosses the bus. Returns a list with one entry per plan: the winner's result dict
-        (download_candidate, `index` inside the plan) or None."""
+        (download_candidate, `index` inside the plan) or None. `fields`: one GridMap per plan (scenario sweeps: every
+        plan is solved and gated against its own scenario's field, all plans share the launches of one solve)."""
         paths = [q for p in plans for q in p[0]]
         bv = np.concatenate([np.asarray(p[1], dtype=np.float64).reshape(len(p[0]), 10, 2) for p in plans])
         ba = np.concatenate([np.asarray(p[2], dtype=np.float64).reshape(len(p[0]), 10, 2) for p in plans])
         self.upload(paths, bv, ba)
+        if fields is not None:      # plan i against its own scenario's field (scenario sweeps)
+            self.assign_fields(fields, np.repeat(np.arange(len(plans)), [len(p[0]) for p in plans]))
         self.run()
         self.d2h_bytes = 0
         if use_gate:
