@@ -363,6 +363,12 @@ public:
     }
     int32_t best_by_duration = -1, best_by_cost = -1;
 
+    // scenario sweeps: candidate c of the uploaded batch is solved and gated against fields[field_of[c]]
+    void assignFields(const std::vector<GridMap*>& fields, const std::vector<int32_t>& field_of) {
+        std::vector<topay_field*> h;
+        for (GridMap* g : fields) h.push_back(g->handle());
+        topay_check(topay_solver_assign_fields(s_, h.data(), (int)h.size(), field_of.data()), "topay_solver_assign_fields");
+    }
 private:
     bool gate(const MomaTraj& traj, bool print_rule) {
         int32_t pn, f = 0, fp = 0;
