@@ -214,6 +214,7 @@ struct TpLaneB {
 
 static int solver_create(const topay_opt_params* opt, const topay_robot_params* robot, topay_field* field,
                          topay_rogfield* rog, int max_cand, int n_slots, int max_pieces, topay_solver** out);
+extern "C" int topay_solver_assign_fields(topay_solver* s, topay_field* const* fields, int n_fields, const int32_t* field_of);
 
 extern "C" int topay_solver_create(const topay_opt_params* opt, const topay_robot_params* robot,
                                    topay_field* field, int max_cand, int max_pieces, topay_solver** out) {
@@ -542,6 +543,7 @@ extern "C" int topay_solver_eval(topay_solver* s, int stage, const topay_problem
         tp_set_error("topay_solver_eval evaluates at most n_slots candidates at a time");
         return TOPAY_ERR_TOO_LARGE;
     }
+    if (s->dev.n_fields > 1) topay_solver_assign_fields(s, nullptr, 0, nullptr);   // evaluations read the solver's own field
     int rc = upload_problem(s, prob->n_cand, prob->piece_num, prob->head_pva, prob->tail_pva, prob->start_xy,
                             prob->end_xy, prob->init_inner_xy, x, x_stride, nullptr, stage, prob->alm_lambda,
                             prob->alm_rho);
